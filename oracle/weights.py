@@ -1,0 +1,54 @@
+"""Seeded weights in Keras ``get_weights()`` order and layout.  TEST INFRASTRUCTURE.
+
+TensorFlow cannot be installed here, so "random-init weights" are drawn by this module (seeded
+numpy) and loaded, unchanged, by both the oracle networks (oracle/nets_torch.py) and the product
+(``processor.set_weights``).  Layouts:
+
+  Conv3D            kernel (kz,ky,kx,Cin,Cout), bias (Cout)
+  Conv3DTranspose   kernel (kz,ky,kx,Cout,Cin), bias (Cout)
+  Dense             kernel (in,out), bias (out)
+  BatchNormalization gamma, beta, moving_mean, moving_variance  (each (C,))
+
+Each spec entry is ``(kind, shape)`` with kind in {"conv_k","conv_b","convT_k","convT_b","dense_k",
+"dense_b","bn_gamma","bn_beta","bn_mean","bn_var"}.  Kernels are glorot-uniform (Keras default,
+``fan_in = k^3 Cin``, ``fan_out = k^3 Cout``) times a He-style gain so that activations stay O(1)
+through 17 LeakyReLU(0.2) layers; BN statistics are randomised so that folding is exercised.
+"""
+import numpy as np
+
+LRELU_GAIN = float(np.sqrt(2.0 / (1.0 + 0.2 ** 2)) * np.sqrt(2.0))  # glorot -> He(fan_in) for fan_in ~ fan_out
+
+
+def draw(spec, seed, gain=LRELU_GAIN):
+    rng = np.random.default_rng(seed)
+    out = []
+    for kind, shape in spec:
+        shape = tuple(int(s) for s in shape)
+        if kind in ("conv_k", "convT_k"):
+            k3 = int(np.prod(shape[:3]))
+            if kind == "conv_k":
+                fan_in, fan_out = k3 * shape[3], k3 * shape[4]
+            else:
+                fan_in, fan_out = k3 * shape[4], k3 * shape[3]
+            g = gain
+            if kind == "convT_k":
+                # each output voxel of a k=2,s=2 transposed conv sees exactly one tap: fan_in is Cin
+                fan_in, fan_out = shape[4], shape[3]
+            lim = g * np.sqrt(6.0 / (fan_in + fan_out))
+            out.append(rng.uniform(-lim, lim, shape).astype(np.float32))
+        elif kind == "dense_k":
+            lim = gain * np.sqrt(6.0 / (shape[0] + shape[1]))
+            out.append(rng.uniform(-lim, lim, shape).astype(np.float32))
+        elif kind in ("conv_b", "convT_b", "dense_b"):
+            out.append(rng.normal(0.0, 0.05, shape).astype(np.float32))
+        elif kind == "bn_gamma":
+            out.append(rng.uniform(0.5, 1.5, shape).astype(np.float32))
+        elif kind == "bn_beta":
+            out.append(rng.normal(0.0, 0.1, shape).astype(np.float32))
+        elif kind == "bn_mean":
+            out.append(rng.normal(0.0, 0.1, shape).astype(np.float32))
+        elif kind == "bn_var":
+            out.append(rng.uniform(0.5, 1.5, shape).astype(np.float32))
+        else:
+            raise ValueError(kind)
+    return out
