@@ -1,0 +1,180 @@
+/* tomoenc.h -- C ABI of libtomoenc.so, the B200 (sm_100a) data plane behind the TomoEncoders hot path.
+ *
+ * The reference (aniketkt/TomoEncoders) is pure Python and has no FFI layer of its own; its boundary for
+ * this path is the Python API (Patches / Grid / SurfaceSegmenter / SelfSupervisedCAE).  The Python
+ * host code in tomoencoders_b200/ keeps that API and routes every data-plane call to the entry points
+ * below through ctypes.  Each entry point cites the reference interface it replaces (paths relative
+ * to /root/reference/tomo_encoders/).
+ *
+ * Conventions
+ *   - all data pointers are DEVICE pointers (e.g. torch.Tensor.data_ptr()) unless marked "host";
+ *   - the caller allocates every output; nothing is retained across calls except opaque handles;
+ *   - `stream` is a cudaStream_t passed as void*; calls enqueue work and return without synchronising
+ *     unless documented otherwise;
+ *   - return value 0 = success, < 0 = error (TE_ERR_*); te_last_error() returns a message for the
+ *     calling thread; nothing throws; a handle may be used from one host thread at a time;
+ *   - coordinates are (z, y, x) corner points, uint32, exactly like Patches.points / Grid.points
+ *     (structures/patches.py:66-67, structures/grid.py:105).
+ */
+#ifndef TOMOENC_H_
+#define TOMOENC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TE_OK 0
+#define TE_ERR_ARG (-1)      /* invalid argument (shape, dtype, null pointer, unsupported configuration) */
+#define TE_ERR_CUDA (-2)     /* a CUDA runtime / driver call failed */
+#define TE_ERR_STATE (-3)    /* handle used in the wrong state (e.g. weights not set) */
+#define TE_ERR_UNSUPPORTED (-4)
+
+/* element types of volumes / patch arrays */
+#define TE_U8 0
+#define TE_U16 1
+#define TE_F16 2
+#define TE_F32 3
+#define TE_BF16 4
+
+/* arithmetic modes of the network entry points */
+#define TE_MODE_BF16 0       /* tcgen05 path: bf16 operands, fp32 TMEM accumulation, bf16 activations */
+#define TE_MODE_FP16 1       /* tcgen05 path: fp16 operands, fp32 TMEM accumulation, fp16 activations */
+#define TE_MODE_FP32_CHECK 2 /* CUDA-core fp32 check mode (slow; used to bound the reduced-precision error) */
+
+int te_version(void);
+const char* te_last_error(void);
+/* Number of kernel launches this library has enqueued since load (process-wide, monotonic). */
+int64_t te_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Patch gather.  Replaces Patches.extract (structures/patches.py:748-781, with _calc_binning
+ * :734-746 and slices :436-453) and Grid.extract (structures/grid.py:313-336):
+ *     out[i] = vol[z:z+wz:b, y:y+wy:b, x:x+wx:b],  b = widths[i] // patch  (isotropic, >= 1)
+ * out is (n, patch[0], patch[1], patch[2]) C-contiguous with the element type of vol; the copy is
+ * bit-exact.  widths is (n,3) uint32 (for a Grid pass the scalar width replicated).  The binning
+ * rules (isotropy, >= 1, widths % patch == 0) are validated by the host code before the call; the
+ * kernel re-derives b = widths[i][0] / patch[0].  elem_size in {1,2,4}.
+ */
+int te_gather(const void* vol, int elem_size, const int64_t vol_shape[3], const uint32_t* points,
+              const uint32_t* widths, int64_t n, const int32_t patch[3], void* out, void* stream);
+
+/* Gather fused with the pre-network clip / rescale.  Replaces extract followed by the per-chunk
+ * np.clip + _rescale_data of SurfaceSegmenter.predict_patches (neural_nets/surface_segmenter.py:
+ * 272-275, misc/voxel_processing.py:81-89):
+ *     out[i] = act((clip(vol[...], lo, hi) - lo) / (hi - lo + 1e-12))   computed in fp32
+ * do_clip = 0 skips the clip (predict_embeddings, neural_nets/autoencoders.py:753); rescale = 0
+ * skips both (min_max=None).  out_dtype in {TE_BF16, TE_F16, TE_F32}.  vol_dtype in
+ * {TE_U8, TE_U16, TE_F16, TE_F32}.
+ */
+int te_gather_norm(const void* vol, int vol_dtype, const int64_t vol_shape[3], const uint32_t* points,
+                   const uint32_t* widths, int64_t n, const int32_t patch[3], int rescale, int do_clip,
+                   float lo, float hi, void* out, int out_dtype, void* stream);
+
+/* Patch scatter / stitch.  Replaces Patches.fill_patches_in_volume (structures/patches.py:811-821)
+ * and Grid.fill_patches_in_volume (structures/grid.py:338-348): sequential
+ *     vol_out[z:z+wz, y:y+wy, x:x+wx] = sub_vols[i]
+ * with "highest patch index wins" on overlap.  sub_vols is (n, wz, wy, wx) of the same element
+ * size as vol_out (the host code performs numpy's assignment cast beforehand); all patches share
+ * one width[3].  If `owner` is NULL the patches must be pairwise disjoint (the host code proves it);
+ * otherwise owner is a uint32 scratch volume of vol_shape elements and the call resolves overlaps
+ * deterministically in two passes (atomicMax of the patch index, then owner-only writes).
+ */
+int te_scatter(const void* sub_vols, int elem_size, const uint32_t* points, int64_t n,
+               const int32_t width[3], void* vol_out, const int64_t vol_shape[3], uint32_t* owner,
+               void* stream);
+
+/* min / max over vol[::s, ::s, ::s].  Replaces _find_min_max (misc/voxel_processing.py:91-104).
+ * out2 = device float[2] {min, max}; scratch = device float[2 * 1024]. */
+int te_minmax_strided(const void* vol, int vol_dtype, const int64_t vol_shape[3], int stride,
+                      float* out2, float* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Convolutional networks.  One handle = one Keras model of the reference:
+ *   kind "unet"    build_Unet_3D            (neural_nets/Unet3D.py:199-291)       -> segmenter / enhancer
+ *   kind "encoder" build_encoder_r          (neural_nets/autoencoders.py:246-347) -> latent vectors
+ *   kind "decoder" build_decoder_r          (neural_nets/autoencoders.py:350-447) -> denoised patches
+ * Weights are supplied once as a flat fp32 blob in Keras get_weights() order and layout
+ * (Conv3D (kz,ky,kx,Cin,Cout), Conv3DTranspose (kz,ky,kx,Cout,Cin), Dense (in,out), BN gamma, beta,
+ * moving_mean, moving_variance); BN (eps 1e-5) is folded at load.
+ */
+typedef struct te_net te_net;
+
+typedef struct te_net_desc {
+  int32_t kind;            /* 0 unet, 1 encoder, 2 decoder */
+  int32_t n_blocks;        /* <= 8 */
+  int32_t n_filters[8];
+  int32_t pool_size[8];
+  int32_t isconcat[8];     /* unet only */
+  int32_t batch_norm;      /* 0/1 */
+  int32_t kern_size;       /* 3 */
+  int32_t kern_size_upconv;/* 2 */
+  int32_t n_hidden;        /* encoder / decoder: len(hidden_units) (<= 8) */
+  int32_t hidden_units[8];
+  int32_t pool_flag;       /* encoder / decoder POOL_FLAG */
+  int32_t patch[3];        /* model input size (z,y,x); the U-net is fully convolutional but a handle is planned for one size */
+  int32_t max_batch;       /* patches per forward call (workspace is sized for it) */
+  float lrelu_alpha;       /* 0.2 */
+  float bn_eps;            /* 1e-5 */
+  int32_t mode;            /* TE_MODE_* */
+} te_net_desc;
+
+/* Number of fp32 values the weight blob must hold for this descriptor (or < 0 on error). */
+int64_t te_net_weight_count(const te_net_desc* desc);
+/* Creates the handle on the current device: plans layers, allocates the activation workspace. */
+int te_net_create(const te_net_desc* desc, te_net** out);
+/* weights: HOST pointer to te_net_weight_count() floats.  Synchronous. */
+int te_net_set_weights(te_net* net, const float* weights_host, int64_t count);
+int te_net_destroy(te_net* net);
+/* Bytes of device memory held by the handle. */
+int64_t te_net_workspace_bytes(const te_net* net);
+
+/* U-net forward.  Replaces models["segmenter"].predict + np.round (surface_segmenter.py:283-291)
+ * and, with out_dtype TE_F32, the enhancer / raw-probability output.
+ *   x        (n, pz, py, px) activations already rescaled, dtype TE_BF16 / TE_F16 (tcgen05 modes) or
+ *            TE_F32 (check mode): the output layout of te_gather_norm
+ *   out      (n, pz, py, px): TE_U8 -> labels, 1 iff sigmoid(logit) > 0.5 (np.round is half-to-even,
+ *            so exactly 0.5 -> 0); TE_F32 -> sigmoid probabilities
+ *   logits   optional (may be NULL) fp32 (n, pz, py, px) pre-sigmoid values
+ * n <= max_batch. */
+int te_unet_forward(te_net* net, const void* x, int64_t n, void* out, int out_dtype, float* logits,
+                    void* stream);
+/* Encoder forward.  Replaces models["encoder"].predict (neural_nets/autoencoders.py:760-767).
+ * z is (n, latent) fp32. */
+int te_encoder_forward(te_net* net, const void* x, int64_t n, float* z, void* stream);
+/* Decoder forward.  Replaces models["decoder"].predict (neural_nets/keras_processor.py:117-131).
+ * z (n, latent) fp32 -> out (n,pz,py,px) fp32 probabilities. */
+int te_decoder_forward(te_net* net, const float* z, int64_t n, float* out, void* stream);
+
+/* Debug / test hook: copies the activation tensor produced by layer `layer_index` during the last
+ * forward call, converted to fp32 NDHWC, into out (device).  Returns the element count. */
+int64_t te_net_layer_output(te_net* net, int layer_index, float* out, int64_t capacity, void* stream);
+int te_net_num_layers(const te_net* net);
+/* Algorithmic FLOPs (2 x MACs, no padding / halo) of one forward pass over one patch. */
+double te_net_flops_per_patch(const te_net* net);
+/* Name, algorithmic FLOPs and kernel class of layer i (host strings owned by the handle). */
+int te_net_layer_info(const te_net* net, int layer_index, const char** name, double* flops, int* uses_tensor_cores);
+
+/* ------------------------------------------------------------------------------------------------
+ * Latent PCA.  Replaces sklearn IncrementalPCA.fit / transform as called by fit_PCA / transform_PCA
+ * (scratchpad/IEEE_ICIP_paper/latent_vis.py:94-143) with exact PCA from streamed moments.
+ */
+/* Accumulates moments[0] += n, moments[1..d] += sum_i h_i, moments[1+d ..] += sum_i h_i h_i^T
+ * (row-major d x d), all float64, h (n,d) fp32, d <= 256.  moments must be zeroed by the caller
+ * before the first call; after the last call the ranks allreduce(SUM) it. */
+int te_pca_accumulate(const float* h, int64_t n, int32_t d, double* moments, void* stream);
+/* Solves the d x d symmetric eigenproblem of the covariance (cyclic Jacobi, float64, one CTA) and
+ * writes mean (d), the top-k components (k,d) with sklearn's sign convention (largest-|v| entry of
+ * each component positive) and their explained variances (k), all float64 device arrays.
+ * work: device float64 scratch of 2*d*d values. */
+int te_pca_solve(const double* moments, int32_t d, int32_t k, double* mean, double* components,
+                 double* explained_variance, double* work, void* stream);
+/* z[i] = (h[i] - mean) @ components^T ; z (n,k) fp32. */
+int te_pca_project(const float* h, int64_t n, int32_t d, const double* mean, const double* components,
+                   int32_t k, float* z, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOMOENC_H_ */

@@ -10,13 +10,15 @@ numpy) and loaded, unchanged, by both the oracle networks (oracle/nets_torch.py)
   BatchNormalization gamma, beta, moving_mean, moving_variance  (each (C,))
 
 Each spec entry is ``(kind, shape)`` with kind in {"conv_k","conv_b","convT_k","convT_b","dense_k",
-"dense_b","bn_gamma","bn_beta","bn_mean","bn_var"}.  Kernels are glorot-uniform (Keras default,
-``fan_in = k^3 Cin``, ``fan_out = k^3 Cout``) times a He-style gain so that activations stay O(1)
-through 17 LeakyReLU(0.2) layers; BN statistics are randomised so that folding is exercised.
+"dense_b","bn_gamma","bn_beta","bn_mean","bn_var"}.  Kernels are He-uniform for LeakyReLU(0.2)
+(``U(+-sqrt(3 g^2 / fan_in))``, ``g^2 = 2/(1+0.2^2)``, ``fan_in = k^3 Cin``) instead of Keras' default
+glorot-uniform, so that activations stay O(1) through 17 layers and bf16/fp16 error is representative
+(SURVEY.md appendix A.2 leaves the scale to the oracle); biases are small non-zero normals and BN
+statistics are randomised so that bias handling and BN folding are exercised.
 """
 import numpy as np
 
-LRELU_GAIN = float(np.sqrt(2.0 / (1.0 + 0.2 ** 2)) * np.sqrt(2.0))  # glorot -> He(fan_in) for fan_in ~ fan_out
+LRELU_GAIN = float(np.sqrt(2.0 / (1.0 + 0.2 ** 2)))
 
 
 def draw(spec, seed, gain=LRELU_GAIN):
@@ -27,17 +29,14 @@ def draw(spec, seed, gain=LRELU_GAIN):
         if kind in ("conv_k", "convT_k"):
             k3 = int(np.prod(shape[:3]))
             if kind == "conv_k":
-                fan_in, fan_out = k3 * shape[3], k3 * shape[4]
+                fan_in = k3 * shape[3]
             else:
-                fan_in, fan_out = k3 * shape[4], k3 * shape[3]
-            g = gain
-            if kind == "convT_k":
-                # each output voxel of a k=2,s=2 transposed conv sees exactly one tap: fan_in is Cin
-                fan_in, fan_out = shape[4], shape[3]
-            lim = g * np.sqrt(6.0 / (fan_in + fan_out))
+                # each output voxel of a k<=s transposed conv sees exactly one tap: fan_in is Cin
+                fan_in = shape[4]
+            lim = gain * np.sqrt(3.0 / fan_in)
             out.append(rng.uniform(-lim, lim, shape).astype(np.float32))
         elif kind == "dense_k":
-            lim = gain * np.sqrt(6.0 / (shape[0] + shape[1]))
+            lim = gain * np.sqrt(3.0 / shape[0])
             out.append(rng.uniform(-lim, lim, shape).astype(np.float32))
         elif kind in ("conv_b", "convT_b", "dense_b"):
             out.append(rng.normal(0.0, 0.05, shape).astype(np.float32))

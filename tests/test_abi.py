@@ -1,0 +1,42 @@
+"""CPU: libtomoenc.so builds for sm_100a, loads, and exports every symbol include/tomoenc.h declares
+(no compute calls -- there is no GPU here)."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "tomoenc.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(te_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_the_header(built_lib):
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    handle = ctypes.CDLL(built_lib.LIB_PATH)
+    missing = [s for s in declared if not hasattr(handle, s)]
+    assert not missing, "declared in tomoenc.h but not exported: %s" % missing
+    assert sorted(built_lib.EXPORTED_SYMBOLS) == declared, "ctypes signature table out of sync with tomoenc.h"
+    L = built_lib.lib()
+    assert L.te_version() >= 100
+    assert L.te_launch_count() == 0
+
+
+def test_argument_errors_are_reported_without_a_gpu(built_lib):
+    L = built_lib.lib()
+    rc = L.te_gather(None, 3, built_lib.i64x3((1, 1, 1)), None, None, 1, built_lib.i32x3((1, 1, 1)), None, None)
+    assert rc == -1 and b"elem_size" in L.te_last_error()
+    rc = L.te_gather(None, 1, built_lib.i64x3((1, 1, 1)), None, None, 0, built_lib.i32x3((1, 1, 1)), None, None)
+    assert rc == 0        # empty input is a no-op
+
+
+def test_sass_contains_blackwell_instructions(built_lib):
+    """The conv kernels must be tcgen05 / TMA code, not recompiled legacy MMA."""
+    import subprocess
+    sass = subprocess.run(["cuobjdump", "-sass", built_lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass, "no tcgen05.mma in the library"
+    assert "UTMALDG" in sass, "no TMA tensor loads in the library"
+    assert "HMMA." not in sass.replace("UTCHMMA", ""), "legacy mma.sync found"

@@ -1,0 +1,141 @@
+"""GPU: gather / scatter / min-max kernels through the reference-facing API, bit-exact against the
+golden vectors, the numpy oracle and size-independent properties."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import seeded_volume
+from oracle import structures_np as S, voxel_np as V
+from tomoencoders_b200 import Grid, Patches, voxel_processing
+
+pytestmark = pytest.mark.gpu
+SVS = (40, 44, 48)
+DTYPES = (("u8", np.uint8), ("u16", np.uint16), ("f16", np.float16), ("f32", np.float32))
+
+
+def _bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view({1: np.uint8, 2: np.uint16, 4: np.uint32}[a.dtype.itemsize])
+
+
+@pytest.mark.parametrize("name,dt", DTYPES)
+def test_golden_vectors(golden, name, dt):
+    vol = seeded_volume(SVS, dt, 100)
+    pg = Patches(SVS, "grid", patch_size=(16,) * 3, stride=1)
+    np.testing.assert_array_equal(pg.points, golden["gs_%s_grid_points" % name])
+    out = pg.extract(vol, (16,) * 3)
+    assert isinstance(out, np.ndarray) and out.dtype == vol.dtype and out.shape == (len(pg), 16, 16, 16)
+    np.testing.assert_array_equal(_bits(out), _bits(golden["gs_%s_grid_extract" % name]))
+    pb = Patches(SVS, "data", points=golden["gs_%s_bin_points" % name], widths=golden["gs_%s_bin_widths" % name])
+    np.testing.assert_array_equal(_bits(pb.extract(vol, (16,) * 3)), _bits(golden["gs_%s_bin_extract" % name]))
+    sub = seeded_volume((len(pg),) + (16,) * 3, dt, 101)
+    vout = seeded_volume(SVS, dt, 102)
+    pg.fill_patches_in_volume(sub, vout)          # overlapping patches: last index wins
+    np.testing.assert_array_equal(_bits(vout), _bits(golden["gs_%s_fill" % name]))
+
+
+def test_grid_extract_golden_and_round_trip(golden):
+    gv = seeded_volume((32, 48, 32), np.uint8, 103)
+    g = Grid(gv.shape, width=16)
+    x = g.extract(gv)
+    np.testing.assert_array_equal(x, golden["grid_extract_u8"])
+    out = np.zeros_like(gv)
+    g.fill_patches_in_volume(x, out)
+    np.testing.assert_array_equal(out, gv)
+
+
+@pytest.mark.parametrize("dt", [np.uint8, np.float16, np.float32])
+def test_random_unaligned_corners_match_oracle(dt):
+    vs = (96, 100, 117)                       # odd pitch: rows start at every byte alignment
+    vol = seeded_volume(vs, dt, 11)
+    np.random.seed(3)
+    p = Patches(vs, "random-fixed-width", patch_size=(32,) * 3, n_points=257)
+    out = p.extract(vol, (32,) * 3)
+    np.testing.assert_array_equal(_bits(out), _bits(S.extract(vol, p.points, p.widths, (32,) * 3)))
+    np.random.seed(4)
+    q = Patches(vs, "random", min_patch_size=(16,) * 3, max_stride=4, n_points=64)
+    np.testing.assert_array_equal(_bits(q.extract(vol, (16,) * 3)), _bits(S.extract(vol, q.points, q.widths, (16,) * 3)))
+    # rows that are not a multiple of 16 bytes take the element-wise kernel
+    r = Patches(vs, "data", points=[[1, 2, 3], [60, 70, 80]], widths=[[20, 24, 28]] * 2)
+    np.testing.assert_array_equal(_bits(r.extract(vol, (20, 24, 28))), _bits(S.extract(vol, r.points, r.widths, (20, 24, 28))))
+
+
+def test_device_in_device_out_and_list_mode():
+    vol = seeded_volume((64, 64, 64), np.uint8, 12)
+    tv = torch.from_numpy(vol).cuda()
+    p = Patches(vol.shape, "data", points=[[0, 0, 0], [10, 20, 30], [5, 5, 5]], widths=[[32] * 3, [16] * 3, [32] * 3])
+    lst = p.extract(tv, None)
+    assert isinstance(lst, list) and all(t.is_cuda for t in lst)
+    for i, t in enumerate(lst):
+        z, y, x = p.points[i].astype(int)
+        w = int(p.widths[i, 0])
+        np.testing.assert_array_equal(t.cpu().numpy(), vol[z:z + w, y:y + w, x:x + w])
+    g = Grid(vol.shape, width=32)
+    x = g.extract(tv)
+    assert x.is_cuda and x.shape == (8, 32, 32, 32)
+    out = torch.zeros_like(tv)
+    g.fill_patches_in_volume(x, out)
+    assert torch.equal(out, tv)
+
+
+def test_empty_and_shape_errors():
+    vol = seeded_volume((64, 64, 64), np.uint8, 13)
+    p = Patches(vol.shape, "data", points=np.zeros((0, 3), int), widths=np.zeros((0, 3), int))
+    assert p.extract(vol, (32,) * 3).shape == (0, 32, 32, 32)
+    g = Grid(vol.shape, width=32)
+    with pytest.raises(AssertionError):
+        g.extract(vol[:32])
+    with pytest.raises(AssertionError):
+        g.fill_patches_in_volume(np.zeros((7, 32, 32, 32), np.uint8), vol.copy())
+
+
+def test_scatter_casts_like_numpy_assignment():
+    vs = (32, 32, 32)
+    g = Grid(vs, width=16)
+    sub = np.random.default_rng(5).uniform(0, 3, (len(g), 16, 16, 16)).astype(np.float32)
+    out = np.zeros(vs, np.uint8)
+    expect = np.zeros(vs, np.uint8)
+    g.fill_patches_in_volume(sub, out)
+    S.fill_patches_in_volume(sub, g.points, np.full_like(g.points, 16), expect)
+    np.testing.assert_array_equal(out, expect)
+
+
+def test_multiple_grids_scatter_order():
+    vs = (70, 66, 80)
+    p = Patches(vs, "multiple-grids", min_patch_size=(32,) * 3, max_stride=2, n_points=None)
+    sub = [seeded_volume(tuple(int(v) for v in w), np.uint8, 200 + i) for i, w in enumerate(p.widths)]
+    out = np.zeros(vs, np.uint8)
+    expect = np.zeros(vs, np.uint8)
+    p.fill_patches_in_volume(sub, out)
+    S.fill_patches_in_volume(sub, p.points, p.widths, expect)
+    np.testing.assert_array_equal(out, expect)
+
+
+def test_config1_scale_gather_properties():
+    """BASELINE config 1 sizes: 4096 x 32^3 patches from a 256^3 uint8 volume.  Checked through
+    size-independent properties: checksum of checksums against a strided-view oracle, and
+    idempotence of fill(extract())."""
+    vol = seeded_volume((256,) * 3, np.uint8, 21)
+    pts = np.stack([np.random.default_rng(3).integers(0, 256 - 32, 4096) for _ in range(3)], axis=1)
+    p = Patches(vol.shape, "data", points=pts, widths=np.full_like(pts, 32))
+    out = p.extract(vol, (32,) * 3)
+    win = np.lib.stride_tricks.sliding_window_view(vol, (32, 32, 32))
+    sums = out.reshape(4096, -1).astype(np.uint64).sum(axis=1)
+    expect = np.array([win[z, y, x].astype(np.uint64).sum() for z, y, x in pts])
+    np.testing.assert_array_equal(sums, expect)
+    idx = np.random.default_rng(0).integers(0, 4096, 64)
+    for i in idx:
+        z, y, x = pts[i]
+        np.testing.assert_array_equal(out[i], vol[z:z + 32, y:y + 32, x:x + 32])
+    back = vol.copy()
+    p.fill_patches_in_volume(out, back)           # writing a volume's own patches back changes nothing
+    np.testing.assert_array_equal(back, vol)
+
+
+def test_find_min_max_matches_oracle():
+    for dt in (np.uint8, np.uint16, np.float16, np.float32):
+        vol = seeded_volume((50, 61, 67), dt, 14)
+        for s in (1, 2, 4):
+            lo, hi = voxel_processing._find_min_max(vol, s)
+            elo, ehi = V.find_min_max(vol, s)
+            assert lo == float(elo) and hi == float(ehi)

@@ -1,0 +1,75 @@
+"""Device-side plumbing: torch tensors are the handle type for HBM buffers and streams.
+
+numpy in -> numpy out (host<->device copies inside the call, like the reference's TF path);
+torch CUDA tensor in -> torch CUDA tensor out (like the reference's cupy-in / cupy-out behaviour,
+structures/patches.py:759, structures/grid.py:324).
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+_NP_TO_TE = {np.dtype(np.uint8): _lib.TE_U8, np.dtype(np.uint16): _lib.TE_U16,
+             np.dtype(np.float16): _lib.TE_F16, np.dtype(np.float32): _lib.TE_F32}
+_TORCH_TO_TE = {torch.uint8: _lib.TE_U8, torch.uint16: _lib.TE_U16, torch.float16: _lib.TE_F16,
+                torch.float32: _lib.TE_F32, torch.bfloat16: _lib.TE_BF16}
+_TE_TO_TORCH = {_lib.TE_U8: torch.uint8, _lib.TE_U16: torch.uint16, _lib.TE_F16: torch.float16,
+                _lib.TE_F32: torch.float32, _lib.TE_BF16: torch.bfloat16}
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.TomoEncError("a CUDA device is required: tomoencoders_b200 has no CPU fallback")
+
+
+def device():
+    require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def is_device_array(a):
+    return isinstance(a, torch.Tensor) and a.is_cuda
+
+
+def te_dtype(t):
+    try:
+        return _TORCH_TO_TE[t.dtype]
+    except KeyError:
+        raise TypeError("unsupported volume dtype %s (supported: uint8, uint16, float16, float32)" % (t.dtype,))
+
+
+def torch_dtype(te_code):
+    return _TE_TO_TORCH[te_code]
+
+
+def to_device(a, non_blocking=True):
+    """numpy array / torch CPU tensor / torch CUDA tensor -> contiguous torch CUDA tensor."""
+    require_cuda()
+    if isinstance(a, torch.Tensor):
+        t = a if a.is_cuda else a.to(device(), non_blocking=non_blocking)
+        return t.contiguous()
+    a = np.ascontiguousarray(a)
+    if a.dtype not in _NP_TO_TE and a.dtype not in (np.dtype(np.int32), np.dtype(np.uint32), np.dtype(np.int64),
+                                                    np.dtype(np.float64)):
+        raise TypeError("unsupported array dtype %s" % (a.dtype,))
+    return torch.from_numpy(a).to(device(), non_blocking=False)
+
+
+def to_host_like(t, like):
+    """Returns t in the array family of ``like`` (numpy for host input, torch CUDA for device input)."""
+    if is_device_array(like):
+        return t
+    out = t.cpu()
+    if isinstance(like, torch.Tensor):
+        return out
+    return out.numpy()
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def points_to_device(points):
+    """(n,3) uint32 coordinates -> int32-typed CUDA tensor holding the same bits."""
+    p = np.ascontiguousarray(np.asarray(points), dtype=np.uint32)
+    return torch.from_numpy(p.view(np.int32)).to(device())

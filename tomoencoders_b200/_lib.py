@@ -1,0 +1,162 @@
+"""ctypes binding of libtomoenc.so (C ABI declared in include/tomoenc.h) and its in-tree build.
+
+There is no CPU fallback: ``lib()`` raises if the shared library is missing or cannot be loaded, and
+every data-plane call in this package goes through it.
+"""
+import ctypes
+import glob
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libtomoenc.so")
+HEADER = os.path.join(_ROOT, "include", "tomoenc.h")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+TE_U8, TE_U16, TE_F16, TE_F32, TE_BF16 = 0, 1, 2, 3, 4
+TE_MODE_BF16, TE_MODE_FP16, TE_MODE_FP32_CHECK = 0, 1, 2
+MODES = {"bf16": TE_MODE_BF16, "fp16": TE_MODE_FP16, "fp32": TE_MODE_FP32_CHECK,
+         "fp32check": TE_MODE_FP32_CHECK}
+
+
+class TomoEncError(RuntimeError):
+    pass
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def _stale():
+    if not os.path.isfile(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + [HEADER]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_library(force=False, verbose=False):
+    """Compiles csrc/*.cu for sm_100a into tomoencoders_b200/libtomoenc.so (nvcc cross-compiles
+    without a GPU).  Returns the library path."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp] + sources()
+    if verbose:
+        print(" ".join(cmd))
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise TomoEncError("nvcc failed:\n%s\n%s" % (r.stdout, r.stderr))
+    os.replace(tmp, LIB_PATH)
+    return LIB_PATH
+
+
+class NetDesc(ctypes.Structure):
+    """struct te_net_desc (include/tomoenc.h)."""
+    _fields_ = [
+        ("kind", ctypes.c_int32),
+        ("n_blocks", ctypes.c_int32),
+        ("n_filters", ctypes.c_int32 * 8),
+        ("pool_size", ctypes.c_int32 * 8),
+        ("isconcat", ctypes.c_int32 * 8),
+        ("batch_norm", ctypes.c_int32),
+        ("kern_size", ctypes.c_int32),
+        ("kern_size_upconv", ctypes.c_int32),
+        ("n_hidden", ctypes.c_int32),
+        ("hidden_units", ctypes.c_int32 * 8),
+        ("pool_flag", ctypes.c_int32),
+        ("patch", ctypes.c_int32 * 3),
+        ("max_batch", ctypes.c_int32),
+        ("lrelu_alpha", ctypes.c_float),
+        ("bn_eps", ctypes.c_float),
+        ("mode", ctypes.c_int32),
+    ]
+
+
+_P = ctypes.c_void_p
+_I64 = ctypes.c_int64
+_I32 = ctypes.c_int32
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    "te_version": (ctypes.c_int, []),
+    "te_last_error": (ctypes.c_char_p, []),
+    "te_launch_count": (_I64, []),
+    "te_gather": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_I64), _P, _P, _I64,
+                                 ctypes.POINTER(_I32), _P, _P]),
+    "te_gather_norm": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_I64), _P, _P, _I64,
+                                      ctypes.POINTER(_I32), ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                      ctypes.c_float, _P, ctypes.c_int, _P]),
+    "te_scatter": (ctypes.c_int, [_P, ctypes.c_int, _P, _I64, ctypes.POINTER(_I32), _P,
+                                  ctypes.POINTER(_I64), _P, _P]),
+    "te_minmax_strided": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_I64), ctypes.c_int, _P, _P, _P]),
+    "te_net_weight_count": (_I64, [ctypes.POINTER(NetDesc)]),
+    "te_net_create": (ctypes.c_int, [ctypes.POINTER(NetDesc), ctypes.POINTER(_P)]),
+    "te_net_set_weights": (ctypes.c_int, [_P, _P, _I64]),
+    "te_net_destroy": (ctypes.c_int, [_P]),
+    "te_net_workspace_bytes": (_I64, [_P]),
+    "te_unet_forward": (ctypes.c_int, [_P, _P, _I64, _P, ctypes.c_int, _P, _P]),
+    "te_encoder_forward": (ctypes.c_int, [_P, _P, _I64, _P, _P]),
+    "te_decoder_forward": (ctypes.c_int, [_P, _P, _I64, _P, _P]),
+    "te_net_layer_output": (_I64, [_P, ctypes.c_int, _P, _I64, _P]),
+    "te_net_num_layers": (ctypes.c_int, [_P]),
+    "te_net_flops_per_patch": (ctypes.c_double, [_P]),
+    "te_net_layer_info": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p),
+                                         ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)]),
+    "te_pca_accumulate": (ctypes.c_int, [_P, _I64, _I32, _P, _P]),
+    "te_pca_solve": (ctypes.c_int, [_P, _I32, _I32, _P, _P, _P, _P, _P]),
+    "te_pca_project": (ctypes.c_int, [_P, _I64, _I32, _P, _P, _I32, _P, _P]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lock = threading.Lock()
+_lib = None
+
+
+def lib():
+    """Loads libtomoenc.so (once).  Raises TomoEncError if it has not been built: the product path
+    never falls back to a CPU implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.isfile(LIB_PATH):
+            raise TomoEncError(
+                "libtomoenc.so is missing (%s): build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'`; there is no CPU fallback" % LIB_PATH)
+        try:
+            handle = ctypes.CDLL(LIB_PATH)
+        except OSError as e:  # pragma: no cover
+            raise TomoEncError("cannot load %s: %s" % (LIB_PATH, e))
+        for name, (res, args) in _SIGNATURES.items():
+            try:
+                fn = getattr(handle, name)
+            except AttributeError:
+                raise TomoEncError("libtomoenc.so does not export %s (stale build?)" % name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().te_last_error().decode("utf-8", "replace")
+        raise TomoEncError("%s failed (%d): %s" % (what or "libtomoenc call", rc, msg))
+
+
+def i64x3(v):
+    return (_I64 * 3)(int(v[0]), int(v[1]), int(v[2]))
+
+
+def i32x3(v):
+    return (_I32 * 3)(int(v[0]), int(v[1]), int(v[2]))

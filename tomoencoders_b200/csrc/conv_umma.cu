@@ -1,0 +1,419 @@
+// Implicit-GEMM 3-D convolution on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), sm_100a.
+//
+// Replaces the cuDNN calls behind L.Conv3D(f, 3, padding="same") + BN + LeakyReLU
+// (/root/reference/tomo_encoders/neural_nets/Unet3D.py:44-81) and L.Conv3DTranspose(C, 2, strides=p)
+// + LeakyReLU (Unet3D.py:175-177), plus the final 1x1x1 sigmoid conv (Unet3D.py:287) as a fused
+// epilogue.
+//
+// GEMM view: M = 128 output voxels (a 16(y) x 8(x) patch of one z plane), N = NT output channels,
+// K = taps x Cin, accumulated in fp32 in TMEM.  One CTA tile is TZ consecutive z planes; its
+// haloed input box (TZ+2, 18, 10, CB channels) is brought into shared memory by ONE 5-D TMA load per
+// CB-channel chunk -- out-of-bounds coordinates are zero-filled by the TMA unit, and because the
+// patch index is its own tensor dimension this is exactly Keras' per-patch "same" padding.  Each of
+// the 27 taps is then just a different START ADDRESS of the A-operand shared-memory descriptor into
+// that one box (the swizzle is a function of the absolute shared-memory address, so shifted windows
+// stay consistent -- verified on hardware by tools/umma_probe.cu, profiles/umma_probe_r01_run*.txt).
+//
+// Warp roles (192 threads): warp 0 = TMA producer (input boxes + pre-swizzled weight slabs),
+// warp 1 = single-thread UMMA issuer, warps 2..5 = epilogue (TMEM -> registers -> bias + LeakyReLU
+// -> 16-bit NDHWC store, optionally pixel-shuffled for the transposed conv or reduced by the fused
+// 1x1x1 head).  Persistent CTAs loop over tiles; the accumulator is double-buffered in TMEM so the
+// epilogue of tile i overlaps the MMAs of tile i+1.
+#include "conv_umma.cuh"
+#include "sm100_ptx.cuh"
+#include "te_common.cuh"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <vector>
+
+namespace te {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kNumWStages = 4;     // weight-slab ring
+constexpr int kNumAStages = 2;     // input-box ring
+
+struct KParams {
+  const uint8_t* w_packed;
+  const float* bias;
+  uint8_t* out;
+  int out_ctot, out_coff;
+  int N, D, H, W;
+  int kchunks;          // Cin / CB
+  int ngroups, taps_g;  // weight slabs per chunk, taps per slab (9 x 3 for a 3x3x3 conv, 1 x 1 for a transposed-conv sub-position)
+  int halo;             // 1 for the 3x3x3 conv, 0 otherwise
+  int nsub;             // 1 or 8
+  int up_stride;
+  int n_ntiles;         // Cout / NT
+  int tiles_x, tiles_y, tiles_z;
+  long long total_tiles;
+  int act_lrelu;
+  float alpha;
+  int fp16;
+  const float* head_w;
+  float head_b;
+  uint8_t* head_labels;
+  float* head_probs;
+  float* head_logits;
+};
+
+struct TileCoord { int ntile, sub, n, z0, y0, x0; };
+
+__device__ __forceinline__ TileCoord decode_tile(const KParams& p, long long t, int TZ) {
+  TileCoord c;
+  c.x0 = static_cast<int>(t % p.tiles_x) * 8;  t /= p.tiles_x;
+  c.y0 = static_cast<int>(t % p.tiles_y) * 16; t /= p.tiles_y;
+  c.z0 = static_cast<int>(t % p.tiles_z) * TZ; t /= p.tiles_z;
+  c.n = static_cast<int>(t % p.N);             t /= p.N;
+  c.sub = static_cast<int>(t % p.nsub);        t /= p.nsub;
+  c.ntile = static_cast<int>(t);
+  return c;
+}
+
+__device__ __forceinline__ uint32_t pack2(float a, float b, int fp16) {
+  if (fp16) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int CB, int NT, int TZ>
+struct Cfg {
+  static constexpr int ROWB = CB * 2;                                   // bytes of one voxel row of a chunk
+  static constexpr uint32_t LAYOUT = CB == 16 ? kLayoutSW32 : (CB == 32 ? kLayoutSW64 : kLayoutSW128);
+  static constexpr int KSTEPS = CB / 16;                                // UMMA K = 16 for 16-bit operands
+  static constexpr int A_STAGE = (((TZ + 2) * 18 * 10 * ROWB) + 1023) / 1024 * 1024;
+  static constexpr int W_STAGE = ((3 * NT * ROWB) + 1023) / 1024 * 1024;
+  static constexpr int ACC_COLS = TZ * NT;                              // fp32 columns of one accumulator set
+  static constexpr int TMEM_COLS_RAW = 2 * ACC_COLS;
+  static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
+                                   : TMEM_COLS_RAW <= 256 ? 256 : 512;
+  static_assert(TMEM_COLS_RAW <= 512, "accumulators do not fit TMEM");
+  static constexpr int SMEM_BYTES = kNumAStages * A_STAGE + kNumWStages * W_STAGE + 1024 /*barriers*/ + 1024 /*align*/;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
+};
+
+template <int CB, int NT, int TZ>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const KParams p) {
+  using C = Cfg<CB, NT, TZ>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_stage = smem;
+  uint8_t* w_stage = smem + kNumAStages * C::A_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_stage + kNumWStages * C::W_STAGE);
+  uint64_t* a_full = bars;                       // [kNumAStages]
+  uint64_t* a_empty = a_full + kNumAStages;      // [kNumAStages]
+  uint64_t* w_full = a_empty + kNumAStages;      // [kNumWStages]
+  uint64_t* w_empty = w_full + kNumWStages;      // [kNumWStages]
+  uint64_t* acc_full = w_empty + kNumWStages;    // [2]
+  uint64_t* acc_empty = acc_full + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kNumAStages; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
+    for (int i = 0; i < kNumWStages; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+    fence_barrier_init();
+    prefetch_tmap(&tmap_in);
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, C::TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int BX = 8 + 2 * p.halo, BY = 16 + 2 * p.halo, BZ = TZ + 2 * p.halo;
+  const uint32_t a_bytes = static_cast<uint32_t>(BZ * BY * BX * C::ROWB);
+  const uint32_t w_bytes = static_cast<uint32_t>(p.taps_g * NT * C::ROWB);
+
+  if (warp == 0) {
+    // ============================== TMA producer (one lane) ==============================
+    if (lane == 0) {
+      uint32_t as = 0, aph = 0, ws = 0, wph = 0;
+      // flattened sequence of (tile, chunk) jobs; the input box of job j+1 is requested before
+      // the weight slabs of job j so that it is in flight while job j is being multiplied.
+      long long tile = blockIdx.x;
+      int kc = 0;
+      bool have = tile < p.total_tiles;
+      if (have) {
+        const TileCoord tc = decode_tile(p, tile, TZ);
+        mbar_wait(a_empty + as, aph ^ 1);
+        mbar_expect_tx(a_full + as, a_bytes);
+        tma_load_5d(a_stage + as * C::A_STAGE, &tmap_in, a_full + as, 0, tc.x0 - p.halo, tc.y0 - p.halo,
+                    tc.z0 - p.halo, tc.n);
+        if (++as == kNumAStages) { as = 0; aph ^= 1; }
+      }
+      while (have) {
+        const TileCoord tc = decode_tile(p, tile, TZ);
+        // next job
+        long long ntile_id = tile;
+        int nkc = kc + 1;
+        if (nkc == p.kchunks) { nkc = 0; ntile_id = tile + gridDim.x; }
+        const bool have_next = ntile_id < p.total_tiles;
+        if (have_next) {
+          const TileCoord nc = decode_tile(p, ntile_id, TZ);
+          mbar_wait(a_empty + as, aph ^ 1);
+          mbar_expect_tx(a_full + as, a_bytes);
+          tma_load_5d(a_stage + as * C::A_STAGE, &tmap_in, a_full + as, nkc * CB, nc.x0 - p.halo, nc.y0 - p.halo,
+                      nc.z0 - p.halo, nc.n);
+          if (++as == kNumAStages) { as = 0; aph ^= 1; }
+        }
+        // weight slabs of the current job
+        const uint8_t* wsrc = p.w_packed +
+            ((static_cast<size_t>(tc.ntile) * p.nsub + tc.sub) * p.kchunks + kc) * p.ngroups * static_cast<size_t>(w_bytes);
+        for (int g = 0; g < p.ngroups; ++g) {
+          mbar_wait(w_empty + ws, wph ^ 1);
+          mbar_expect_tx(w_full + ws, w_bytes);
+          bulk_load(w_stage + ws * C::W_STAGE, wsrc + static_cast<size_t>(g) * w_bytes, w_bytes, w_full + ws);
+          if (++ws == kNumWStages) { ws = 0; wph ^= 1; }
+        }
+        tile = ntile_id;
+        kc = nkc;
+        have = have_next;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ============================== UMMA issuer (one lane) ==============================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(128, NT, p.fp16 ? 0u : 1u);
+      const uint32_t sbo_a = static_cast<uint32_t>(BX * C::ROWB);
+      const uint32_t sbo_w = 8u * C::ROWB;
+      uint32_t as = 0, aph = 0, ws = 0, wph = 0, ab = 0, abph = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(acc_empty + ab, abph ^ 1);
+        tc_fence_after();
+        const uint32_t acc_col = tmem_base + ab * C::ACC_COLS;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(a_full + as, aph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(a_stage + as * C::A_STAGE);
+          for (int g = 0; g < p.ngroups; ++g) {
+            mbar_wait(w_full + ws, wph);
+            tc_fence_after();
+            const uint32_t w_addr = smem_u32(w_stage + ws * C::W_STAGE);
+            const int dz = p.halo ? g / 3 : 0, dy = p.halo ? g % 3 : 0;
+            for (int t = 0; t < p.taps_g; ++t) {
+              const uint64_t wdesc0 = make_smem_desc(w_addr + t * NT * C::ROWB, 16, sbo_w, C::LAYOUT);
+#pragma unroll
+              for (int pz = 0; pz < TZ; ++pz) {
+                const uint32_t a_off = static_cast<uint32_t>((((pz + dz) * BY + dy) * BX + t) * C::ROWB);
+                const uint64_t adesc0 = make_smem_desc(a_addr + a_off, 16, sbo_a, C::LAYOUT);
+#pragma unroll
+                for (int ks = 0; ks < C::KSTEPS; ++ks) {
+                  const uint32_t accumulate = (kc | g | t | ks) != 0 ? 1u : 0u;
+                  umma_ss(acc_col + pz * NT, adesc0 + static_cast<uint64_t>(ks * 2), wdesc0 + static_cast<uint64_t>(ks * 2),
+                          idesc, accumulate);
+                }
+              }
+            }
+            umma_commit(w_empty + ws);            // slab free once these MMAs retire
+            if (++ws == kNumWStages) { ws = 0; wph ^= 1; }
+          }
+          umma_commit(a_empty + as);
+          if (++as == kNumAStages) { as = 0; aph ^= 1; }
+        }
+        umma_commit(acc_full + ab);
+        if (++ab == 2) { ab = 0; abph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================== epilogue warps ==============================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;                  // accumulator row = voxel (y = m / 8, x = m % 8)
+    const int my = m >> 3, mx = m & 7;
+    uint32_t ab = 0, abph = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile, TZ);
+      mbar_wait(acc_full + ab, abph);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ab * C::ACC_COLS;
+      const int iy = tc.y0 + my, ix = tc.x0 + mx;
+      const float* bias = p.bias + tc.ntile * NT;
+#pragma unroll 1
+      for (int pz = 0; pz < TZ; ++pz) {
+        const int iz = tc.z0 + pz;
+        const bool valid = iz < p.D && iy < p.H && ix < p.W;
+        long long ovox;
+        if (p.up_stride) {
+          const int s = p.up_stride;
+          const int a = (tc.sub >> 2) & 1, b = (tc.sub >> 1) & 1, c = tc.sub & 1;
+          ovox = ((static_cast<long long>(tc.n) * (p.D * s) + (iz * s + a)) * (p.H * s) + (iy * s + b)) * (p.W * s) +
+                 (ix * s + c);
+        } else {
+          ovox = ((static_cast<long long>(tc.n) * p.D + iz) * p.H + iy) * p.W + ix;
+        }
+        float head_acc = 0.f;
+#pragma unroll
+        for (int c0 = 0; c0 < NT; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(tbase + pz * NT + c0, r);     // warp-collective: executed by all lanes, valid or not
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float x = __uint_as_float(r[j]) + __ldg(bias + c0 + j);
+            if (p.act_lrelu) x = x > 0.f ? x : p.alpha * x;
+            v[j] = x;
+          }
+          if (p.head_w != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) head_acc = fmaf(v[j], __ldg(p.head_w + c0 + j), head_acc);
+          }
+          if (p.out != nullptr && valid) {
+            uint8_t* dst = p.out + (ovox * p.out_ctot + p.out_coff + tc.ntile * NT + c0) * 2;
+            uint4 lo = make_uint4(pack2(v[0], v[1], p.fp16), pack2(v[2], v[3], p.fp16), pack2(v[4], v[5], p.fp16),
+                                  pack2(v[6], v[7], p.fp16));
+            uint4 hi = make_uint4(pack2(v[8], v[9], p.fp16), pack2(v[10], v[11], p.fp16), pack2(v[12], v[13], p.fp16),
+                                  pack2(v[14], v[15], p.fp16));
+            reinterpret_cast<uint4*>(dst)[0] = lo;
+            reinterpret_cast<uint4*>(dst)[1] = hi;
+          }
+        }
+        if (p.head_w != nullptr && valid) {
+          const float logit = head_acc + p.head_b;
+          if (p.head_labels) p.head_labels[ovox] = logit > 0.f ? 1 : 0;
+          if (p.head_probs) p.head_probs[ovox] = 1.f / (1.f + __expf(-logit));
+          if (p.head_logits) p.head_logits[ovox] = logit;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + ab);
+      if (++ab == 2) { ab = 0; abph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+template <int CB, int NT, int TZ>
+cudaError_t launch_cfg(const ConvUmmaLaunch& L, const KParams& p, int grid, cudaStream_t stream) {
+  using C = Cfg<CB, NT, TZ>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<CB, NT, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  conv_umma_kernel<CB, NT, TZ><<<grid, kThreads, C::SMEM_BYTES, stream>>>(L.tmap_in, p);
+  return cudaGetLastError();
+}
+
+KParams make_params(const ConvUmmaLaunch& L) {
+  KParams p;
+  p.w_packed = static_cast<const uint8_t*>(L.w_packed);
+  p.bias = L.bias;
+  p.out = static_cast<uint8_t*>(L.out);
+  p.out_ctot = L.out_ctot;
+  p.out_coff = L.out_coff;
+  p.N = L.N; p.D = L.D; p.H = L.H; p.W = L.W;
+  p.kchunks = L.Cin / L.CB;
+  p.halo = L.ntaps == 27 ? 1 : 0;
+  p.ngroups = L.ntaps == 27 ? 9 : 1;
+  p.taps_g = L.ntaps == 27 ? 3 : 1;
+  p.nsub = L.up_stride ? 8 : 1;
+  p.up_stride = L.up_stride;
+  p.n_ntiles = L.Cout / L.NT;
+  p.tiles_x = (L.W + 7) / 8;
+  p.tiles_y = (L.H + 15) / 16;
+  p.tiles_z = (L.D + L.TZ - 1) / L.TZ;
+  p.total_tiles = static_cast<long long>(p.n_ntiles) * p.nsub * L.N * p.tiles_z * p.tiles_y * p.tiles_x;
+  p.act_lrelu = L.act_lrelu;
+  p.alpha = L.alpha;
+  p.fp16 = L.fp16;
+  p.head_w = L.head_w;
+  p.head_b = L.head_b;
+  p.head_labels = L.head_labels;
+  p.head_probs = L.head_probs;
+  p.head_logits = L.head_logits;
+  return p;
+}
+
+}  // namespace
+
+bool conv_umma_config(int Cin, int Cout, ConvUmmaConfig* cfg) {
+  if (Cin % 16 != 0 || Cout % 16 != 0 || Cin <= 0 || Cout <= 0) return false;
+  int NT;
+  if (Cout % 128 == 0) NT = 128;
+  else if (Cout == 64 || Cout == 32 || Cout == 16) NT = Cout;
+  else if (Cout % 64 == 0) NT = 64;
+  else if (Cout % 32 == 0) NT = 32;
+  else NT = 16;
+  cfg->NT = NT;
+  cfg->CB = (Cin % 32 == 0) ? 32 : 16;
+  cfg->TZ = NT == 128 ? 2 : 4;
+  return true;
+}
+
+size_t conv_umma_packed_bytes(int Cin, int Cout, int ntaps, int nsub, const ConvUmmaConfig& cfg) {
+  (void)cfg;
+  return static_cast<size_t>(nsub) * ntaps * Cin * Cout * 2;
+}
+
+void conv_umma_pack(const float* w, int Cin, int Cout, int ntaps, int nsub, const ConvUmmaConfig& cfg, int fp16,
+                    void* dst_host) {
+  const int CB = cfg.CB, NT = cfg.NT;
+  const int rowb = CB * 2;
+  const uint32_t mask = CB == 16 ? 1u : (CB == 32 ? 3u : 7u);
+  const int kchunks = Cin / CB, n_ntiles = Cout / NT;
+  const int ngroups = ntaps == 27 ? 9 : 1, taps_g = ntaps == 27 ? 3 : 1;
+  const size_t slab = static_cast<size_t>(taps_g) * NT * rowb;
+  uint16_t* dst = static_cast<uint16_t*>(dst_host);
+  for (int nt = 0; nt < n_ntiles; ++nt)
+    for (int sub = 0; sub < nsub; ++sub)
+      for (int kc = 0; kc < kchunks; ++kc)
+        for (int g = 0; g < ngroups; ++g) {
+          uint8_t* base = reinterpret_cast<uint8_t*>(dst) +
+                          (((static_cast<size_t>(nt) * nsub + sub) * kchunks + kc) * ngroups + g) * slab;
+          for (int t = 0; t < taps_g; ++t)
+            for (int r = 0; r < NT; ++r)
+              for (int kk = 0; kk < CB; ++kk) {
+                const int tap = g * taps_g + t;
+                const int cout = nt * NT + r, cin = kc * CB + kk;
+                const float val = w[((static_cast<size_t>(sub) * ntaps + tap) * Cout + cout) * Cin + cin];
+                uint16_t bits;
+                if (fp16) { __half h = __float2half_rn(val); bits = *reinterpret_cast<uint16_t*>(&h); }
+                else { __nv_bfloat16 h = __float2bfloat16_rn(val); bits = *reinterpret_cast<uint16_t*>(&h); }
+                const uint32_t Lo = static_cast<uint32_t>((t * NT + r) * rowb + kk * 2);
+                const uint32_t P = Lo ^ (((Lo >> 7) & mask) << 4);
+                *reinterpret_cast<uint16_t*>(base + P) = bits;
+              }
+        }
+}
+
+int conv_umma_grid(const ConvUmmaLaunch& L) {
+  const KParams p = make_params(L);
+  return static_cast<int>(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs);
+}
+
+cudaError_t conv_umma_launch(const ConvUmmaLaunch& L, cudaStream_t stream) {
+  const KParams p = make_params(L);
+  if (p.total_tiles <= 0) return cudaSuccess;
+  const int grid = static_cast<int>(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs);
+#define TE_CONV_CASE(cb, nt, tz) \
+  if (L.CB == cb && L.NT == nt && L.TZ == tz) return launch_cfg<cb, nt, tz>(L, p, grid, stream);
+  TE_CONV_CASE(16, 16, 4)
+  TE_CONV_CASE(16, 32, 4)
+  TE_CONV_CASE(16, 64, 4)
+  TE_CONV_CASE(16, 128, 2)
+  TE_CONV_CASE(32, 16, 4)
+  TE_CONV_CASE(32, 32, 4)
+  TE_CONV_CASE(32, 64, 4)
+  TE_CONV_CASE(32, 128, 2)
+#undef TE_CONV_CASE
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace te

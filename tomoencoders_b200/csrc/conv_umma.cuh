@@ -1,0 +1,48 @@
+// Launch interface of the tcgen05 implicit-GEMM convolution kernel (conv_umma.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace te {
+
+// One launch = one layer over a batch of patches.  Activations are NDHWC with 16-bit elements
+// (bf16 or fp16); the output may be a channel slice [out_coff, out_coff + Cout) of a wider buffer
+// (this is how the skip concatenation disappears: both producers write into one buffer).
+struct ConvUmmaLaunch {
+  CUtensorMap tmap_in;      // 5-D (C, W, H, D, N) map of the input tensor, box (CB, 8+2h, 16+2h, TZ+2h, 1)
+  const void* w_packed;     // pre-swizzled weights, see pack_conv_weights() in net.cu
+  const float* bias;        // Cout fp32 (conv bias with BN folded in)
+  void* out;                // output activations (16-bit) or nullptr when the head is fused
+  int out_ctot, out_coff;   // channel pitch / offset of the output buffer
+  int N, D, H, W;           // batch and INPUT spatial extents
+  int Cin, Cout;
+  int ntaps;                // 27 (3x3x3 'same' conv) or 1 (one sub-position of a transposed conv)
+  int up_stride;            // 0: conv.  s > 0: transposed conv k=2, stride s; 8 sub-positions
+  int act_lrelu;            // 1: LeakyReLU(alpha) after bias
+  float alpha;
+  int fp16;                 // 0: bf16 operands / activations, 1: fp16
+  // fused 1x1x1 head (Cout -> 1): logits = dot(act, head_w) + head_b
+  const float* head_w;      // nullptr = no fused head
+  float head_b;
+  uint8_t* head_labels;     // optional (n,D,H,W) uint8: logit > 0
+  float* head_probs;        // optional fp32 sigmoid(logit)
+  float* head_logits;       // optional fp32 logits
+  // kernel configuration chosen by conv_umma_config()
+  int CB, NT, TZ;
+};
+
+struct ConvUmmaConfig { int CB, NT, TZ; };
+// Picks (channel chunk, Cout tile, z planes per tile) for a layer; returns false if unsupported.
+bool conv_umma_config(int Cin, int Cout, ConvUmmaConfig* cfg);
+// Bytes of one packed weight tensor for the given layer shape.
+size_t conv_umma_packed_bytes(int Cin, int Cout, int ntaps, int nsub, const ConvUmmaConfig& cfg);
+// Packs fp32 weights w[sub][tap][cout][cin] (already BN-folded) into the kernel's layout.
+void conv_umma_pack(const float* w, int Cin, int Cout, int ntaps, int nsub, const ConvUmmaConfig& cfg, int fp16,
+                    void* dst_host);
+// Enqueues the layer.  Returns cudaSuccess or the launch error.
+cudaError_t conv_umma_launch(const ConvUmmaLaunch& L, cudaStream_t stream);
+// Number of CTAs the launch uses (for accounting / tests).
+int conv_umma_grid(const ConvUmmaLaunch& L);
+
+}  // namespace te

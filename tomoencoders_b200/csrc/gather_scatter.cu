@@ -1,0 +1,464 @@
+// Patch gather / scatter / strided min-max kernels (HBM-bound data movement; sm_100a).
+//
+// Reference semantics (paths relative to /root/reference/tomo_encoders/):
+//   gather   Patches.extract structures/patches.py:748-781 (+ _calc_binning :734-746, slices :436-453),
+//            Grid.extract structures/grid.py:313-336
+//   scatter  Patches.fill_patches_in_volume structures/patches.py:811-821, Grid :338-348
+//   minmax   _find_min_max misc/voxel_processing.py:91-104
+//   norm     np.clip + _rescale_data  neural_nets/surface_segmenter.py:272-275, misc/voxel_processing.py:81-89
+//
+// Layout: the volume is (Z, Y, X) C-contiguous; patch arrays are (n, pz, py, px) C-contiguous.
+// Work is decomposed into 16-byte chunks of the PATCH array (always 16-byte aligned), so the
+// contiguous side moves with 128-bit accesses; the volume side, whose alignment depends on the
+// corner coordinate, is read with aligned 32-bit words and re-aligned with funnel shifts (or with a
+// single 128-bit access when the corner happens to be aligned, which is always the case for Grid tiles).
+#include "te_common.cuh"
+
+namespace te {
+
+struct GatherParams {
+  const uint8_t* vol;
+  uint8_t* out;
+  const uint32_t* points;
+  const uint32_t* widths;
+  long long n;
+  long long Y, X;           // volume extents (elements)
+  int pz, py, px;           // patch extents (elements)
+  int chunks_per_row;       // px * ES / 16
+  long long total_chunks;
+};
+
+__device__ __forceinline__ uint4 ldg_nc_u4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_cs_u4(void* p, uint4 v) {
+  asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+
+// 16 bytes from an arbitrarily aligned global address (see the note on over-read in DESIGN.md: at
+// most 3 bytes past `src + 16`, inside the same aligned 32-bit word as valid bytes).
+__device__ __forceinline__ uint4 load16_unaligned(const uint8_t* src) {
+  const uintptr_t s = reinterpret_cast<uintptr_t>(src);
+  if ((s & 15) == 0) return ldg_nc_u4(src);
+  const uint32_t sh = (static_cast<uint32_t>(s) & 3u) * 8u;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(s & ~uintptr_t(3));
+  const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+  if (sh == 0) return make_uint4(w0, w1, w2, w3);
+  const uint32_t w4 = __ldg(w + 4);
+  return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh),
+                    __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+}
+
+template <int ES>
+__global__ void __launch_bounds__(256) gather_chunks_kernel(GatherParams p) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const int rows_per_patch = p.pz * p.py;
+  for (long long c = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; c < p.total_chunks;
+       c += stride) {
+    const int cx = static_cast<int>(c % p.chunks_per_row);
+    const long long row = c / p.chunks_per_row;
+    const long long i = row / rows_per_patch;
+    const int r = static_cast<int>(row - i * rows_per_patch);
+    const int iz = r / p.py, iy = r - iz * p.py;
+    const uint32_t z0 = __ldg(p.points + 3 * i), y0 = __ldg(p.points + 3 * i + 1),
+                   x0 = __ldg(p.points + 3 * i + 2);
+    const uint32_t b = __ldg(p.widths + 3 * i) / static_cast<uint32_t>(p.pz);
+    const long long src_row = ((static_cast<long long>(z0) + static_cast<long long>(iz) * b) * p.Y +
+                               (static_cast<long long>(y0) + static_cast<long long>(iy) * b)) * p.X + x0;
+    uint4 v;
+    if (b == 1) {
+      v = load16_unaligned(p.vol + src_row * ES + static_cast<long long>(cx) * 16);
+    } else {
+      // decimation (not averaging): element xi of the patch row comes from x0 + xi * b
+      constexpr int EPC = 16 / ES;
+      uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int e = 0; e < EPC; ++e) {
+        const long long xi = static_cast<long long>(cx) * EPC + e;
+        const uint8_t* s = p.vol + (src_row + xi * b) * ES;
+        uint32_t val;
+        if (ES == 1) val = *s;
+        else if (ES == 2) val = *reinterpret_cast<const uint16_t*>(s);
+        else val = *reinterpret_cast<const uint32_t*>(s);
+        w[(e * ES) / 4] |= val << (((e * ES) % 4) * 8);
+      }
+      v = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    stg_cs_u4(p.out + c * 16, v);
+  }
+}
+
+// Fallback when a patch row is not a multiple of 16 bytes: one thread per element.
+template <typename T>
+__global__ void __launch_bounds__(256) gather_elems_kernel(GatherParams p) {
+  const long long total = p.n * p.pz * p.py * p.px;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const T* vol = reinterpret_cast<const T*>(p.vol);
+  T* out = reinterpret_cast<T*>(p.out);
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int ix = static_cast<int>(e % p.px);
+    long long t = e / p.px;
+    const int iy = static_cast<int>(t % p.py);
+    t /= p.py;
+    const int iz = static_cast<int>(t % p.pz);
+    const long long i = t / p.pz;
+    const uint32_t b = p.widths[3 * i] / static_cast<uint32_t>(p.pz);
+    const long long src = ((static_cast<long long>(p.points[3 * i]) + static_cast<long long>(iz) * b) * p.Y +
+                           (static_cast<long long>(p.points[3 * i + 1]) + static_cast<long long>(iy) * b)) * p.X +
+                          p.points[3 * i + 2] + static_cast<long long>(ix) * b;
+    out[e] = vol[src];
+  }
+}
+
+// ----------------------------------------------------------------------------------- gather + norm
+template <typename TIn> __device__ __forceinline__ float to_f32(TIn v);
+template <> __device__ __forceinline__ float to_f32<uint8_t>(uint8_t v) { return static_cast<float>(v); }
+template <> __device__ __forceinline__ float to_f32<uint16_t>(uint16_t v) { return static_cast<float>(v); }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+
+struct NormParams {
+  int rescale, do_clip;
+  float lo, hi, inv;   // inv = 1 / (hi - lo + 1e-12) evaluated in fp32 as a division below
+};
+
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) gather_norm_kernel(GatherParams p, NormParams q) {
+  // one thread per group of 8 consecutive output elements (px % 8 == 0 checked on the host)
+  const int groups_per_row = p.px / 8;
+  const long long total = p.n * p.pz * p.py * groups_per_row;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const TIn* vol = reinterpret_cast<const TIn*>(p.vol);
+  const float denom = q.hi - q.lo + 1e-12f;
+  for (long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; g < total; g += stride) {
+    const int gx = static_cast<int>(g % groups_per_row);
+    long long t = g / groups_per_row;
+    const int iy = static_cast<int>(t % p.py);
+    t /= p.py;
+    const int iz = static_cast<int>(t % p.pz);
+    const long long i = t / p.pz;
+    const uint32_t b = __ldg(p.widths + 3 * i) / static_cast<uint32_t>(p.pz);
+    const long long src = ((static_cast<long long>(__ldg(p.points + 3 * i)) + static_cast<long long>(iz) * b) * p.Y +
+                           (static_cast<long long>(__ldg(p.points + 3 * i + 1)) + static_cast<long long>(iy) * b)) * p.X +
+                          __ldg(p.points + 3 * i + 2) + static_cast<long long>(gx) * 8 * b;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = to_f32<TIn>(vol[src + static_cast<long long>(e) * b]);
+      if (q.rescale) {
+        if (q.do_clip) v = fminf(fmaxf(v, q.lo), q.hi);
+        v = (v - q.lo) / denom;
+      }
+      f[e] = v;
+    }
+    TOut* o = reinterpret_cast<TOut*>(p.out) + g * 8;
+    if constexpr (sizeof(TOut) == 4) {
+      reinterpret_cast<float4*>(o)[0] = make_float4(f[0], f[1], f[2], f[3]);
+      reinterpret_cast<float4*>(o)[1] = make_float4(f[4], f[5], f[6], f[7]);
+    } else {
+      uint32_t w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if constexpr (std::is_same<TOut, __nv_bfloat16>::value) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+          w[e] = *reinterpret_cast<uint32_t*>(&h);
+        } else {
+          __half2 h = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+          w[e] = *reinterpret_cast<uint32_t*>(&h);
+        }
+      }
+      *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------- scatter
+struct ScatterParams {
+  const uint8_t* sub;
+  uint8_t* vol;
+  const uint32_t* points;
+  uint32_t* owner;
+  long long n;
+  long long Y, X;
+  int wz, wy, wx;
+  int chunks_per_row;
+  long long total_chunks;
+};
+
+template <int ES>
+__global__ void __launch_bounds__(256) scatter_chunks_kernel(ScatterParams p) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const int rows_per_patch = p.wz * p.wy;
+  for (long long c = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; c < p.total_chunks;
+       c += stride) {
+    const int cx = static_cast<int>(c % p.chunks_per_row);
+    const long long row = c / p.chunks_per_row;
+    const long long i = row / rows_per_patch;
+    const int r = static_cast<int>(row - i * rows_per_patch);
+    const int iz = r / p.wy, iy = r - iz * p.wy;
+    const long long dst_row = ((static_cast<long long>(__ldg(p.points + 3 * i)) + iz) * p.Y +
+                               (static_cast<long long>(__ldg(p.points + 3 * i + 1)) + iy)) * p.X +
+                              __ldg(p.points + 3 * i + 2);
+    const uint4 v = ldg_nc_u4(p.sub + c * 16);
+    uint8_t* d = p.vol + dst_row * ES + static_cast<long long>(cx) * 16;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(d);
+    if ((a & 15) == 0) {
+      *reinterpret_cast<uint4*>(d) = v;
+    } else if ((a & 3) == 0) {
+      uint32_t* d4 = reinterpret_cast<uint32_t*>(d);
+      d4[0] = v.x; d4[1] = v.y; d4[2] = v.z; d4[3] = v.w;
+    } else {
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      if (ES == 2 && (a & 1) == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          reinterpret_cast<uint16_t*>(d)[e] = static_cast<uint16_t>(w[e / 2] >> ((e & 1) * 16));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) d[e] = static_cast<uint8_t>(w[e / 4] >> ((e & 3) * 8));
+      }
+    }
+  }
+}
+
+// Overlap-safe two-pass scatter: PASS 0 claims voxels with atomicMax(owner, i + 1), PASS 1 writes
+// only the voxels a patch owns -> identical to the reference's sequential assignment order.
+template <typename T, int PASS>
+__global__ void __launch_bounds__(256) scatter_owner_kernel(ScatterParams p) {
+  const long long total = p.n * p.wz * p.wy * p.wx;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int ix = static_cast<int>(e % p.wx);
+    long long t = e / p.wx;
+    const int iy = static_cast<int>(t % p.wy);
+    t /= p.wy;
+    const int iz = static_cast<int>(t % p.wz);
+    const long long i = t / p.wz;
+    const long long dst = ((static_cast<long long>(p.points[3 * i]) + iz) * p.Y +
+                           (static_cast<long long>(p.points[3 * i + 1]) + iy)) * p.X + p.points[3 * i + 2] + ix;
+    if (PASS == 0) {
+      atomicMax(p.owner + dst, static_cast<uint32_t>(i + 1));
+    } else if (p.owner[dst] == static_cast<uint32_t>(i + 1)) {
+      reinterpret_cast<T*>(p.vol)[dst] = reinterpret_cast<const T*>(p.sub)[e];
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------- min / max
+template <typename TIn>
+__global__ void __launch_bounds__(256) minmax_partial_kernel(const TIn* vol, long long Z, long long Y, long long X,
+                                                              int s, float* partial) {
+  const long long nz = (Z + s - 1) / s, ny = (Y + s - 1) / s, nx = (X + s - 1) / s;
+  const long long total = nz * ny * nx;
+  float lo = INFINITY, hi = -INFINITY;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const long long ix = e % nx;
+    const long long t = e / nx;
+    const long long iy = t % ny, iz = t / ny;
+    const float v = to_f32<TIn>(vol[(iz * s * Y + iy * s) * X + ix * s]);
+    lo = fminf(lo, v);
+    hi = fmaxf(hi, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  __shared__ float slo[8], shi[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { slo[warp] = lo; shi[warp] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { lo = fminf(lo, slo[w]); hi = fmaxf(hi, shi[w]); }
+    partial[2 * blockIdx.x] = lo;
+    partial[2 * blockIdx.x + 1] = hi;
+  }
+}
+__global__ void minmax_final_kernel(const float* partial, int nblocks, float* out2) {
+  float lo = INFINITY, hi = -INFINITY;
+  for (int i = threadIdx.x; i < nblocks; i += 32) {
+    lo = fminf(lo, partial[2 * i]);
+    hi = fmaxf(hi, partial[2 * i + 1]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if (threadIdx.x == 0) { out2[0] = lo; out2[1] = hi; }
+}
+
+static int grid_for(long long work_items, int threads, int waves = 8) {
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = static_cast<long long>(kNumSMs) * waves;
+  if (blocks > cap) blocks = cap;   // persistent grid-stride: a multiple of the SM count
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace te
+
+using namespace te;
+
+extern "C" int te_gather(const void* vol, int elem_size, const int64_t vol_shape[3], const uint32_t* points,
+                         const uint32_t* widths, int64_t n, const int32_t patch[3], void* out, void* stream) {
+  TE_CHECK_ARG(elem_size == 1 || elem_size == 2 || elem_size == 4, "te_gather: elem_size must be 1, 2 or 4");
+  TE_CHECK_ARG(n >= 0, "te_gather: n < 0");
+  if (n == 0) return TE_OK;
+  TE_CHECK_ARG(vol && points && widths && out, "te_gather: null pointer");
+  TE_CHECK_ARG(patch[0] > 0 && patch[1] > 0 && patch[2] > 0, "te_gather: patch extents must be positive");
+  GatherParams p;
+  p.vol = static_cast<const uint8_t*>(vol);
+  p.out = static_cast<uint8_t*>(out);
+  p.points = points;
+  p.widths = widths;
+  p.n = n;
+  p.Y = vol_shape[1];
+  p.X = vol_shape[2];
+  p.pz = patch[0]; p.py = patch[1]; p.px = patch[2];
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long row_bytes = static_cast<long long>(p.px) * elem_size;
+  if (row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    p.chunks_per_row = static_cast<int>(row_bytes / 16);
+    p.total_chunks = n * p.pz * p.py * p.chunks_per_row;
+    const int grid = grid_for(p.total_chunks, 256, 16);
+    if (elem_size == 1) gather_chunks_kernel<1><<<grid, 256, 0, st>>>(p);
+    else if (elem_size == 2) gather_chunks_kernel<2><<<grid, 256, 0, st>>>(p);
+    else gather_chunks_kernel<4><<<grid, 256, 0, st>>>(p);
+  } else {
+    p.chunks_per_row = 0;
+    p.total_chunks = 0;
+    const int grid = grid_for(n * p.pz * p.py * p.px, 256, 16);
+    if (elem_size == 1) gather_elems_kernel<uint8_t><<<grid, 256, 0, st>>>(p);
+    else if (elem_size == 2) gather_elems_kernel<uint16_t><<<grid, 256, 0, st>>>(p);
+    else gather_elems_kernel<uint32_t><<<grid, 256, 0, st>>>(p);
+  }
+  TE_LAUNCH_CHECK();
+  return TE_OK;
+}
+
+template <typename TIn>
+static int launch_gather_norm(const GatherParams& p, const NormParams& q, int out_dtype, cudaStream_t st) {
+  const long long total = p.n * p.pz * p.py * (p.px / 8);
+  const int grid = grid_for(total, 256, 16);
+  if (out_dtype == TE_BF16) gather_norm_kernel<TIn, __nv_bfloat16><<<grid, 256, 0, st>>>(p, q);
+  else if (out_dtype == TE_F16) gather_norm_kernel<TIn, __half><<<grid, 256, 0, st>>>(p, q);
+  else gather_norm_kernel<TIn, float><<<grid, 256, 0, st>>>(p, q);
+  TE_LAUNCH_CHECK();
+  return TE_OK;
+}
+
+extern "C" int te_gather_norm(const void* vol, int vol_dtype, const int64_t vol_shape[3], const uint32_t* points,
+                              const uint32_t* widths, int64_t n, const int32_t patch[3], int rescale, int do_clip,
+                              float lo, float hi, void* out, int out_dtype, void* stream) {
+  TE_CHECK_ARG(n >= 0, "te_gather_norm: n < 0");
+  if (n == 0) return TE_OK;
+  TE_CHECK_ARG(vol && points && widths && out, "te_gather_norm: null pointer");
+  TE_CHECK_ARG(out_dtype == TE_BF16 || out_dtype == TE_F16 || out_dtype == TE_F32,
+               "te_gather_norm: out_dtype must be bf16, f16 or f32");
+  TE_CHECK_ARG(patch[2] % 8 == 0, "te_gather_norm: patch x extent must be a multiple of 8");
+  TE_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "te_gather_norm: out must be 16-byte aligned");
+  GatherParams p;
+  p.vol = static_cast<const uint8_t*>(vol);
+  p.out = static_cast<uint8_t*>(out);
+  p.points = points;
+  p.widths = widths;
+  p.n = n;
+  p.Y = vol_shape[1];
+  p.X = vol_shape[2];
+  p.pz = patch[0]; p.py = patch[1]; p.px = patch[2];
+  p.chunks_per_row = 0;
+  p.total_chunks = 0;
+  NormParams q{rescale, do_clip, lo, hi, 0.f};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (vol_dtype) {
+    case TE_U8: return launch_gather_norm<uint8_t>(p, q, out_dtype, st);
+    case TE_U16: return launch_gather_norm<uint16_t>(p, q, out_dtype, st);
+    case TE_F16: return launch_gather_norm<__half>(p, q, out_dtype, st);
+    case TE_F32: return launch_gather_norm<float>(p, q, out_dtype, st);
+    default: set_error("te_gather_norm: unsupported vol_dtype %d", vol_dtype); return TE_ERR_ARG;
+  }
+}
+
+extern "C" int te_scatter(const void* sub_vols, int elem_size, const uint32_t* points, int64_t n,
+                          const int32_t width[3], void* vol_out, const int64_t vol_shape[3], uint32_t* owner,
+                          void* stream) {
+  TE_CHECK_ARG(elem_size == 1 || elem_size == 2 || elem_size == 4, "te_scatter: elem_size must be 1, 2 or 4");
+  TE_CHECK_ARG(n >= 0, "te_scatter: n < 0");
+  if (n == 0) return TE_OK;
+  TE_CHECK_ARG(sub_vols && points && vol_out, "te_scatter: null pointer");
+  TE_CHECK_ARG(width[0] > 0 && width[1] > 0 && width[2] > 0, "te_scatter: width must be positive");
+  ScatterParams p;
+  p.sub = static_cast<const uint8_t*>(sub_vols);
+  p.vol = static_cast<uint8_t*>(vol_out);
+  p.points = points;
+  p.owner = owner;
+  p.n = n;
+  p.Y = vol_shape[1];
+  p.X = vol_shape[2];
+  p.wz = width[0]; p.wy = width[1]; p.wx = width[2];
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (owner != nullptr) {
+    const long long nvox = static_cast<long long>(vol_shape[0]) * vol_shape[1] * vol_shape[2];
+    TE_CUDA(cudaMemsetAsync(owner, 0, static_cast<size_t>(nvox) * 4, st));
+    p.chunks_per_row = 0;
+    p.total_chunks = 0;
+    const int grid = grid_for(n * p.wz * p.wy * p.wx, 256, 16);
+    if (elem_size == 1) {
+      scatter_owner_kernel<uint8_t, 0><<<grid, 256, 0, st>>>(p);
+      TE_LAUNCH_CHECK();
+      scatter_owner_kernel<uint8_t, 1><<<grid, 256, 0, st>>>(p);
+    } else if (elem_size == 2) {
+      scatter_owner_kernel<uint16_t, 0><<<grid, 256, 0, st>>>(p);
+      TE_LAUNCH_CHECK();
+      scatter_owner_kernel<uint16_t, 1><<<grid, 256, 0, st>>>(p);
+    } else {
+      scatter_owner_kernel<uint32_t, 0><<<grid, 256, 0, st>>>(p);
+      TE_LAUNCH_CHECK();
+      scatter_owner_kernel<uint32_t, 1><<<grid, 256, 0, st>>>(p);
+    }
+    TE_LAUNCH_CHECK();
+    return TE_OK;
+  }
+  const long long row_bytes = static_cast<long long>(p.wx) * elem_size;
+  TE_CHECK_ARG(row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(sub_vols) & 15) == 0,
+               "te_scatter: patch rows must be a multiple of 16 bytes (pass an owner buffer otherwise)");
+  p.chunks_per_row = static_cast<int>(row_bytes / 16);
+  p.total_chunks = n * p.wz * p.wy * p.chunks_per_row;
+  const int grid = grid_for(p.total_chunks, 256, 16);
+  if (elem_size == 1) scatter_chunks_kernel<1><<<grid, 256, 0, st>>>(p);
+  else if (elem_size == 2) scatter_chunks_kernel<2><<<grid, 256, 0, st>>>(p);
+  else scatter_chunks_kernel<4><<<grid, 256, 0, st>>>(p);
+  TE_LAUNCH_CHECK();
+  return TE_OK;
+}
+
+extern "C" int te_minmax_strided(const void* vol, int vol_dtype, const int64_t vol_shape[3], int stride,
+                                 float* out2, float* scratch, void* stream) {
+  TE_CHECK_ARG(vol && out2 && scratch, "te_minmax_strided: null pointer");
+  TE_CHECK_ARG(stride >= 1, "te_minmax_strided: stride must be >= 1");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long Z = vol_shape[0], Y = vol_shape[1], X = vol_shape[2];
+  const long long total = ((Z + stride - 1) / stride) * ((Y + stride - 1) / stride) * ((X + stride - 1) / stride);
+  TE_CHECK_ARG(total > 0, "te_minmax_strided: empty volume");
+  int grid = grid_for(total, 256, 4);
+  if (grid > 1024) grid = 1024;
+  switch (vol_dtype) {
+    case TE_U8: minmax_partial_kernel<uint8_t><<<grid, 256, 0, st>>>(static_cast<const uint8_t*>(vol), Z, Y, X, stride, scratch); break;
+    case TE_U16: minmax_partial_kernel<uint16_t><<<grid, 256, 0, st>>>(static_cast<const uint16_t*>(vol), Z, Y, X, stride, scratch); break;
+    case TE_F16: minmax_partial_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(vol), Z, Y, X, stride, scratch); break;
+    case TE_F32: minmax_partial_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(vol), Z, Y, X, stride, scratch); break;
+    default: set_error("te_minmax_strided: unsupported vol_dtype %d", vol_dtype); return TE_ERR_ARG;
+  }
+  TE_LAUNCH_CHECK();
+  minmax_final_kernel<<<1, 32, 0, st>>>(scratch, grid, out2);
+  TE_LAUNCH_CHECK();
+  return TE_OK;
+}

@@ -1,0 +1,285 @@
+// CUDA-core layer kernels (see layers_simt.cuh).  Semantics follow the Keras layers the reference
+// builds its graphs from (/root/reference/tomo_encoders/neural_nets/Unet3D.py:44-194,
+// neural_nets/autoencoders.py:60-243): Conv3D(k=3,'same'), Conv3DTranspose(k=2, strides=s, 'same'),
+// MaxPool3D(p, 'same' on divisible extents), Dense, LeakyReLU(0.2), sigmoid.
+#include "layers_simt.cuh"
+#include "te_common.cuh"
+
+namespace te {
+namespace {
+
+template <typename T> __device__ __forceinline__ float ld(const T* p);
+template <> __device__ __forceinline__ float ld<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ld<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <> __device__ __forceinline__ float ld<__half>(const __half* p) { return __half2float(*p); }
+template <typename T> __device__ __forceinline__ void st(T* p, float v);
+template <> __device__ __forceinline__ void st<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void st<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ void st<__half>(__half* p, float v) { *p = __float2half_rn(v); }
+
+inline int blocks_for(long long items, int threads) {
+  long long b = (items + threads - 1) / threads;
+  const long long cap = static_cast<long long>(kNumSMs) * 32;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) conv3_kernel(TView in, TView out, const float* __restrict__ w,
+                                                     const float* __restrict__ bias, int lrelu, float alpha) {
+  const int Cin = in.C, Cout = out.C;
+  const long long total = out.voxels() * Cout;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const T* ip = static_cast<const T*>(in.ptr);
+  T* op = static_cast<T*>(out.ptr);
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int co = static_cast<int>(e % Cout);
+    long long v = e / Cout;
+    const int x = static_cast<int>(v % in.W); v /= in.W;
+    const int y = static_cast<int>(v % in.H); v /= in.H;
+    const int z = static_cast<int>(v % in.D);
+    const long long n = v / in.D;
+    float acc = bias[co];
+    for (int dz = -1; dz <= 1; ++dz) {
+      const int zz = z + dz;
+      if (zz < 0 || zz >= in.D) continue;
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int yy = y + dy;
+        if (yy < 0 || yy >= in.H) continue;
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int xx = x + dx;
+          if (xx < 0 || xx >= in.W) continue;
+          const int tap = ((dz + 1) * 3 + (dy + 1)) * 3 + (dx + 1);
+          const T* src = ip + (((n * in.D + zz) * in.H + yy) * in.W + xx) * in.ctot + in.coff;
+          const float* wt = w + (static_cast<long long>(tap) * Cin) * Cout + co;
+          for (int ci = 0; ci < Cin; ++ci) acc = fmaf(ld<T>(src + ci), wt[static_cast<long long>(ci) * Cout], acc);
+        }
+      }
+    }
+    if (lrelu) acc = acc > 0.f ? acc : alpha * acc;
+    st<T>(op + (e / Cout) * out.ctot + out.coff + co, acc);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) upconv_kernel(TView in, TView out, const float* __restrict__ w,
+                                                      const float* __restrict__ bias, int s, int lrelu, float alpha) {
+  const int Cin = in.C, Cout = out.C;
+  const long long total = out.voxels() * Cout;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const T* ip = static_cast<const T*>(in.ptr);
+  T* op = static_cast<T*>(out.ptr);
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int co = static_cast<int>(e % Cout);
+    long long v = e / Cout;
+    const int x = static_cast<int>(v % out.W); v /= out.W;
+    const int y = static_cast<int>(v % out.H); v /= out.H;
+    const int z = static_cast<int>(v % out.D);
+    const long long n = v / out.D;
+    const int a = z % s, b = y % s, c = x % s;
+    float acc = bias[co];
+    if (a < 2 && b < 2 && c < 2) {
+      const int sub = (a * 2 + b) * 2 + c;
+      const T* src = ip + (((n * in.D + z / s) * in.H + y / s) * in.W + x / s) * in.ctot + in.coff;
+      const float* wt = w + (static_cast<long long>(sub) * Cout + co) * Cin;
+      for (int ci = 0; ci < Cin; ++ci) acc = fmaf(ld<T>(src + ci), wt[ci], acc);
+    }
+    if (lrelu) acc = acc > 0.f ? acc : alpha * acc;
+    st<T>(op + (e / Cout) * out.ctot + out.coff + co, acc);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_kernel(TView in, TView out, int p) {
+  const int C = out.C;
+  const long long total = out.voxels() * C;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const T* ip = static_cast<const T*>(in.ptr);
+  T* op = static_cast<T*>(out.ptr);
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int c = static_cast<int>(e % C);
+    long long v = e / C;
+    const int x = static_cast<int>(v % out.W); v /= out.W;
+    const int y = static_cast<int>(v % out.H); v /= out.H;
+    const int z = static_cast<int>(v % out.D);
+    const long long n = v / out.D;
+    float m = -INFINITY;
+    for (int dz = 0; dz < p; ++dz)
+      for (int dy = 0; dy < p; ++dy)
+        for (int dx = 0; dx < p; ++dx)
+          m = fmaxf(m, ld<T>(ip + (((n * in.D + z * p + dz) * in.H + y * p + dy) * in.W + x * p + dx) * in.ctot +
+                             in.coff + c));
+    st<T>(op + (e / C) * out.ctot + out.coff + c, m);
+  }
+}
+
+// 16-bit fast path: one thread per (output voxel, 8-channel group), 128-bit loads/stores.
+template <typename T2>
+__global__ void __launch_bounds__(256) maxpool_vec8_kernel(TView in, TView out, int p) {
+  const int G = out.C / 8;
+  const long long total = out.voxels() * G;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const uint8_t* ip = static_cast<const uint8_t*>(in.ptr);
+  uint8_t* op = static_cast<uint8_t*>(out.ptr);
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int g = static_cast<int>(e % G);
+    long long v = e / G;
+    const int x = static_cast<int>(v % out.W); v /= out.W;
+    const int y = static_cast<int>(v % out.H); v /= out.H;
+    const int z = static_cast<int>(v % out.D);
+    const long long n = v / out.D;
+    T2 m[4];
+    bool first = true;
+    for (int dz = 0; dz < p; ++dz)
+      for (int dy = 0; dy < p; ++dy)
+        for (int dx = 0; dx < p; ++dx) {
+          const long long vox = ((n * in.D + z * p + dz) * in.H + y * p + dy) * in.W + x * p + dx;
+          const uint4 r = *reinterpret_cast<const uint4*>(ip + (vox * in.ctot + in.coff + g * 8) * 2);
+          const T2* h = reinterpret_cast<const T2*>(&r);
+          if (first) { m[0] = h[0]; m[1] = h[1]; m[2] = h[2]; m[3] = h[3]; first = false; }
+          else { m[0] = __hmax2(m[0], h[0]); m[1] = __hmax2(m[1], h[1]); m[2] = __hmax2(m[2], h[2]); m[3] = __hmax2(m[3], h[3]); }
+        }
+    *reinterpret_cast<uint4*>(op + ((e / G) * out.ctot + out.coff + g * 8) * 2) = *reinterpret_cast<uint4*>(m);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) head_kernel(TView in, const float* __restrict__ w, float b, uint8_t* labels,
+                                                    float* probs, float* logits) {
+  const long long total = in.voxels();
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const T* ip = static_cast<const T*>(in.ptr);
+  for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < total; v += stride) {
+    const T* src = ip + v * in.ctot + in.coff;
+    float acc = b;
+    for (int c = 0; c < in.C; ++c) acc = fmaf(ld<T>(src + c), w[c], acc);
+    if (labels) labels[v] = acc > 0.f ? 1 : 0;     // sigmoid(x) > 0.5 <=> x > 0; np.round(0.5) == 0
+    if (probs) probs[v] = 1.f / (1.f + expf(-acc));
+    if (logits) logits[v] = acc;
+  }
+}
+
+// One warp per (patch n, 32 outputs): lanes own consecutive outputs j (coalesced weight rows), the
+// block's 8 warps split the input range and reduce through shared memory.
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) dense_kernel(const TIn* __restrict__ x, long long n, int nin, int nout,
+                                                     const float* __restrict__ w, const float* __restrict__ b, int lrelu,
+                                                     float alpha, TOut* __restrict__ out) {
+  __shared__ float part[8][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = blockIdx.y;
+  const int j = blockIdx.x * 32 + lane;
+  const int chunk = (nin + 7) / 8;
+  const int i0 = warp * chunk, i1 = min(nin, i0 + chunk);
+  float acc = 0.f;
+  if (j < nout) {
+    const TIn* xr = x + row * nin;
+    for (int i = i0; i < i1; ++i) acc = fmaf(ld<TIn>(xr + i), w[static_cast<long long>(i) * nout + j], acc);
+  }
+  part[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && j < nout) {
+    float s = b[j];
+    for (int k = 0; k < 8; ++k) s += part[k][lane];
+    if (lrelu) s = s > 0.f ? s : alpha * s;
+    st<TOut>(out + row * nout + j, s);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) to_f32_kernel(TView in, float* out) {
+  const long long total = in.voxels() * in.C;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const T* ip = static_cast<const T*>(in.ptr);
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride)
+    out[e] = ld<T>(ip + (e / in.C) * in.ctot + in.coff + (e % in.C));
+}
+template <typename T>
+__global__ void __launch_bounds__(256) from_f32_kernel(const float* in, T* out, long long count) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < count; e += stride)
+    st<T>(out + e, in[e]);
+}
+
+}  // namespace
+
+#define TE_DISPATCH_ACT(act_type, CALL)                      \
+  switch (act_type) {                                        \
+    case ACT_F32: { using T = float; CALL; } break;          \
+    case ACT_BF16: { using T = __nv_bfloat16; CALL; } break; \
+    case ACT_F16: { using T = __half; CALL; } break;         \
+    default: return cudaErrorInvalidValue;                   \
+  }
+
+cudaError_t simt_conv3(const TView& in, const TView& out, const float* w, const float* bias, int lrelu, float alpha,
+                       int act_type, cudaStream_t st) {
+  const int grid = blocks_for(out.voxels() * out.C, 256);
+  TE_DISPATCH_ACT(act_type, (conv3_kernel<T><<<grid, 256, 0, st>>>(in, out, w, bias, lrelu, alpha)));
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t simt_upconv(const TView& in, const TView& out, const float* w, const float* bias, int stride, int lrelu,
+                        float alpha, int act_type, cudaStream_t st) {
+  const int grid = blocks_for(out.voxels() * out.C, 256);
+  TE_DISPATCH_ACT(act_type, (upconv_kernel<T><<<grid, 256, 0, st>>>(in, out, w, bias, stride, lrelu, alpha)));
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t simt_maxpool(const TView& in, const TView& out, int pool, int act_type, cudaStream_t st) {
+  const bool vec = act_type != ACT_F32 && out.C % 8 == 0 && in.ctot % 8 == 0 && in.coff % 8 == 0 &&
+                   out.ctot % 8 == 0 && out.coff % 8 == 0;
+  if (vec) {
+    const int grid = blocks_for(out.voxels() * (out.C / 8), 256);
+    if (act_type == ACT_BF16) maxpool_vec8_kernel<__nv_bfloat162><<<grid, 256, 0, st>>>(in, out, pool);
+    else maxpool_vec8_kernel<__half2><<<grid, 256, 0, st>>>(in, out, pool);
+  } else {
+    const int grid = blocks_for(out.voxels() * out.C, 256);
+    TE_DISPATCH_ACT(act_type, (maxpool_kernel<T><<<grid, 256, 0, st>>>(in, out, pool)));
+  }
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t simt_head(const TView& in, const float* w, float b, uint8_t* labels, float* probs, float* logits,
+                      int act_type, cudaStream_t st) {
+  const int grid = blocks_for(in.voxels(), 256);
+  TE_DISPATCH_ACT(act_type, (head_kernel<T><<<grid, 256, 0, st>>>(in, w, b, labels, probs, logits)));
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t simt_dense(const void* x, int in_type, long long n, int nin, int nout, const float* w, const float* b,
+                       int lrelu, float alpha, void* out, int out_type, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  dim3 grid((nout + 31) / 32, static_cast<unsigned>(n));
+#define TE_DENSE(TI, TO) \
+  dense_kernel<TI, TO><<<grid, 256, 0, st>>>(static_cast<const TI*>(x), n, nin, nout, w, b, lrelu, alpha, static_cast<TO*>(out))
+  if (in_type == ACT_F32 && out_type == ACT_F32) TE_DENSE(float, float);
+  else if (in_type == ACT_F32 && out_type == ACT_BF16) TE_DENSE(float, __nv_bfloat16);
+  else if (in_type == ACT_F32 && out_type == ACT_F16) TE_DENSE(float, __half);
+  else if (in_type == ACT_BF16 && out_type == ACT_F32) TE_DENSE(__nv_bfloat16, float);
+  else if (in_type == ACT_F16 && out_type == ACT_F32) TE_DENSE(__half, float);
+  else return cudaErrorInvalidValue;
+#undef TE_DENSE
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t simt_to_f32(const TView& in, float* out, int act_type, cudaStream_t st) {
+  const int grid = blocks_for(in.voxels() * in.C, 256);
+  TE_DISPATCH_ACT(act_type, (to_f32_kernel<T><<<grid, 256, 0, st>>>(in, out)));
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t simt_from_f32(const float* in, void* out, long long count, int act_type, cudaStream_t st) {
+  const int grid = blocks_for(count, 256);
+  TE_DISPATCH_ACT(act_type, (from_f32_kernel<T><<<grid, 256, 0, st>>>(in, static_cast<T*>(out), count)));
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace te

@@ -1,0 +1,139 @@
+"""Data-plane calls shared by Patches and Grid: gather (extract) and scatter (fill) on the GPU.
+
+The coordinate bookkeeping stays in numpy on the host (it is O(n) metadata); the voxel movement is
+done by libtomoenc.so (csrc/gather_scatter.cu) through the C ABI in include/tomoenc.h.
+"""
+import numpy as np
+import torch
+
+from .. import _device, _lib
+
+
+def as_3d(vol_shape):
+    """2-D volumes (images) are handled as a single-slice 3-D volume."""
+    vs = tuple(int(v) for v in vol_shape)
+    if len(vs) == 2:
+        return (1,) + vs
+    if len(vs) != 3:
+        raise ValueError("vol_shape must have 2 or 3 dimensions")
+    return vs
+
+
+def pad_cols(a, fill):
+    """(n,2) -> (n,3) by prepending a z column (2-D support)."""
+    a = np.asarray(a)
+    if a.shape[1] == 3:
+        return a
+    return np.concatenate([np.full((len(a), 1), fill, dtype=a.dtype), a], axis=1)
+
+
+def gather(vol, vol_shape, points, widths, patch_size):
+    """out[i] = vol[z:z+wz:b, y:y+wy:b, x:x+wx:b]; returns (n,) + patch_size, dtype of vol.
+
+    vol: numpy array, torch CPU tensor or torch CUDA tensor; the result lives where vol lives.
+    """
+    ndim = len(vol_shape)
+    vs3 = as_3d(vol_shape)
+    n = len(points)
+    t_vol = _device.to_device(vol)
+    if tuple(t_vol.shape) != tuple(vol_shape):
+        raise AssertionError("Shape of big volume does not match vol_shape attribute of patches data")
+    es = t_vol.element_size()
+    if es not in (1, 2, 4):
+        raise TypeError("unsupported volume dtype %s" % (t_vol.dtype,))
+    patch3 = (1,) * (3 - ndim) + tuple(int(p) for p in patch_size)
+    out = torch.empty((n,) + patch3, dtype=t_vol.dtype, device=t_vol.device)
+    if n > 0:
+        d_pts = _device.points_to_device(pad_cols(points, 0))
+        d_wds = _device.points_to_device(pad_cols(widths, 1))
+        L = _lib.lib()
+        _lib.check(L.te_gather(t_vol.data_ptr(), es, _lib.i64x3(vs3), d_pts.data_ptr(), d_wds.data_ptr(), n,
+                               _lib.i32x3(patch3), out.data_ptr(), _device.stream_ptr()), "te_gather")
+    out = out.reshape((n,) + tuple(int(p) for p in patch_size))
+    return _device.to_host_like(out, vol)
+
+
+def _disjoint(points, width, vs3):
+    """True when the patches are provably pairwise disjoint: equal widths, corners on the width
+    lattice, no duplicates (always the case for Grid / regular-grid)."""
+    p = np.asarray(points, dtype=np.int64)
+    w = np.asarray(width, dtype=np.int64)
+    if np.any(p % w[None, :]):
+        return False
+    cells = p // w[None, :]
+    dims = np.asarray(vs3, dtype=np.int64) // w + 1
+    lin = (cells[:, 0] * dims[1] + cells[:, 1]) * dims[2] + cells[:, 2]
+    return len(np.unique(lin)) == len(lin)
+
+
+def scatter(sub_vols, vol_out, vol_shape, points, widths):
+    """Sequential-assignment semantics of fill_patches_in_volume: vol_out[slices_i] = sub_vols[i]
+    for i = 0..n-1, later patches overwrite earlier ones; values are cast to vol_out.dtype the way a
+    numpy assignment would.  vol_out is modified in place (numpy or torch, host or device)."""
+    ndim = len(vol_shape)
+    vs3 = as_3d(vol_shape)
+    n = len(points)
+    if len(sub_vols) != n:
+        raise AssertionError("number of sub-volumes do not match the number of items in patches")
+    if tuple(vol_out.shape) != tuple(vol_shape):
+        raise AssertionError("shape of volume enclosing the patches does not match that of the output volume")
+    if n == 0:
+        return
+    widths = np.asarray(widths)
+    # group by width (Grid and fixed-width Patches have a single group); groups are processed in
+    # order of their first patch index only when they are provably independent, otherwise the
+    # whole call goes through the ordered (owner-map) path group by group in index order.
+    uniq = np.unique(widths, axis=0)
+    if len(uniq) != 1:
+        # variable-width patches: order matters across groups, fall back to index-ordered runs
+        runs = _runs_of_equal_width(widths)
+    else:
+        runs = [(0, n)]
+    host_out = not _device.is_device_array(vol_out)
+    t_out = _device.to_device(vol_out)
+    es = t_out.element_size()
+    if es not in (1, 2, 4):
+        raise TypeError("unsupported volume dtype %s" % (t_out.dtype,))
+    L = _lib.lib()
+    owner = None
+    for (a, b) in runs:
+        w3 = (1,) * (3 - ndim) + tuple(int(v) for v in widths[a])
+        sv = sub_vols[a:b] if not isinstance(sub_vols, list) else np.asarray(sub_vols[a:b])
+        t_sub = _device.to_device(sv)
+        if tuple(t_sub.shape[1:]) != tuple(int(v) for v in widths[a]):
+            raise AssertionError("width mismatch between sub_vol and patch")
+        if t_sub.dtype != t_out.dtype:
+            t_sub = _numpy_cast(t_sub, t_out.dtype)
+        pts = pad_cols(np.asarray(points[a:b]), 0)
+        d_pts = _device.points_to_device(pts)
+        row_ok = (w3[2] * es) % 16 == 0
+        if row_ok and _disjoint(pts, w3, vs3):
+            owner_ptr = None
+        else:
+            if owner is None:
+                owner = torch.empty(vs3, dtype=torch.int32, device=t_out.device)
+            owner_ptr = owner.data_ptr()
+        _lib.check(L.te_scatter(t_sub.data_ptr(), es, d_pts.data_ptr(), b - a, _lib.i32x3(w3), t_out.data_ptr(),
+                                _lib.i64x3(vs3), owner_ptr, _device.stream_ptr()), "te_scatter")
+    if host_out:
+        res = t_out.cpu()
+        if isinstance(vol_out, torch.Tensor):
+            vol_out.copy_(res)
+        else:
+            vol_out[...] = res.numpy()
+    elif t_out.data_ptr() != vol_out.data_ptr():
+        vol_out.copy_(t_out)
+
+
+def _runs_of_equal_width(widths):
+    change = np.any(widths[1:] != widths[:-1], axis=1)
+    starts = np.concatenate([[0], np.nonzero(change)[0] + 1])
+    ends = np.concatenate([starts[1:], [len(widths)]])
+    return [(int(a), int(b)) for a, b in zip(starts, ends)]
+
+
+def _numpy_cast(t, dtype):
+    """numpy's assignment cast (C-style truncation for float -> integer)."""
+    if dtype in (torch.uint8, torch.uint16) and t.dtype.is_floating_point:
+        return t.to(torch.int64).to(dtype)
+    return t.to(dtype)
