@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""Benchmark of the TomoEncoders hot path on B200 (contract: see the task statement / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload at N=1 = BASELINE.json configs[1]: 3-D U-net segmenter (M_a01: n_filters [16,32,64], pools
+[2,2,2], skip concatenation on) over a synthetic 512^3 float16 volume tiled into 512 patches of 64^3,
+chunked 32 patches at a time: fused gather+clip+rescale -> U-net (tcgen05) -> labels -> stitch.
+One "step" = one full pass over the volume.  With N ranks (torchrun) every rank segments its own
+512^3 slab (patches are independent: no data-path collective; weak scaling) and additionally encodes
+random 64^3 patches to latents whose PCA moments are all-reduced over NCCL (the only exchange step
+of the path).  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+M_A01 = dict(n_filters=[16, 32, 64], n_blocks=3, activation="lrelu", batch_norm=True, isconcat=[True] * 3,
+             pool_size=[2, 2, 2])
+ENC = dict(n_filters=[16, 32, 64], n_blocks=3, activation="lrelu", batch_norm=True, pool_size=[2, 2, 2],
+           hidden_units=[128, 128], POOL_FLAG=True)
+VOL = (512, 512, 512)
+PATCH = 64
+CHUNK = 32
+ENC_PATCHES = 4096          # 64^3 patches encoded per rank per step in the "encode" leg
+METRIC = "voxels/sec segmented (3-D U-net M_a01, 64^3 tiles of a 512^3 fp16 volume per GPU)"
+
+
+def synth_volume_torch(shape, seed, device):
+    """Smooth blobs + noise in [0,1], float16, generated on the device (structure does not affect
+    the arithmetic; BASELINE configs only fix shape and dtype)."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    coarse = torch.randn((1, 1) + tuple(s // 16 for s in shape), generator=g, device=device)
+    up = torch.nn.functional.interpolate(coarse, size=shape, mode="trilinear", align_corners=False)[0, 0]
+    y = (up > up.median()).float()
+    del up
+    x = y + 0.1 * torch.randn(shape, generator=g, device=device)
+    x = (x - x.min()) / (x.max() - x.min())
+    return x.to(torch.float16).contiguous()
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons for one GPU while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = []
+        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
+            if any(r[col].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]),
+                "power_w_max": max(float(r[2]) for r in self.rows), "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_reference_leg(n_patches, threads=None):
+    """The reference's CPU path for the same workload, restated by the oracle (TensorFlow is not
+    installable here): extract -> clip/rescale -> U-net (torch CPU fp32, all host
+    threads) -> round -> fill, on `n_patches` 64^3 tiles of a float16 volume.  Returns voxels/s."""
+    import torch
+    from oracle import nets_torch as O, structures_np as S, weights as OW
+    if threads:
+        torch.set_num_threads(threads)
+    g = np.random.default_rng(5)
+    nz = max(1, (n_patches + 3) // 4)
+    vol = g.uniform(0, 1, (PATCH * nz, PATCH * 2, PATCH * 2)).astype(np.float16)
+    pts, wds = S.regular_grid_points(vol.shape, (PATCH,) * 3)
+    pts, wds = pts[:n_patches], wds[:n_patches]
+    w = OW.draw(O.unet_spec(**M_A01), 11)
+    t0 = time.perf_counter()
+    x = S.extract(vol, pts, wds, (PATCH,) * 3)
+    y = O.segmenter_predict_patches(x[..., np.newaxis], CHUNK, w, min_max=(0.0, 1.0), **M_A01)
+    out = np.zeros(vol.shape, np.uint8)
+    S.fill_patches_in_volume(y[..., 0], pts, wds, out)
+    dt = time.perf_counter() - t0
+    return n_patches * PATCH ** 3 / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_patches = 2
+    times = []
+    for i in range(args.warmup + args.steps):
+        v, dt, threads = cpu_reference_leg(n_patches)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = n_patches * PATCH ** 3 / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1] model and patch size on the host CPU: %d tiles of 64^3 per step (bounded sample)" % n_patches,
+                   "model": "M_a01", "patch": PATCH, "chunk": CHUNK},
+        "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": threads, "kind": "port",
+                         "sample": "%d x 64^3 tiles per step: oracle extract + torch-CPU fp32 U-net + fill" % n_patches},
+        "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from tomoencoders_b200 import Grid, Patches, _lib
+    from tomoencoders_b200.neural_nets import LatentPCA, SelfSupervisedCAE, SurfaceSegmenter
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    mode = os.environ.get("TOMOENC_MODE", "fp16")
+    fe = SurfaceSegmenter(model_initialization="define-new", descriptor_tag="M_a01", mode=mode, **M_A01)
+    # random-init weights: Keras-default glorot-uniform draws of the product's own initialiser (seeded)
+    from tomoencoders_b200.neural_nets import _spec
+    fe.models["segmenter"].set_weights(_spec.keras_default_init(fe.models["segmenter"].spec, seed=11))
+    ae = SelfSupervisedCAE(model_initialization="define-new", model_size=(PATCH,) * 3, descriptor_tag="enc", mode=mode, **ENC)
+    ae.models["encoder"].set_weights(_spec.keras_default_init(ae.models["encoder"].spec, seed=12))
+
+    vol = synth_volume_torch(VOL, 4 + rank, dev)
+    grid = Grid(VOL, width=PATCH)
+    n_tiles = len(grid)
+    min_max = fe.calc_voxel_min_max(vol, 4)
+    seg = torch.zeros(VOL, dtype=torch.uint8, device=dev)
+    rng = np.random.default_rng(7 + rank)
+    enc_pts = np.stack([rng.integers(0, VOL[a] - PATCH, ENC_PATCHES) for a in range(3)], axis=1)
+    enc_patches = Patches(VOL, "data", points=enc_pts, widths=np.full_like(enc_pts, PATCH))
+    lat = torch.empty((ENC_PATCHES, 128), dtype=torch.float32, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def seg_step():
+        fe.segment_volume(vol, grid, CHUNK, min_max=min_max, out=seg)
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ------------------------------------------------------------------ segmentation, device resident
+    for _ in range(args.warmup):
+        seg_step()
+    net = fe.models["segmenter"].net_for((PATCH,) * 3, CHUNK)
+    barrier()
+    launches0 = _lib.lib().te_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        ev0.record()
+        for _ in range(args.steps):
+            seg_step()
+        ev1.record()
+        barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = int(_lib.lib().te_launch_count() - launches0)
+    ms_per_step = ms_total / args.steps
+    vox_per_step = VOL[0] * VOL[1] * VOL[2]
+    value = world * vox_per_step / (ms_per_step / 1e3)
+
+    # ------------------------------------------------------------------ per-layer roofline leg (separate pass, events per launch)
+    net.set_profiling(True)
+    seg_step()
+    torch.cuda.synchronize()
+    lt = net.layer_times()
+    net.set_profiling(False)
+    by_kernel = {}
+    for name, kernel, flops, ms, cnt in lt:
+        if cnt == 0:
+            continue
+        k = by_kernel.setdefault(kernel.replace("+head", ""), {"ms": 0.0, "launches": 0, "flops": 0.0, "layers": []})
+        k["ms"] += ms
+        k["launches"] += cnt
+        k["flops"] += flops * n_tiles          # algorithmic FLOPs over the whole step
+        k["layers"].append(name)
+    tot_ms = sum(k["ms"] for k in by_kernel.values())
+    dom_name, dom = max(by_kernel.items(), key=lambda kv: kv[1]["ms"])
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(peaks_path):
+        peaks = json.load(open(peaks_path))
+        tf_peak, peak_src = float(peaks.get("bf16_tflops_sustained", 1390.1)), "MEASURED_PEAKS.json bf16_tflops_sustained"
+        hbm_peak = float(peaks.get("hbm_gbs", 6545.6))
+    else:
+        tf_peak, peak_src, hbm_peak = 1400.0, "fallback (B200_PROFILING.md sustained)", 6650.0
+    achieved = dom["flops"] / (dom["ms"] / 1e3) / 1e12
+    roofline = {"bound": "tensor", "kernel": dom_name, "layers": dom["layers"], "achieved": achieved, "peak": tf_peak,
+                "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None, "peak_source": peak_src,
+                "launches_per_step": dom["launches"], "avg_launch_ms": dom["ms"] / dom["launches"],
+                "share_of_step": dom["ms"] / tot_ms}
+    all_tc_flops = sum(k["flops"] for n_, k in by_kernel.items() if n_.startswith("conv_umma"))
+    all_tc_ms = sum(k["ms"] for n_, k in by_kernel.items() if n_.startswith("conv_umma"))
+    kernels = {n_: {"ms_per_step": round(k["ms"], 3), "launches": k["launches"],
+                    "tflops": (k["flops"] / (k["ms"] / 1e3) / 1e12) if k["flops"] else None} for n_, k in by_kernel.items()}
+
+    # ------------------------------------------------------------------ gather / stitch bandwidth (HBM roofline of the data-movement kernels)
+    x_tiles = grid.extract(vol)                                    # device in -> device out
+    torch.cuda.synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(5):
+        x_tiles = grid.extract(vol)
+    g1.record()
+    torch.cuda.synchronize()
+    gather_gbs = 2 * vol.numel() * 2 / (g0.elapsed_time(g1) / 5 / 1e3) / 1e9
+    lab = torch.zeros((n_tiles,) + (PATCH,) * 3, dtype=torch.uint8, device=dev)
+    g0.record()
+    for _ in range(5):
+        grid.fill_patches_in_volume(lab, seg)
+    g1.record()
+    torch.cuda.synchronize()
+    scatter_gbs = 2 * seg.numel() / (g0.elapsed_time(g1) / 5 / 1e3) / 1e9
+    del x_tiles, lab
+
+    # ------------------------------------------------------------------ end to end: host volume -> host mask through the public API
+    host_vol = torch.empty(VOL, dtype=torch.float16).pin_memory()
+    host_vol.copy_(vol)
+    host_seg = torch.empty(VOL, dtype=torch.uint8).pin_memory()
+
+    def e2e_step():
+        dvol = host_vol.to(dev, non_blocking=True)
+        mm = fe.calc_voxel_min_max(dvol, 4)
+        fe.segment_volume(dvol, grid, CHUNK, min_max=mm, out=seg)
+        host_seg.copy_(seg, non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    e2e_value = world * vox_per_step / (e2e_ms / 1e3)
+
+    # ------------------------------------------------------------------ encode + PCA leg (patches/s)
+    def enc_step():
+        pca = LatentPCA(2)
+        ae.embed_volume(vol, enc_patches, CHUNK, min_max=min_max, out=lat)
+        pca.partial_fit(lat)
+        pca.finalize()                      # all-reduce of the moments when world > 1
+        return pca.transform_all_gather(lat)
+
+    enc_step()
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    n_enc_steps = max(1, min(args.steps, 3))
+    for _ in range(n_enc_steps):
+        z2 = enc_step()
+    c1.record()
+    barrier()
+    enc_ms = max_over_ranks(c0.elapsed_time(c1)) / n_enc_steps
+    enc_value = world * ENC_PATCHES / (enc_ms / 1e3)
+    enc_flops = ae.models["encoder"].net_for((PATCH,) * 3, CHUNK).flops_per_patch
+
+    if rank == 0:
+        cpu_v, cpu_dt, cpu_threads = cpu_reference_leg(4)
+        flops_patch = net.flops_per_patch
+        line = {
+            "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": mode, "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: U-net M_a01 segmenter, 512^3 float16 volume per GPU, 512 tiles of 64^3, chunk %d" % CHUNK,
+                       "model": "M_a01 n_filters=[16,32,64] pool=[2,2,2] isconcat=True", "patch": PATCH, "chunk": CHUNK,
+                       "parallelism": "independent slabs (1 per rank), no data-path collective" if world > 1 else "single GPU",
+                       "l2": "inputs_exceed_l2 (268 MB volume + %.1f GB activations per chunk vs 126 MB L2)" % (net.workspace_bytes / 1e9),
+                       "gflop_per_patch": flops_patch / 1e9},
+            "tflops_effective": world * n_tiles * flops_patch / (ms_per_step / 1e3) / 1e12,
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_value, "unit": "voxels/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(host_vol.numel() * 2), "d2h_bytes_per_step": int(host_seg.numel()),
+                    "api": "SurfaceSegmenter.segment_volume(host volume) incl. min/max, pinned H2D and D2H"},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "roofline_all_tensor_core_layers": {"achieved": all_tc_flops / (all_tc_ms / 1e3) / 1e12, "unit": "TFLOP/s",
+                                                "frac": all_tc_flops / (all_tc_ms / 1e3) / 1e12 / tf_peak,
+                                                "share_of_step": all_tc_ms / tot_ms},
+            "kernels": kernels,
+            "hbm": {"gather_gbs": gather_gbs, "gather_frac": gather_gbs / hbm_peak, "scatter_gbs": scatter_gbs,
+                    "scatter_frac": scatter_gbs / hbm_peak, "peak": hbm_peak, "unit": "GB/s",
+                    "note": "Grid.extract of the 512^3 fp16 volume (read+write 537 MB) and fill of the uint8 mask (268 MB)"},
+            "encode": {"metric": "64^3 patches/sec encoded + PCA-projected (encoder [16,32,64], latent 128)",
+                       "value": enc_value, "unit": "patches/s", "ms_per_step": enc_ms, "patches_per_rank_per_step": ENC_PATCHES,
+                       "tflops_effective": enc_value * enc_flops / 1e12,
+                       "collectives": "allreduce(16513 f64 PCA moments) + allgather((n,2) projections)" if world > 1 else "none (1 rank)"},
+            "cpu_baseline": {"value": cpu_v, "unit": "voxels/s", "cores": cpu_threads, "kind": "port",
+                             "sample": "4 x 64^3 tiles: oracle extract + torch-CPU fp32 U-net M_a01 + fill (%.1f s)" % cpu_dt},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -156,6 +156,14 @@ double te_net_flops_per_patch(const te_net* net);
 /* Name, algorithmic FLOPs and kernel class of layer i (host strings owned by the handle). */
 int te_net_layer_info(const te_net* net, int layer_index, const char** name, double* flops, int* uses_tensor_cores);
 
+/* Per-layer device timing (bench.py's roofline leg): when enabled, every layer launch of a forward
+ * call is bracketed by CUDA events on the launching stream.  te_net_layer_time synchronises on the
+ * recorded events and returns the accumulated milliseconds and launch count since enabling. */
+int te_net_set_profiling(te_net* net, int enable);
+int te_net_layer_time(te_net* net, int layer_index, double* total_ms, int64_t* launches);
+/* Name of the kernel (template instantiation) that executes layer i, written into buf. */
+int te_net_layer_kernel(const te_net* net, int layer_index, char* buf, int buflen);
+
 /* ------------------------------------------------------------------------------------------------
  * Latent PCA.  Replaces sklearn IncrementalPCA.fit / transform as called by fit_PCA / transform_PCA
  * (scratchpad/IEEE_ICIP_paper/latent_vis.py:94-143) with exact PCA from streamed moments.

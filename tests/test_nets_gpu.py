@@ -1,0 +1,168 @@
+"""GPU: networks through the reference-facing API against the torch-CPU oracle (same seeded inputs
+and weights).  Tolerances are those of BASELINE.json north_star: latents within 1e-2 relative error
+in the 16-bit tensor-core modes and 1e-4 in the fp32 check mode; segmentation masks >= 99.9 % voxel
+agreement."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nets_torch as O, pca_np, phantom, weights as OW
+from tomoencoders_b200 import Grid, Patches
+from tomoencoders_b200.neural_nets import Enhancer_fCNN, LatentPCA, SelfSupervisedCAE, SurfaceSegmenter
+
+pytestmark = pytest.mark.gpu
+
+M_A01 = dict(n_filters=[16, 32, 64], n_blocks=3, activation="lrelu", batch_norm=True, isconcat=[True] * 3, pool_size=[2, 2, 2])
+M_A02 = dict(n_filters=[16, 32], n_blocks=2, activation="lrelu", batch_norm=True, isconcat=[True] * 2, pool_size=[2, 4])
+SMALL = dict(n_filters=[16, 32], n_blocks=2, activation="lrelu", batch_norm=True, isconcat=[True] * 2, pool_size=[2, 2])
+ENC = dict(n_filters=[16, 32, 64], n_blocks=3, activation="lrelu", batch_norm=True, pool_size=[2, 2, 2],
+           hidden_units=[128, 128], POOL_FLAG=True)
+
+
+def oparams(p):
+    return {k: v for k, v in p.items()}
+
+
+def relerr(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+@pytest.fixture(scope="module")
+def vol_f16():
+    v, _ = phantom.volume_f16((128, 128, 128))
+    return v
+
+
+def test_unet_fp32_check_mode_matches_oracle(vol_f16):
+    w = OW.draw(O.unet_spec(**oparams(SMALL)), 11)
+    fe = SurfaceSegmenter(model_initialization="define-new", descriptor_tag="t", mode="fp32", **SMALL)
+    fe.models["segmenter"].set_weights(w)
+    g = Grid((64, 64, 64), width=32)
+    x = g.extract(vol_f16[:64, :64, :64])[..., np.newaxis]
+    probs = fe.models["segmenter"].predict(x.astype(np.float32))
+    ref = O.unet_forward(x.astype(np.float32), w, **oparams(SMALL))
+    assert probs.shape == ref.shape
+    assert np.abs(probs - ref).max() < 1e-4
+
+
+@pytest.mark.parametrize("mode,min_agree", [("fp16", 0.999), ("bf16", 0.99)])
+def test_segmenter_config2_masks_agree_with_oracle(vol_f16, mode, min_agree):
+    """BASELINE config 2 model (M_a01, 64^3 tiles, fp16 volume), 8 tiles of a 128^3 phantom."""
+    w = OW.draw(O.unet_spec(**oparams(M_A01)), 11)
+    fe = SurfaceSegmenter(model_initialization="define-new", descriptor_tag="M_a01", mode=mode, **M_A01)
+    fe.models["segmenter"].set_weights(w)
+    g = Grid(vol_f16.shape, width=64)
+    min_max = (vol_f16[::4, ::4, ::4].min(), vol_f16[::4, ::4, ::4].max())
+    x = g.extract(vol_f16)
+    y = fe.predict_patches("segmenter", x[..., np.newaxis], 3, None, min_max=min_max)   # ragged last chunk
+    assert y.dtype == np.uint8 and y.shape == x.shape + (1,)
+    ref = O.segmenter_predict_patches(x[..., np.newaxis].astype(np.float32), 4, w, min_max=min_max, **oparams(M_A01))
+    agree = float((y == ref).mean())
+    assert 0.02 < ref.mean() < 0.98, "degenerate oracle mask"
+    assert agree >= min_agree, "voxel agreement %.5f" % agree
+    # stitched volume == fused device path
+    seg = np.zeros(vol_f16.shape, np.uint8)
+    g.fill_patches_in_volume(y[..., 0], seg)
+    fused = fe.segment_volume(vol_f16, g, 3, min_max=min_max)
+    np.testing.assert_array_equal(fused, seg)
+    # device in -> device out
+    tv = torch.from_numpy(vol_f16).cuda()
+    fused_dev = fe.segment_volume(tv, g, 8, min_max=min_max)
+    assert fused_dev.is_cuda and np.array_equal(fused_dev.cpu().numpy(), seg)
+
+
+def test_pool4_model_and_enhancer_float_output(vol_f16):
+    """M_a02: pools [2,4]; the k=2, stride-4 transposed conv leaves bias-only gaps."""
+    w = OW.draw(O.unet_spec(**oparams(M_A02)), 12)
+    en = Enhancer_fCNN(model_initialization="define-new", descriptor_tag="M_a02", mode="fp32", **M_A02)
+    en.models["enhancer"].set_weights(w)
+    p = Patches(vol_f16.shape, "regular-grid", patch_size=(32,) * 3).select_by_range((0, 6))
+    x = p.extract(vol_f16, (32,) * 3)[..., np.newaxis].astype(np.float32)
+    y = en.predict_patches("enhancer", x, 4, None, min_max=(0.0, 1.0))
+    ref = O.unet_forward(O._rescale_reference(x, (0.0, 1.0), False).astype(np.float32), w, **oparams(M_A02))
+    assert y.dtype == np.float32 and np.abs(y - ref).max() < 1e-4
+    en16 = Enhancer_fCNN(model_initialization="define-new", descriptor_tag="M_a02", mode="fp16", **M_A02)
+    en16.models["enhancer"].set_weights(w)
+    y16 = en16.predict_patches("enhancer", x, 4, None, min_max=(0.0, 1.0))
+    assert np.abs(y16 - ref).max() < 2e-2
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("bf16", 1e-2), ("fp16", 2e-3)])
+def test_encoder_config1_latents(mode, tol):
+    """BASELINE config 1: 32^3 patches at random corners of a uint8 phantom, latent 128."""
+    vol, _ = phantom.volume_u8((96, 96, 96))
+    pts = phantom.random_points(vol.shape, 32, 48, 3)
+    p = Patches(vol.shape, "data", points=pts, widths=np.full_like(pts, 32))
+    w = OW.draw(O.encoder_spec((32,) * 3, **oparams(ENC))[0], 10)
+    fe = SelfSupervisedCAE(model_initialization="define-new", model_size=(32,) * 3, descriptor_tag="t", mode=mode, **ENC)
+    fe.models["encoder"].set_weights(w)
+    min_max = (float(vol[::2, ::2, ::2].min()), float(vol[::2, ::2, ::2].max()))
+    x = p.extract(vol, (32,) * 3)[..., np.newaxis]
+    z = fe.predict_embeddings(x, 20, min_max=min_max)
+    ref = O.encoder_predict_embeddings(x, 32, w, min_max=min_max, **oparams(ENC))
+    assert z.shape == (48, 128) and z.dtype == np.float32
+    assert relerr(z, ref) < tol, relerr(z, ref)
+    z2 = fe.embed_volume(vol, p, 20, min_max=min_max)          # fused gather + encoder
+    np.testing.assert_array_equal(z2, z)
+    p.add_features(z, names=["h%d" % i for i in range(128)])
+    assert p.features.shape == (48, 128)
+
+
+def test_autoencoder_round_trip_matches_oracle():
+    params = dict(n_filters=[16, 32], n_blocks=2, activation="lrelu", batch_norm=True, pool_size=[2, 2],
+                  hidden_units=[64, 16], POOL_FLAG=True)
+    size = (32, 32, 32)
+    we = OW.draw(O.encoder_spec(size, **oparams(params))[0], 20)
+    wd = OW.draw(O.decoder_spec(size, **oparams(params)), 21)
+    x = np.random.default_rng(2).uniform(0, 1, (5,) + size + (1,)).astype(np.float32)
+    zr = O.encoder_forward(x, we, **oparams(params))
+    yr = O.decoder_forward(zr, wd, size, **oparams(params))
+    for mode, tol in (("fp32", 1e-4), ("fp16", 2e-2)):
+        fe = SelfSupervisedCAE(model_initialization="define-new", model_size=size, descriptor_tag="t", mode=mode, **params)
+        fe.models["encoder"].set_weights(we)
+        fe.models["decoder"].set_weights(wd)
+        y = fe.predict_patches("autoencoder", x, 2, None)
+        assert y.shape == x.shape and np.abs(y - yr).max() < tol, (mode, np.abs(y - yr).max())
+
+
+def test_latent_pca_matches_exact_pca_oracle():
+    g = np.random.default_rng(5)
+    d = 128
+    basis = np.linalg.qr(g.standard_normal((d, d)))[0]
+    scales = np.concatenate([[8.0, 4.0], np.full(d - 2, 0.3)])
+    h = ((g.standard_normal((20000, d)) * scales) @ basis + g.standard_normal(d)).astype(np.float32)
+    pca = LatentPCA(n_components=2)
+    for a in range(0, len(h), 7000):                      # streamed fit
+        pca.partial_fit(h[a:a + 7000])
+    pca.finalize()
+    mean, comps, evar, z = pca_np.exact_pca(h, 2)
+    np.testing.assert_allclose(pca.mean_, mean, atol=1e-6)
+    np.testing.assert_allclose(pca.components_, comps, atol=1e-6)
+    np.testing.assert_allclose(pca.explained_variance_, evar, rtol=1e-7)
+    zz = pca.transform(h)
+    assert zz.dtype == np.float32 and np.abs(zz - z).max() < 1e-4
+    # odd dimension, k = 3, torch in / torch out
+    h2 = torch.from_numpy(h[:5000, :37].copy()).cuda()
+    p2 = LatentPCA(n_components=3).fit(h2)
+    m2, c2, e2, z2 = pca_np.exact_pca(h[:5000, :37], 3)
+    np.testing.assert_allclose(p2.components_, c2, atol=1e-6)
+    assert p2.transform(h2).is_cuda
+    # subspace of the reference's literal IncrementalPCA call (information + sanity)
+    ipca, _ = pca_np.incremental_pca_reference(h)
+    s = np.linalg.svd(ipca.components_ @ pca.components_.T, compute_uv=False)
+    assert s.min() > 0.99
+
+
+def test_predict_patches_argument_checks():
+    fe = SurfaceSegmenter(model_initialization="define-new", descriptor_tag="t", **SMALL)
+    with pytest.raises(AssertionError):
+        fe.predict_patches("segmenter", np.zeros((2, 32, 32, 32), np.float32), 2, None)
+    with pytest.raises(AssertionError):
+        fe.predict_patches("segmenter", np.zeros((2, 32, 32, 32, 1), np.float32), 2, np.zeros((3, 32, 32, 32, 1), np.uint8))
+    with pytest.raises(NotImplementedError):
+        SurfaceSegmenter(model_initialization="nope")
+    y = fe.predict_patches("segmenter", np.zeros((0, 32, 32, 32, 1), np.float32), 2, None)
+    assert y.shape == (0, 32, 32, 32, 1)
+    with pytest.raises(NotImplementedError):
+        fe.train(None, None, (32,) * 3, 2, 4, 0.1, False, 0.1, 1)

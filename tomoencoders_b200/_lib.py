@@ -110,6 +110,9 @@ _SIGNATURES = {
     "te_net_flops_per_patch": (ctypes.c_double, [_P]),
     "te_net_layer_info": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p),
                                          ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)]),
+    "te_net_set_profiling": (ctypes.c_int, [_P, ctypes.c_int]),
+    "te_net_layer_time": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_I64)]),
+    "te_net_layer_kernel": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_char_p, ctypes.c_int]),
     "te_pca_accumulate": (ctypes.c_int, [_P, _I64, _I32, _P, _P]),
     "te_pca_solve": (ctypes.c_int, [_P, _I32, _I32, _P, _P, _P, _P, _P]),
     "te_pca_project": (ctypes.c_int, [_P, _I64, _I32, _P, _P, _I32, _P, _P]),

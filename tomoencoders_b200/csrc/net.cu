@@ -50,6 +50,10 @@ struct Layer {
   CUtensorMap tmap{};
   double flops = 0.0;
   float head_b = 0.f;
+  // optional per-layer timing (te_net_set_profiling): event pairs recorded around every launch
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+  double prof_ms = 0.0;
+  long long prof_launches = 0;
 };
 
 }  // namespace
@@ -67,6 +71,7 @@ struct te_net {
   bool fuse_head = true;
   int latent = 0;
   int last_n = 0;
+  bool profiling = false;
   float* d_dense_tmp[2] = {nullptr, nullptr};
   te::TView input{};                // network input view (C = 1)
 };
@@ -351,6 +356,7 @@ int plan(te_net* net, bool count_only, long long* weight_count) {
 void free_net(te_net* net) {
   for (void* p : net->allocations) cudaFree(p);
   for (auto& L : net->layers) {
+    for (auto& ev : L.events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     if (L.d_w) cudaFree(L.d_w);
     if (L.d_bias) cudaFree(L.d_bias);
     if (L.d_wpacked) cudaFree(L.d_wpacked);
@@ -547,6 +553,12 @@ int run_layers(te_net* net, int n, const HeadOut& ho, cudaStream_t st) {
     Layer& L = net->layers[i];
     if (L.skip) continue;
     cudaError_t e = cudaSuccess;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (net->profiling) {
+      cudaEventCreate(&ev0);
+      cudaEventCreate(&ev1);
+      cudaEventRecord(ev0, st);
+    }
     switch (L.op) {
       case OP_CONV3:
       case OP_UPCONV: {
@@ -598,6 +610,10 @@ int run_layers(te_net* net, int n, const HeadOut& ho, cudaStream_t st) {
         dense_src_type = L.dense_out_type;
         tmp_idx ^= 1;
       } break;
+    }
+    if (net->profiling) {
+      cudaEventRecord(ev1, st);
+      L.events.emplace_back(ev0, ev1);
     }
     if (e != cudaSuccess) {
       set_error("layer %s failed to launch: %s", L.name.c_str(), cudaGetErrorString(e));
@@ -681,4 +697,46 @@ extern "C" int64_t te_net_layer_output(te_net* net, int i, float* out, int64_t c
   cudaError_t e = simt_to_f32(v, out, net->act_type, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) { set_error("te_net_layer_output: %s", cudaGetErrorString(e)); return TE_ERR_CUDA; }
   return count;
+}
+
+extern "C" int te_net_set_profiling(te_net* net, int enable) {
+  TE_CHECK_ARG(net, "te_net_set_profiling: null handle");
+  net->profiling = enable != 0;
+  for (auto& L : net->layers) {
+    for (auto& ev : L.events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    L.events.clear();
+    L.prof_ms = 0.0;
+    L.prof_launches = 0;
+  }
+  return TE_OK;
+}
+
+extern "C" int te_net_layer_time(te_net* net, int i, double* total_ms, int64_t* launches) {
+  TE_CHECK_ARG(net && i >= 0 && i < static_cast<int>(net->layers.size()), "te_net_layer_time: bad index");
+  Layer& L = net->layers[i];
+  for (auto& ev : L.events) {
+    TE_CUDA(cudaEventSynchronize(ev.second));
+    float ms = 0.f;
+    TE_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
+    L.prof_ms += ms;
+    L.prof_launches += 1;
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  L.events.clear();
+  if (total_ms) *total_ms = L.prof_ms;
+  if (launches) *launches = L.prof_launches;
+  return TE_OK;
+}
+
+extern "C" int te_net_layer_kernel(const te_net* net, int i, char* buf, int buflen) {
+  TE_CHECK_ARG(net && buf && buflen > 0 && i >= 0 && i < static_cast<int>(net->layers.size()), "te_net_layer_kernel: bad argument");
+  const Layer& L = net->layers[i];
+  if (L.skip) snprintf(buf, buflen, "fused into previous layer");
+  else if (L.use_umma) snprintf(buf, buflen, "conv_umma_kernel<%d,%d,%d>%s", L.cfg.CB, L.cfg.NT, L.cfg.TZ, L.fused_head ? "+head" : "");
+  else {
+    static const char* names[] = {"conv3_kernel", "upconv_kernel", "maxpool_kernel", "head_kernel", "dense_kernel"};
+    snprintf(buf, buflen, "%s", names[L.op]);
+  }
+  return TE_OK;
 }

@@ -104,6 +104,20 @@ class Net:
             out.append((name.value.decode(), fl.value, bool(tc.value)))
         return out
 
+    def set_profiling(self, enable):
+        _lib.check(self._L.te_net_set_profiling(self._h, 1 if enable else 0), "te_net_set_profiling")
+
+    def layer_times(self):
+        """[(name, kernel, flops_per_patch, total_ms, launches)] accumulated since set_profiling(True)."""
+        out = []
+        buf = ctypes.create_string_buffer(128)
+        for i, (name, fl, tc) in enumerate(self.layers()):
+            ms, cnt = ctypes.c_double(), ctypes.c_int64()
+            _lib.check(self._L.te_net_layer_time(self._h, i, ctypes.byref(ms), ctypes.byref(cnt)), "te_net_layer_time")
+            _lib.check(self._L.te_net_layer_kernel(self._h, i, buf, 128), "te_net_layer_kernel")
+            out.append((name, buf.value.decode(), fl, ms.value, cnt.value))
+        return out
+
     def layer_output(self, index, shape):
         """fp32 NDHWC copy of a layer's activation tensor from the last forward call (test hook)."""
         out = torch.empty(shape, dtype=torch.float32, device=_device.device())

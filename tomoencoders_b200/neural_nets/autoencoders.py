@@ -1,0 +1,117 @@
+"""``SelfSupervisedCAE``: drop-in for /root/reference/tomo_encoders/neural_nets/autoencoders.py:529-777
+on the inference path: conv encoder -> latent vectors (``predict_embeddings``) and
+encoder + decoder reconstruction (``predict_patches("autoencoder", ...)``)."""
+import os
+import time
+
+import numpy as np
+import torch
+
+from .. import _device
+from ..structures.patches import Patches
+from .keras_processor import EmbeddingLearner, Model, gather_normalized, normalize_chunk
+
+
+def build_encoder_r(input_shape, **model_params):
+    """autoencoders.py:246-347.  Returns (encoder, flatten_shape, preflatten_shape)."""
+    from . import _spec
+    mode = model_params.pop("mode", None)
+    model_size = tuple(input_shape[:3])
+    m = Model("encoder", model_params, model_size=model_size, mode=mode, name="encoder")
+    p = m.model_params
+    flat, pre = _spec.encoder_shapes(model_size, p["n_filters"], p["n_blocks"], p.get("pool_size", 2),
+                                     p.get("POOL_FLAG", True))
+    return m, flat, pre
+
+
+def build_decoder_r(flatten_shape, preflatten_shape, model_size=None, **model_params):
+    """autoencoders.py:350-447 (model_size is needed here because the plan is sized per input)."""
+    mode = model_params.pop("mode", None)
+    return Model("decoder", model_params, model_size=model_size, mode=mode, name="decoder")
+
+
+class SelfSupervisedCAE(EmbeddingLearner):
+    output_type = "data"
+
+    def __init__(self, **kwargs):
+        self.model_keys = ["encoder", "decoder", "autoencoder"]
+        super().__init__(**kwargs)
+
+    def _build_models(self, model_size=(64, 64, 64), descriptor_tag="misc", **model_params):
+        """autoencoders.py:551-577."""
+        if model_params is None:
+            raise ValueError("Need model hyperparameters or instance of model. Neither were provided")
+        self.models = {}
+        self.model_size = tuple(int(s) for s in model_size)
+        self.model_tag = "%s" % descriptor_tag
+        enc, flat, pre = build_encoder_r(self.model_size + (1,), mode=self.mode, **model_params)
+        self.models["encoder"] = enc
+        self.models["decoder"] = build_decoder_r(flat, pre, model_size=self.model_size, mode=self.mode, **model_params)
+        self.models["autoencoder"] = None
+
+    def _load_models(self, model_tag=None, model_size=(64, 64, 64), model_path="some-path", **model_params):
+        """autoencoders.py:579-602 with ``.npz`` weight files (see SurfaceSegmenter._load_models)."""
+        assert model_tag is not None, "need model_tag"
+        self._build_models(model_size=model_size, descriptor_tag=model_tag, **model_params)
+        for model_key in ("encoder", "decoder"):
+            self.models[model_key].load_weights(os.path.join(model_path, "%s_%s.npz" % (model_key, model_tag)))
+
+    def get_patches(self, vol_shape, sampling_method, batch_size, max_stride=None):
+        """autoencoders.py:657-672."""
+        if sampling_method in ["grid", "regular-grid", "random-fixed-width"]:
+            return Patches(vol_shape, initialize_by=sampling_method, patch_size=self.model_size, n_points=batch_size)
+        if sampling_method in ["random"]:
+            return Patches(vol_shape, initialize_by=sampling_method, min_patch_size=self.model_size,
+                           max_stride=max_stride, n_points=batch_size)
+        raise ValueError("sampling method not supported")
+
+    def predict_embeddings(self, x, chunk_size, min_max=None, TIMEIT=False):
+        """autoencoders.py:729-777: x (nb,pz,py,px,1) -> (nb, latent) float32 (rescale, no clip)."""
+        assert x.ndim == 5, "x must be 5-dimensional (batch_size, nz, ny, nx, 1)."
+        t0 = time.time()
+        nb = len(x)
+        on_device = _device.is_device_array(x)
+        enc = self.models["encoder"]
+        patch = tuple(int(s) for s in x.shape[1:4])
+        out = torch.empty((nb, enc.latent), dtype=torch.float32, device=_device.device())
+        for a in range(0, nb, chunk_size):
+            b = min(a + chunk_size, nb)
+            xc = x[a:b, ..., 0]
+            xc = _device.to_device(xc if on_device else np.ascontiguousarray(xc))
+            net = enc.net_for(patch, max(chunk_size, b - a))
+            net.encoder_forward(normalize_chunk(xc, min_max, False, net), out=out[a:b])
+        res = out if on_device else out.cpu().numpy()
+        t_unit = (time.time() - t0) * 1000.0 / max(nb, 1)
+        if TIMEIT:
+            print("inf. time p. input patch size %s = %.2f ms, nb = %i" % (str(patch), t_unit, nb))
+            print("\n")
+            return res, t_unit
+        return res
+
+    def embed_volume(self, vol, patches, chunk_size, min_max=None, out=None):
+        """Fused patches.extract(vol, model_size) -> predict_embeddings: the (n,P,P,P) patch array is
+        never materialised; each chunk is gathered (with binning) and rescaled straight into the
+        encoder's input layout.  Returns (n, latent) float32 where vol lives (host / device)."""
+        vs = tuple(int(v) for v in patches.vol_shape)
+        assert tuple(vol.shape) == vs, "Shape of big volume does not match vol_shape attribute of patches data"
+        widths = patches.widths if hasattr(patches, "widths") else patches._widths()
+        if hasattr(patches, "_calc_binning"):
+            patches._calc_binning(self.model_size)
+        n = len(patches)
+        host = not _device.is_device_array(vol)
+        t_vol = _device.to_device(vol)
+        enc = self.models["encoder"]
+        z = out if (out is not None and _device.is_device_array(out)) else \
+            torch.empty((n, enc.latent), dtype=torch.float32, device=t_vol.device)
+        if n:
+            net = enc.net_for(self.model_size, min(chunk_size, n))
+            d_pts = _device.points_to_device(patches.points)
+            d_wds = _device.points_to_device(widths)
+            for a in range(0, n, chunk_size):
+                b = min(a + chunk_size, n)
+                xa = gather_normalized(t_vol, vs, d_pts[a:b], d_wds[a:b], b - a, self.model_size, min_max, False, net)
+                net.encoder_forward(xa, out=z[a:b])
+        if out is not None and not _device.is_device_array(out):
+            out[...] = z.cpu().numpy()
+            return out
+        return z.cpu().numpy() if (host and out is None) else z

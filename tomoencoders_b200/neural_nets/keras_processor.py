@@ -1,0 +1,378 @@
+"""Processor base classes and the model handle they own.
+
+Drop-in for /root/reference/tomo_encoders/neural_nets/keras_processor.py:25-253
+(``GenericKerasProcessor`` -> ``Vox2VoxProcessor_fCNN`` / ``EmbeddingLearner``): same constructor
+(``model_initialization``, ``descriptor_tag``, ``**model_params``), ``self.models`` dict,
+``predict_patches(model_key, x, chunk_size, out_arr, min_max=None, TIMEIT=False)``,
+``calc_voxel_min_max``, ``rescale_data``, ``test_speeds``.  ``keras.Model`` is replaced by ``Model``
+below, which keeps the few Keras methods callers use (``predict``, ``get_weights``,
+``set_weights``, ``count_params``, ``input_shape`` / ``output_shape``) and runs on libtomoenc.so.
+
+Differences: the per-chunk clip / rescale is evaluated in fp32 on the
+GPU, fused into the kernel that stages the chunk, instead of numpy arithmetic in the input dtype;
+the last chunk is not edge-padded (patches are independent, so the result is identical); the
+reference's quirks Q4/Q5/Q7 (NameError with min_max, autoencoder branch on output_type, rounding of
+embeddings) are not reproduced.
+"""
+import os
+import time
+
+import numpy as np
+import torch
+
+from .. import _device, _lib
+from ..misc.voxel_processing import _find_min_max
+from . import _spec
+from ._net import Net
+
+DEFAULT_MODE = os.environ.get("TOMOENC_MODE", "fp16")
+
+
+class Model:
+    """One network of the reference (kind: "unet", "encoder" or "decoder") with its weights.
+
+    The U-net is fully convolutional (Input((None,None,None,1)), Unet3D.py:242): execution plans
+    (``Net`` handles: workspace + TMA descriptors) are created per (patch size, batch) on first use
+    and cached."""
+
+    def __init__(self, kind, model_params, model_size=None, mode=None, name="model", seed=None):
+        self.kind = kind
+        self.name = name
+        self.mode = mode or DEFAULT_MODE
+        self.model_params = dict(model_params)
+        self.model_size = None if model_size is None else tuple(int(s) for s in model_size)
+        p = self.model_params
+        if "n_blocks" not in p:
+            p["n_blocks"] = len(p["n_filters"])
+        if kind == "unet":
+            self.spec = _spec.unet_spec(**p)
+        elif kind == "encoder":
+            self.spec = _spec.encoder_spec(self.model_size, **p)
+        elif kind == "decoder":
+            self.spec = _spec.decoder_spec(self.model_size, **p)
+        else:
+            raise ValueError(kind)
+        self._weights = _spec.keras_default_init(self.spec, seed)
+        self._nets = {}
+
+    # ---- Keras-like surface
+    def get_weights(self):
+        return [w.copy() for w in self._weights]
+
+    def set_weights(self, weights):
+        weights = [np.asarray(w, dtype=np.float32) for w in weights]
+        if len(weights) != len(self.spec):
+            raise ValueError("expected %d weight arrays, got %d" % (len(self.spec), len(weights)))
+        for w, (kind, shape) in zip(weights, self.spec):
+            if tuple(w.shape) != tuple(shape):
+                raise ValueError("weight %s: expected shape %s, got %s" % (kind, shape, w.shape))
+        self._weights = weights
+        for net in self._nets.values():
+            net.set_weights(self._weights)
+
+    def count_params(self):
+        return int(sum(int(np.prod(s)) for _, s in self.spec))
+
+    @property
+    def input_shape(self):
+        if self.kind == "decoder":
+            return (None, self.latent)
+        return (None,) + (self.model_size or (None, None, None)) + (1,)
+
+    @property
+    def output_shape(self):
+        if self.kind == "encoder":
+            return (None, self.latent)
+        return (None,) + (self.model_size or (None, None, None)) + (1,)
+
+    @property
+    def latent(self):
+        hu = self.model_params.get("hidden_units")
+        return int(hu[-1]) if hu else 0
+
+    def save(self, filepath, include_optimizer=False):
+        np.savez(filepath, **{"w%04d" % i: w for i, w in enumerate(self._weights)})
+
+    def load_weights(self, filepath):
+        with np.load(filepath) as f:
+            self.set_weights([f["w%04d" % i] for i in range(len(f.files))])
+
+    # ---- execution
+    def net(self, patch, max_batch):
+        patch = tuple(int(p) for p in patch)
+        if self.model_size is not None and patch != self.model_size:
+            raise ValueError("model was built for input size %s, got %s" % (self.model_size, patch))
+        key = (patch, int(max_batch))
+        if key not in self._nets:
+            # keep the cache small: plans for smaller batches of the same patch size are superseded
+            for k in [k for k in self._nets if k[0] == patch and k[1] < max_batch]:
+                del self._nets[k]
+            net = Net(self.kind, patch, max_batch, mode=self.mode, **self.model_params)
+            net.set_weights(self._weights)
+            self._nets[key] = net
+        return self._nets[key]
+
+    def net_for(self, patch, n):
+        patch = tuple(int(p) for p in patch)
+        best = None
+        for (pp, mb), net in self._nets.items():
+            if pp == patch and mb >= n and (best is None or mb < best.max_batch):
+                best = net
+        return best if best is not None else self.net(patch, n)
+
+    def predict(self, x, batch_size=32, verbose=0):
+        """keras.Model.predict: x (nb,pz,py,px,1) -> same shape float32 (unet / decoder input is
+        (nb, latent)); encoder -> (nb, latent) float32.  Host arrays in, host arrays out."""
+        x = np.asarray(x)
+        dev = _device.device()
+        if self.kind == "decoder":
+            z = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(dev)
+            out = []
+            for a in range(0, len(z), batch_size):
+                zc = z[a:a + batch_size].contiguous()
+                out.append(self.net_for(self.model_size, len(zc)).decoder_forward(zc))
+            return torch.cat(out).cpu().numpy()[..., np.newaxis]
+        assert x.ndim == 5 and x.shape[-1] == 1, "x must be 5-dimensional (batch_size, nz, ny, nx, 1)."
+        patch = x.shape[1:4]
+        outs = []
+        for a in range(0, len(x), batch_size):
+            net = self.net_for(patch, min(batch_size, len(x) - a))
+            xc = torch.from_numpy(np.ascontiguousarray(x[a:a + batch_size, ..., 0], dtype=np.float32)).to(dev)
+            xc = xc.to(net.act_dtype).contiguous()
+            if self.kind == "unet":
+                outs.append(net.unet_forward(xc, out_dtype=torch.float32))
+            else:
+                outs.append(net.encoder_forward(xc))
+        out = torch.cat(outs).cpu().numpy()
+        return out[..., np.newaxis] if self.kind == "unet" else out
+
+
+def normalize_chunk(x_dev, min_max, clip, net):
+    """(n,pz,py,px) device tensor of any supported dtype -> activation dtype of ``net``, with the
+    clip / rescale of predict_patches fused (te_gather_norm on the chunk viewed as a volume)."""
+    n, pz, py, px = x_dev.shape
+    out = torch.empty((n, pz, py, px), dtype=net.act_dtype, device=x_dev.device)
+    pts = torch.zeros((n, 3), dtype=torch.int32, device=x_dev.device)
+    pts[:, 0] = torch.arange(n, device=x_dev.device, dtype=torch.int32) * pz
+    wds = torch.tensor([pz, py, px], dtype=torch.int32, device=x_dev.device).repeat(n, 1).contiguous()
+    lo, hi = (0.0, 1.0) if min_max is None else (float(min_max[0]), float(min_max[1]))
+    L = _lib.lib()
+    _lib.check(L.te_gather_norm(x_dev.data_ptr(), _device.te_dtype(x_dev), _lib.i64x3((n * pz, py, px)),
+                                pts.data_ptr(), wds.data_ptr(), n, _lib.i32x3((pz, py, px)),
+                                0 if min_max is None else 1, 1 if clip else 0, lo, hi, out.data_ptr(), net.act_te,
+                                _device.stream_ptr()), "te_gather_norm")
+    return out
+
+
+def gather_normalized(vol_dev, vol_shape, d_points, d_widths, n, patch, min_max, clip, net):
+    """Fused gather + clip + rescale straight from the volume into network-input layout."""
+    out = torch.empty((n,) + tuple(patch), dtype=net.act_dtype, device=vol_dev.device)
+    lo, hi = (0.0, 1.0) if min_max is None else (float(min_max[0]), float(min_max[1]))
+    L = _lib.lib()
+    _lib.check(L.te_gather_norm(vol_dev.data_ptr(), _device.te_dtype(vol_dev), _lib.i64x3(vol_shape),
+                                d_points.data_ptr(), d_widths.data_ptr(), n, _lib.i32x3(patch),
+                                0 if min_max is None else 1, 1 if clip else 0, lo, hi, out.data_ptr(), net.act_te,
+                                _device.stream_ptr()), "te_gather_norm")
+    return out
+
+
+class GenericKerasProcessor:
+    """keras_processor.py:25-196."""
+
+    def __init__(self, model_initialization="define-new", descriptor_tag="misc", **kwargs):
+        self.input_type = "data"
+        self.output_type = getattr(self, "output_type", "data")
+        self.mode = kwargs.pop("mode", None) or DEFAULT_MODE
+        if model_initialization == "define-new":
+            self._build_models(descriptor_tag=descriptor_tag, **kwargs)
+        elif model_initialization == "load-model":
+            self._load_models(**kwargs)
+        else:
+            raise NotImplementedError("method is not implemented")
+
+    # ---- helpers shared by the subclasses
+    _clip_input = False      # SurfaceSegmenter clips to min_max before rescaling (surface_segmenter.py:272-275)
+
+    def print_layers(self, modelkey):
+        model = self.models[modelkey]
+        print("\n".join("%s    ::    %s" % (str(s), k) for k, s in model.spec))
+
+    def _run_model(self, model_key, x_act, net_cache):
+        raise NotImplementedError
+
+    def predict_patches(self, model_key, x, chunk_size, out_arr, min_max=None, TIMEIT=False):
+        """keras_processor.py:78-146.  x: (nb,pz,py,px,1) numpy / torch (host or CUDA); returns an
+        array of the same shape: uint8 labels if output_type == "labels", otherwise float."""
+        assert x.ndim == 5, "x must be 5-dimensional (batch_size, nz, ny, nx, 1)."
+        t0 = time.time()
+        nb = len(x)
+        on_device = _device.is_device_array(x)
+        labels = self.output_type == "labels"
+        if out_arr is not None:
+            assert tuple(out_arr.shape) == tuple(x.shape), \
+                "x and out_arr shapes must be equal and 4-dimensional (batch_size, nz, ny, nx, 1)"
+        patch = tuple(int(s) for s in x.shape[1:4])
+        dev = _device.device()
+        out_t_dtype = torch.uint8 if labels else torch.float32
+        res = torch.empty((nb,) + patch, dtype=out_t_dtype, device=dev)
+        for a in range(0, nb, chunk_size):
+            b = min(a + chunk_size, nb)
+            xc = x[a:b, ..., 0]
+            xc = _device.to_device(xc if on_device else np.ascontiguousarray(xc))
+            self._predict_chunk(model_key, xc, res[a:b], min_max, chunk_size)
+        if on_device:
+            out = res.unsqueeze(-1)
+            if out_arr is not None:
+                out_arr.copy_(out)
+                out = out_arr
+        else:
+            host = res.cpu().numpy()[..., np.newaxis]
+            if labels:
+                out = host                                      # np.round(...).astype(np.uint8) (:135)
+            else:
+                tgt = out_arr.dtype if out_arr is not None else (x.dtype if np.issubdtype(np.asarray(x[:0]).dtype, np.floating) else np.float32)
+                out = host.astype(tgt, copy=False)
+            if out_arr is not None and not labels:
+                out_arr[...] = out
+                out = out_arr
+        t_unit = (time.time() - t0) * 1000.0 / max(nb, 1)
+        if TIMEIT:
+            print("inf. time p. input patch size %s = %.2f ms, nb = %i" % (str(patch), t_unit, nb))
+            print("\n")
+            return out, t_unit
+        return out
+
+    def _predict_chunk(self, model_key, xc, out, min_max, chunk_size):
+        """xc: (n,pz,py,px) device tensor (raw values); out: (n,pz,py,px) uint8 / float32 view."""
+        patch = tuple(xc.shape[1:])
+        if model_key == "autoencoder":
+            enc = self.models["encoder"].net_for(patch, max(chunk_size, len(xc)))
+            dec = self.models["decoder"].net_for(patch, max(chunk_size, len(xc)))
+            xa = normalize_chunk(xc, min_max, self._clip_input, enc)
+            y = dec.decoder_forward(enc.encoder_forward(xa))
+            out.copy_(y if out.dtype == torch.float32 else (y > 0.5).to(torch.uint8))
+            return
+        model = self.models[model_key]
+        net = model.net_for(patch, max(chunk_size, len(xc)))
+        xa = normalize_chunk(xc, min_max, self._clip_input, net)
+        if model.kind == "unet":
+            net.unet_forward_into(xa, out)
+        elif model.kind == "decoder":
+            raise ValueError("the decoder takes latent vectors; use model_key='autoencoder'")
+        else:
+            raise ValueError("model %s does not produce patches; use predict_embeddings" % model_key)
+
+    def calc_voxel_min_max(self, vol, sampling_factor, TIMEIT=False):
+        return _find_min_max(vol, sampling_factor, TIMEIT=TIMEIT)
+
+    def rescale_data(self, data, min_val, max_val):
+        eps = 1e-12
+        return (data - min_val) / (max_val - min_val + eps)
+
+    def _msg_exec_time(self, func, t_exec):
+        print("TIME: %s: %.2f seconds" % (func.__name__, t_exec))
+
+    # ---- persistence (npz instead of Keras HDF5: h5py / TF are not dependencies of this package)
+    def save_models(self, model_path):
+        for model_key, model in self.models.items():
+            if model is None:
+                continue
+            model.save(os.path.join(model_path, "%s_%s.npz" % (model_key, self.model_tag)))
+
+    def train(self, *args, **kwargs):
+        raise NotImplementedError(
+            "training (SURVEY.md section 8 row a11) is not implemented in this round; load weights with "
+            "models[key].set_weights(...) or model_initialization='load-model'")
+
+
+class Vox2VoxProcessor_fCNN(GenericKerasProcessor):
+    """keras_processor.py:199-243."""
+
+    def test_speeds(self, chunk_size, n_reps=3, input_size=None, model_key="segmenter"):
+        if input_size is None:
+            input_size = (64, 64, 64)
+        for _ in range(n_reps):
+            x = np.random.uniform(0, 1, tuple([chunk_size] + list(input_size) + [1])).astype(np.float32)
+            t0 = time.time()
+            self.predict_patches(model_key, x, chunk_size, None, min_max=(-1, 1))
+            t_unit = (time.time() - t0) * 1000.0 / len(x)
+            print(f"inf. time per patch {input_size} = {t_unit:.2f} ms, nb = {len(x)}")
+            print(f"inf. time per voxel {(t_unit / (np.prod(input_size)) * 1.0e6):.2f} ns")
+            print("\n")
+
+    def random_data_generator(self, batch_size, input_size=(64, 64, 64)):
+        while True:
+            x_shape = tuple([batch_size] + list(input_size) + [1])
+            x = np.random.uniform(0, 1, x_shape)
+            y = np.random.uniform(0, 1, x_shape)
+            x[x == 0] = 1.0e-12
+            y[y == 0] = 1.0e-12
+            yield x, y
+
+    # ---- fused volume path (gather -> net -> stitch on the device; the patches never exist in HBM
+    #      as an (n,P,P,P) array of the volume dtype)
+    def process_volume(self, vol, patches, chunk_size, min_max=None, model_key="segmenter", out=None):
+        """Equivalent to
+            x = patches.extract(vol[, patch_size]); y = self.predict_patches(model_key, x[...,None], chunk_size, None, min_max)
+            patches.fill_patches_in_volume(y[...,0], out)
+        (/root/reference/scratchpad/void_metrology_v2/bin/vis_voids.py:64-73) for fixed-width
+        patches, executed chunk by chunk on the device.  vol: numpy / torch (host or CUDA).  Returns
+        ``out`` (allocated as zeros of vol's shape if None): uint8 for labels, float32 otherwise."""
+        from ..structures import _table
+        vs = tuple(int(v) for v in patches.vol_shape)
+        assert tuple(vol.shape) == vs, "Shape of big volume does not match vol_shape attribute of patches data"
+        widths = patches.widths if hasattr(patches, "widths") else patches._widths()
+        if len(np.unique(np.asarray(widths), axis=0)) > 1:
+            raise ValueError("process_volume needs fixed-width patches")
+        n = len(patches)
+        labels = self.output_type == "labels"
+        host = not _device.is_device_array(vol)
+        t_vol = _device.to_device(vol)
+        dev = t_vol.device
+        o_dtype = torch.uint8 if labels else torch.float32
+        if out is None:
+            t_out = torch.zeros(vs, dtype=o_dtype, device=dev)
+        else:
+            t_out = _device.to_device(out)
+            if t_out.dtype != o_dtype:
+                raise TypeError("out must be %s" % o_dtype)
+        if n == 0:
+            return _device.to_host_like(t_out, vol) if out is None else out
+        w3 = tuple(int(v) for v in widths[0])
+        model = self.models[model_key]
+        net = model.net_for(w3, min(chunk_size, n))
+        d_pts = _device.points_to_device(patches.points)
+        d_wds = _device.points_to_device(widths)
+        disjoint = _table._disjoint(patches.points, w3, vs) and (w3[2] * t_out.element_size()) % 16 == 0
+        if not disjoint:
+            # overlapping patches: stitch once at the end through the ordered path
+            all_out = torch.empty((n,) + w3, dtype=o_dtype, device=dev)
+        L = _lib.lib()
+        for a in range(0, n, chunk_size):
+            b = min(a + chunk_size, n)
+            xa = gather_normalized(t_vol, vs, d_pts[a:b], d_wds[a:b], b - a, w3, min_max, self._clip_input, net)
+            y = all_out[a:b] if not disjoint else torch.empty((b - a,) + w3, dtype=o_dtype, device=dev)
+            net.unet_forward_into(xa, y)
+            if disjoint:
+                _lib.check(L.te_scatter(y.data_ptr(), y.element_size(), d_pts[a:b].data_ptr(), b - a, _lib.i32x3(w3),
+                                        t_out.data_ptr(), _lib.i64x3(vs), None, _device.stream_ptr()), "te_scatter")
+        if not disjoint:
+            _table.scatter(all_out, t_out, vs, patches.points, widths)
+        if out is None:
+            return _device.to_host_like(t_out, vol) if host else t_out
+        if host:
+            res = t_out.cpu()
+            if isinstance(out, torch.Tensor):
+                out.copy_(res)
+            else:
+                out[...] = res.numpy()
+        elif t_out.data_ptr() != out.data_ptr():
+            out.copy_(t_out)
+        return out
+
+
+class EmbeddingLearner(GenericKerasProcessor):
+    """keras_processor.py:245-253."""
+
+    def predict_embeddings(self, x, chunk_size, min_max=None, TIMEIT=False):
+        raise NotImplementedError
