@@ -14,10 +14,10 @@
 // that one box (the swizzle is a function of the absolute shared-memory address, so shifted windows
 // stay consistent -- verified on hardware by tools/umma_probe.cu, profiles/umma_probe_r01_run*.txt).
 //
-// Warp roles (192 threads): warp 0 = TMA producer (input boxes + pre-swizzled weight slabs),
-// warp 1 = single-thread UMMA issuer, warps 2..5 = epilogue (TMEM -> registers -> bias + LeakyReLU
-// -> 16-bit NDHWC store, optionally pixel-shuffled for the transposed conv or reduced by the fused
-// 1x1x1 head).  Persistent CTAs loop over tiles; the accumulator is double-buffered in TMEM so the
+// Warp roles (224 threads): warp 0 = TMA producer of the input boxes, warp 6 = bulk-copy producer of
+// the pre-swizzled weight slabs, warp 1 = UMMA issuer (warp-uniform loop, one elected lane issues),
+// warps 2..5 = epilogue (TMEM -> registers -> bias + LeakyReLU -> 16-bit NDHWC store, optionally
+// pixel-shuffled for the transposed conv or reduced by the fused 1x1x1 head).  Persistent CTAs loop over tiles; the accumulator is double-buffered in TMEM so the
 // epilogue of tile i overlaps the MMAs of tile i+1.
 #include "conv_umma.cuh"
 #include "sm100_ptx.cuh"
@@ -31,9 +31,8 @@ namespace te {
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 224;
 constexpr int kNumWStages = 4;     // weight-slab ring
-constexpr int kNumAStages = 2;     // input-box ring
 
 struct KParams {
   const uint8_t* w_packed;
@@ -81,26 +80,35 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int fp16) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int CB, int NT, int TZ>
+template <int CB, int NT, int TZ, int HALO>
 struct Cfg {
   static constexpr int ROWB = CB * 2;                                   // bytes of one voxel row of a chunk
   static constexpr uint32_t LAYOUT = CB == 16 ? kLayoutSW32 : (CB == 32 ? kLayoutSW64 : kLayoutSW128);
   static constexpr int KSTEPS = CB / 16;                                // UMMA K = 16 for 16-bit operands
-  static constexpr int A_STAGE = (((TZ + 2) * 18 * 10 * ROWB) + 1023) / 1024 * 1024;
-  static constexpr int W_STAGE = ((3 * NT * ROWB) + 1023) / 1024 * 1024;
+  static constexpr int A_STAGE = (((TZ + 2 * HALO) * (16 + 2 * HALO) * (8 + 2 * HALO) * ROWB) + 1023) / 1024 * 1024;
+  static constexpr int W_STAGE = (((HALO ? 3 : 1) * NT * ROWB) + 1023) / 1024 * 1024;
+  // input-box ring: the haloed boxes of the 3x3x3 conv are large (2 stages); the un-haloed boxes of
+  // the transposed conv are small and each feeds few MMAs, so more of them are kept in flight
+  static constexpr int NUM_A = HALO ? 2 : 4;
+  // plane-fused MMA schedule (see the UMMA issuer): needs 3 * NT <= 256 result columns per instruction
+  static constexpr bool FUSE = HALO && (3 * NT <= 256);
   static constexpr int ACC_COLS = TZ * NT;                              // fp32 columns of one accumulator set
   static constexpr int TMEM_COLS_RAW = 2 * ACC_COLS;
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
                                    : TMEM_COLS_RAW <= 256 ? 256 : 512;
   static_assert(TMEM_COLS_RAW <= 512, "accumulators do not fit TMEM");
-  static constexpr int SMEM_BYTES = kNumAStages * A_STAGE + kNumWStages * W_STAGE + 1024 /*barriers*/ + 1024 /*align*/;
+  static constexpr int SMEM_BYTES = NUM_A * A_STAGE + kNumWStages * W_STAGE + 1024 /*barriers*/ + 1024 /*align*/;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
 };
 
-template <int CB, int NT, int TZ>
+template <int CB, int NT, int TZ, int HALO>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const KParams p) {
-  using C = Cfg<CB, NT, TZ>;
+  using C = Cfg<CB, NT, TZ, HALO>;
+  constexpr int kNumAStages = C::NUM_A;
+  constexpr int BX = 8 + 2 * HALO, BY = 16 + 2 * HALO, BZ = TZ + 2 * HALO;   // input box (voxels)
+  constexpr int NGROUPS = HALO ? 9 : 1;    // weight slabs per channel chunk: one per (dz, dy)
+  constexpr int TAPS_G = HALO ? 3 : 1;     // taps per slab: the three dx of a (dz, dy) row
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_stage = smem;
@@ -129,102 +137,137 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const KParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int BX = 8 + 2 * p.halo, BY = 16 + 2 * p.halo, BZ = TZ + 2 * p.halo;
-  const uint32_t a_bytes = static_cast<uint32_t>(BZ * BY * BX * C::ROWB);
-  const uint32_t w_bytes = static_cast<uint32_t>(p.taps_g * NT * C::ROWB);
+  constexpr uint32_t a_bytes = static_cast<uint32_t>(BZ * BY * BX * C::ROWB);
+  constexpr uint32_t w_bytes = static_cast<uint32_t>(TAPS_G * NT * C::ROWB);
 
   if (warp == 0) {
-    // ============================== TMA producer (one lane) ==============================
-    if (lane == 0) {
-      uint32_t as = 0, aph = 0, ws = 0, wph = 0;
-      // flattened sequence of (tile, chunk) jobs; the input box of job j+1 is requested before
-      // the weight slabs of job j so that it is in flight while job j is being multiplied.
-      long long tile = blockIdx.x;
-      int kc = 0;
-      bool have = tile < p.total_tiles;
-      if (have) {
-        const TileCoord tc = decode_tile(p, tile, TZ);
+    // ============================== TMA producer ==============================
+    // The whole warp runs the (warp-uniform) control flow; one elected lane issues the copies and
+    // runs ahead of the MMAs by the depth of the ring.
+    uint32_t as = 0, aph = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile, TZ);
+#pragma unroll 1
+      for (int kc = 0; kc < p.kchunks; ++kc) {
         mbar_wait(a_empty + as, aph ^ 1);
-        mbar_expect_tx(a_full + as, a_bytes);
-        tma_load_5d(a_stage + as * C::A_STAGE, &tmap_in, a_full + as, 0, tc.x0 - p.halo, tc.y0 - p.halo,
-                    tc.z0 - p.halo, tc.n);
+        if (elect_one()) {
+          mbar_expect_tx(a_full + as, a_bytes);
+          tma_load_5d(a_stage + as * C::A_STAGE, &tmap_in, a_full + as, kc * CB, tc.x0 - HALO, tc.y0 - HALO,
+                      tc.z0 - HALO, tc.n);
+        }
+        __syncwarp();
         if (++as == kNumAStages) { as = 0; aph ^= 1; }
       }
-      while (have) {
-        const TileCoord tc = decode_tile(p, tile, TZ);
-        // next job
-        long long ntile_id = tile;
-        int nkc = kc + 1;
-        if (nkc == p.kchunks) { nkc = 0; ntile_id = tile + gridDim.x; }
-        const bool have_next = ntile_id < p.total_tiles;
-        if (have_next) {
-          const TileCoord nc = decode_tile(p, ntile_id, TZ);
-          mbar_wait(a_empty + as, aph ^ 1);
-          mbar_expect_tx(a_full + as, a_bytes);
-          tma_load_5d(a_stage + as * C::A_STAGE, &tmap_in, a_full + as, nkc * CB, nc.x0 - p.halo, nc.y0 - p.halo,
-                      nc.z0 - p.halo, nc.n);
-          if (++as == kNumAStages) { as = 0; aph ^= 1; }
-        }
-        // weight slabs of the current job
-        const uint8_t* wsrc = p.w_packed +
-            ((static_cast<size_t>(tc.ntile) * p.nsub + tc.sub) * p.kchunks + kc) * p.ngroups * static_cast<size_t>(w_bytes);
-        for (int g = 0; g < p.ngroups; ++g) {
-          mbar_wait(w_empty + ws, wph ^ 1);
+    }
+  } else if (warp == 6) {
+    // ============================== weight-slab producer ==============================
+    uint32_t ws = 0, wph = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile, TZ);
+      const uint8_t* wsrc = p.w_packed + (static_cast<size_t>(tc.ntile) * p.nsub + tc.sub) * p.kchunks * NGROUPS *
+                                             static_cast<size_t>(w_bytes);
+      const int nslabs = p.kchunks * NGROUPS;
+#pragma unroll 1
+      for (int g = 0; g < nslabs; ++g) {
+        mbar_wait(w_empty + ws, wph ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(w_full + ws, w_bytes);
           bulk_load(w_stage + ws * C::W_STAGE, wsrc + static_cast<size_t>(g) * w_bytes, w_bytes, w_full + ws);
-          if (++ws == kNumWStages) { ws = 0; wph ^= 1; }
         }
-        tile = ntile_id;
-        kc = nkc;
-        have = have_next;
+        __syncwarp();
+        if (++ws == kNumWStages) { ws = 0; wph ^= 1; }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ============================== UMMA issuer (one lane) ==============================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(128, NT, p.fp16 ? 0u : 1u);
-      const uint32_t sbo_a = static_cast<uint32_t>(BX * C::ROWB);
-      const uint32_t sbo_w = 8u * C::ROWB;
-      uint32_t as = 0, aph = 0, ws = 0, wph = 0, ab = 0, abph = 0;
-      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(acc_empty + ab, abph ^ 1);
-        tc_fence_after();
-        const uint32_t acc_col = tmem_base + ab * C::ACC_COLS;
-        for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(a_full + as, aph);
+    // ============================== UMMA issuer ==============================
+    // Warp-uniform loop; the elected lane issues a fully unrolled burst of TAPS_G x TZ x KSTEPS
+    // UMMAs per weight slab.  Descriptors differ from a per-slab base only by compile-time
+    // constants (start-address field, 16-byte units).
+    const uint32_t idesc = make_idesc_f16(128, NT, p.fp16 ? 0u : 1u);
+    constexpr uint32_t sbo_a = BX * C::ROWB;
+    constexpr uint32_t sbo_w = 8u * C::ROWB;
+    uint32_t as = 0, aph = 0, ws = 0, wph = 0, ab = 0, abph = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(acc_empty + ab, abph ^ 1);
+      tc_fence_after();
+      const uint32_t acc_col = tmem_base + ab * C::ACC_COLS;
+#pragma unroll 1
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        mbar_wait(a_full + as, aph);
+        const uint32_t a_addr = smem_u32(a_stage + as * C::A_STAGE);
+#pragma unroll 1
+        for (int g = 0; g < NGROUPS; ++g) {
+          mbar_wait(w_full + ws, wph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(a_stage + as * C::A_STAGE);
-          for (int g = 0; g < p.ngroups; ++g) {
-            mbar_wait(w_full + ws, wph);
-            tc_fence_after();
-            const uint32_t w_addr = smem_u32(w_stage + ws * C::W_STAGE);
-            const int dz = p.halo ? g / 3 : 0, dy = p.halo ? g % 3 : 0;
-            for (int t = 0; t < p.taps_g; ++t) {
-              const uint64_t wdesc0 = make_smem_desc(w_addr + t * NT * C::ROWB, 16, sbo_w, C::LAYOUT);
+          // slab g of the plain schedule = (dz, dy) with the three dx taps; slab g of the
+          // plane-fused schedule = (dy, dx) with the three dz taps (ordered dz = +1, 0, -1)
+          const int g3 = g / 3, gr = g - 3 * g3;
+          const uint32_t a_off_g = !HALO ? 0u
+                                   : (C::FUSE ? static_cast<uint32_t>((g3 * BX + gr) * C::ROWB)
+                                              : static_cast<uint32_t>((g3 * BY + gr) * BX * C::ROWB));
+          const uint64_t adesc_g = make_smem_desc(a_addr + a_off_g, 16, sbo_a, C::LAYOUT);
+          const uint64_t wdesc_g = make_smem_desc(smem_u32(w_stage + ws * C::W_STAGE), 16, sbo_w, C::LAYOUT);
+          const uint32_t first = (kc | g) == 0 ? 0u : 1u;
+          if (elect_one()) {
+            if constexpr (!C::FUSE) {
+#pragma unroll
+              for (int t = 0; t < TAPS_G; ++t) {
+#pragma unroll
+                for (int pz = 0; pz < TZ; ++pz) {
+#pragma unroll
+                  for (int ks = 0; ks < C::KSTEPS; ++ks) {
+                    const uint64_t ad = adesc_g + static_cast<uint64_t>(((pz * BY * BX + t) * C::ROWB + ks * 32) >> 4);
+                    const uint64_t wd = wdesc_g + static_cast<uint64_t>((t * NT * C::ROWB + ks * 32) >> 4);
+                    umma_ss(acc_col + pz * NT, ad, wd, idesc, (t | ks) == 0 ? first : 1u);
+                  }
+                }
+              }
+            } else if (first == 0u) {
+              // very first slab of a tile: every output plane must start from accumulate = 0, so the
+              // three dz taps are issued as separate N = NT instructions per output plane
 #pragma unroll
               for (int pz = 0; pz < TZ; ++pz) {
-                const uint32_t a_off = static_cast<uint32_t>((((pz + dz) * BY + dy) * BX + t) * C::ROWB);
-                const uint64_t adesc0 = make_smem_desc(a_addr + a_off, 16, sbo_a, C::LAYOUT);
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {                 // dz = 1 - t reads input plane pz + dz (box plane pz + 2 - t)
+#pragma unroll
+                  for (int ks = 0; ks < C::KSTEPS; ++ks) {
+                    const uint64_t ad = adesc_g + static_cast<uint64_t>((((pz + 2 - t) * BY * BX) * C::ROWB + ks * 32) >> 4);
+                    const uint64_t wd = wdesc_g + static_cast<uint64_t>((t * NT * C::ROWB + ks * 32) >> 4);
+                    umma_ss(acc_col + pz * NT, ad, wd, idesc, (t | ks) == 0 ? 0u : 1u);
+                  }
+                }
+              }
+            } else {
+              // plane-fused schedule: input plane i (box plane i + 1) is read from shared memory ONCE
+              // per (dy, dx) and multiplied against the weights of all the dz taps that use it; the
+              // N = NT * nblk result columns land directly in the accumulators of the adjacent output
+              // planes lo..hi (their TMEM columns are contiguous), so the sum over dz happens in TMEM.
+#pragma unroll
+              for (int i = -1; i <= TZ; ++i) {
+                const int lo = i - 1 < 0 ? 0 : i - 1, hi = i + 1 > TZ - 1 ? TZ - 1 : i + 1;
+                const int nblk = hi - lo + 1, toff = lo - (i - 1);
+                const uint32_t idesc_n = make_idesc_f16(128, NT * nblk, p.fp16 ? 0u : 1u);
 #pragma unroll
                 for (int ks = 0; ks < C::KSTEPS; ++ks) {
-                  const uint32_t accumulate = (kc | g | t | ks) != 0 ? 1u : 0u;
-                  umma_ss(acc_col + pz * NT, adesc0 + static_cast<uint64_t>(ks * 2), wdesc0 + static_cast<uint64_t>(ks * 2),
-                          idesc, accumulate);
+                  const uint64_t ad = adesc_g + static_cast<uint64_t>((((i + 1) * BY * BX) * C::ROWB + ks * 32) >> 4);
+                  const uint64_t wd = wdesc_g + static_cast<uint64_t>((toff * NT * C::ROWB + ks * 32) >> 4);
+                  umma_ss(acc_col + lo * NT, ad, wd, idesc_n, 1u);
                 }
               }
             }
             umma_commit(w_empty + ws);            // slab free once these MMAs retire
-            if (++ws == kNumWStages) { ws = 0; wph ^= 1; }
+            if (g == NGROUPS - 1) {
+              umma_commit(a_empty + as);
+              if (kc == p.kchunks - 1) umma_commit(acc_full + ab);
+            }
           }
-          umma_commit(a_empty + as);
-          if (++as == kNumAStages) { as = 0; aph ^= 1; }
+          __syncwarp();
+          if (++ws == kNumWStages) { ws = 0; wph ^= 1; }
         }
-        umma_commit(acc_full + ab);
-        if (++ab == 2) { ab = 0; abph ^= 1; }
+        if (++as == kNumAStages) { as = 0; aph ^= 1; }
       }
+      if (++ab == 2) { ab = 0; abph ^= 1; }
     }
-    __syncwarp();
   } else {
     // ============================== epilogue warps ==============================
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
@@ -297,17 +340,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const KParams p) {
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
-template <int CB, int NT, int TZ>
+template <int CB, int NT, int TZ, int HALO>
 cudaError_t launch_cfg(const ConvUmmaLaunch& L, const KParams& p, int grid, cudaStream_t stream) {
-  using C = Cfg<CB, NT, TZ>;
+  using C = Cfg<CB, NT, TZ, HALO>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<CB, NT, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<CB, NT, TZ, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  conv_umma_kernel<CB, NT, TZ><<<grid, kThreads, C::SMEM_BYTES, stream>>>(L.tmap_in, p);
+  conv_umma_kernel<CB, NT, TZ, HALO><<<grid, kThreads, C::SMEM_BYTES, stream>>>(L.tmap_in, p);
   return cudaGetLastError();
 }
 
@@ -380,7 +423,10 @@ void conv_umma_pack(const float* w, int Cin, int Cout, int ntaps, int nsub, cons
           for (int t = 0; t < taps_g; ++t)
             for (int r = 0; r < NT; ++r)
               for (int kk = 0; kk < CB; ++kk) {
-                const int tap = g * taps_g + t;
+                // plain schedule: slab g = (dz, dy), t = dx.  Plane-fused schedule (3 * NT <= 256):
+                // slab g = (dy, dx), t <-> dz = 1 - t.
+                const bool fuse = ntaps == 27 && 3 * NT <= 256;
+                const int tap = fuse ? ((2 - t) * 9 + g) : (g * taps_g + t);
                 const int cout = nt * NT + r, cin = kc * CB + kk;
                 const float val = w[((static_cast<size_t>(sub) * ntaps + tap) * Cout + cout) * Cin + cin];
                 uint16_t bits;
@@ -402,8 +448,9 @@ cudaError_t conv_umma_launch(const ConvUmmaLaunch& L, cudaStream_t stream) {
   const KParams p = make_params(L);
   if (p.total_tiles <= 0) return cudaSuccess;
   const int grid = static_cast<int>(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs);
-#define TE_CONV_CASE(cb, nt, tz) \
-  if (L.CB == cb && L.NT == nt && L.TZ == tz) return launch_cfg<cb, nt, tz>(L, p, grid, stream);
+#define TE_CONV_CASE(cb, nt, tz)                                                          \
+  if (L.CB == cb && L.NT == nt && L.TZ == tz)                                             \
+    return p.halo ? launch_cfg<cb, nt, tz, 1>(L, p, grid, stream) : launch_cfg<cb, nt, tz, 0>(L, p, grid, stream);
   TE_CONV_CASE(16, 16, 4)
   TE_CONV_CASE(16, 32, 4)
   TE_CONV_CASE(16, 64, 4)
