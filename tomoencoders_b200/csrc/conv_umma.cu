@@ -41,6 +41,7 @@ struct KParams {
   int out_ctot, out_coff;
   int N, D, H, W;
   int kchunks;          // Cin / CB
+  int k1_chunks;        // chunks read through the first tensor map (== kchunks for a single input)
   int ngroups, taps_g;  // weight slabs per chunk, taps per slab (9 x 3 for a 3x3x3 conv, 1 x 1 for a transposed-conv sub-position)
   int halo;             // 1 for the 3x3x3 conv, 0 otherwise
   int nsub;             // 1 or 8
@@ -56,6 +57,8 @@ struct KParams {
   uint8_t* head_labels;
   float* head_probs;
   float* head_logits;
+  uint8_t* pool_out;    // fused MaxPool3D(2) output (nullptr = none)
+  int pool_ctot, pool_coff;
 };
 
 struct TileCoord { int ntile, sub, n, z0, y0, x0; };
@@ -66,6 +69,8 @@ __device__ __forceinline__ TileCoord decode_tile(const KParams& p, long long t, 
   c.y0 = static_cast<int>(t % p.tiles_y) * 16; t /= p.tiles_y;
   c.z0 = static_cast<int>(t % p.tiles_z) * TZ; t /= p.tiles_z;
   c.n = static_cast<int>(t % p.N);             t /= p.N;
+  // sub-positions of a transposed conv are the slowest index: measured faster on B200 than
+  // interleaving the 8 sub-position CTAs of one output block (623 vs 706 us for dec0.upconv)
   c.sub = static_cast<int>(t % p.nsub);        t /= p.nsub;
   c.ntile = static_cast<int>(t);
   return c;
@@ -103,7 +108,8 @@ struct Cfg {
 
 template <int CB, int NT, int TZ, int HALO>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const KParams p) {
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_in2,
+                 const KParams p) {
   using C = Cfg<CB, NT, TZ, HALO>;
   constexpr int kNumAStages = C::NUM_A;
   constexpr int BX = 8 + 2 * HALO, BY = 16 + 2 * HALO, BZ = TZ + 2 * HALO;   // input box (voxels)
@@ -152,8 +158,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const KParams p) {
         mbar_wait(a_empty + as, aph ^ 1);
         if (elect_one()) {
           mbar_expect_tx(a_full + as, a_bytes);
-          tma_load_5d(a_stage + as * C::A_STAGE, &tmap_in, a_full + as, kc * CB, tc.x0 - HALO, tc.y0 - HALO,
-                      tc.z0 - HALO, tc.n);
+          // channel chunks [0, k1) come from the first input tensor, the rest from the second
+          // (planar skip concatenation: the two halves are separate dense tensors)
+          const bool second = kc >= p.k1_chunks;
+          tma_load_5d(a_stage + as * C::A_STAGE, second ? &tmap_in2 : &tmap_in, a_full + as,
+                      (second ? kc - p.k1_chunks : kc) * CB, tc.x0 - HALO, tc.y0 - HALO, tc.z0 - HALO, tc.n);
         }
         __syncwarp();
         if (++as == kNumAStages) { as = 0; aph ^= 1; }
@@ -281,51 +290,93 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const KParams p) {
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ab * C::ACC_COLS;
       const int iy = tc.y0 + my, ix = tc.x0 + mx;
       const float* bias = p.bias + tc.ntile * NT;
+      static_assert(TZ % 2 == 0, "the epilogue walks the z planes of a tile in pairs");
+      {
+        // one z plane at a time: a voxel's channels are written back to back (interleaving the
+        // stores of two planes measured 10-50 % slower on the store-bound layers)
 #pragma unroll 1
-      for (int pz = 0; pz < TZ; ++pz) {
-        const int iz = tc.z0 + pz;
-        const bool valid = iz < p.D && iy < p.H && ix < p.W;
-        long long ovox;
-        if (p.up_stride) {
-          const int s = p.up_stride;
-          const int a = (tc.sub >> 2) & 1, b = (tc.sub >> 1) & 1, c = tc.sub & 1;
-          ovox = ((static_cast<long long>(tc.n) * (p.D * s) + (iz * s + a)) * (p.H * s) + (iy * s + b)) * (p.W * s) +
-                 (ix * s + c);
-        } else {
-          ovox = ((static_cast<long long>(tc.n) * p.D + iz) * p.H + iy) * p.W + ix;
-        }
-        float head_acc = 0.f;
-#pragma unroll
-        for (int c0 = 0; c0 < NT; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(tbase + pz * NT + c0, r);     // warp-collective: executed by all lanes, valid or not
-          tmem_ld_wait();
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float x = __uint_as_float(r[j]) + __ldg(bias + c0 + j);
-            if (p.act_lrelu) x = x > 0.f ? x : p.alpha * x;
-            v[j] = x;
+        for (int pz = 0; pz < TZ; ++pz) {
+          const int iz = tc.z0 + pz;
+          const bool valid = iz < p.D && iy < p.H && ix < p.W;
+          long long ovox;
+          if (p.up_stride) {
+            const int s = p.up_stride;
+            const int a = (tc.sub >> 2) & 1, b = (tc.sub >> 1) & 1, c = tc.sub & 1;
+            ovox = ((static_cast<long long>(tc.n) * (p.D * s) + (iz * s + a)) * (p.H * s) + (iy * s + b)) * (p.W * s) +
+                   (ix * s + c);
+          } else {
+            ovox = ((static_cast<long long>(tc.n) * p.D + iz) * p.H + iy) * p.W + ix;
           }
-          if (p.head_w != nullptr) {
+          float head_acc = 0.f;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) head_acc = fmaf(v[j], __ldg(p.head_w + c0 + j), head_acc);
-          }
-          if (p.out != nullptr && valid) {
-            uint8_t* dst = p.out + (ovox * p.out_ctot + p.out_coff + tc.ntile * NT + c0) * 2;
-            uint4 lo = make_uint4(pack2(v[0], v[1], p.fp16), pack2(v[2], v[3], p.fp16), pack2(v[4], v[5], p.fp16),
+          for (int c0 = 0; c0 < NT; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(tbase + pz * NT + c0, r);     // warp-collective: executed by all lanes, valid or not
+            tmem_ld_wait();
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float x = __uint_as_float(r[j]) + __ldg(bias + c0 + j);
+              if (p.act_lrelu) x = x > 0.f ? x : p.alpha * x;
+              v[j] = x;
+            }
+            if (p.head_w != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) head_acc = fmaf(v[j], __ldg(p.head_w + c0 + j), head_acc);
+            }
+            if (p.out != nullptr && valid) {
+              uint4* dst = reinterpret_cast<uint4*>(p.out + (ovox * p.out_ctot + p.out_coff + tc.ntile * NT + c0) * 2);
+              dst[0] = make_uint4(pack2(v[0], v[1], p.fp16), pack2(v[2], v[3], p.fp16), pack2(v[4], v[5], p.fp16),
                                   pack2(v[6], v[7], p.fp16));
-            uint4 hi = make_uint4(pack2(v[8], v[9], p.fp16), pack2(v[10], v[11], p.fp16), pack2(v[12], v[13], p.fp16),
+              dst[1] = make_uint4(pack2(v[8], v[9], p.fp16), pack2(v[10], v[11], p.fp16), pack2(v[12], v[13], p.fp16),
                                   pack2(v[14], v[15], p.fp16));
-            reinterpret_cast<uint4*>(dst)[0] = lo;
-            reinterpret_cast<uint4*>(dst)[1] = hi;
+            }
+          }
+          if (p.head_w != nullptr && valid) {
+            const float logit = head_acc + p.head_b;
+            if (p.head_labels) p.head_labels[ovox] = logit > 0.f ? 1 : 0;
+            if (p.head_probs) p.head_probs[ovox] = 1.f / (1.f + __expf(-logit));
+            if (p.head_logits) p.head_logits[ovox] = logit;
           }
         }
-        if (p.head_w != nullptr && valid) {
-          const float logit = head_acc + p.head_b;
-          if (p.head_labels) p.head_labels[ovox] = logit > 0.f ? 1 : 0;
-          if (p.head_probs) p.head_probs[ovox] = 1.f / (1.f + __expf(-logit));
-          if (p.head_logits) p.head_logits[ovox] = logit;
+      }
+      if (p.pool_out != nullptr) {
+        // fused MaxPool3D(2): a separate pass over the accumulators (TMEM reads are cheap) so that
+        // the full-resolution stores above stay one voxel row at a time.  max over the z pair
+        // (two accumulator planes of the same thread), the x pair (lane ^ 1) and the y pair
+        // (lane ^ 8); extents are even, so the partners of a valid even voxel are valid too.
+#pragma unroll 1
+        for (int pz = 0; pz < TZ; pz += 2) {
+          const int iz = tc.z0 + pz;
+          const bool valid = iz < p.D && iy < p.H && ix < p.W && ((mx | my) & 1) == 0;
+          const long long pvox = ((static_cast<long long>(tc.n) * (p.D >> 1) + (iz >> 1)) * (p.H >> 1) + (iy >> 1)) *
+                                     (p.W >> 1) + (ix >> 1);
+#pragma unroll
+          for (int c0 = 0; c0 < NT; c0 += 16) {
+            uint32_t r0[16], r1[16];
+            tmem_ld16(tbase + pz * NT + c0, r0);
+            tmem_ld16(tbase + (pz + 1) * NT + c0, r1);
+            tmem_ld_wait();
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              // bias + LeakyReLU are monotonic: pool the raw accumulators, activate once
+              float mval = fmaxf(__uint_as_float(r0[j]), __uint_as_float(r1[j]));
+              mval = fmaxf(mval, __shfl_xor_sync(0xffffffffu, mval, 1));
+              mval = fmaxf(mval, __shfl_xor_sync(0xffffffffu, mval, 8));
+              mval += __ldg(bias + c0 + j);
+              if (p.act_lrelu) mval = mval > 0.f ? mval : p.alpha * mval;
+              v[j] = mval;
+            }
+            if (valid) {
+              uint4* dst = reinterpret_cast<uint4*>(p.pool_out +
+                                                    (pvox * p.pool_ctot + p.pool_coff + tc.ntile * NT + c0) * 2);
+              dst[0] = make_uint4(pack2(v[0], v[1], p.fp16), pack2(v[2], v[3], p.fp16), pack2(v[4], v[5], p.fp16),
+                                  pack2(v[6], v[7], p.fp16));
+              dst[1] = make_uint4(pack2(v[8], v[9], p.fp16), pack2(v[10], v[11], p.fp16), pack2(v[12], v[13], p.fp16),
+                                  pack2(v[14], v[15], p.fp16));
+            }
+          }
         }
       }
       tc_fence_before();
@@ -350,7 +401,7 @@ cudaError_t launch_cfg(const ConvUmmaLaunch& L, const KParams& p, int grid, cuda
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  conv_umma_kernel<CB, NT, TZ, HALO><<<grid, kThreads, C::SMEM_BYTES, stream>>>(L.tmap_in, p);
+  conv_umma_kernel<CB, NT, TZ, HALO><<<grid, kThreads, C::SMEM_BYTES, stream>>>(L.tmap_in, L.tmap_in2, p);
   return cudaGetLastError();
 }
 
@@ -363,6 +414,7 @@ KParams make_params(const ConvUmmaLaunch& L) {
   p.out_coff = L.out_coff;
   p.N = L.N; p.D = L.D; p.H = L.H; p.W = L.W;
   p.kchunks = L.Cin / L.CB;
+  p.k1_chunks = L.Cin2 > 0 ? (L.Cin - L.Cin2) / L.CB : p.kchunks;
   p.halo = L.ntaps == 27 ? 1 : 0;
   p.ngroups = L.ntaps == 27 ? 9 : 1;
   p.taps_g = L.ntaps == 27 ? 3 : 1;
@@ -381,6 +433,9 @@ KParams make_params(const ConvUmmaLaunch& L) {
   p.head_labels = L.head_labels;
   p.head_probs = L.head_probs;
   p.head_logits = L.head_logits;
+  p.pool_out = static_cast<uint8_t*>(L.pool_out);
+  p.pool_ctot = L.pool_ctot;
+  p.pool_coff = L.pool_coff;
   return p;
 }
 

@@ -11,6 +11,8 @@ namespace te {
 // (this is how the skip concatenation disappears: both producers write into one buffer).
 struct ConvUmmaLaunch {
   CUtensorMap tmap_in;      // 5-D (C, W, H, D, N) map of the input tensor, box (CB, 8+2h, 16+2h, TZ+2h, 1)
+  CUtensorMap tmap_in2;     // second input tensor holding the last Cin2 channels (planar concat); unused if Cin2 == 0
+  int Cin2;                 // channels taken from tmap_in2 (multiple of CB; Cin - Cin2 from tmap_in)
   const void* w_packed;     // pre-swizzled weights, see pack_conv_weights() in net.cu
   const float* bias;        // Cout fp32 (conv bias with BN folded in)
   void* out;                // output activations (16-bit) or nullptr when the head is fused
@@ -28,6 +30,9 @@ struct ConvUmmaLaunch {
   uint8_t* head_labels;     // optional (n,D,H,W) uint8: logit > 0
   float* head_probs;        // optional fp32 sigmoid(logit)
   float* head_logits;       // optional fp32 logits
+  // fused MaxPool3D(2) of the activated output (conv only; D, H, W even): written next to `out`
+  void* pool_out;           // nullptr = no fused pool
+  int pool_ctot, pool_coff;
   // kernel configuration chosen by conv_umma_config()
   int CB, NT, TZ;
 };

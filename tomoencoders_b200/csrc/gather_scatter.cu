@@ -57,20 +57,23 @@ __device__ __forceinline__ uint4 load16_unaligned(const uint8_t* src) {
 
 template <int ES>
 __global__ void __launch_bounds__(256) gather_chunks_kernel(GatherParams p) {
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  const int rows_per_patch = p.pz * p.py;
-  for (long long c = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; c < p.total_chunks;
-       c += stride) {
-    const int cx = static_cast<int>(c % p.chunks_per_row);
-    const long long row = c / p.chunks_per_row;
-    const long long i = row / rows_per_patch;
-    const int r = static_cast<int>(row - i * rows_per_patch);
-    const int iz = r / p.py, iy = r - iz * p.py;
+  // work unit of a block = one z plane of one patch (py rows); the per-unit index arithmetic is
+  // 64-bit, everything inside a unit is 32-bit
+  const long long units = p.n * p.pz;
+  const int chunks_per_plane = p.py * p.chunks_per_row;
+  for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+    const long long i = u / p.pz;
+    const int iz = static_cast<int>(u - i * p.pz);
     const uint32_t z0 = __ldg(p.points + 3 * i), y0 = __ldg(p.points + 3 * i + 1),
                    x0 = __ldg(p.points + 3 * i + 2);
     const uint32_t b = __ldg(p.widths + 3 * i) / static_cast<uint32_t>(p.pz);
-    const long long src_row = ((static_cast<long long>(z0) + static_cast<long long>(iz) * b) * p.Y +
-                               (static_cast<long long>(y0) + static_cast<long long>(iy) * b)) * p.X + x0;
+    const long long plane0 = ((static_cast<long long>(z0) + static_cast<long long>(iz) * b) * p.Y + y0) * p.X + x0;
+    const long long row_pitch = static_cast<long long>(b) * p.X;
+    const long long cbase = u * chunks_per_plane;
+   for (int cc = threadIdx.x; cc < chunks_per_plane; cc += blockDim.x) {
+    const int iy = cc / p.chunks_per_row, cx = cc - iy * p.chunks_per_row;
+    const long long src_row = plane0 + iy * row_pitch;
+    const long long c = cbase + cc;
     uint4 v;
     if (b == 1) {
       v = load16_unaligned(p.vol + src_row * ES + static_cast<long long>(cx) * 16);
@@ -91,6 +94,7 @@ __global__ void __launch_bounds__(256) gather_chunks_kernel(GatherParams p) {
       v = make_uint4(w[0], w[1], w[2], w[3]);
     }
     stg_cs_u4(p.out + c * 16, v);
+   }
   }
 }
 
@@ -193,18 +197,19 @@ struct ScatterParams {
 
 template <int ES>
 __global__ void __launch_bounds__(256) scatter_chunks_kernel(ScatterParams p) {
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  const int rows_per_patch = p.wz * p.wy;
-  for (long long c = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; c < p.total_chunks;
-       c += stride) {
-    const int cx = static_cast<int>(c % p.chunks_per_row);
-    const long long row = c / p.chunks_per_row;
-    const long long i = row / rows_per_patch;
-    const int r = static_cast<int>(row - i * rows_per_patch);
-    const int iz = r / p.wy, iy = r - iz * p.wy;
-    const long long dst_row = ((static_cast<long long>(__ldg(p.points + 3 * i)) + iz) * p.Y +
-                               (static_cast<long long>(__ldg(p.points + 3 * i + 1)) + iy)) * p.X +
-                              __ldg(p.points + 3 * i + 2);
+  // work unit of a block = one z plane of one patch; 32-bit index arithmetic inside a unit
+  const long long units = p.n * p.wz;
+  const int chunks_per_plane = p.wy * p.chunks_per_row;
+  for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+   const long long i = u / p.wz;
+   const int iz = static_cast<int>(u - i * p.wz);
+   const long long plane0 = ((static_cast<long long>(__ldg(p.points + 3 * i)) + iz) * p.Y +
+                             __ldg(p.points + 3 * i + 1)) * p.X + __ldg(p.points + 3 * i + 2);
+   const long long cbase = u * chunks_per_plane;
+   for (int cc = threadIdx.x; cc < chunks_per_plane; cc += blockDim.x) {
+    const int iy = cc / p.chunks_per_row, cx = cc - iy * p.chunks_per_row;
+    const long long dst_row = plane0 + static_cast<long long>(iy) * p.X;
+    const long long c = cbase + cc;
     const uint4 v = ldg_nc_u4(p.sub + c * 16);
     uint8_t* d = p.vol + dst_row * ES + static_cast<long long>(cx) * 16;
     const uintptr_t a = reinterpret_cast<uintptr_t>(d);
@@ -224,6 +229,7 @@ __global__ void __launch_bounds__(256) scatter_chunks_kernel(ScatterParams p) {
         for (int e = 0; e < 16; ++e) d[e] = static_cast<uint8_t>(w[e / 4] >> ((e & 3) * 8));
       }
     }
+   }
   }
 }
 

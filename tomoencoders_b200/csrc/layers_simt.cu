@@ -62,10 +62,11 @@ __global__ void __launch_bounds__(256) conv3_kernel(TView in, TView out, const f
   }
 }
 
-// First layer of every graph: Cin = 1.  One thread per output voxel keeps the 27 input taps in
-// registers and produces all Cout channels (16 at a time) from weights staged in shared memory;
-// 16-bit NDHWC output is written as 32-byte vectors.  HBM-bound on the output write.
-template <typename T>
+// First layer of every graph: Cin = 1.  One thread computes XV consecutive x voxels: the 3 x 3 x
+// (XV + 2) input window lives in registers and every weight vector fetched from shared memory is
+// reused for the XV voxels; all Cout channels are produced 16 at a time and written as 32-byte
+// vectors of the 16-bit NDHWC output.
+template <typename T, int XV>
 __global__ void __launch_bounds__(256) conv3_c1_kernel(TView in, TView out, const float* __restrict__ w,
                                                         const float* __restrict__ bias, int lrelu, float alpha) {
   extern __shared__ float sw[];                 // [27][Cout] weights followed by [Cout] bias
@@ -74,68 +75,79 @@ __global__ void __launch_bounds__(256) conv3_c1_kernel(TView in, TView out, cons
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[27 * Cout + i] = bias[i];
   __syncthreads();
   const float* sb = sw + 27 * Cout;
-  const long long total = out.voxels();
+  const int W = in.W, H = in.H, D = in.D;
+  const int WX = W / XV;
+  const long long total = static_cast<long long>(in.N) * D * H * WX;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   const T* ip = static_cast<const T*>(in.ptr);
   T* op = static_cast<T*>(out.ptr);
-  const int W = in.W, H = in.H, D = in.D;
   for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < total; v += stride) {
-    const int x = static_cast<int>(v % W);
-    long long t = v / W;
+    const int x0 = static_cast<int>(v % WX) * XV;
+    long long t = v / WX;
     const int y = static_cast<int>(t % H); t /= H;
     const int z = static_cast<int>(t % D);
     const long long n = t / D;
-    float val[27];
+    float val[9][XV + 2];
 #pragma unroll
     for (int dz = 0; dz < 3; ++dz)
 #pragma unroll
-      for (int dy = 0; dy < 3; ++dy)
+      for (int dy = 0; dy < 3; ++dy) {
+        const int zz = z + dz - 1, yy = y + dy - 1;
+        const bool okr = zz >= 0 && zz < D && yy >= 0 && yy < H;
+        const T* row = ip + (((n * D + zz) * H + yy) * W) * in.ctot + in.coff;
+#pragma unroll
+        for (int dx = 0; dx < XV + 2; ++dx) {
+          const int xx = x0 + dx - 1;
+          val[dz * 3 + dy][dx] = (okr && xx >= 0 && xx < W) ? ld<T>(row + static_cast<long long>(xx) * in.ctot) : 0.f;
+        }
+      }
+    T* dst = op + ((((n * D + z) * H + y) * W) + x0) * out.ctot + out.coff;
+    for (int c0 = 0; c0 < Cout; c0 += 16) {
+      float acc[XV][16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float bj = sb[c0 + j];
+#pragma unroll
+        for (int i = 0; i < XV; ++i) acc[i][j] = bj;
+      }
+#pragma unroll
+      for (int r = 0; r < 9; ++r)
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
-          const int zz = z + dz - 1, yy = y + dy - 1, xx = x + dx - 1;
-          const bool ok = zz >= 0 && zz < D && yy >= 0 && yy < H && xx >= 0 && xx < W;
-          val[(dz * 3 + dy) * 3 + dx] =
-              ok ? ld<T>(ip + (((n * D + zz) * H + yy) * W + xx) * in.ctot + in.coff) : 0.f;
+          const float4* wr = reinterpret_cast<const float4*>(sw + (r * 3 + dx) * Cout + c0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 ww = wr[q];
+#pragma unroll
+            for (int i = 0; i < XV; ++i) {
+              const float a = val[r][i + dx];
+              acc[i][4 * q + 0] = fmaf(a, ww.x, acc[i][4 * q + 0]);
+              acc[i][4 * q + 1] = fmaf(a, ww.y, acc[i][4 * q + 1]);
+              acc[i][4 * q + 2] = fmaf(a, ww.z, acc[i][4 * q + 2]);
+              acc[i][4 * q + 3] = fmaf(a, ww.w, acc[i][4 * q + 3]);
+            }
+          }
         }
-    T* dst = op + v * out.ctot + out.coff;
-    for (int c0 = 0; c0 < Cout; c0 += 16) {
-      float acc[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = sb[c0 + j];
+      for (int i = 0; i < XV; ++i) {
+        if (lrelu) {
 #pragma unroll
-      for (int tap = 0; tap < 27; ++tap) {
-        const float4* wr = reinterpret_cast<const float4*>(sw + tap * Cout + c0);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 ww = wr[q];
-          acc[4 * q + 0] = fmaf(val[tap], ww.x, acc[4 * q + 0]);
-          acc[4 * q + 1] = fmaf(val[tap], ww.y, acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(val[tap], ww.z, acc[4 * q + 2]);
-          acc[4 * q + 3] = fmaf(val[tap], ww.w, acc[4 * q + 3]);
+          for (int j = 0; j < 16; ++j) acc[i][j] = acc[i][j] > 0.f ? acc[i][j] : alpha * acc[i][j];
         }
-      }
-      if (lrelu) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = acc[j] > 0.f ? acc[j] : alpha * acc[j];
-      }
-      if constexpr (sizeof(T) == 2) {
         uint32_t pk[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           if constexpr (std::is_same<T, __half>::value) {
-            __half2 h = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+            __half2 h = __floats2half2_rn(acc[i][2 * j], acc[i][2 * j + 1]);
             pk[j] = *reinterpret_cast<uint32_t*>(&h);
           } else {
-            __nv_bfloat162 h = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+            __nv_bfloat162 h = __floats2bfloat162_rn(acc[i][2 * j], acc[i][2 * j + 1]);
             pk[j] = *reinterpret_cast<uint32_t*>(&h);
           }
         }
-        uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+        uint4* d4 = reinterpret_cast<uint4*>(dst + static_cast<long long>(i) * out.ctot + c0);
         d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) st<T>(dst + c0 + j, acc[j]);
       }
     }
   }
@@ -294,10 +306,16 @@ __global__ void __launch_bounds__(256) from_f32_kernel(const float* in, T* out, 
 cudaError_t simt_conv3(const TView& in, const TView& out, const float* w, const float* bias, int lrelu, float alpha,
                        int act_type, cudaStream_t st) {
   if (in.C == 1 && act_type != ACT_F32 && out.C % 16 == 0 && out.ctot % 8 == 0 && out.coff % 8 == 0 && out.C <= 256) {
-    const int grid = blocks_for(out.voxels(), 256);
     const size_t smem = static_cast<size_t>(28) * out.C * sizeof(float);
-    if (act_type == ACT_BF16) conv3_c1_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(in, out, w, bias, lrelu, alpha);
-    else conv3_c1_kernel<__half><<<grid, 256, smem, st>>>(in, out, w, bias, lrelu, alpha);
+    if (in.W % 4 == 0) {
+      const int grid = blocks_for(out.voxels() / 4, 128);
+      if (act_type == ACT_BF16) conv3_c1_kernel<__nv_bfloat16, 4><<<grid, 128, smem, st>>>(in, out, w, bias, lrelu, alpha);
+      else conv3_c1_kernel<__half, 4><<<grid, 128, smem, st>>>(in, out, w, bias, lrelu, alpha);
+    } else {
+      const int grid = blocks_for(out.voxels(), 256);
+      if (act_type == ACT_BF16) conv3_c1_kernel<__nv_bfloat16, 1><<<grid, 256, smem, st>>>(in, out, w, bias, lrelu, alpha);
+      else conv3_c1_kernel<__half, 1><<<grid, 256, smem, st>>>(in, out, w, bias, lrelu, alpha);
+    }
     count_launch();
     return cudaGetLastError();
   }

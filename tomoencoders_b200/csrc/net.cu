@@ -29,6 +29,8 @@ struct Layer {
   Op op;
   std::string name;
   TView in{}, out{};
+  TView in2{};               // second input (planar skip concatenation): channels [in.C, Cin)
+  bool has_in2 = false;
   int Cin = 0, Cout = 0;
   int stride = 0;            // pool size / transposed-conv stride
   bool bn = false, lrelu = false;
@@ -45,9 +47,12 @@ struct Layer {
   void* d_wpacked = nullptr; // tensor-core layout
   bool use_umma = false;
   bool fused_head = false;   // this conv also evaluates the following 1x1x1 head
+  bool fused_pool = false;   // this conv also writes the MaxPool3D(2) of its output
+  bool store_out = true;     // false: only the pooled tensor is consumed downstream
+  TView pool_view{};
   bool skip = false;         // layer folded into its predecessor (the fused head)
   ConvUmmaConfig cfg{};
-  CUtensorMap tmap{};
+  CUtensorMap tmap{}, tmap2{};
   double flops = 0.0;
   float head_b = 0.f;
   // optional per-layer timing (te_net_set_profiling): event pairs recorded around every launch
@@ -148,9 +153,10 @@ struct Planner {
     return L;
   }
 
-  void conv3(const std::string& name, const TView& in, const TView& out, bool bn) {
+  void conv3(const std::string& name, const TView& in, const TView& out, bool bn, const TView* in2 = nullptr) {
     Layer& L = add(OP_CONV3, name.c_str());
     L.in = in; L.out = out; L.Cin = in.C; L.Cout = out.C; L.bn = bn; L.lrelu = true;
+    if (in2) { L.in2 = *in2; L.has_in2 = true; L.Cin += in2->C; }
     L.off_k = cursor; cursor += 27LL * L.Cin * L.Cout;
     L.off_b = cursor; cursor += L.Cout;
     if (bn) { L.off_bn = cursor; cursor += 4LL * L.Cout; }
@@ -215,6 +221,19 @@ int plan(te_net* net, bool count_only, long long* weight_count) {
     std::vector<TView> concat_bufs(nb);
     std::vector<int> c_up(nb);
     for (int i = 0; i < nb; ++i) c_up[i] = (i == nb - 1) ? 4 * d.n_filters[nb - 1] : 2 * d.n_filters[i + 1];
+    // Skip concatenation.  Tensor-core modes: "planar" -- the up-sampled and the skip tensor stay two
+    // dense tensors and the consuming conv reads its channel chunks through two TMA descriptors
+    // (every voxel row is then a whole number of 128-byte lines for both producers).  Otherwise:
+    // both producers write channel slices of one buffer.  Either way no concat copy exists.
+    std::vector<char> planar(nb, 0);
+    if (net->act_type != ACT_F32) {
+      for (int i = 0; i < nb; ++i) {
+        ConvUmmaConfig cfg;
+        const int f2 = 2 * d.n_filters[i];
+        planar[i] = d.pool_size[i] > 1 && d.isconcat[i] && conv_umma_config(c_up[i] + f2, f2, &cfg) &&
+                    c_up[i] % cfg.CB == 0 && f2 % cfg.CB == 0;
+      }
+    }
     TView cur = P.alloc_tensor(1, D, H, W);
     net->input = cur;
     for (int i = 0; i < nb; ++i) {
@@ -223,7 +242,7 @@ int plan(te_net* net, bool count_only, long long* weight_count) {
       TView t1 = P.alloc_tensor(f, D, H, W);
       snprintf(nm, sizeof nm, "enc%d.conv1", i); P.conv3(nm, cur, t1, bn);
       TView t2;
-      if (p > 1 && d.isconcat[i]) {
+      if (p > 1 && d.isconcat[i] && !planar[i]) {
         concat_bufs[i] = P.alloc_tensor(c_up[i] + 2 * f, D, H, W);
         t2 = Planner::slice(concat_bufs[i], c_up[i], 2 * f);          // up first, skip second (Unet3D.py:180)
       } else {
@@ -250,14 +269,16 @@ int plan(te_net* net, bool count_only, long long* weight_count) {
       if (p > 1) {
         D *= p; H *= p; W *= p;
         TView up;
-        if (d.isconcat[i]) up = Planner::slice(concat_bufs[i], 0, cur.C);
+        if (d.isconcat[i] && !planar[i]) up = Planner::slice(concat_bufs[i], 0, cur.C);
         else up = P.alloc_tensor(cur.C, D, H, W);
         if (d.isconcat[i] && cur.C != c_up[i]) { set_error("te_net: internal channel bookkeeping error"); return TE_ERR_STATE; }
         snprintf(nm, sizeof nm, "dec%d.upconv", i); P.upconv(nm, cur, up, p);
-        cur = d.isconcat[i] ? concat_bufs[i] : up;
+        cur = (d.isconcat[i] && !planar[i]) ? concat_bufs[i] : up;
       }
       TView t1 = P.alloc_tensor(2 * f, D, H, W);
-      snprintf(nm, sizeof nm, "dec%d.conv1", i); P.conv3(nm, cur, t1, bn);
+      snprintf(nm, sizeof nm, "dec%d.conv1", i);
+      if (p > 1 && planar[i]) P.conv3(nm, cur, t1, bn, &skips[i]);
+      else P.conv3(nm, cur, t1, bn);
       TView t2 = P.alloc_tensor(2 * f, D, H, W);
       snprintf(nm, sizeof nm, "dec%d.conv2", i); P.conv3(nm, t1, t2, bn);
       cur = t2;
@@ -420,7 +441,12 @@ extern "C" int te_net_create(const te_net_desc* desc, te_net** out) {
         L.use_umma = true;
         L.cfg = cfg;
         rc = make_tmap(&L.tmap, L.in, cfg, L.op == OP_CONV3 ? 1 : 0, net->act_type == ACT_F16);
+        if (rc == TE_OK && L.has_in2) rc = make_tmap(&L.tmap2, L.in2, cfg, 1, net->act_type == ACT_F16);
         if (rc != TE_OK) { free_net(net); return rc; }
+      } else if (L.has_in2) {
+        set_error("te_net_create: internal error: planar concat planned for a layer without a tensor-core kernel");
+        free_net(net);
+        return TE_ERR_STATE;
       }
     }
   }
@@ -431,6 +457,22 @@ extern "C" int te_net_create(const te_net_desc* desc, te_net** out) {
     if (H.op == OP_HEAD && Cv.op == OP_CONV3 && Cv.use_umma && Cv.cfg.NT == Cv.Cout) {
       Cv.fused_head = true;
       H.skip = true;
+    }
+  }
+  // fuse MaxPool3D(2) into the epilogue of the tensor-core conv that feeds it; in the encoder graph
+  // the un-pooled tensor has no other consumer, so it is not written at all
+  const char* nfp = getenv("TOMOENC_NO_FUSE_POOL");
+  if (tc && !(nfp && nfp[0] == '1')) {
+    for (size_t i = 0; i + 1 < net->layers.size(); ++i) {
+      Layer& Cv = net->layers[i];
+      Layer& Pl = net->layers[i + 1];
+      if (Cv.op == OP_CONV3 && Cv.use_umma && Pl.op == OP_POOL && Pl.stride == 2 && Cv.in.D % 2 == 0 &&
+          Cv.in.H % 2 == 0 && Cv.in.W % 2 == 0 && Pl.in.ptr == Cv.out.ptr && Pl.in.coff == Cv.out.coff) {
+        Cv.fused_pool = true;
+        Cv.pool_view = Pl.out;
+        Cv.store_out = desc->kind == 0;      // U-net: the skip connection still needs the full tensor
+        Pl.skip = true;
+      }
     }
   }
   if (desc->kind != 0) {
@@ -565,6 +607,8 @@ int run_layers(te_net* net, int n, const HeadOut& ho, cudaStream_t st) {
         if (L.use_umma) {
           ConvUmmaLaunch C{};
           C.tmap_in = L.tmap;
+          C.tmap_in2 = L.has_in2 ? L.tmap2 : L.tmap;
+          C.Cin2 = L.has_in2 ? L.in2.C : 0;
           C.w_packed = L.d_wpacked;
           C.bias = L.d_bias;
           C.out = L.out.ptr;
@@ -586,6 +630,12 @@ int run_layers(te_net* net, int n, const HeadOut& ho, cudaStream_t st) {
             C.head_probs = ho.probs;
             C.head_logits = ho.logits;
             C.out = nullptr;                      // the 32-channel activation is never written
+          }
+          if (L.fused_pool) {
+            C.pool_out = L.pool_view.ptr;
+            C.pool_ctot = L.pool_view.ctot;
+            C.pool_coff = L.pool_view.coff;
+            if (!L.store_out) C.out = nullptr;
           }
           e = conv_umma_launch(C, st);
           count_launch();
@@ -686,7 +736,7 @@ extern "C" int te_decoder_forward(te_net* net, const float* z, int64_t n, float*
 extern "C" int64_t te_net_layer_output(te_net* net, int i, float* out, int64_t capacity, void* stream) {
   if (!net || i < 0 || i >= static_cast<int>(net->layers.size())) { set_error("te_net_layer_output: bad index"); return TE_ERR_ARG; }
   const Layer& L = net->layers[i];
-  if (L.op == OP_HEAD || L.op == OP_DENSE || L.fused_head || L.out.ptr == nullptr) {
+  if (L.op == OP_HEAD || L.op == OP_DENSE || L.fused_head || !L.store_out || L.out.ptr == nullptr) {
     set_error("te_net_layer_output: layer %s has no stored activation tensor", L.name.c_str());
     return TE_ERR_STATE;
   }
