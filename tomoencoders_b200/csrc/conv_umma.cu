@@ -32,7 +32,6 @@ namespace te {
 namespace {
 
 constexpr int kThreads = 224;
-constexpr int kNumWStages = 4;     // weight-slab ring
 
 struct KParams {
   const uint8_t* w_packed;
@@ -91,7 +90,13 @@ struct Cfg {
   static constexpr uint32_t LAYOUT = CB == 16 ? kLayoutSW32 : (CB == 32 ? kLayoutSW64 : kLayoutSW128);
   static constexpr int KSTEPS = CB / 16;                                // UMMA K = 16 for 16-bit operands
   static constexpr int A_STAGE = (((TZ + 2 * HALO) * (16 + 2 * HALO) * (8 + 2 * HALO) * ROWB) + 1023) / 1024 * 1024;
-  static constexpr int W_STAGE = (((HALO ? 3 : 1) * NT * ROWB) + 1023) / 1024 * 1024;
+  static constexpr int SLAB = (HALO ? 3 : 1) * NT * ROWB;              // bytes of one weight slab (3 taps of a conv)
+  // Weight slabs per pipeline stage.  Every stage boundary costs a barrier wait plus a drain of the
+  // UMMA issue queue (ncu: the uniform registers of queued UTCHMMAs are recycled there), so the
+  // thin-channel layers, whose slabs are small, take 3 or 9 slabs per stage -> bursts of 36 / 108 UMMAs.
+  static constexpr int G = !HALO ? 1 : (NT >= 128 ? 1 : (SLAB * 9 <= 28 * 1024 ? 9 : 3));
+  static constexpr int NGROUPS = HALO ? 9 / G : 1;                      // stages per channel chunk
+  static constexpr int W_STAGE = ((G * SLAB) + 1023) / 1024 * 1024;
   // input-box ring: the haloed boxes of the 3x3x3 conv are large (2 stages); the un-haloed boxes of
   // the transposed conv are small and each feeds few MMAs, so more of them are kept in flight
   static constexpr int NUM_A = HALO ? 2 : 4;
@@ -102,7 +107,10 @@ struct Cfg {
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
                                    : TMEM_COLS_RAW <= 256 ? 256 : 512;
   static_assert(TMEM_COLS_RAW <= 512, "accumulators do not fit TMEM");
-  static constexpr int SMEM_BYTES = NUM_A * A_STAGE + kNumWStages * W_STAGE + 1024 /*barriers*/ + 1024 /*align*/;
+  static constexpr int W_ROOM = 227 * 1024 - 2048 - NUM_A * A_STAGE;
+  static constexpr int NUM_W = W_ROOM / W_STAGE >= 4 ? 4 : W_ROOM / W_STAGE;
+  static_assert(NUM_W >= 2, "weight ring needs two stages");
+  static constexpr int SMEM_BYTES = NUM_A * A_STAGE + NUM_W * W_STAGE + 1024 /*barriers*/ + 1024 /*align*/;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
 };
 
@@ -113,8 +121,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   using C = Cfg<CB, NT, TZ, HALO>;
   constexpr int kNumAStages = C::NUM_A;
   constexpr int BX = 8 + 2 * HALO, BY = 16 + 2 * HALO, BZ = TZ + 2 * HALO;   // input box (voxels)
-  constexpr int NGROUPS = HALO ? 9 : 1;    // weight slabs per channel chunk: one per (dz, dy)
-  constexpr int TAPS_G = HALO ? 3 : 1;     // taps per slab: the three dx of a (dz, dy) row
+  constexpr int kNumWStages = C::NUM_W;
+  constexpr int G = C::G;                  // weight slabs per pipeline stage
+  constexpr int NGROUPS = C::NGROUPS;      // weight stages per channel chunk
+  constexpr int TAPS_G = HALO ? 3 : 1;     // taps per slab: the three dx of a (dz, dy) row (plane-fused: the three dz of a (dy, dx))
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_stage = smem;
@@ -144,7 +154,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   constexpr uint32_t a_bytes = static_cast<uint32_t>(BZ * BY * BX * C::ROWB);
-  constexpr uint32_t w_bytes = static_cast<uint32_t>(TAPS_G * NT * C::ROWB);
+  constexpr uint32_t slab_bytes = static_cast<uint32_t>(C::SLAB);
+  constexpr uint32_t w_bytes = static_cast<uint32_t>(G) * slab_bytes;     // one stage
+  // all the weights of the layer fit the ring: load them once, never release them
+  const bool w_resident = p.n_ntiles == 1 && p.nsub == 1 && p.kchunks * NGROUPS <= kNumWStages;
 
   if (warp == 0) {
     // ============================== TMA producer ==============================
@@ -175,9 +188,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       const TileCoord tc = decode_tile(p, tile, TZ);
       const uint8_t* wsrc = p.w_packed + (static_cast<size_t>(tc.ntile) * p.nsub + tc.sub) * p.kchunks * NGROUPS *
                                              static_cast<size_t>(w_bytes);
-      const int nslabs = p.kchunks * NGROUPS;
+      const int nstages = p.kchunks * NGROUPS;
 #pragma unroll 1
-      for (int g = 0; g < nslabs; ++g) {
+      for (int g = 0; g < nstages; ++g) {
         mbar_wait(w_empty + ws, wph ^ 1);
         if (elect_one()) {
           mbar_expect_tx(w_full + ws, w_bytes);
@@ -186,86 +199,100 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         __syncwarp();
         if (++ws == kNumWStages) { ws = 0; wph ^= 1; }
       }
+      if (w_resident) break;
     }
   } else if (warp == 1) {
     // ============================== UMMA issuer ==============================
-    // Warp-uniform loop; the elected lane issues a fully unrolled burst of TAPS_G x TZ x KSTEPS
-    // UMMAs per weight slab.  Descriptors differ from a per-slab base only by compile-time
+    // Warp-uniform loop; the elected lane issues a fully unrolled burst of G x TAPS_G x TZ x KSTEPS
+    // UMMAs per weight stage.  Descriptors differ from a per-stage base only by compile-time
     // constants (start-address field, 16-byte units).
     const uint32_t idesc = make_idesc_f16(128, NT, p.fp16 ? 0u : 1u);
     constexpr uint32_t sbo_a = BX * C::ROWB;
     constexpr uint32_t sbo_w = 8u * C::ROWB;
     uint32_t as = 0, aph = 0, ws = 0, wph = 0, ab = 0, abph = 0;
+    bool w_ready = false;                       // resident weights: every stage has been waited for once
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(acc_empty + ab, abph ^ 1);
       tc_fence_after();
       const uint32_t acc_col = tmem_base + ab * C::ACC_COLS;
+      if (w_resident) ws = 0;
 #pragma unroll 1
       for (int kc = 0; kc < p.kchunks; ++kc) {
         mbar_wait(a_full + as, aph);
-        const uint32_t a_addr = smem_u32(a_stage + as * C::A_STAGE);
+        const uint64_t adesc0 = make_smem_desc(smem_u32(a_stage + as * C::A_STAGE), 16, sbo_a, C::LAYOUT);
 #pragma unroll 1
-        for (int g = 0; g < NGROUPS; ++g) {
-          mbar_wait(w_full + ws, wph);
+        for (int gs = 0; gs < NGROUPS; ++gs) {
+          if (!w_ready) mbar_wait(w_full + ws, wph);
           tc_fence_after();
-          // slab g of the plain schedule = (dz, dy) with the three dx taps; slab g of the
-          // plane-fused schedule = (dy, dx) with the three dz taps (ordered dz = +1, 0, -1)
-          const int g3 = g / 3, gr = g - 3 * g3;
-          const uint32_t a_off_g = !HALO ? 0u
-                                   : (C::FUSE ? static_cast<uint32_t>((g3 * BX + gr) * C::ROWB)
-                                              : static_cast<uint32_t>((g3 * BY + gr) * BX * C::ROWB));
-          const uint64_t adesc_g = make_smem_desc(a_addr + a_off_g, 16, sbo_a, C::LAYOUT);
-          const uint64_t wdesc_g = make_smem_desc(smem_u32(w_stage + ws * C::W_STAGE), 16, sbo_w, C::LAYOUT);
-          const uint32_t first = (kc | g) == 0 ? 0u : 1u;
+          const uint64_t wdesc0 = make_smem_desc(smem_u32(w_stage + ws * C::W_STAGE), 16, sbo_w, C::LAYOUT);
+          // slab g = gs * G + gi of the plain schedule = (dz, dy) with the three dx taps; slab g of
+          // the plane-fused schedule = (dy, dx) with the three dz taps (ordered dz = +1, 0, -1).
+          // Run-time part of its input-window offset (the rest is a compile-time constant per gi):
+          const int g3r = G == 1 ? gs / 3 : (G == 3 ? gs : 0), grr = G == 1 ? gs - 3 * g3r : 0;
+          const uint32_t a_off_r = !HALO ? 0u
+                                   : (C::FUSE ? static_cast<uint32_t>((g3r * BX + grr) * C::ROWB)
+                                              : static_cast<uint32_t>((g3r * BY + grr) * BX * C::ROWB));
+          const uint64_t adesc_s = adesc0 + static_cast<uint64_t>(a_off_r >> 4);
+          const bool tile_start = (kc | gs) == 0;
           if (elect_one()) {
-            if constexpr (!C::FUSE) {
 #pragma unroll
-              for (int t = 0; t < TAPS_G; ++t) {
+            for (int gi = 0; gi < G; ++gi) {
+              const int g3c = G == 9 ? gi / 3 : 0, grc = G == 9 ? gi % 3 : (G == 3 ? gi : 0);
+              const uint32_t a_off_c = !HALO ? 0u
+                                       : (C::FUSE ? static_cast<uint32_t>((g3c * BX + grc) * C::ROWB)
+                                                  : static_cast<uint32_t>((g3c * BY + grc) * BX * C::ROWB));
+              const uint64_t adesc_g = adesc_s + static_cast<uint64_t>(a_off_c >> 4);
+              const uint64_t wdesc_g = wdesc0 + static_cast<uint64_t>((gi * C::SLAB) >> 4);
+              const bool first_slab = gi == 0 && tile_start;
+              if constexpr (!C::FUSE) {
+#pragma unroll
+                for (int t = 0; t < TAPS_G; ++t) {
+#pragma unroll
+                  for (int pz = 0; pz < TZ; ++pz) {
+#pragma unroll
+                    for (int ks = 0; ks < C::KSTEPS; ++ks) {
+                      const uint64_t ad = adesc_g + static_cast<uint64_t>(((pz * BY * BX + t) * C::ROWB + ks * 32) >> 4);
+                      const uint64_t wd = wdesc_g + static_cast<uint64_t>((t * NT * C::ROWB + ks * 32) >> 4);
+                      umma_ss(acc_col + pz * NT, ad, wd, idesc, (t | ks) == 0 ? (first_slab ? 0u : 1u) : 1u);
+                    }
+                  }
+                }
+              } else if (first_slab) {
+                // very first slab of a tile: every output plane must start from accumulate = 0, so the
+                // three dz taps are issued as separate N = NT instructions per output plane
 #pragma unroll
                 for (int pz = 0; pz < TZ; ++pz) {
 #pragma unroll
-                  for (int ks = 0; ks < C::KSTEPS; ++ks) {
-                    const uint64_t ad = adesc_g + static_cast<uint64_t>(((pz * BY * BX + t) * C::ROWB + ks * 32) >> 4);
-                    const uint64_t wd = wdesc_g + static_cast<uint64_t>((t * NT * C::ROWB + ks * 32) >> 4);
-                    umma_ss(acc_col + pz * NT, ad, wd, idesc, (t | ks) == 0 ? first : 1u);
+                  for (int t = 0; t < 3; ++t) {                 // dz = 1 - t reads input plane pz + dz (box plane pz + 2 - t)
+#pragma unroll
+                    for (int ks = 0; ks < C::KSTEPS; ++ks) {
+                      const uint64_t ad = adesc_g + static_cast<uint64_t>((((pz + 2 - t) * BY * BX) * C::ROWB + ks * 32) >> 4);
+                      const uint64_t wd = wdesc_g + static_cast<uint64_t>((t * NT * C::ROWB + ks * 32) >> 4);
+                      umma_ss(acc_col + pz * NT, ad, wd, idesc, (t | ks) == 0 ? 0u : 1u);
+                    }
                   }
                 }
-              }
-            } else if (first == 0u) {
-              // very first slab of a tile: every output plane must start from accumulate = 0, so the
-              // three dz taps are issued as separate N = NT instructions per output plane
+              } else {
+                // plane-fused schedule: input plane i (box plane i + 1) is read from shared memory ONCE
+                // per (dy, dx) and multiplied against the weights of all the dz taps that use it; the
+                // N = NT * nblk result columns land directly in the accumulators of the adjacent output
+                // planes lo..hi (their TMEM columns are contiguous), so the sum over dz happens in TMEM.
 #pragma unroll
-              for (int pz = 0; pz < TZ; ++pz) {
-#pragma unroll
-                for (int t = 0; t < 3; ++t) {                 // dz = 1 - t reads input plane pz + dz (box plane pz + 2 - t)
+                for (int i = -1; i <= TZ; ++i) {
+                  const int lo = i - 1 < 0 ? 0 : i - 1, hi = i + 1 > TZ - 1 ? TZ - 1 : i + 1;
+                  const int nblk = hi - lo + 1, toff = lo - (i - 1);
+                  const uint32_t idesc_n = make_idesc_f16(128, NT * nblk, p.fp16 ? 0u : 1u);
 #pragma unroll
                   for (int ks = 0; ks < C::KSTEPS; ++ks) {
-                    const uint64_t ad = adesc_g + static_cast<uint64_t>((((pz + 2 - t) * BY * BX) * C::ROWB + ks * 32) >> 4);
-                    const uint64_t wd = wdesc_g + static_cast<uint64_t>((t * NT * C::ROWB + ks * 32) >> 4);
-                    umma_ss(acc_col + pz * NT, ad, wd, idesc, (t | ks) == 0 ? 0u : 1u);
+                    const uint64_t ad = adesc_g + static_cast<uint64_t>((((i + 1) * BY * BX) * C::ROWB + ks * 32) >> 4);
+                    const uint64_t wd = wdesc_g + static_cast<uint64_t>((toff * NT * C::ROWB + ks * 32) >> 4);
+                    umma_ss(acc_col + lo * NT, ad, wd, idesc_n, 1u);
                   }
-                }
-              }
-            } else {
-              // plane-fused schedule: input plane i (box plane i + 1) is read from shared memory ONCE
-              // per (dy, dx) and multiplied against the weights of all the dz taps that use it; the
-              // N = NT * nblk result columns land directly in the accumulators of the adjacent output
-              // planes lo..hi (their TMEM columns are contiguous), so the sum over dz happens in TMEM.
-#pragma unroll
-              for (int i = -1; i <= TZ; ++i) {
-                const int lo = i - 1 < 0 ? 0 : i - 1, hi = i + 1 > TZ - 1 ? TZ - 1 : i + 1;
-                const int nblk = hi - lo + 1, toff = lo - (i - 1);
-                const uint32_t idesc_n = make_idesc_f16(128, NT * nblk, p.fp16 ? 0u : 1u);
-#pragma unroll
-                for (int ks = 0; ks < C::KSTEPS; ++ks) {
-                  const uint64_t ad = adesc_g + static_cast<uint64_t>((((i + 1) * BY * BX) * C::ROWB + ks * 32) >> 4);
-                  const uint64_t wd = wdesc_g + static_cast<uint64_t>((toff * NT * C::ROWB + ks * 32) >> 4);
-                  umma_ss(acc_col + lo * NT, ad, wd, idesc_n, 1u);
                 }
               }
             }
-            umma_commit(w_empty + ws);            // slab free once these MMAs retire
-            if (g == NGROUPS - 1) {
+            if (!w_resident) umma_commit(w_empty + ws);   // stage free once these MMAs retire
+            if (gs == NGROUPS - 1) {
               umma_commit(a_empty + as);
               if (kc == p.kchunks - 1) umma_commit(acc_full + ab);
             }
@@ -275,6 +302,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         }
         if (++as == kNumAStages) { as = 0; aph ^= 1; }
       }
+      if (w_resident) w_ready = true;
       if (++ab == 2) { ab = 0; abph ^= 1; }
     }
   } else {
