@@ -56,9 +56,15 @@ int64_t te_launch_count(void);
  * bit-exact.  widths is (n,3) uint32 (for a Grid pass the scalar width replicated).  The binning
  * rules (isotropy, >= 1, widths % patch == 0) are validated by the host code before the call; the
  * kernel re-derives b = widths[i][0] / patch[0].  elem_size in {1,2,4}.
+ *
+ * flags: TE_HINT_ALIGNED promises that every patch is unbinned and that its x corner is a multiple
+ * of 16 bytes (true for every Grid / regular-grid tiling with width * elem_size % 16 == 0); the
+ * call may then take the TMA-staged kernel (one box load + one bulk store per group of planes).
+ * The hint only selects the kernel: a violated promise costs speed, never correctness.
  */
+#define TE_HINT_ALIGNED 1
 int te_gather(const void* vol, int elem_size, const int64_t vol_shape[3], const uint32_t* points,
-              const uint32_t* widths, int64_t n, const int32_t patch[3], void* out, void* stream);
+              const uint32_t* widths, int64_t n, const int32_t patch[3], void* out, int flags, void* stream);
 
 /* Gather fused with the pre-network clip / rescale.  Replaces extract followed by the per-chunk
  * np.clip + _rescale_data of SurfaceSegmenter.predict_patches (neural_nets/surface_segmenter.py:
@@ -80,10 +86,11 @@ int te_gather_norm(const void* vol, int vol_dtype, const int64_t vol_shape[3], c
  * one width[3].  If `owner` is NULL the patches must be pairwise disjoint (the host code proves it);
  * otherwise owner is a uint32 scratch volume of vol_shape elements and the call resolves overlaps
  * deterministically in two passes (atomicMax of the patch index, then owner-only writes).
+ * flags: TE_HINT_ALIGNED as for te_gather (disjoint path only).
  */
 int te_scatter(const void* sub_vols, int elem_size, const uint32_t* points, int64_t n,
                const int32_t width[3], void* vol_out, const int64_t vol_shape[3], uint32_t* owner,
-               void* stream);
+               int flags, void* stream);
 
 /* min / max over vol[::s, ::s, ::s].  Replaces _find_min_max (misc/voxel_processing.py:91-104).
  * out2 = device float[2] {min, max}; scratch = device float[2 * 1024]. */

@@ -27,9 +27,9 @@ def test_library_builds_and_exports_the_header(built_lib):
 
 def test_argument_errors_are_reported_without_a_gpu(built_lib):
     L = built_lib.lib()
-    rc = L.te_gather(None, 3, built_lib.i64x3((1, 1, 1)), None, None, 1, built_lib.i32x3((1, 1, 1)), None, None)
+    rc = L.te_gather(None, 3, built_lib.i64x3((1, 1, 1)), None, None, 1, built_lib.i32x3((1, 1, 1)), None, 0, None)
     assert rc == -1 and b"elem_size" in L.te_last_error()
-    rc = L.te_gather(None, 1, built_lib.i64x3((1, 1, 1)), None, None, 0, built_lib.i32x3((1, 1, 1)), None, None)
+    rc = L.te_gather(None, 1, built_lib.i64x3((1, 1, 1)), None, None, 0, built_lib.i32x3((1, 1, 1)), None, 0, None)
     assert rc == 0        # empty input is a no-op
 
 

@@ -13,6 +13,17 @@ SVS = (40, 44, 48)
 DTYPES = (("u8", np.uint8), ("u16", np.uint16), ("f16", np.float16), ("f32", np.float32))
 
 
+@pytest.fixture(autouse=True, params=["default", "tma", "simt"])
+def gather_path(request, monkeypatch):
+    """Every test runs three times: default kernel selection (TMA-staged kernels for 16-byte-aligned
+    2- and 4-byte tilings, SIMT otherwise), TMA kernels forced wherever the row pitch allows (covers
+    their per-unit unaligned / binned paths), and SIMT kernels forced.  The variables are read on
+    every call."""
+    monkeypatch.setenv("TOMOENC_NO_TMA_GATHER", "1" if request.param == "simt" else "0")
+    monkeypatch.setenv("TOMOENC_FORCE_TMA_GATHER", "1" if request.param == "tma" else "0")
+    return request.param
+
+
 def _bits(a):
     a = np.ascontiguousarray(a)
     return a.view({1: np.uint8, 2: np.uint16, 4: np.uint32}[a.dtype.itemsize])
@@ -42,6 +53,34 @@ def test_grid_extract_golden_and_round_trip(golden):
     out = np.zeros_like(gv)
     g.fill_patches_in_volume(x, out)
     np.testing.assert_array_equal(out, gv)
+
+
+@pytest.mark.parametrize("dt", [np.uint8, np.uint16, np.float16, np.float32])
+def test_aligned_pitch_random_corners_and_mixed_binning(dt):
+    """Row pitch a multiple of 16 bytes -> TMA box loads at arbitrary (odd) corners; the 'random'
+    initialiser mixes binning factors 1..3 in one call (binned units take the in-kernel slow path)."""
+    vs = (96, 100, 128)
+    vol = seeded_volume(vs, dt, 12)
+    np.random.seed(5)
+    p = Patches(vs, "random-fixed-width", patch_size=(32,) * 3, n_points=301)
+    assert np.any(p.points % 2 == 1)
+    np.testing.assert_array_equal(_bits(p.extract(vol, (32,) * 3)), _bits(S.extract(vol, p.points, p.widths, (32,) * 3)))
+    np.random.seed(6)
+    q = Patches(vs, "random", min_patch_size=(16,) * 3, max_stride=4, n_points=97)
+    assert len(np.unique(q.widths[:, 0])) > 1
+    np.testing.assert_array_equal(_bits(q.extract(vol, (16,) * 3)), _bits(S.extract(vol, q.points, q.widths, (16,) * 3)))
+    # non-cubic patches, several z chunks per patch
+    r = Patches(vs, "data", points=[[1, 2, 3], [40, 30, 61], [0, 0, 0]], widths=[[48, 40, 64]] * 3)
+    np.testing.assert_array_equal(_bits(r.extract(vol, (48, 40, 64))), _bits(S.extract(vol, r.points, r.widths, (48, 40, 64))))
+    # disjoint scatter at unaligned corners (explicit points, so the lattice test of the host code
+    # fails and the ordered path is used) and on the lattice (TMA box stores)
+    g = Grid(vs[:1] + (96, 128), width=32)
+    sub = seeded_volume((len(g), 32, 32, 32), dt, 13)
+    out = seeded_volume(vs[:1] + (96, 128), dt, 14)
+    exp = out.copy()
+    g.fill_patches_in_volume(sub, out)
+    S.fill_patches_in_volume(sub, g.points, np.full((len(g), 3), 32), exp)
+    np.testing.assert_array_equal(_bits(out), _bits(exp))
 
 
 @pytest.mark.parametrize("dt", [np.uint8, np.float16, np.float32])

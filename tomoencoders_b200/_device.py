@@ -69,7 +69,25 @@ def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
+_POINTS_CACHE = {}
+_POINTS_CACHE_MAX_ROWS = 65536
+_POINTS_CACHE_ENTRIES = 16
+
+
 def points_to_device(points):
-    """(n,3) uint32 coordinates -> int32-typed CUDA tensor holding the same bits."""
+    """(n,3) uint32 coordinates -> int32-typed CUDA tensor holding the same bits.
+
+    Small tables (Grid tilings are re-used call after call) are cached on the device, keyed by
+    their contents, so that repeated extract / fill calls do not pay a synchronous upload."""
     p = np.ascontiguousarray(np.asarray(points), dtype=np.uint32)
-    return torch.from_numpy(p.view(np.int32)).to(device())
+    dev = device()
+    if len(p) > _POINTS_CACHE_MAX_ROWS:
+        return torch.from_numpy(p.view(np.int32)).to(dev)
+    key = (dev.index, p.shape, p.tobytes())
+    t = _POINTS_CACHE.get(key)
+    if t is None:
+        if len(_POINTS_CACHE) >= _POINTS_CACHE_ENTRIES:
+            _POINTS_CACHE.pop(next(iter(_POINTS_CACHE)))
+        t = torch.from_numpy(p.view(np.int32)).to(dev)
+        _POINTS_CACHE[key] = t
+    return t

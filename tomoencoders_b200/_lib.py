@@ -22,6 +22,7 @@ NVCC_FLAGS = [
 
 TE_U8, TE_U16, TE_F16, TE_F32, TE_BF16 = 0, 1, 2, 3, 4
 TE_MODE_BF16, TE_MODE_FP16, TE_MODE_FP32_CHECK = 0, 1, 2
+TE_HINT_ALIGNED = 1
 MODES = {"bf16": TE_MODE_BF16, "fp16": TE_MODE_FP16, "fp32": TE_MODE_FP32_CHECK,
          "fp32check": TE_MODE_FP32_CHECK}
 
@@ -90,12 +91,12 @@ _SIGNATURES = {
     "te_last_error": (ctypes.c_char_p, []),
     "te_launch_count": (_I64, []),
     "te_gather": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_I64), _P, _P, _I64,
-                                 ctypes.POINTER(_I32), _P, _P]),
+                                 ctypes.POINTER(_I32), _P, ctypes.c_int, _P]),
     "te_gather_norm": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_I64), _P, _P, _I64,
                                       ctypes.POINTER(_I32), ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                       ctypes.c_float, _P, ctypes.c_int, _P]),
     "te_scatter": (ctypes.c_int, [_P, ctypes.c_int, _P, _I64, ctypes.POINTER(_I32), _P,
-                                  ctypes.POINTER(_I64), _P, _P]),
+                                  ctypes.POINTER(_I64), _P, ctypes.c_int, _P]),
     "te_minmax_strided": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_I64), ctypes.c_int, _P, _P, _P]),
     "te_net_weight_count": (_I64, [ctypes.POINTER(NetDesc)]),
     "te_net_create": (ctypes.c_int, [ctypes.POINTER(NetDesc), ctypes.POINTER(_P)]),

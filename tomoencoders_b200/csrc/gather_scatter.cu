@@ -12,7 +12,10 @@
 // contiguous side moves with 128-bit accesses; the volume side, whose alignment depends on the
 // corner coordinate, is read with aligned 32-bit words and re-aligned with funnel shifts (or with a
 // single 128-bit access when the corner happens to be aligned, which is always the case for Grid tiles).
+#include "gather_tma.cuh"
 #include "te_common.cuh"
+
+#include <cstdlib>
 
 namespace te {
 
@@ -26,7 +29,20 @@ struct GatherParams {
   int pz, py, px;           // patch extents (elements)
   int chunks_per_row;       // px * ES / 16
   long long total_chunks;
+  int ppu;                  // z planes per work unit of a block (divides pz; sized for >= 1024 items)
 };
+
+// Work decomposition shared by the chunked kernels: a block takes `ppu` consecutive z planes of one
+// patch (>= 1024 16-byte items when the patch is large enough), so that the per-unit index
+// arithmetic (64-bit, coordinates from global memory) is amortised and every thread has several
+// independent items; everything inside a unit is 32-bit.
+static int planes_per_unit(int pz, int items_per_plane) {
+  int ppu = (1024 + items_per_plane - 1) / items_per_plane;
+  if (ppu > pz) ppu = pz;
+  if (ppu < 1) ppu = 1;
+  while (pz % ppu) --ppu;
+  return ppu;
+}
 
 __device__ __forceinline__ uint4 ldg_nc_u4(const void* p) {
   uint4 v;
@@ -57,44 +73,59 @@ __device__ __forceinline__ uint4 load16_unaligned(const uint8_t* src) {
 
 template <int ES>
 __global__ void __launch_bounds__(256) gather_chunks_kernel(GatherParams p) {
-  // work unit of a block = one z plane of one patch (py rows); the per-unit index arithmetic is
-  // 64-bit, everything inside a unit is 32-bit
-  const long long units = p.n * p.pz;
+  const int upp = p.pz / p.ppu;                              // units per patch
+  const long long units = p.n * upp;
   const int chunks_per_plane = p.py * p.chunks_per_row;
+  const int chunks_per_unit = p.ppu * chunks_per_plane;
   for (long long u = blockIdx.x; u < units; u += gridDim.x) {
-    const long long i = u / p.pz;
-    const int iz = static_cast<int>(u - i * p.pz);
+    const long long i = u / upp;
+    const int iz0 = static_cast<int>(u - i * upp) * p.ppu;
     const uint32_t z0 = __ldg(p.points + 3 * i), y0 = __ldg(p.points + 3 * i + 1),
                    x0 = __ldg(p.points + 3 * i + 2);
     const uint32_t b = __ldg(p.widths + 3 * i) / static_cast<uint32_t>(p.pz);
-    const long long plane0 = ((static_cast<long long>(z0) + static_cast<long long>(iz) * b) * p.Y + y0) * p.X + x0;
-    const long long row_pitch = static_cast<long long>(b) * p.X;
-    const long long cbase = u * chunks_per_plane;
-   for (int cc = threadIdx.x; cc < chunks_per_plane; cc += blockDim.x) {
-    const int iy = cc / p.chunks_per_row, cx = cc - iy * p.chunks_per_row;
-    const long long src_row = plane0 + iy * row_pitch;
-    const long long c = cbase + cc;
-    uint4 v;
+    const uint8_t* src0 = p.vol + (((static_cast<long long>(z0) + static_cast<long long>(iz0) * b) * p.Y + y0) * p.X + x0) * ES;
+    const long long row_pitch = static_cast<long long>(b) * p.X * ES;          // bytes between sampled rows
+    const long long plane_pitch = static_cast<long long>(b) * p.Y * p.X * ES;  // bytes between sampled planes
+    uint8_t* dst0 = p.out + u * static_cast<long long>(chunks_per_unit) * 16;
     if (b == 1) {
-      v = load16_unaligned(p.vol + src_row * ES + static_cast<long long>(cx) * 16);
+      // four independent 16-byte loads in flight per thread before the first store
+      for (int c0 = threadIdx.x; c0 < chunks_per_unit; c0 += 4 * 256) {
+        uint4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int cc = c0 + k * 256;
+          if (cc < chunks_per_unit) {
+            const int pl = cc / chunks_per_plane, r = cc - pl * chunks_per_plane;
+            const int iy = r / p.chunks_per_row, cx = r - iy * p.chunks_per_row;
+            v[k] = load16_unaligned(src0 + pl * plane_pitch + iy * row_pitch + cx * 16);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int cc = c0 + k * 256;
+          if (cc < chunks_per_unit) stg_cs_u4(dst0 + static_cast<long long>(cc) * 16, v[k]);
+        }
+      }
     } else {
       // decimation (not averaging): element xi of the patch row comes from x0 + xi * b
       constexpr int EPC = 16 / ES;
-      uint32_t w[4] = {0, 0, 0, 0};
+      for (int cc = threadIdx.x; cc < chunks_per_unit; cc += 256) {
+        const int pl = cc / chunks_per_plane, r = cc - pl * chunks_per_plane;
+        const int iy = r / p.chunks_per_row, cx = r - iy * p.chunks_per_row;
+        const uint8_t* row = src0 + pl * plane_pitch + iy * row_pitch;
+        uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
-      for (int e = 0; e < EPC; ++e) {
-        const long long xi = static_cast<long long>(cx) * EPC + e;
-        const uint8_t* s = p.vol + (src_row + xi * b) * ES;
-        uint32_t val;
-        if (ES == 1) val = *s;
-        else if (ES == 2) val = *reinterpret_cast<const uint16_t*>(s);
-        else val = *reinterpret_cast<const uint32_t*>(s);
-        w[(e * ES) / 4] |= val << (((e * ES) % 4) * 8);
+        for (int e = 0; e < EPC; ++e) {
+          const uint8_t* sp = row + static_cast<long long>(cx * EPC + e) * b * ES;
+          uint32_t val;
+          if (ES == 1) val = *sp;
+          else if (ES == 2) val = *reinterpret_cast<const uint16_t*>(sp);
+          else val = *reinterpret_cast<const uint32_t*>(sp);
+          w[(e * ES) / 4] |= val << (((e * ES) % 4) * 8);
+        }
+        stg_cs_u4(dst0 + static_cast<long long>(cc) * 16, make_uint4(w[0], w[1], w[2], w[3]));
       }
-      v = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    stg_cs_u4(p.out + c * 16, v);
-   }
   }
 }
 
@@ -132,52 +163,105 @@ struct NormParams {
   float lo, hi, inv;   // inv = 1 / (hi - lo + 1e-12) evaluated in fp32 as a division below
 };
 
+template <typename TIn>
+__device__ __forceinline__ void load8(const TIn* src, uint32_t b, float (&f)[8]) {
+  if (b == 1) {
+    // unbinned: 8 consecutive elements = 8 * sizeof(TIn) contiguous bytes at an arbitrary alignment
+    const uint8_t* s8 = reinterpret_cast<const uint8_t*>(src);
+    if constexpr (sizeof(TIn) == 1) {
+      const uintptr_t a = reinterpret_cast<uintptr_t>(s8);
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+      const uint32_t sh = (static_cast<uint32_t>(a) & 3u) * 8u;
+      uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);
+      if (sh) { const uint32_t w2 = __ldg(w + 2); w0 = __funnelshift_r(w0, w1, sh); w1 = __funnelshift_r(w1, w2, sh); }
+      const uint32_t ww[2] = {w0, w1};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = static_cast<float>((ww[e >> 2] >> ((e & 3) * 8)) & 0xffu);
+    } else if constexpr (sizeof(TIn) == 2) {
+      const uint4 raw = load16_unaligned(s8);
+      const uint32_t ww[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const uint16_t h = static_cast<uint16_t>(ww[e >> 1] >> ((e & 1) * 16));
+        if constexpr (std::is_same<TIn, __half>::value) f[e] = __half2float(__ushort_as_half(h));
+        else f[e] = static_cast<float>(h);
+      }
+    } else {
+      const uint4 r0 = load16_unaligned(s8), r1 = load16_unaligned(s8 + 16);
+      f[0] = __uint_as_float(r0.x); f[1] = __uint_as_float(r0.y); f[2] = __uint_as_float(r0.z); f[3] = __uint_as_float(r0.w);
+      f[4] = __uint_as_float(r1.x); f[5] = __uint_as_float(r1.y); f[6] = __uint_as_float(r1.z); f[7] = __uint_as_float(r1.w);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = to_f32<TIn>(src[static_cast<long long>(e) * b]);
+  }
+}
+
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256) gather_norm_kernel(GatherParams p, NormParams q) {
-  // one thread per group of 8 consecutive output elements (px % 8 == 0 checked on the host)
+  // item = 8 consecutive output elements (px % 8 == 0 checked on the host); unit = ppu planes of a patch
+  const int upp = p.pz / p.ppu;
+  const long long units = p.n * upp;
   const int groups_per_row = p.px / 8;
-  const long long total = p.n * p.pz * p.py * groups_per_row;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  const TIn* vol = reinterpret_cast<const TIn*>(p.vol);
+  const int items_per_plane = p.py * groups_per_row;
+  const int items_per_unit = p.ppu * items_per_plane;
   const float denom = q.hi - q.lo + 1e-12f;
-  for (long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; g < total; g += stride) {
-    const int gx = static_cast<int>(g % groups_per_row);
-    long long t = g / groups_per_row;
-    const int iy = static_cast<int>(t % p.py);
-    t /= p.py;
-    const int iz = static_cast<int>(t % p.pz);
-    const long long i = t / p.pz;
+  const float inv = 1.0f / denom;
+  for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+    const long long i = u / upp;
+    const int iz0 = static_cast<int>(u - i * upp) * p.ppu;
+    const uint32_t z0 = __ldg(p.points + 3 * i), y0 = __ldg(p.points + 3 * i + 1),
+                   x0 = __ldg(p.points + 3 * i + 2);
     const uint32_t b = __ldg(p.widths + 3 * i) / static_cast<uint32_t>(p.pz);
-    const long long src = ((static_cast<long long>(__ldg(p.points + 3 * i)) + static_cast<long long>(iz) * b) * p.Y +
-                           (static_cast<long long>(__ldg(p.points + 3 * i + 1)) + static_cast<long long>(iy) * b)) * p.X +
-                          __ldg(p.points + 3 * i + 2) + static_cast<long long>(gx) * 8 * b;
-    float f[8];
+    const TIn* src0 = reinterpret_cast<const TIn*>(p.vol) +
+                      ((static_cast<long long>(z0) + static_cast<long long>(iz0) * b) * p.Y + y0) * p.X + x0;
+    const long long row_pitch = static_cast<long long>(b) * p.X, plane_pitch = static_cast<long long>(b) * p.Y * p.X;
+    TOut* dst0 = reinterpret_cast<TOut*>(p.out) + u * static_cast<long long>(items_per_unit) * 8;
+    for (int it0 = threadIdx.x; it0 < items_per_unit; it0 += 2 * 256) {
+      float f[2][8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float v = to_f32<TIn>(vol[src + static_cast<long long>(e) * b]);
-      if (q.rescale) {
-        if (q.do_clip) v = fminf(fmaxf(v, q.lo), q.hi);
-        v = (v - q.lo) / denom;
-      }
-      f[e] = v;
-    }
-    TOut* o = reinterpret_cast<TOut*>(p.out) + g * 8;
-    if constexpr (sizeof(TOut) == 4) {
-      reinterpret_cast<float4*>(o)[0] = make_float4(f[0], f[1], f[2], f[3]);
-      reinterpret_cast<float4*>(o)[1] = make_float4(f[4], f[5], f[6], f[7]);
-    } else {
-      uint32_t w[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if constexpr (std::is_same<TOut, __nv_bfloat16>::value) {
-          __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-          w[e] = *reinterpret_cast<uint32_t*>(&h);
-        } else {
-          __half2 h = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
-          w[e] = *reinterpret_cast<uint32_t*>(&h);
+      for (int k = 0; k < 2; ++k) {
+        const int it = it0 + k * 256;
+        if (it < items_per_unit) {
+          const int pl = it / items_per_plane, r = it - pl * items_per_plane;
+          const int iy = r / groups_per_row, gx = r - iy * groups_per_row;
+          load8<TIn>(src0 + pl * plane_pitch + iy * row_pitch + static_cast<long long>(gx) * 8 * b, b, f[k]);
         }
       }
-      *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int it = it0 + k * 256;
+        if (it >= items_per_unit) continue;
+        if (q.rescale) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float v = f[k][e];
+            if (q.do_clip) v = fminf(fmaxf(v, q.lo), q.hi);
+            // fp32 output (check mode): IEEE division like the reference; 16-bit outputs: the
+            // quotient is rounded to 8 / 11 significant bits anyway, so multiply by the reciprocal
+            if constexpr (sizeof(TOut) == 4) f[k][e] = (v - q.lo) / denom;
+            else f[k][e] = (v - q.lo) * inv;
+          }
+        }
+        TOut* o = dst0 + static_cast<long long>(it) * 8;
+        if constexpr (sizeof(TOut) == 4) {
+          reinterpret_cast<float4*>(o)[0] = make_float4(f[k][0], f[k][1], f[k][2], f[k][3]);
+          reinterpret_cast<float4*>(o)[1] = make_float4(f[k][4], f[k][5], f[k][6], f[k][7]);
+        } else {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if constexpr (std::is_same<TOut, __nv_bfloat16>::value) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(f[k][2 * e], f[k][2 * e + 1]);
+              w[e] = *reinterpret_cast<uint32_t*>(&h);
+            } else {
+              __half2 h = __floats2half2_rn(f[k][2 * e], f[k][2 * e + 1]);
+              w[e] = *reinterpret_cast<uint32_t*>(&h);
+            }
+          }
+          *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
     }
   }
 }
@@ -193,43 +277,60 @@ struct ScatterParams {
   int wz, wy, wx;
   int chunks_per_row;
   long long total_chunks;
+  int ppu;
 };
 
 template <int ES>
-__global__ void __launch_bounds__(256) scatter_chunks_kernel(ScatterParams p) {
-  // work unit of a block = one z plane of one patch; 32-bit index arithmetic inside a unit
-  const long long units = p.n * p.wz;
-  const int chunks_per_plane = p.wy * p.chunks_per_row;
-  for (long long u = blockIdx.x; u < units; u += gridDim.x) {
-   const long long i = u / p.wz;
-   const int iz = static_cast<int>(u - i * p.wz);
-   const long long plane0 = ((static_cast<long long>(__ldg(p.points + 3 * i)) + iz) * p.Y +
-                             __ldg(p.points + 3 * i + 1)) * p.X + __ldg(p.points + 3 * i + 2);
-   const long long cbase = u * chunks_per_plane;
-   for (int cc = threadIdx.x; cc < chunks_per_plane; cc += blockDim.x) {
-    const int iy = cc / p.chunks_per_row, cx = cc - iy * p.chunks_per_row;
-    const long long dst_row = plane0 + static_cast<long long>(iy) * p.X;
-    const long long c = cbase + cc;
-    const uint4 v = ldg_nc_u4(p.sub + c * 16);
-    uint8_t* d = p.vol + dst_row * ES + static_cast<long long>(cx) * 16;
-    const uintptr_t a = reinterpret_cast<uintptr_t>(d);
-    if ((a & 15) == 0) {
-      *reinterpret_cast<uint4*>(d) = v;
-    } else if ((a & 3) == 0) {
-      uint32_t* d4 = reinterpret_cast<uint32_t*>(d);
-      d4[0] = v.x; d4[1] = v.y; d4[2] = v.z; d4[3] = v.w;
+__device__ __forceinline__ void store16_unaligned(uint8_t* d, const uint4& v) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(d);
+  if ((a & 15) == 0) {
+    *reinterpret_cast<uint4*>(d) = v;
+  } else if ((a & 3) == 0) {
+    uint32_t* d4 = reinterpret_cast<uint32_t*>(d);
+    d4[0] = v.x; d4[1] = v.y; d4[2] = v.z; d4[3] = v.w;
+  } else {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    if (ES == 2 && (a & 1) == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) reinterpret_cast<uint16_t*>(d)[e] = static_cast<uint16_t>(w[e / 2] >> ((e & 1) * 16));
     } else {
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-      if (ES == 2 && (a & 1) == 0) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-          reinterpret_cast<uint16_t*>(d)[e] = static_cast<uint16_t>(w[e / 2] >> ((e & 1) * 16));
-      } else {
+      for (int e = 0; e < 16; ++e) d[e] = static_cast<uint8_t>(w[e / 4] >> ((e & 3) * 8));
+    }
+  }
+}
+
+template <int ES>
+__global__ void __launch_bounds__(256) scatter_chunks_kernel(ScatterParams p) {
+  // work unit of a block = ppu z planes of one patch; 32-bit index arithmetic inside a unit
+  const int upp = p.wz / p.ppu;
+  const long long units = p.n * upp;
+  const int chunks_per_plane = p.wy * p.chunks_per_row;
+  const int chunks_per_unit = p.ppu * chunks_per_plane;
+  const long long row_pitch = p.X * ES, plane_pitch = p.Y * p.X * ES;
+  for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+    const long long i = u / upp;
+    const int iz0 = static_cast<int>(u - i * upp) * p.ppu;
+    uint8_t* dst0 = p.vol + (((static_cast<long long>(__ldg(p.points + 3 * i)) + iz0) * p.Y + __ldg(p.points + 3 * i + 1)) * p.X +
+                             __ldg(p.points + 3 * i + 2)) * ES;
+    const uint8_t* src0 = p.sub + u * static_cast<long long>(chunks_per_unit) * 16;
+    for (int c0 = threadIdx.x; c0 < chunks_per_unit; c0 += 4 * 256) {
+      uint4 v[4];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) d[e] = static_cast<uint8_t>(w[e / 4] >> ((e & 3) * 8));
+      for (int k = 0; k < 4; ++k) {
+        const int cc = c0 + k * 256;
+        if (cc < chunks_per_unit) v[k] = ldg_nc_u4(src0 + static_cast<long long>(cc) * 16);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int cc = c0 + k * 256;
+        if (cc < chunks_per_unit) {
+          const int pl = cc / chunks_per_plane, r = cc - pl * chunks_per_plane;
+          const int iy = r / p.chunks_per_row, cx = r - iy * p.chunks_per_row;
+          store16_unaligned<ES>(dst0 + pl * plane_pitch + iy * row_pitch + cx * 16, v[k]);
+        }
       }
     }
-   }
   }
 }
 
@@ -301,6 +402,19 @@ __global__ void minmax_final_kernel(const float* partial, int nblocks, float* ou
   if (threadIdx.x == 0) { out2[0] = lo; out2[1] = hi; }
 }
 
+// TOMOENC_NO_TMA_GATHER=1 forces the SIMT kernels (tests exercise both paths).
+static bool tma_enabled() {
+  const char* e = getenv("TOMOENC_NO_TMA_GATHER");
+  return !(e && e[0] == '1');
+}
+
+// TOMOENC_FORCE_TMA_GATHER=1 takes the TMA kernels whenever they apply, hint or not (tests: covers
+// their per-unit unaligned / binned paths).
+static bool tma_forced() {
+  const char* e = getenv("TOMOENC_FORCE_TMA_GATHER");
+  return e && e[0] == '1';
+}
+
 static int grid_for(long long work_items, int threads, int waves = 8) {
   long long blocks = (work_items + threads - 1) / threads;
   const long long cap = static_cast<long long>(kNumSMs) * waves;
@@ -314,7 +428,8 @@ static int grid_for(long long work_items, int threads, int waves = 8) {
 using namespace te;
 
 extern "C" int te_gather(const void* vol, int elem_size, const int64_t vol_shape[3], const uint32_t* points,
-                         const uint32_t* widths, int64_t n, const int32_t patch[3], void* out, void* stream) {
+                         const uint32_t* widths, int64_t n, const int32_t patch[3], void* out, int flags,
+                         void* stream) {
   TE_CHECK_ARG(elem_size == 1 || elem_size == 2 || elem_size == 4, "te_gather: elem_size must be 1, 2 or 4");
   TE_CHECK_ARG(n >= 0, "te_gather: n < 0");
   if (n == 0) return TE_OK;
@@ -330,11 +445,20 @@ extern "C" int te_gather(const void* vol, int elem_size, const int64_t vol_shape
   p.X = vol_shape[2];
   p.pz = patch[0]; p.py = patch[1]; p.px = patch[2];
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (tma_enabled() && (((flags & TE_HINT_ALIGNED) && elem_size >= 2) || tma_forced())) {
+    cudaError_t e = cudaSuccess;
+    if (gather_tma(vol, elem_size, vol_shape, points, widths, n, patch, out, st, &e)) {
+      count_launch();
+      if (e != cudaSuccess) { set_error("te_gather: TMA kernel launch failed: %s", cudaGetErrorString(e)); return TE_ERR_CUDA; }
+      return TE_OK;
+    }
+  }
   const long long row_bytes = static_cast<long long>(p.px) * elem_size;
   if (row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
     p.chunks_per_row = static_cast<int>(row_bytes / 16);
     p.total_chunks = n * p.pz * p.py * p.chunks_per_row;
-    const int grid = grid_for(p.total_chunks, 256, 16);
+    p.ppu = planes_per_unit(p.pz, p.py * p.chunks_per_row);
+    const int grid = grid_for(n * (p.pz / p.ppu), 1, 8);
     if (elem_size == 1) gather_chunks_kernel<1><<<grid, 256, 0, st>>>(p);
     else if (elem_size == 2) gather_chunks_kernel<2><<<grid, 256, 0, st>>>(p);
     else gather_chunks_kernel<4><<<grid, 256, 0, st>>>(p);
@@ -352,11 +476,12 @@ extern "C" int te_gather(const void* vol, int elem_size, const int64_t vol_shape
 
 template <typename TIn>
 static int launch_gather_norm(const GatherParams& p, const NormParams& q, int out_dtype, cudaStream_t st) {
-  const long long total = p.n * p.pz * p.py * (p.px / 8);
-  const int grid = grid_for(total, 256, 16);
-  if (out_dtype == TE_BF16) gather_norm_kernel<TIn, __nv_bfloat16><<<grid, 256, 0, st>>>(p, q);
-  else if (out_dtype == TE_F16) gather_norm_kernel<TIn, __half><<<grid, 256, 0, st>>>(p, q);
-  else gather_norm_kernel<TIn, float><<<grid, 256, 0, st>>>(p, q);
+  GatherParams pp = p;
+  pp.ppu = planes_per_unit(p.pz, p.py * (p.px / 8));
+  const int grid = grid_for(p.n * (p.pz / pp.ppu), 1, 8);
+  if (out_dtype == TE_BF16) gather_norm_kernel<TIn, __nv_bfloat16><<<grid, 256, 0, st>>>(pp, q);
+  else if (out_dtype == TE_F16) gather_norm_kernel<TIn, __half><<<grid, 256, 0, st>>>(pp, q);
+  else gather_norm_kernel<TIn, float><<<grid, 256, 0, st>>>(pp, q);
   TE_LAUNCH_CHECK();
   return TE_OK;
 }
@@ -384,6 +509,14 @@ extern "C" int te_gather_norm(const void* vol, int vol_dtype, const int64_t vol_
   p.total_chunks = 0;
   NormParams q{rescale, do_clip, lo, hi, 0.f};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (tma_enabled() && tma_forced()) {   // measured slower than the SIMT kernel: opt-in only
+    cudaError_t e = cudaSuccess;
+    if (gather_norm_tma(vol, vol_dtype, vol_shape, points, widths, n, patch, rescale, do_clip, lo, hi, out, out_dtype, st, &e)) {
+      count_launch();
+      if (e != cudaSuccess) { set_error("te_gather_norm: TMA kernel launch failed: %s", cudaGetErrorString(e)); return TE_ERR_CUDA; }
+      return TE_OK;
+    }
+  }
   switch (vol_dtype) {
     case TE_U8: return launch_gather_norm<uint8_t>(p, q, out_dtype, st);
     case TE_U16: return launch_gather_norm<uint16_t>(p, q, out_dtype, st);
@@ -395,7 +528,7 @@ extern "C" int te_gather_norm(const void* vol, int vol_dtype, const int64_t vol_
 
 extern "C" int te_scatter(const void* sub_vols, int elem_size, const uint32_t* points, int64_t n,
                           const int32_t width[3], void* vol_out, const int64_t vol_shape[3], uint32_t* owner,
-                          void* stream) {
+                          int flags, void* stream) {
   TE_CHECK_ARG(elem_size == 1 || elem_size == 2 || elem_size == 4, "te_scatter: elem_size must be 1, 2 or 4");
   TE_CHECK_ARG(n >= 0, "te_scatter: n < 0");
   if (n == 0) return TE_OK;
@@ -433,12 +566,21 @@ extern "C" int te_scatter(const void* sub_vols, int elem_size, const uint32_t* p
     TE_LAUNCH_CHECK();
     return TE_OK;
   }
+  if (tma_enabled() && (((flags & TE_HINT_ALIGNED) && elem_size >= 2) || tma_forced())) {
+    cudaError_t e = cudaSuccess;
+    if (scatter_tma(sub_vols, elem_size, points, n, width, vol_out, vol_shape, st, &e)) {
+      count_launch();
+      if (e != cudaSuccess) { set_error("te_scatter: TMA kernel launch failed: %s", cudaGetErrorString(e)); return TE_ERR_CUDA; }
+      return TE_OK;
+    }
+  }
   const long long row_bytes = static_cast<long long>(p.wx) * elem_size;
   TE_CHECK_ARG(row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(sub_vols) & 15) == 0,
                "te_scatter: patch rows must be a multiple of 16 bytes (pass an owner buffer otherwise)");
   p.chunks_per_row = static_cast<int>(row_bytes / 16);
   p.total_chunks = n * p.wz * p.wy * p.chunks_per_row;
-  const int grid = grid_for(p.total_chunks, 256, 16);
+  p.ppu = planes_per_unit(p.wz, p.wy * p.chunks_per_row);
+  const int grid = grid_for(n * (p.wz / p.ppu), 1, 8);
   if (elem_size == 1) scatter_chunks_kernel<1><<<grid, 256, 0, st>>>(p);
   else if (elem_size == 2) scatter_chunks_kernel<2><<<grid, 256, 0, st>>>(p);
   else scatter_chunks_kernel<4><<<grid, 256, 0, st>>>(p);

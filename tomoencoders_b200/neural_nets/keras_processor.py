@@ -348,6 +348,7 @@ class Vox2VoxProcessor_fCNN(GenericKerasProcessor):
             # overlapping patches: stitch once at the end through the ordered path
             all_out = torch.empty((n,) + w3, dtype=o_dtype, device=dev)
         L = _lib.lib()
+        hint = _table._aligned_hint(np.asarray(patches.points), None, w3, t_out.element_size()) if disjoint else 0
         for a in range(0, n, chunk_size):
             b = min(a + chunk_size, n)
             xa = gather_normalized(t_vol, vs, d_pts[a:b], d_wds[a:b], b - a, w3, min_max, self._clip_input, net)
@@ -355,7 +356,7 @@ class Vox2VoxProcessor_fCNN(GenericKerasProcessor):
             net.unet_forward_into(xa, y)
             if disjoint:
                 _lib.check(L.te_scatter(y.data_ptr(), y.element_size(), d_pts[a:b].data_ptr(), b - a, _lib.i32x3(w3),
-                                        t_out.data_ptr(), _lib.i64x3(vs), None, _device.stream_ptr()), "te_scatter")
+                                        t_out.data_ptr(), _lib.i64x3(vs), None, hint, _device.stream_ptr()), "te_scatter")
         if not disjoint:
             _table.scatter(all_out, t_out, vs, patches.points, widths)
         if out is None:

@@ -47,15 +47,59 @@ def gather(vol, vol_shape, points, widths, patch_size):
         d_pts = _device.points_to_device(pad_cols(points, 0))
         d_wds = _device.points_to_device(pad_cols(widths, 1))
         L = _lib.lib()
+        hint = _aligned_hint(pad_cols(points, 0), pad_cols(widths, 1), patch3, es)
         _lib.check(L.te_gather(t_vol.data_ptr(), es, _lib.i64x3(vs3), d_pts.data_ptr(), d_wds.data_ptr(), n,
-                               _lib.i32x3(patch3), out.data_ptr(), _device.stream_ptr()), "te_gather")
+                               _lib.i32x3(patch3), out.data_ptr(), hint, _device.stream_ptr()), "te_gather")
     out = out.reshape((n,) + tuple(int(p) for p in patch_size))
     return _device.to_host_like(out, vol)
 
 
+_DISJOINT_CACHE = {}
+_HINT_CACHE = {}
+
+
+def _aligned_hint(points3, widths3, patch3, es):
+    """TE_HINT_ALIGNED when every patch is unbinned and starts on a 16-byte boundary in x (every
+    Grid / regular-grid tiling whose width * itemsize is a multiple of 16): libtomoenc may then use
+    its TMA-staged kernels (include/tomoenc.h).  Memoised on the table contents for small tables."""
+    pts = np.ascontiguousarray(points3)
+    wds = None if widths3 is None else np.ascontiguousarray(widths3)
+    if len(pts) > 65536:
+        return _aligned_hint_uncached(pts, wds, patch3, es)
+    key = (pts.shape, pts.tobytes(), None if wds is None else wds.tobytes(), tuple(patch3), es)
+    r = _HINT_CACHE.get(key)
+    if r is None:
+        if len(_HINT_CACHE) >= 16:
+            _HINT_CACHE.pop(next(iter(_HINT_CACHE)))
+        r = _HINT_CACHE[key] = _aligned_hint_uncached(pts, wds, patch3, es)
+    return r
+
+
+def _aligned_hint_uncached(pts, wds, patch3, es):
+    if wds is not None and np.any(np.asarray(wds, dtype=np.int64) != np.asarray(patch3, dtype=np.int64)[None, :]):
+        return 0
+    if np.any((pts[:, 2].astype(np.int64) * es) % 16):
+        return 0
+    return _lib.TE_HINT_ALIGNED
+
+
 def _disjoint(points, width, vs3):
     """True when the patches are provably pairwise disjoint: equal widths, corners on the width
-    lattice, no duplicates (always the case for Grid / regular-grid)."""
+    lattice, no duplicates (always the case for Grid / regular-grid).  Memoised on the table
+    contents for small tables (the same tiling is stitched call after call)."""
+    pts = np.ascontiguousarray(points)
+    if len(pts) > 65536:
+        return _disjoint_uncached(pts, width, vs3)
+    key = (pts.shape, str(pts.dtype), pts.tobytes(), tuple(int(w) for w in width), tuple(int(v) for v in vs3))
+    r = _DISJOINT_CACHE.get(key)
+    if r is None:
+        if len(_DISJOINT_CACHE) >= 16:
+            _DISJOINT_CACHE.pop(next(iter(_DISJOINT_CACHE)))
+        r = _DISJOINT_CACHE[key] = _disjoint_uncached(pts, width, vs3)
+    return r
+
+
+def _disjoint_uncached(points, width, vs3):
     p = np.asarray(points, dtype=np.int64)
     w = np.asarray(width, dtype=np.int64)
     if np.any(p % w[None, :]):
@@ -113,8 +157,9 @@ def scatter(sub_vols, vol_out, vol_shape, points, widths):
             if owner is None:
                 owner = torch.empty(vs3, dtype=torch.int32, device=t_out.device)
             owner_ptr = owner.data_ptr()
+        hint = 0 if owner_ptr is not None else _aligned_hint(pts, None, w3, es)
         _lib.check(L.te_scatter(t_sub.data_ptr(), es, d_pts.data_ptr(), b - a, _lib.i32x3(w3), t_out.data_ptr(),
-                                _lib.i64x3(vs3), owner_ptr, _device.stream_ptr()), "te_scatter")
+                                _lib.i64x3(vs3), owner_ptr, hint, _device.stream_ptr()), "te_scatter")
     if host_out:
         res = t_out.cpu()
         if isinstance(vol_out, torch.Tensor):

@@ -38,6 +38,8 @@ def timed(fn, reps=20, flush=None):
 
 
 def case(name, vshape, dtype, patch, pts, flush):
+    es_ = torch.empty((), dtype=dtype).element_size()
+    hint = _lib.TE_HINT_ALIGNED if not np.any((np.asarray(pts)[:, 2] * es_) % 16) else 0
     L = _lib.lib()
     dev = torch.device("cuda")
     n = len(pts)
@@ -51,8 +53,9 @@ def case(name, vshape, dtype, patch, pts, flush):
 
     def g():
         _lib.check(L.te_gather(vol.data_ptr(), es, _lib.i64x3(vshape), d_pts.data_ptr(), d_wds.data_ptr(), n,
-                               _lib.i32x3((patch,) * 3), out.data_ptr(), st))
+                               _lib.i32x3((patch,) * 3), out.data_ptr(), hint, st))
     ms = timed(g, flush=flush)
+    name = name + (" [tma]" if hint and es >= 2 else " [simt]")
     nv = n * patch ** 3
     alg = nv * es + min(nv, vol.numel()) * es + n * 24
     print("%-44s gather  %8.1f us  %7.1f GB/s  %5.1f%% of measured copy peak" % (name, ms * 1e3, alg / ms / 1e6, 100 * alg / ms / 1e6 / PEAK))
@@ -83,10 +86,11 @@ def scatter_case(name, vshape, dtype, patch, pts, flush):
     vol = torch.zeros(vshape, dtype=dtype, device=dev)
     d_pts = torch.from_numpy(np.ascontiguousarray(pts, dtype=np.uint32).view(np.int32)).to(dev)
     st = _device.stream_ptr()
+    hint = _lib.TE_HINT_ALIGNED if not np.any((np.asarray(pts)[:, 2] * es) % 16) else 0
 
     def s():
         _lib.check(L.te_scatter(sub.data_ptr(), es, d_pts.data_ptr(), n, _lib.i32x3((patch,) * 3), vol.data_ptr(),
-                                _lib.i64x3(vshape), None, st))
+                                _lib.i64x3(vshape), None, hint, st))
     ms = timed(s, flush=flush)
     alg = 2 * n * patch ** 3 * es
     print("%-44s scatter %8.1f us  %7.1f GB/s  %5.1f%% of measured copy peak" % (name, ms * 1e3, alg / ms / 1e6, 100 * alg / ms / 1e6 / PEAK))
