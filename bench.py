@@ -146,7 +146,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from tomoencoders_b200 import Grid, Patches, _lib
+    from tomoencoders_b200 import Grid, Patches, _device, _lib
     from tomoencoders_b200.neural_nets import LatentPCA, SelfSupervisedCAE, SurfaceSegmenter
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -245,23 +245,45 @@ def run_ours(args):
                     "tflops": (k["flops"] / (k["ms"] / 1e3) / 1e12) if k["flops"] else None} for n_, k in by_kernel.items()}
 
     # ------------------------------------------------------------------ gather / stitch bandwidth (HBM roofline of the data-movement kernels)
-    x_tiles = grid.extract(vol)                                    # device in -> device out
-    torch.cuda.synchronize()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record()
-    for _ in range(5):
-        x_tiles = grid.extract(vol)
-    g1.record()
-    torch.cuda.synchronize()
-    gather_gbs = 2 * vol.numel() * 2 / (g0.elapsed_time(g1) / 5 / 1e3) / 1e9
+    # kernel-only: C-ABI calls with device-resident coordinates, CUDA events on the launching stream,
+    # L2 flushed between repetitions; "api" = the same through Grid.extract / fill_patches_in_volume
+    L = _lib.lib()
+    d_pts = _device.points_to_device(grid.points)
+    d_wds = _device.points_to_device(np.full((n_tiles, 3), PATCH))
+    x_tiles = torch.empty((n_tiles,) + (PATCH,) * 3, dtype=vol.dtype, device=dev)
     lab = torch.zeros((n_tiles,) + (PATCH,) * 3, dtype=torch.uint8, device=dev)
-    g0.record()
-    for _ in range(5):
-        grid.fill_patches_in_volume(lab, seg)
-    g1.record()
-    torch.cuda.synchronize()
-    scatter_gbs = 2 * seg.numel() / (g0.elapsed_time(g1) / 5 / 1e3) / 1e9
-    del x_tiles, lab
+    act = torch.empty((n_tiles,) + (PATCH,) * 3, dtype=net.act_dtype, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    st = _device.stream_ptr()
+    p3, vs3 = _lib.i32x3((PATCH,) * 3), _lib.i64x3(VOL)
+
+    def timed_us(fn, reps=10):
+        fn()
+        tot = 0.0
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+        return 1e3 * tot / reps
+
+    t_gather = timed_us(lambda: _lib.check(L.te_gather(vol.data_ptr(), 2, vs3, d_pts.data_ptr(), d_wds.data_ptr(), n_tiles, p3,
+                                                       x_tiles.data_ptr(), _lib.TE_HINT_ALIGNED, st)))
+    t_gnorm = timed_us(lambda: _lib.check(L.te_gather_norm(vol.data_ptr(), _lib.TE_F16, vs3, d_pts.data_ptr(), d_wds.data_ptr(),
+                                                           n_tiles, p3, 1, 1, float(min_max[0]), float(min_max[1]),
+                                                           act.data_ptr(), net.act_te, st)))
+    t_scatter = timed_us(lambda: _lib.check(L.te_scatter(lab.data_ptr(), 1, d_pts.data_ptr(), n_tiles, p3, seg.data_ptr(), vs3,
+                                                         None, _lib.TE_HINT_ALIGNED, st)))
+    t_gather_api = timed_us(lambda: grid.extract(vol))
+    t_scatter_api = timed_us(lambda: grid.fill_patches_in_volume(lab, seg))
+    nvox = vol.numel()
+    gather_gbs = 2 * nvox * 2 / t_gather / 1e3                     # read f16 + write f16
+    gnorm_gbs = (nvox * 2 + nvox * act.element_size()) / t_gnorm / 1e3
+    scatter_gbs = 2 * nvox / t_scatter / 1e3                       # read u8 + write u8
+    del x_tiles, lab, act, flush
 
     # ------------------------------------------------------------------ end to end: host volume -> host mask through the public API
     host_vol = torch.empty(VOL, dtype=torch.float16).pin_memory()
@@ -331,9 +353,14 @@ def run_ours(args):
                                                 "frac": all_tc_flops / (all_tc_ms / 1e3) / 1e12 / tf_peak,
                                                 "share_of_step": all_tc_ms / tot_ms},
             "kernels": kernels,
-            "hbm": {"gather_gbs": gather_gbs, "gather_frac": gather_gbs / hbm_peak, "scatter_gbs": scatter_gbs,
-                    "scatter_frac": scatter_gbs / hbm_peak, "peak": hbm_peak, "unit": "GB/s",
-                    "note": "Grid.extract of the 512^3 fp16 volume (read+write 537 MB) and fill of the uint8 mask (268 MB)"},
+            "hbm": {"gather_gbs": gather_gbs, "gather_frac": gather_gbs / hbm_peak,
+                    "gather_norm_gbs": gnorm_gbs, "gather_norm_frac": gnorm_gbs / hbm_peak,
+                    "scatter_gbs": scatter_gbs, "scatter_frac": scatter_gbs / hbm_peak, "peak": hbm_peak, "unit": "GB/s",
+                    "us": {"gather": t_gather, "gather_norm": t_gnorm, "scatter": t_scatter,
+                           "gather_api": t_gather_api, "scatter_api": t_scatter_api},
+                    "note": "kernel-only (C ABI, CUDA events, L2 flushed): te_gather of the 512^3 fp16 volume into 512 tiles "
+                            "(read+write 537 MB), te_gather_norm (fused clip/rescale, the product path), te_scatter of the "
+                            "uint8 mask (read+write 268 MB); *_api = the same through Grid.extract / fill_patches_in_volume"},
             "encode": {"metric": "64^3 patches/sec encoded + PCA-projected (encoder [16,32,64], latent 128)",
                        "value": enc_value, "unit": "patches/s", "ms_per_step": enc_ms, "patches_per_rank_per_step": ENC_PATCHES,
                        "tflops_effective": enc_value * enc_flops / 1e12,

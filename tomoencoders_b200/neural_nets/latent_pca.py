@@ -12,7 +12,7 @@ retained components is itself a lossy streaming approximation of this (SURVEY.md
 import numpy as np
 import torch
 
-from .. import _device, _lib
+from .. import _device, _lib, sharding
 
 
 class LatentPCA:
@@ -47,15 +47,13 @@ class LatentPCA:
     def finalize(self, distributed=None):
         """All-reduces the moments across ranks (when torch.distributed is initialised) and solves
         the d x d eigenproblem on the GPU.  Every rank ends with identical components."""
-        import torch.distributed as dist
         if self._moments is None:
             raise ValueError("no data: call partial_fit first")
         if distributed is None:
-            distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.process_group) > 1
+            distributed = sharding.world(self.process_group)[1] > 1
         m = self._moments
         if distributed:
-            m = m.clone()
-            dist.all_reduce(m, op=dist.ReduceOp.SUM, group=self.process_group)
+            m = sharding.allreduce_sum_(m.clone(), self.process_group)
         d, k = self._d, self.n_components
         dev = m.device
         self._d_mean = torch.empty(d, dtype=torch.float64, device=dev)
@@ -96,13 +94,8 @@ class LatentPCA:
 
     def transform_all_gather(self, h):
         """Projects this rank's latents and all-gathers the (n_local, k) projections (equal n per rank)."""
-        import torch.distributed as dist
         z = self.transform(_device.to_device(h))
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.process_group) == 1:
-            return z
-        outs = [torch.empty_like(z) for _ in range(dist.get_world_size(self.process_group))]
-        dist.all_gather(outs, z, group=self.process_group)
-        return torch.cat(outs, dim=0)
+        return sharding.allgather_rows(z, self.process_group)
 
 
 def _latent_columns(N):
