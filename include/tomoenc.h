@@ -189,6 +189,63 @@ int te_pca_solve(const double* moments, int32_t d, int32_t k, double* mean, doub
 int te_pca_project(const float* h, int64_t n, int32_t d, const double* mean, const double* components,
                    int32_t k, float* z, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Training operators.  Replace the Keras fit step of
+ * SurfaceSegmenter.train (neural_nets/surface_segmenter.py:43-66; compile with Adam + BinaryCrossentropy
+ * :322-323; BatchNormalization(momentum 0.9, eps 1e-5) in training mode, Unet3D.py:78).  One entry per
+ * operator; the host walks the graph (tomoencoders_b200/neural_nets/_train.py).  Tensors are NDHWC
+ * channel slices described by te_tensor; dtype TE_F32 (check mode) or TE_BF16 / TE_F16; weights,
+ * gradients and reductions are fp32 / fp64 device arrays in Keras layout.
+ */
+typedef struct te_tensor {
+  void* ptr;
+  int32_t dtype;          /* TE_F32 / TE_F16 / TE_BF16 */
+  int32_t ctot, coff, C;  /* channel pitch of the buffer, first channel and channel count of this view */
+  int32_t N, D, H, W;
+} te_tensor;
+
+/* y = Conv3D(3, 'same')(concat(x, x2)) + bias, no activation (BN follows).  w: [27][Cin][Cout].  16-bit
+ * dense inputs with channel counts % 16 run on the tcgen05 kernel; wpack = device scratch of
+ * te_tr_conv3_wpack_bytes(Cin, Cout) bytes (weights are re-packed on the device at every call). */
+int64_t te_tr_conv3_wpack_bytes(int32_t Cin, int32_t Cout);
+int te_tr_conv3(const te_tensor* x, const te_tensor* x2, const float* w, const float* bias, const te_tensor* y,
+                void* wpack, void* stream);
+/* wf[27][Cout][ci_n]: spatially flipped, channel-transposed slice [ci_lo, ci_lo + ci_n) of w[27][Cin][Cout];
+ * te_tr_conv3(dy, NULL, wf, zero_bias, dx, ...) is then the data gradient of the convolution. */
+int te_tr_flip_weights(const float* w, int32_t Cin, int32_t Cout, int32_t ci_lo, int32_t ci_n, float* wf, void* stream);
+/* dw[27][dw_cin][Cout] += sum_v x[v + tap][ci] dy[v][co] for input channels [ci_off, ci_off + x.C);
+ * dbias2c (double [2 * Cout], optional): [0, Cout) += sum_v dy.  16-bit tensors: mma.sync tensor-core tiles. */
+int te_tr_conv3_wgrad(const te_tensor* x, const te_tensor* dy, float* dw, int32_t dw_cin, int32_t ci_off,
+                      double* dbias2c, void* stream);
+/* stats2c (double [2C]) += per-channel sum and sum of squares of y (BN batch statistics). */
+int te_tr_bn_stats(const te_tensor* y, double* stats2c, void* stream);
+/* a = LeakyReLU(scale[c] * y + shift[c]) with scale = gamma * rstd, shift = beta - mean * scale. */
+int te_tr_bn_act_fwd(const te_tensor* y, const te_tensor* a, const float* scale, const float* shift, float alpha, void* stream);
+/* red2c (double [2C]) += [sum dz, sum dz * xhat], dz = da * LeakyReLU'(z). */
+int te_tr_bn_act_bwd_reduce(const te_tensor* y, const te_tensor* da, const float* scale, const float* shift,
+                            const float* mean, const float* rstd, float alpha, double* red2c, void* stream);
+/* dy = scale * (dz - dbeta_n - xhat * dgamma_n), dbeta_n = sum dz / n, dgamma_n = sum dz xhat / n. */
+int te_tr_bn_act_bwd_apply(const te_tensor* y, const te_tensor* da, const te_tensor* dy, const float* scale,
+                           const float* shift, const float* mean, const float* rstd, const float* dbeta_n,
+                           const float* dgamma_n, float alpha, void* stream);
+int te_tr_maxpool_fwd(const te_tensor* x, const te_tensor* out, int32_t pool, void* stream);
+/* dx (+)= gradient routed to the first maximum of every window. */
+int te_tr_maxpool_bwd(const te_tensor* x, const te_tensor* dpool, const te_tensor* dx, int32_t pool, int32_t accumulate,
+                      void* stream);
+/* a = LeakyReLU(Conv3DTranspose(k 2, strides s)(x) + bias); w: (2,2,2,Cout,Cin). */
+int te_tr_upconv_fwd(const te_tensor* x, const float* w, const float* bias, const te_tensor* a, int32_t stride,
+                     float alpha, void* stream);
+/* da <- dz = da * LeakyReLU'(a); dbias2c[0..C) += sum dz; dw += weight gradient; dx = data gradient (optional). */
+int te_tr_upconv_bwd(const te_tensor* x, const te_tensor* a, const te_tensor* da, const float* w, int32_t stride,
+                     float alpha, float* dw, double* dbias2c, const te_tensor* dx, void* stream);
+/* 1x1x1 head + sigmoid + Keras binary cross-entropy (mean over n_total voxels), forward and backward. */
+int te_tr_head_loss(const te_tensor* a, const float* w, const float* b, const uint8_t* y, const te_tensor* da,
+                    double* loss, double* dwb2c, double n_total, float* dl, float* probs, void* stream);
+/* Keras Adam on a flat parameter buffer; g is multiplied by grad_scale first (1 / world size after an all-reduce). */
+int te_tr_adam(float* w, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+               int64_t step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

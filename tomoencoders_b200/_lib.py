@@ -82,9 +82,19 @@ class NetDesc(ctypes.Structure):
     ]
 
 
+class TeTensor(ctypes.Structure):
+    """struct te_tensor (include/tomoenc.h): an NDHWC channel slice handed to the training operators."""
+    _fields_ = [("ptr", ctypes.c_void_p), ("dtype", ctypes.c_int32), ("ctot", ctypes.c_int32), ("coff", ctypes.c_int32),
+                ("C", ctypes.c_int32), ("N", ctypes.c_int32), ("D", ctypes.c_int32), ("H", ctypes.c_int32),
+                ("W", ctypes.c_int32)]
+
+
 _P = ctypes.c_void_p
 _I64 = ctypes.c_int64
 _I32 = ctypes.c_int32
+_F = ctypes.c_float
+_D = ctypes.c_double
+_TP = ctypes.POINTER(TeTensor)
 _SIGNATURES = {
     # name: (restype, argtypes)
     "te_version": (ctypes.c_int, []),
@@ -117,6 +127,21 @@ _SIGNATURES = {
     "te_pca_accumulate": (ctypes.c_int, [_P, _I64, _I32, _P, _P]),
     "te_pca_solve": (ctypes.c_int, [_P, _I32, _I32, _P, _P, _P, _P, _P]),
     "te_pca_project": (ctypes.c_int, [_P, _I64, _I32, _P, _P, _I32, _P, _P]),
+    # training operators
+    "te_tr_conv3_wpack_bytes": (_I64, [_I32, _I32]),
+    "te_tr_conv3": (ctypes.c_int, [_TP, _TP, _P, _P, _TP, _P, _P]),
+    "te_tr_flip_weights": (ctypes.c_int, [_P, _I32, _I32, _I32, _I32, _P, _P]),
+    "te_tr_conv3_wgrad": (ctypes.c_int, [_TP, _TP, _P, _I32, _I32, _P, _P]),
+    "te_tr_bn_stats": (ctypes.c_int, [_TP, _P, _P]),
+    "te_tr_bn_act_fwd": (ctypes.c_int, [_TP, _TP, _P, _P, _F, _P]),
+    "te_tr_bn_act_bwd_reduce": (ctypes.c_int, [_TP, _TP, _P, _P, _P, _P, _F, _P, _P]),
+    "te_tr_bn_act_bwd_apply": (ctypes.c_int, [_TP, _TP, _TP, _P, _P, _P, _P, _P, _P, _F, _P]),
+    "te_tr_maxpool_fwd": (ctypes.c_int, [_TP, _TP, _I32, _P]),
+    "te_tr_maxpool_bwd": (ctypes.c_int, [_TP, _TP, _TP, _I32, _I32, _P]),
+    "te_tr_upconv_fwd": (ctypes.c_int, [_TP, _P, _P, _TP, _I32, _F, _P]),
+    "te_tr_upconv_bwd": (ctypes.c_int, [_TP, _TP, _TP, _P, _I32, _F, _P, _P, _TP, _P]),
+    "te_tr_head_loss": (ctypes.c_int, [_TP, _P, _P, _P, _TP, _P, _P, _D, _P, _P, _P]),
+    "te_tr_adam": (ctypes.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I64, _F, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

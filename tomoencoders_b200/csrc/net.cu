@@ -637,6 +637,13 @@ int run_layers(te_net* net, int n, const HeadOut& ho, cudaStream_t st) {
             C.pool_coff = L.pool_view.coff;
             if (!L.store_out) C.out = nullptr;
           }
+          {
+            // timing experiments only (results are wrong): TOMOENC_DBG_SKIP bit 0 drops the activation
+            // stores, bit 1 the pooled stores
+            static const int dbg = getenv("TOMOENC_DBG_SKIP") ? atoi(getenv("TOMOENC_DBG_SKIP")) : 0;
+            if (dbg & 1) C.out = nullptr;
+            if (dbg & 2) C.pool_out = nullptr;
+          }
           e = conv_umma_launch(C, st);
           count_launch();
         } else if (L.op == OP_CONV3) {

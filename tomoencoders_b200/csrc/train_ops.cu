@@ -1,0 +1,857 @@
+// Training-step operators of the U-net segmenter:
+//   SurfaceSegmenter.train / Keras Model.fit with Adam + BinaryCrossentropy, BatchNormalization in
+//   training mode (/root/reference/tomo_encoders/neural_nets/surface_segmenter.py:43-66, 322-323;
+//   Unet3D.py:44-194 for the layer semantics; SURVEY.md appendix A.3 for the Keras conventions).
+// One C-ABI entry per operator (include/tomoenc.h, "training operators"); the graph is walked by the
+// host code (tomoencoders_b200/neural_nets/_train.py).  Activations are NDHWC in fp32 (check mode)
+// or bf16 / fp16; master weights, gradients and every reduction are fp32 / fp64.
+//
+// Tensor-core use: the forward 3x3x3 convolutions and their data gradients (a 3x3x3 convolution of
+// dy with the flipped, transposed kernel) run on conv_umma_kernel (tcgen05) through te_tr_conv3 with
+// device-side weight packing; the weight gradients use warp-level mma.sync tiles (wgrad_mma_kernel);
+// normalisation / activation / pooling / loss operators are HBM-bound element-wise kernels.
+#include "conv_umma.cuh"
+#include "layers_simt.cuh"
+#include "te_common.cuh"
+
+#include <cstdlib>
+#include <type_traits>
+
+namespace te {
+namespace {
+
+template <typename T> __device__ __forceinline__ float ldv(const T* p);
+template <> __device__ __forceinline__ float ldv<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ldv<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <> __device__ __forceinline__ float ldv<__half>(const __half* p) { return __half2float(*p); }
+template <typename T> __device__ __forceinline__ void stv(T* p, float v);
+template <> __device__ __forceinline__ void stv<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void stv<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ void stv<__half>(__half* p, float v) { *p = __float2half_rn(v); }
+
+inline int blocks_for(long long items, int threads, int waves = 16) {
+  long long b = (items + threads - 1) / threads;
+  const long long cap = static_cast<long long>(kNumSMs) * waves;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+TView view_of(const te_tensor& t) {
+  TView v;
+  v.ptr = t.ptr; v.ctot = t.ctot; v.coff = t.coff; v.C = t.C; v.N = t.N; v.D = t.D; v.H = t.H; v.W = t.W;
+  return v;
+}
+int act_of(int dtype) { return dtype == TE_F32 ? ACT_F32 : (dtype == TE_F16 ? ACT_F16 : ACT_BF16); }
+
+#define TE_DISPATCH_T(dtype, ...)                                         \
+  do {                                                                    \
+    if ((dtype) == TE_F32) { using T = float; __VA_ARGS__; }              \
+    else if ((dtype) == TE_F16) { using T = __half; __VA_ARGS__; }        \
+    else if ((dtype) == TE_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+    else { set_error("unsupported tensor dtype %d", (int)(dtype)); return TE_ERR_ARG; } \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// Per-channel reductions: every thread owns channel (tid % C) of a strided set of voxels (needs
+// blockDim % C == 0 or C % blockDim... handled by the generic path: thread t walks elements
+// e = t, t + stride, ... with stride a multiple of C so that its channel is fixed).
+// ------------------------------------------------------------------------------------------------
+template <typename T, typename F>
+__device__ __forceinline__ void per_channel_reduce2(const TView& v, double* out, F f) {
+  // out[c] += sum a, out[C + c] += sum b where (a, b) = f(voxel, channel)
+  const int C = v.C;
+  const long long total = v.voxels() * C;
+  long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  stride -= stride % C;                       // host guarantees gridDim * blockDim >= C
+  const long long start = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (start >= stride) return;
+  const int c = static_cast<int>(start % C);
+  float sa = 0.f, sb = 0.f;
+  double da = 0.0, db = 0.0;
+  int cnt = 0;
+  for (long long e = start; e < total; e += stride) {
+    float a, b;
+    f(e / C, c, a, b);
+    sa += a; sb += b;
+    if (++cnt == 64) { da += sa; db += sb; sa = sb = 0.f; cnt = 0; }   // bounded fp32 partial sums
+  }
+  da += sa; db += sb;
+  atomicAdd(out + c, da);
+  atomicAdd(out + C + c, db);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_stats_kernel(TView y, double* stats) {
+  const T* p = static_cast<const T*>(y.ptr);
+  per_channel_reduce2<T>(y, stats, [&](long long vox, int c, float& a, float& b) {
+    const float v = ldv<T>(p + vox * y.ctot + y.coff + c);
+    a = v; b = v * v;
+  });
+}
+
+// a = lrelu(scale[c] * y + shift[c])
+template <typename T>
+__global__ void __launch_bounds__(256) bn_act_fwd_kernel(TView y, TView a, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, float alpha) {
+  const int C = y.C;
+  const long long total = y.voxels() * C;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const T* yp = static_cast<const T*>(y.ptr);
+  T* ap = static_cast<T*>(a.ptr);
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const long long vox = e / C;
+    const int c = static_cast<int>(e - vox * C);
+    float z = fmaf(scale[c], ldv<T>(yp + vox * y.ctot + y.coff + c), shift[c]);
+    z = z > 0.f ? z : alpha * z;
+    stv<T>(ap + vox * a.ctot + a.coff + c, z);
+  }
+}
+
+// red[c] += sum dz, red[C + c] += sum dz * xhat, with z = scale*y + shift, dz = da * lrelu'(z),
+// xhat = (y - mean) * rstd
+template <typename T>
+__global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(TView y, TView da, const float* __restrict__ scale,
+                                                                 const float* __restrict__ shift,
+                                                                 const float* __restrict__ mean,
+                                                                 const float* __restrict__ rstd, float alpha, double* red) {
+  const T* yp = static_cast<const T*>(y.ptr);
+  const T* dp = static_cast<const T*>(da.ptr);
+  per_channel_reduce2<T>(y, red, [&](long long vox, int c, float& a, float& b) {
+    const float yv = ldv<T>(yp + vox * y.ctot + y.coff + c);
+    const float z = fmaf(scale[c], yv, shift[c]);
+    const float dz = ldv<T>(dp + vox * da.ctot + da.coff + c) * (z > 0.f ? 1.f : alpha);
+    a = dz; b = dz * (yv - mean[c]) * rstd[c];
+  });
+}
+
+// dy = gamma * rstd * (dz - dbeta / n - xhat * dgamma / n)
+template <typename T>
+__global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(TView y, TView da, TView dy, const float* __restrict__ scale,
+                                                                const float* __restrict__ shift,
+                                                                const float* __restrict__ mean,
+                                                                const float* __restrict__ rstd,
+                                                                const float* __restrict__ dbeta_n,
+                                                                const float* __restrict__ dgamma_n, float alpha) {
+  const int C = y.C;
+  const long long total = y.voxels() * C;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const T* yp = static_cast<const T*>(y.ptr);
+  const T* dp = static_cast<const T*>(da.ptr);
+  T* op = static_cast<T*>(dy.ptr);
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const long long vox = e / C;
+    const int c = static_cast<int>(e - vox * C);
+    const float yv = ldv<T>(yp + vox * y.ctot + y.coff + c);
+    const float z = fmaf(scale[c], yv, shift[c]);
+    const float dz = ldv<T>(dp + vox * da.ctot + da.coff + c) * (z > 0.f ? 1.f : alpha);
+    const float xhat = (yv - mean[c]) * rstd[c];
+    stv<T>(op + vox * dy.ctot + dy.coff + c, scale[c] * (dz - dbeta_n[c] - xhat * dgamma_n[c]));
+  }
+}
+
+// MaxPool3D(p) backward: the gradient of a pooled voxel goes to the FIRST window element (z, y, x
+// scan order) equal to the maximum (torch / TF argmax convention); every input voxel is written.
+// accumulate = 1 adds to dx (the skip connection already deposited its gradient there).
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(TView x, TView dpool, TView dx, int p, int accumulate) {
+  const int C = x.C;
+  const int Do = x.D / p, Ho = x.H / p, Wo = x.W / p;
+  const long long total = static_cast<long long>(x.N) * Do * Ho * Wo * C;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const T* xp = static_cast<const T*>(x.ptr);
+  const T* gp = static_cast<const T*>(dpool.ptr);
+  T* op = static_cast<T*>(dx.ptr);
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int c = static_cast<int>(e % C);
+    long long t = e / C;
+    const int ox = static_cast<int>(t % Wo); t /= Wo;
+    const int oy = static_cast<int>(t % Ho); t /= Ho;
+    const int oz = static_cast<int>(t % Do);
+    const long long n = t / Do;
+    float best = -INFINITY;
+    int arg = 0;
+    for (int k = 0; k < p * p * p; ++k) {
+      const int dz = k / (p * p), dy = (k / p) % p, dxx = k % p;
+      const long long vox = ((n * x.D + oz * p + dz) * x.H + oy * p + dy) * x.W + ox * p + dxx;
+      const float v = ldv<T>(xp + vox * x.ctot + x.coff + c);
+      if (v > best) { best = v; arg = k; }
+    }
+    const float g = ldv<T>(gp + (((n * Do + oz) * Ho + oy) * Wo + ox) * dpool.ctot + dpool.coff + c);
+    for (int k = 0; k < p * p * p; ++k) {
+      const int dz = k / (p * p), dy = (k / p) % p, dxx = k % p;
+      const long long vox = ((n * x.D + oz * p + dz) * x.H + oy * p + dy) * x.W + ox * p + dxx;
+      T* dst = op + vox * dx.ctot + dx.coff + c;
+      const float add = k == arg ? g : 0.f;
+      stv<T>(dst, accumulate ? ldv<T>(dst) + add : add);
+    }
+  }
+}
+
+// Transposed conv (k = 2, stride s) backward, part 1: dz = da * lrelu'(a) in place (a and z have the
+// same sign) and dbias[c] += sum dz.
+template <typename T>
+__global__ void __launch_bounds__(256) lrelu_bwd_bias_kernel(TView a, TView da, float alpha, double* dbias2) {
+  const T* ap = static_cast<const T*>(a.ptr);
+  T* dp = static_cast<T*>(da.ptr);
+  per_channel_reduce2<T>(a, dbias2, [&](long long vox, int c, float& s0, float& s1) {
+    const float av = ldv<T>(ap + vox * a.ctot + a.coff + c);
+    T* d = dp + vox * da.ctot + da.coff + c;
+    const float dz = ldv<T>(d) * (av > 0.f ? 1.f : alpha);
+    stv<T>(d, dz);
+    s0 = dz; s1 = 0.f;
+  });
+}
+
+// part 2: dx[v][ci] = sum_sub sum_co dz[s*v + sub][co] * w[sub][co][ci]   (w Keras layout (2,2,2,Cout,Cin))
+template <typename T>
+__global__ void __launch_bounds__(256) upconv_dgrad_kernel(TView dz, TView dx, const float* __restrict__ w, int s) {
+  const int Ci = dx.C, Co = dz.C;
+  const long long total = dx.voxels() * Ci;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const T* gp = static_cast<const T*>(dz.ptr);
+  T* op = static_cast<T*>(dx.ptr);
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int ci = static_cast<int>(e % Ci);
+    long long t = e / Ci;
+    const int x = static_cast<int>(t % dx.W); t /= dx.W;
+    const int y = static_cast<int>(t % dx.H); t /= dx.H;
+    const int z = static_cast<int>(t % dx.D);
+    const long long n = t / dx.D;
+    float acc = 0.f;
+    for (int sub = 0; sub < 8; ++sub) {
+      const int a = sub >> 2, b = (sub >> 1) & 1, c = sub & 1;
+      const long long vox = ((n * dz.D + z * s + a) * dz.H + y * s + b) * dz.W + x * s + c;
+      const T* g = gp + vox * dz.ctot + dz.coff;
+      const float* ws = w + static_cast<long long>(sub) * Co * Ci + ci;
+      for (int co = 0; co < Co; ++co) acc = fmaf(ldv<T>(g + co), ws[static_cast<long long>(co) * Ci], acc);
+    }
+    stv<T>(op + (e / Ci) * dx.ctot + dx.coff + ci, acc);
+  }
+}
+
+// part 3: dw[sub][co][ci] += sum_v dz[s*v + sub][co] * x[v][ci].  One block per (sub, co-tile of 8),
+// threads over ci x voxel slices; block-level reduction in shared memory, one atomicAdd per element.
+template <typename T>
+__global__ void __launch_bounds__(256) upconv_wgrad_kernel(TView x, TView dz, float* dw, int s, int vox_splits) {
+  const int Ci = x.C, Co = dz.C;
+  const int sub = blockIdx.y, split = blockIdx.z;
+  const int a = sub >> 2, b = (sub >> 1) & 1, c = sub & 1;
+  const T* xp = static_cast<const T*>(x.ptr);
+  const T* gp = static_cast<const T*>(dz.ptr);
+  const long long nvox = x.voxels();
+  const long long per = (nvox + vox_splits - 1) / vox_splits;
+  const long long v0 = split * per, v1 = v0 + per < nvox ? v0 + per : nvox;
+  // element (co, ci) handled by thread: idx = blockIdx.x * 256 + tid over Co * Ci
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(Co) * Ci) return;
+  const int co = static_cast<int>(idx / Ci), ci = static_cast<int>(idx % Ci);
+  float acc = 0.f;
+  for (long long v = v0; v < v1; ++v) {
+    long long t = v;
+    const int xx = static_cast<int>(t % x.W); t /= x.W;
+    const int yy = static_cast<int>(t % x.H); t /= x.H;
+    const int zz = static_cast<int>(t % x.D);
+    const long long n = t / x.D;
+    const long long hv = ((n * dz.D + zz * s + a) * dz.H + yy * s + b) * dz.W + xx * s + c;
+    acc = fmaf(ldv<T>(gp + hv * dz.ctot + dz.coff + co), ldv<T>(xp + v * x.ctot + x.coff + ci), acc);
+  }
+  atomicAdd(dw + (static_cast<long long>(sub) * Co + co) * Ci + ci, acc);
+}
+
+// 3x3x3 conv weight gradient, CUDA-core version (fp32 check mode and shapes the tensor-core kernel
+// does not take): dw[tap][ci][co] += sum_v x[v + tap][ci] * dy[v][co].  Block = (tap, voxel split);
+// thread = one (ci, co) element group.
+template <typename T>
+__global__ void __launch_bounds__(256) conv3_wgrad_simt_kernel(TView x, TView dy, float* dw, int dw_cin, int ci_off,
+                                                                int vox_splits) {
+  const int Ci = x.C, Co = dy.C;
+  const int tap = blockIdx.y, split = blockIdx.z;
+  const int dz = tap / 9 - 1, dyy = (tap / 3) % 3 - 1, dxx = tap % 3 - 1;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(Ci) * Co) return;
+  const int ci = static_cast<int>(idx / Co), co = static_cast<int>(idx % Co);
+  const T* xp = static_cast<const T*>(x.ptr);
+  const T* gp = static_cast<const T*>(dy.ptr);
+  const long long nvox = dy.voxels();
+  const long long per = (nvox + vox_splits - 1) / vox_splits;
+  const long long v0 = split * per, v1 = v0 + per < nvox ? v0 + per : nvox;
+  float acc = 0.f;
+  for (long long v = v0; v < v1; ++v) {
+    long long t = v;
+    const int xx = static_cast<int>(t % dy.W) + dxx; t /= dy.W;
+    const int yy = static_cast<int>(t % dy.H) + dyy; t /= dy.H;
+    const int zz = static_cast<int>(t % dy.D) + dz;
+    const long long n = t / dy.D;
+    if (xx < 0 || xx >= x.W || yy < 0 || yy >= x.H || zz < 0 || zz >= x.D) continue;
+    const long long xv = ((n * x.D + zz) * x.H + yy) * x.W + xx;
+    acc = fmaf(ldv<T>(xp + xv * x.ctot + x.coff + ci), ldv<T>(gp + v * dy.ctot + dy.coff + co), acc);
+  }
+  atomicAdd(dw + (static_cast<long long>(tap) * dw_cin + ci_off + ci) * Co + co, acc);
+}
+
+// dbias[c] += sum_v dy[v][c]
+template <typename T>
+__global__ void __launch_bounds__(256) channel_sum_kernel(TView dy, double* out2) {
+  const T* p = static_cast<const T*>(dy.ptr);
+  per_channel_reduce2<T>(dy, out2, [&](long long vox, int c, float& a, float& b) {
+    a = ldv<T>(p + vox * dy.ctot + dy.coff + c); b = 0.f;
+  });
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3x3x3 conv weight gradient on the tensor cores (warp-level mma.sync m16n8k16, fp32 accumulate).
+// CTA = (32 input channels) x (32 output channels) x all 27 taps, persistent over voxel tiles of
+// TZ z-planes x 16 x 8; the 27 x 32 x 32 fp32 accumulators live in the registers of 8 warps
+// (warp w owns the (16 ci) x (8 co) mma tile (w & 1, w >> 1) of every tap: 108 registers per lane)
+// and are flushed with atomicAdd once at the end.  Both operands have the voxel index as the GEMM K
+// dimension, i.e. they are "transposed" in shared memory ([voxel][channel]) and are fetched with
+// ldmatrix.trans.  Voxel rows are padded to 80 bytes (32 ch x 2 B + 16) to spread the 8 row
+// addresses of an ldmatrix over distinct banks.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWgTZ = 2;
+constexpr int kWgRow = 80;                                           // bytes per voxel row in shared memory
+constexpr int kWgXVox = (kWgTZ + 2) * 18 * 10;                       // haloed x box
+constexpr int kWgDVox = kWgTZ * 16 * 8;                              // dy box
+constexpr int kWgStage = (kWgXVox + kWgDVox) * kWgRow;               // 78 080 B
+constexpr int kWgSmem = 2 * kWgStage;
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+  const int sz = valid ? 16 : 0;                                     // src-size 0 -> zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t (&r)[2], const void* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
+}
+template <bool FP16>
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  if constexpr (FP16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+struct WgParams {
+  const uint8_t* x; int x_ctot, x_coff;       // 16-bit NDHWC
+  const uint8_t* dy; int dy_ctot, dy_coff;
+  float* dw; int dw_cin, ci_off, Cout;        // dw[27][dw_cin][Cout]
+  int Ci, N, D, H, W;
+  int tiles_x, tiles_y, tiles_z;
+  long long total_tiles;
+};
+
+template <bool FP16>
+__global__ void __launch_bounds__(256, 1) wgrad_mma_kernel(const WgParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ci0 = blockIdx.y * 32, co0 = blockIdx.z * 32;
+  const int mt = warp & 1, nt = warp >> 1;                // this warp's mma tile: ci [16 mt, +16), co [8 nt, +8)
+  float acc[27][4];
+#pragma unroll
+  for (int t = 0; t < 27; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
+
+  auto load_tile = [&](long long tile, int stage) {
+    long long t = tile;
+    const int x0 = static_cast<int>(t % p.tiles_x) * 8; t /= p.tiles_x;
+    const int y0 = static_cast<int>(t % p.tiles_y) * 16; t /= p.tiles_y;
+    const int z0 = static_cast<int>(t % p.tiles_z) * kWgTZ; t /= p.tiles_z;
+    const long long n = t;
+    uint8_t* sx = smem + stage * kWgStage;
+    uint8_t* sd = sx + kWgXVox * kWgRow;
+    // x box: (TZ+2, 18, 10) voxels x 32 channels = 4 chunks of 16 B per voxel
+    for (int i = tid; i < kWgXVox * 4; i += 256) {
+      const int vox = i >> 2, ch = i & 3;
+      const int bx = vox % 10, by = (vox / 10) % 18, bz = vox / 180;
+      const int xx = x0 + bx - 1, yy = y0 + by - 1, zz = z0 + bz - 1;
+      const bool ok = xx >= 0 && xx < p.W && yy >= 0 && yy < p.H && zz >= 0 && zz < p.D && ci0 + ch * 8 < p.Ci;
+      const long long gv = ((n * p.D + (ok ? zz : 0)) * p.H + (ok ? yy : 0)) * p.W + (ok ? xx : 0);
+      cp_async16(sx + vox * kWgRow + ch * 16, p.x + (gv * p.x_ctot + p.x_coff + ci0 + (ok ? ch * 8 : 0)) * 2, ok);
+    }
+    for (int i = tid; i < kWgDVox * 4; i += 256) {
+      const int vox = i >> 2, ch = i & 3;
+      const int bx = vox & 7, by = (vox >> 3) & 15, bz = vox >> 7;
+      const int xx = x0 + bx, yy = y0 + by, zz = z0 + bz;
+      const bool ok = xx < p.W && yy < p.H && zz < p.D && co0 + ch * 8 < p.Cout;
+      const long long gv = ((n * p.D + (ok ? zz : 0)) * p.H + (ok ? yy : 0)) * p.W + (ok ? xx : 0);
+      cp_async16(sd + vox * kWgRow + ch * 16, p.dy + (gv * p.dy_ctot + p.dy_coff + co0 + (ok ? ch * 8 : 0)) * 2, ok);
+    }
+    cp_async_commit();
+  };
+
+  const long long first = blockIdx.x, step = gridDim.x;
+  int stage = 0;
+  if (first < p.total_tiles) load_tile(first, 0);
+  for (long long tile = first; tile < p.total_tiles; tile += step) {
+    const long long next = tile + step;
+    if (next < p.total_tiles) { load_tile(next, stage ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+    const uint8_t* sx = smem + stage * kWgStage;
+    const uint8_t* sd = sx + kWgXVox * kWgRow;
+    // k-steps: 16 voxels = two x rows (y, y+1) of 8 voxels of one z plane
+#pragma unroll 1
+    for (int ks = 0; ks < kWgTZ * 8; ++ks) {
+      const int pz = ks >> 3, yr = (ks & 7) * 2;
+      // B fragment (dy): k = voxel (16), n = co (8): two 8x8 matrices (k 0-7, k 8-15), rows = voxels
+      uint32_t bfrag[2];
+      {
+        const int r = lane & 15;                                    // lanes 0-15 supply the 16 row addresses
+        const int vox = (pz * 16 + yr + (r >> 3)) * 8 + (r & 7);
+        ldmatrix_x2_trans(bfrag, sd + vox * kWgRow + nt * 16);
+      }
+#pragma unroll
+      for (int tap = 0; tap < 27; ++tap) {
+        const int dz = tap / 9, dyy = (tap / 3) % 3, dxx = tap % 3;  // +1 biased box offsets
+        // A fragment (x window): m = ci (16), k = voxel (16): four 8x8 matrices
+        //   a0: m 0-7,k 0-7   a1: m 8-15,k 0-7   a2: m 0-7,k 8-15   a3: m 8-15,k 8-15
+        // stored [voxel][channel]: matrix rows = voxels (k), 16-byte row chunk = 8 channels (m) -> .trans
+        uint32_t afrag[4];
+        const int mi = lane >> 3, r = lane & 7;                      // lane supplies row r of matrix mi
+        const int kh = mi >> 1, mh = mi & 1;
+        const int vox = ((pz + dz) * 18 + (yr + kh + dyy)) * 10 + (r + dxx);
+        ldmatrix_x4_trans(afrag, sx + vox * kWgRow + (mt * 16 + mh * 8) * 2);
+        mma16816<FP16>(acc[tap], afrag, bfrag);
+      }
+    }
+    __syncthreads();
+    stage ^= 1;
+  }
+  // flush: c0,c1 -> (row g, cols 2t, 2t+1); c2,c3 -> (row g + 8)
+  const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+  for (int tap = 0; tap < 27; ++tap) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int ci = ci0 + mt * 16 + g + h * 8;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int co = co0 + nt * 8 + tq * 2 + j;
+        if (ci < p.Ci && co < p.Cout)
+          atomicAdd(p.dw + (static_cast<long long>(tap) * p.dw_cin + p.ci_off + ci) * p.Cout + co, acc[tap][h * 2 + j]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1x1x1 head + sigmoid + binary cross-entropy, forward and backward in one pass:
+//   logit = a . w + b ; p = sigmoid(logit)
+//   loss += -[y log(clip(p) + eps) + (1 - y) log(1 - clip(p) + eps)] / n_total   (Keras backend, eps = 1e-7)
+//   dl = dloss/dlogit ; dw[c] += a[c] dl ; db += dl ; da[c] = dl w[c]
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) head_loss_kernel(TView a, const float* __restrict__ w, const float* __restrict__ b,
+                                                         const uint8_t* __restrict__ y, TView da, double* loss,
+                                                         float inv_n, float* __restrict__ dl_out, float* probs) {
+  const int C = a.C;
+  const long long nvox = a.voxels();
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const T* ap = static_cast<const T*>(a.ptr);
+  T* dp = static_cast<T*>(da.ptr);
+  extern __shared__ float sw[];                 // [C] weights
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const float bias = b[0];
+  double lsum = 0.0;
+  for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < nvox; v += stride) {
+    const T* row = ap + v * a.ctot + a.coff;
+    float logit = bias;
+    for (int c = 0; c < C; ++c) logit = fmaf(ldv<T>(row + c), sw[c], logit);
+    const float pr = 1.f / (1.f + expf(-logit));
+    if (probs) probs[v] = pr;
+    const float yt = static_cast<float>(y[v]);
+    const float eps = 1e-7f;
+    const float pc = fminf(fmaxf(pr, eps), 1.f - eps);
+    lsum += -(yt * logf(pc + eps) + (1.f - yt) * logf(1.f - pc + eps));
+    // d/dp of the clipped expression (zero outside the clip range), times dp/dlogit = p (1 - p)
+    const float dldp = (pr > eps && pr < 1.f - eps) ? -(yt / (pc + eps) - (1.f - yt) / (1.f - pc + eps)) : 0.f;
+    const float dl = dldp * pr * (1.f - pr) * inv_n;
+    dl_out[v] = dl;
+    T* drow = dp + v * da.ctot + da.coff;
+    for (int c = 0; c < C; ++c) stv<T>(drow + c, dl * sw[c]);
+  }
+  __shared__ double sl[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+  if ((threadIdx.x & 31) == 0) sl[threadIdx.x >> 5] = lsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < 8; ++i) tot += sl[i];
+    atomicAdd(loss, tot * inv_n);
+  }
+}
+
+// dwb[c] += sum_v a[v][c] dl[v]  (c < C);  dwb[C + c] += sum_v dl[v]  (identical for every c; the host reads c = 0)
+template <typename T>
+__global__ void __launch_bounds__(256) head_wgrad_kernel(TView a, const float* __restrict__ dl, double* dwb2c) {
+  const T* p = static_cast<const T*>(a.ptr);
+  per_channel_reduce2<T>(a, dwb2c, [&](long long vox, int c, float& s0, float& s1) {
+    const float d = dl[vox];
+    s0 = ldv<T>(p + vox * a.ctot + a.coff + c) * d; s1 = d;
+  });
+}
+
+// Keras Adam: lr_t = lr sqrt(1 - b2^t) / (1 - b1^t); theta -= lr_t m / (sqrt(v) + eps)
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
+                                                    float* __restrict__ v, long long n, float lr_t, float b1, float b2,
+                                                    float eps, float grad_scale) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gi = g[i] * grad_scale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    w[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+// w[tap][ci][co] -> wf[26 - tap][co][ci]  (the data gradient of a 'same' 3x3x3 conv is the same conv
+// of dy with the spatially flipped, channel-transposed kernel)
+__global__ void __launch_bounds__(256) flip_weights_kernel(const float* __restrict__ w, float* __restrict__ wf, int Ci, int Co,
+                                                            int ci_lo, int ci_n) {
+  // output covers input channels [ci_lo, ci_lo + ci_n) of the forward conv: wf[27][Co][ci_n]
+  const long long total = 27LL * Co * ci_n;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int ci = static_cast<int>(e % ci_n);
+    const int co = static_cast<int>((e / ci_n) % Co);
+    const int tap = static_cast<int>(e / (static_cast<long long>(ci_n) * Co));
+    wf[e] = w[(static_cast<long long>(26 - tap) * Ci + ci_lo + ci) * Co + co];
+  }
+}
+
+// Device-side twin of conv_umma_pack(): fp32 w[tap][cin][cout] (Keras layout) -> swizzled 16-bit slabs.
+__global__ void __launch_bounds__(256) pack_umma_kernel(const float* __restrict__ w, uint8_t* __restrict__ dst, int Cin, int Cout,
+                                                         int CB, int NT, int fuse, int fp16) {
+  const long long total = 27LL * Cin * Cout;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const int rowb = CB * 2;
+  const uint32_t mask = CB == 16 ? 1u : (CB == 32 ? 3u : 7u);
+  const int kchunks = Cin / CB;
+  const long long slab = 3LL * NT * rowb;
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int cout = static_cast<int>(e % Cout);
+    const int cin = static_cast<int>((e / Cout) % Cin);
+    const int tap = static_cast<int>(e / (static_cast<long long>(Cin) * Cout));
+    const int nt = cout / NT, r = cout % NT, kc = cin / CB, kk = cin % CB;
+    int g, t;
+    if (fuse) { g = tap % 9; t = 2 - tap / 9; } else { g = tap / 3; t = tap % 3; }
+    uint8_t* base = dst + ((static_cast<long long>(nt) * kchunks + kc) * 9 + g) * slab;
+    const uint32_t Lo = static_cast<uint32_t>((t * NT + r) * rowb + kk * 2);
+    const uint32_t P = Lo ^ (((Lo >> 7) & mask) << 4);
+    const float val = w[e];
+    uint16_t bits;
+    if (fp16) { __half h = __float2half_rn(val); bits = *reinterpret_cast<uint16_t*>(&h); }
+    else { __nv_bfloat16 h = __float2bfloat16_rn(val); bits = *reinterpret_cast<uint16_t*>(&h); }
+    *reinterpret_cast<uint16_t*>(base + P) = bits;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult q;
+    void* p = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess) fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+int make_tmap5(CUtensorMap* tm, const te_tensor& v, const ConvUmmaConfig& cfg) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available"); return TE_ERR_CUDA; }
+  cuuint64_t gdim[5] = {(cuuint64_t)v.ctot, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.D, (cuuint64_t)v.N};
+  cuuint64_t gstr[4] = {(cuuint64_t)v.ctot * 2, (cuuint64_t)v.W * v.ctot * 2, (cuuint64_t)v.H * v.W * v.ctot * 2,
+                        (cuuint64_t)v.D * v.H * v.W * v.ctot * 2};
+  cuuint32_t box[5] = {(cuuint32_t)cfg.CB, 10, 18, (cuuint32_t)(cfg.TZ + 2), 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = cfg.CB == 16 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                : (cfg.CB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+  CUresult r = enc(tm, v.dtype == TE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, v.ptr, gdim,
+                   gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return TE_ERR_CUDA; }
+  return TE_OK;
+}
+
+bool same_grid(const te_tensor& a, const te_tensor& b) {
+  return a.N == b.N && a.D == b.D && a.H == b.H && a.W == b.W;
+}
+
+}  // namespace
+}  // namespace te
+
+using namespace te;
+
+#define TE_TR_CHECK_T(t, name) TE_CHECK_ARG((t) && (t)->ptr && (t)->C > 0 && (t)->ctot >= (t)->coff + (t)->C, name ": bad tensor")
+
+// y = conv3x3x3_same(x [, x2]) + bias.  w: device fp32 [27][Cin][Cout] with Cin = x.C (+ x2.C).
+// 16-bit tensors with Cin, Cout multiples of 16 (and dense inputs) run on the tcgen05 kernel: the
+// weights are packed on the device into wpack (te_tr_conv3_wpack_bytes) first.
+extern "C" int64_t te_tr_conv3_wpack_bytes(int32_t Cin, int32_t Cout) {
+  ConvUmmaConfig cfg;
+  if (!conv_umma_config(Cin, Cout, &cfg)) return 0;
+  return static_cast<int64_t>(conv_umma_packed_bytes(Cin, Cout, 27, 1, cfg));
+}
+
+extern "C" int te_tr_conv3(const te_tensor* x, const te_tensor* x2, const float* w, const float* bias, const te_tensor* y,
+                           void* wpack, void* stream) {
+  TE_TR_CHECK_T(x, "te_tr_conv3"); TE_TR_CHECK_T(y, "te_tr_conv3");
+  TE_CHECK_ARG(w && bias, "te_tr_conv3: null pointer");
+  TE_CHECK_ARG(same_grid(*x, *y) && x->dtype == y->dtype, "te_tr_conv3: x and y must share grid and dtype");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int Cin = x->C + (x2 ? x2->C : 0), Cout = y->C;
+  ConvUmmaConfig cfg;
+  const bool dense_in = x->coff == 0 && x->C == x->ctot && (!x2 || (x2->coff == 0 && x2->C == x2->ctot));
+  const bool umma = x->dtype != TE_F32 && wpack && dense_in && conv_umma_config(Cin, Cout, &cfg) &&
+                    (!x2 || (x->C % cfg.CB == 0 && x2->C % cfg.CB == 0));
+  if (umma) {
+    const int fuse = 3 * cfg.NT <= 256;
+    pack_umma_kernel<<<blocks_for(27LL * Cin * Cout, 256), 256, 0, st>>>(w, static_cast<uint8_t*>(wpack), Cin, Cout, cfg.CB,
+                                                                         cfg.NT, fuse, x->dtype == TE_F16);
+    TE_LAUNCH_CHECK();
+    ConvUmmaLaunch C{};
+    int rc = make_tmap5(&C.tmap_in, *x, cfg);
+    if (rc != TE_OK) return rc;
+    if (x2) { rc = make_tmap5(&C.tmap_in2, *x2, cfg); if (rc != TE_OK) return rc; } else C.tmap_in2 = C.tmap_in;
+    C.Cin2 = x2 ? x2->C : 0;
+    C.w_packed = wpack; C.bias = bias;
+    C.out = y->ptr; C.out_ctot = y->ctot; C.out_coff = y->coff;
+    C.N = x->N; C.D = x->D; C.H = x->H; C.W = x->W;
+    C.Cin = Cin; C.Cout = Cout; C.ntaps = 27; C.up_stride = 0; C.act_lrelu = 0; C.alpha = 0.f;
+    C.fp16 = x->dtype == TE_F16;
+    C.CB = cfg.CB; C.NT = cfg.NT; C.TZ = cfg.TZ;
+    cudaError_t e = conv_umma_launch(C, st);
+    count_launch();
+    if (e != cudaSuccess) { set_error("te_tr_conv3: launch failed: %s", cudaGetErrorString(e)); return TE_ERR_CUDA; }
+    return TE_OK;
+  }
+  TE_CHECK_ARG(!x2, "te_tr_conv3: two-input form needs the tensor-core path (16-bit, dense, channel counts % 16)");
+  cudaError_t e = simt_conv3(view_of(*x), view_of(*y), w, bias, 0, 0.f, act_of(x->dtype), st);
+  count_launch();
+  if (e != cudaSuccess) { set_error("te_tr_conv3: launch failed: %s", cudaGetErrorString(e)); return TE_ERR_CUDA; }
+  return TE_OK;
+}
+
+// wf[27][Cout][ci_n] = flipped / transposed slice of w[27][Cin][Cout] (dgrad weights)
+extern "C" int te_tr_flip_weights(const float* w, int32_t Cin, int32_t Cout, int32_t ci_lo, int32_t ci_n, float* wf, void* stream) {
+  TE_CHECK_ARG(w && wf && ci_lo >= 0 && ci_n > 0 && ci_lo + ci_n <= Cin, "te_tr_flip_weights: bad argument");
+  flip_weights_kernel<<<blocks_for(27LL * Cout * ci_n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(w, wf, Cin, Cout, ci_lo, ci_n);
+  TE_LAUNCH_CHECK();
+  return TE_OK;
+}
+
+extern "C" int te_tr_bn_stats(const te_tensor* y, double* stats2c, void* stream) {
+  TE_TR_CHECK_T(y, "te_tr_bn_stats");
+  TE_CHECK_ARG(stats2c && y->C <= 4096, "te_tr_bn_stats: bad argument");
+  const TView v = view_of(*y);
+  int grid = blocks_for(v.voxels() * v.C, 256, 8);
+  if (static_cast<long long>(grid) * 256 < v.C) grid = (v.C + 255) / 256;
+  TE_DISPATCH_T(y->dtype, (bn_stats_kernel<T><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(v, stats2c)));
+  TE_LAUNCH_CHECK();
+  return TE_OK;
+}
+
+extern "C" int te_tr_bn_act_fwd(const te_tensor* y, const te_tensor* a, const float* scale, const float* shift, float alpha,
+                                void* stream) {
+  TE_TR_CHECK_T(y, "te_tr_bn_act_fwd"); TE_TR_CHECK_T(a, "te_tr_bn_act_fwd");
+  TE_CHECK_ARG(scale && shift && same_grid(*y, *a) && y->C == a->C && y->dtype == a->dtype, "te_tr_bn_act_fwd: bad argument");
+  const TView vy = view_of(*y), va = view_of(*a);
+  TE_DISPATCH_T(y->dtype, (bn_act_fwd_kernel<T><<<blocks_for(vy.voxels() * vy.C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+                              vy, va, scale, shift, alpha)));
+  TE_LAUNCH_CHECK();
+  return TE_OK;
+}
+
+extern "C" int te_tr_bn_act_bwd_reduce(const te_tensor* y, const te_tensor* da, const float* scale, const float* shift,
+                                       const float* mean, const float* rstd, float alpha, double* red2c, void* stream) {
+  TE_TR_CHECK_T(y, "te_tr_bn_act_bwd_reduce"); TE_TR_CHECK_T(da, "te_tr_bn_act_bwd_reduce");
+  TE_CHECK_ARG(scale && shift && mean && rstd && red2c && same_grid(*y, *da) && y->C == da->C && y->dtype == da->dtype,
+               "te_tr_bn_act_bwd_reduce: bad argument");
+  const TView vy = view_of(*y), vd = view_of(*da);
+  int grid = blocks_for(vy.voxels() * vy.C, 256, 8);
+  if (static_cast<long long>(grid) * 256 < vy.C) grid = (vy.C + 255) / 256;
+  TE_DISPATCH_T(y->dtype, (bn_act_bwd_reduce_kernel<T><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+                              vy, vd, scale, shift, mean, rstd, alpha, red2c)));
+  TE_LAUNCH_CHECK();
+  return TE_OK;
+}
+
+extern "C" int te_tr_bn_act_bwd_apply(const te_tensor* y, const te_tensor* da, const te_tensor* dy, const float* scale,
+                                      const float* shift, const float* mean, const float* rstd, const float* dbeta_n,
+                                      const float* dgamma_n, float alpha, void* stream) {
+  TE_TR_CHECK_T(y, "te_tr_bn_act_bwd_apply"); TE_TR_CHECK_T(da, "te_tr_bn_act_bwd_apply"); TE_TR_CHECK_T(dy, "te_tr_bn_act_bwd_apply");
+  TE_CHECK_ARG(scale && shift && mean && rstd && dbeta_n && dgamma_n && same_grid(*y, *da) && same_grid(*y, *dy) &&
+                   y->C == da->C && y->C == dy->C && y->dtype == da->dtype && y->dtype == dy->dtype,
+               "te_tr_bn_act_bwd_apply: bad argument");
+  const TView vy = view_of(*y), vd = view_of(*da), vo = view_of(*dy);
+  TE_DISPATCH_T(y->dtype, (bn_act_bwd_apply_kernel<T><<<blocks_for(vy.voxels() * vy.C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+                              vy, vd, vo, scale, shift, mean, rstd, dbeta_n, dgamma_n, alpha)));
+  TE_LAUNCH_CHECK();
+  return TE_OK;
+}
+
+extern "C" int te_tr_maxpool_fwd(const te_tensor* x, const te_tensor* out, int32_t pool, void* stream) {
+  TE_TR_CHECK_T(x, "te_tr_maxpool_fwd"); TE_TR_CHECK_T(out, "te_tr_maxpool_fwd");
+  TE_CHECK_ARG(pool >= 1 && x->D % pool == 0 && x->H % pool == 0 && x->W % pool == 0 && x->C == out->C && x->dtype == out->dtype,
+               "te_tr_maxpool_fwd: bad argument");
+  cudaError_t e = simt_maxpool(view_of(*x), view_of(*out), pool, act_of(x->dtype), static_cast<cudaStream_t>(stream));
+  count_launch();
+  if (e != cudaSuccess) { set_error("te_tr_maxpool_fwd: %s", cudaGetErrorString(e)); return TE_ERR_CUDA; }
+  return TE_OK;
+}
+
+extern "C" int te_tr_maxpool_bwd(const te_tensor* x, const te_tensor* dpool, const te_tensor* dx, int32_t pool, int32_t accumulate,
+                                 void* stream) {
+  TE_TR_CHECK_T(x, "te_tr_maxpool_bwd"); TE_TR_CHECK_T(dpool, "te_tr_maxpool_bwd"); TE_TR_CHECK_T(dx, "te_tr_maxpool_bwd");
+  TE_CHECK_ARG(pool >= 1 && same_grid(*x, *dx) && x->C == dx->C && x->C == dpool->C && x->dtype == dx->dtype &&
+                   x->dtype == dpool->dtype, "te_tr_maxpool_bwd: bad argument");
+  const TView vx = view_of(*x), vg = view_of(*dpool), vd = view_of(*dx);
+  TE_DISPATCH_T(x->dtype, (maxpool_bwd_kernel<T><<<blocks_for(vg.voxels() * vg.C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+                              vx, vg, vd, pool, accumulate)));
+  TE_LAUNCH_CHECK();
+  return TE_OK;
+}
+
+// a = lrelu(convT_{k=2,stride}(x) + bias); w Keras layout (2,2,2,Cout,Cin) fp32 on the device
+extern "C" int te_tr_upconv_fwd(const te_tensor* x, const float* w, const float* bias, const te_tensor* a, int32_t stride,
+                                float alpha, void* stream) {
+  TE_TR_CHECK_T(x, "te_tr_upconv_fwd"); TE_TR_CHECK_T(a, "te_tr_upconv_fwd");
+  TE_CHECK_ARG(w && bias && stride >= 2 && a->D == x->D * stride && a->H == x->H * stride && a->W == x->W * stride &&
+                   a->N == x->N && x->dtype == a->dtype, "te_tr_upconv_fwd: bad argument");
+  cudaError_t e = simt_upconv(view_of(*x), view_of(*a), w, bias, stride, 1, alpha, act_of(x->dtype), static_cast<cudaStream_t>(stream));
+  count_launch();
+  if (e != cudaSuccess) { set_error("te_tr_upconv_fwd: %s", cudaGetErrorString(e)); return TE_ERR_CUDA; }
+  return TE_OK;
+}
+
+// da is overwritten with dz = da * lrelu'(a); dbias2c[0..C) += sum dz; dw += wgrad; dx = dgrad (if dx)
+extern "C" int te_tr_upconv_bwd(const te_tensor* x, const te_tensor* a, const te_tensor* da, const float* w, int32_t stride,
+                                float alpha, float* dw, double* dbias2c, const te_tensor* dx, void* stream) {
+  TE_TR_CHECK_T(x, "te_tr_upconv_bwd"); TE_TR_CHECK_T(a, "te_tr_upconv_bwd"); TE_TR_CHECK_T(da, "te_tr_upconv_bwd");
+  TE_CHECK_ARG(w && dw && dbias2c && stride == 2 && same_grid(*a, *da) && a->C == da->C && x->dtype == a->dtype && a->dtype == da->dtype,
+               "te_tr_upconv_bwd: bad argument (stride 2 only)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const TView vx = view_of(*x), va = view_of(*a), vd = view_of(*da);
+  int grid = blocks_for(va.voxels() * va.C, 256, 8);
+  if (static_cast<long long>(grid) * 256 < va.C) grid = (va.C + 255) / 256;
+  TE_DISPATCH_T(a->dtype, (lrelu_bwd_bias_kernel<T><<<grid, 256, 0, st>>>(va, vd, alpha, dbias2c)));
+  TE_LAUNCH_CHECK();
+  const long long elems = static_cast<long long>(va.C) * vx.C;
+  const long long nvox = vx.voxels();
+  int splits = static_cast<int>(nvox / 2048);
+  if (splits < 1) splits = 1;
+  if (splits > 512) splits = 512;
+  dim3 g(static_cast<unsigned>((elems + 255) / 256), 8, splits);
+  TE_DISPATCH_T(a->dtype, (upconv_wgrad_kernel<T><<<g, 256, 0, st>>>(vx, vd, dw, stride, splits)));
+  TE_LAUNCH_CHECK();
+  if (dx) {
+    TE_TR_CHECK_T(dx, "te_tr_upconv_bwd");
+    TE_CHECK_ARG(same_grid(*x, *dx) && x->C == dx->C && x->dtype == dx->dtype, "te_tr_upconv_bwd: dx must match x");
+    const TView vo = view_of(*dx);
+    TE_DISPATCH_T(a->dtype, (upconv_dgrad_kernel<T><<<blocks_for(vo.voxels() * vo.C, 256, 32), 256, 0, st>>>(vd, vo, w, stride)));
+    TE_LAUNCH_CHECK();
+  }
+  return TE_OK;
+}
+
+// dw[27][dw_cin][Cout] (+)= wgrad(x, dy) for the input channels [ci_off, ci_off + x.C); dbias2c may be null
+extern "C" int te_tr_conv3_wgrad(const te_tensor* x, const te_tensor* dy, float* dw, int32_t dw_cin, int32_t ci_off,
+                                 double* dbias2c, void* stream) {
+  TE_TR_CHECK_T(x, "te_tr_conv3_wgrad"); TE_TR_CHECK_T(dy, "te_tr_conv3_wgrad");
+  TE_CHECK_ARG(dw && same_grid(*x, *dy) && x->dtype == dy->dtype && ci_off >= 0 && ci_off + x->C <= dw_cin,
+               "te_tr_conv3_wgrad: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const TView vx = view_of(*x), vd = view_of(*dy);
+  static const bool no_mma = getenv("TOMOENC_NO_MMA_WGRAD") != nullptr;
+  const bool mma = !no_mma && x->dtype != TE_F32 && x->C % 8 == 0 && dy->C % 8 == 0 && x->ctot % 8 == 0 && dy->ctot % 8 == 0 &&
+                   x->coff % 8 == 0 && dy->coff % 8 == 0 && x->C >= 8;
+  if (mma) {
+    WgParams p;
+    p.x = static_cast<const uint8_t*>(x->ptr); p.x_ctot = x->ctot; p.x_coff = x->coff;
+    p.dy = static_cast<const uint8_t*>(dy->ptr); p.dy_ctot = dy->ctot; p.dy_coff = dy->coff;
+    p.dw = dw; p.dw_cin = dw_cin; p.ci_off = ci_off; p.Cout = dy->C;
+    p.Ci = x->C; p.N = x->N; p.D = x->D; p.H = x->H; p.W = x->W;
+    p.tiles_x = (x->W + 7) / 8; p.tiles_y = (x->H + 15) / 16; p.tiles_z = (x->D + kWgTZ - 1) / kWgTZ;
+    p.total_tiles = static_cast<long long>(p.N) * p.tiles_z * p.tiles_y * p.tiles_x;
+    const int cib = (x->C + 31) / 32, cob = (dy->C + 31) / 32;
+    long long gx = (static_cast<long long>(kNumSMs) + cib * cob - 1) / (cib * cob);
+    if (gx < 1) gx = 1;
+    if (gx > p.total_tiles) gx = p.total_tiles;
+    static bool attr[2] = {false, false};
+    const int fp16 = x->dtype == TE_F16;
+    if (!attr[fp16]) {
+      cudaError_t e = fp16 ? cudaFuncSetAttribute(wgrad_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem)
+                           : cudaFuncSetAttribute(wgrad_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem);
+      if (e != cudaSuccess) { set_error("te_tr_conv3_wgrad: %s", cudaGetErrorString(e)); return TE_ERR_CUDA; }
+      attr[fp16] = true;
+    }
+    dim3 g(static_cast<unsigned>(gx), cib, cob);
+    if (fp16) wgrad_mma_kernel<true><<<g, 256, kWgSmem, st>>>(p);
+    else wgrad_mma_kernel<false><<<g, 256, kWgSmem, st>>>(p);
+    TE_LAUNCH_CHECK();
+  } else {
+    const long long elems = static_cast<long long>(vx.C) * vd.C;
+    const long long nvox = vd.voxels();
+    int splits = static_cast<int>(nvox / 4096);
+    if (splits < 1) splits = 1;
+    if (splits > 256) splits = 256;
+    dim3 g(static_cast<unsigned>((elems + 255) / 256), 27, splits);
+    TE_DISPATCH_T(x->dtype, (conv3_wgrad_simt_kernel<T><<<g, 256, 0, st>>>(vx, vd, dw, dw_cin, ci_off, splits)));
+    TE_LAUNCH_CHECK();
+  }
+  if (dbias2c) {
+    int grid = blocks_for(vd.voxels() * vd.C, 256, 8);
+    if (static_cast<long long>(grid) * 256 < vd.C) grid = (vd.C + 255) / 256;
+    TE_DISPATCH_T(dy->dtype, (channel_sum_kernel<T><<<grid, 256, 0, st>>>(vd, dbias2c)));
+    TE_LAUNCH_CHECK();
+  }
+  return TE_OK;
+}
+
+// loss (double, accumulated); dwb2c (double [2C], accumulated): [0, C) = d head weights, [C] = d head bias;
+// da written; dl = device fp32 scratch of one value per voxel; probs optional
+extern "C" int te_tr_head_loss(const te_tensor* a, const float* w, const float* b, const uint8_t* y, const te_tensor* da,
+                               double* loss, double* dwb2c, double n_total, float* dl, float* probs, void* stream) {
+  TE_TR_CHECK_T(a, "te_tr_head_loss"); TE_TR_CHECK_T(da, "te_tr_head_loss");
+  TE_CHECK_ARG(w && b && y && loss && dwb2c && dl && n_total > 0 && same_grid(*a, *da) && a->C == da->C && a->dtype == da->dtype &&
+                   a->C <= 1024, "te_tr_head_loss: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const TView va = view_of(*a), vd = view_of(*da);
+  const size_t sh = static_cast<size_t>(a->C) * sizeof(float);
+  TE_DISPATCH_T(a->dtype, (head_loss_kernel<T><<<blocks_for(va.voxels(), 256, 8), 256, sh, st>>>(
+                              va, w, b, y, vd, loss, static_cast<float>(1.0 / n_total), dl, probs)));
+  TE_LAUNCH_CHECK();
+  int grid = blocks_for(va.voxels() * va.C, 256, 8);
+  if (static_cast<long long>(grid) * 256 < va.C) grid = (va.C + 255) / 256;
+  TE_DISPATCH_T(a->dtype, (head_wgrad_kernel<T><<<grid, 256, 0, st>>>(va, dl, dwb2c)));
+  TE_LAUNCH_CHECK();
+  return TE_OK;
+}
+
+extern "C" int te_tr_adam(float* w, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                          int64_t step, float grad_scale, void* stream) {
+  TE_CHECK_ARG(w && g && m && v && n >= 0 && step >= 1, "te_tr_adam: bad argument");
+  if (n == 0) return TE_OK;
+  const double lr_t = static_cast<double>(lr) * sqrt(1.0 - pow(static_cast<double>(beta2), static_cast<double>(step))) /
+                      (1.0 - pow(static_cast<double>(beta1), static_cast<double>(step)));
+  adam_kernel<<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(w, g, m, v, n, static_cast<float>(lr_t), beta1, beta2,
+                                                                                  eps, grad_scale);
+  TE_LAUNCH_CHECK();
+  return TE_OK;
+}

@@ -1,0 +1,359 @@
+"""Training step of the U-net segmenter on the GPU.
+
+Replaces the Keras ``fit`` step behind ``SurfaceSegmenter.train``
+(/root/reference/tomo_encoders/neural_nets/surface_segmenter.py:43-66; model compiled with ``Adam()``
+and ``BinaryCrossentropy()`` at :322-323; graph ``build_Unet_3D`` neural_nets/Unet3D.py:199-291 with
+``BatchNormalization(momentum=0.9, epsilon=1e-5)`` in training mode, :78).  The graph is walked here;
+every operator is a C-ABI call into libtomoenc.so (include/tomoenc.h, "training operators"):
+forward convolutions and their data gradients on the tcgen05 implicit-GEMM kernel, weight gradients
+on mma.sync tiles, BN / LeakyReLU / pooling / loss as HBM-bound element-wise kernels.  Master
+weights, Adam moments and gradients are fp32 in ONE flat buffer in Keras ``get_weights()`` order, so
+that the data-parallel exchange is a single all-reduce; BN batch statistics are all-reduced as well
+(``sync_bn``), which reproduces the reference's single-device batch semantics on any number of GPUs.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _device, _lib, sharding
+from . import _spec
+
+BN_MOMENTUM = 0.9      # Unet3D.py:78
+BN_EPS = 1e-5
+LRELU_ALPHA = 0.2      # Unet3D.py:38
+
+
+TeTensor = _lib.TeTensor
+
+
+class _Act:
+    """One NDHWC activation tensor (torch buffer) plus, lazily, the buffer of its gradient."""
+
+    def __init__(self, n, size, c, dtype, device, te_dtype, need_grad=True):
+        self.n, self.size, self.c = n, tuple(size), c
+        self.t = torch.empty((n,) + self.size + (c,), dtype=dtype, device=device)
+        self.g = torch.empty_like(self.t) if need_grad else None
+        self.te_dtype = te_dtype
+
+    def _desc(self, t):
+        d = TeTensor()
+        d.ptr, d.dtype, d.ctot, d.coff, d.C = t.data_ptr(), self.te_dtype, self.c, 0, self.c
+        d.N, (d.D, d.H, d.W) = self.n, self.size
+        return d
+
+    @property
+    def x(self):
+        return self._desc(self.t)
+
+    @property
+    def dx(self):
+        return self._desc(self.g)
+
+    @property
+    def nvox(self):
+        return self.n * int(np.prod(self.size))
+
+
+class UnetTrainer:
+    """Owns the weights of one U-net and runs fit steps on batches of (x, y) patch pairs.
+
+    mode: "fp32" (CUDA-core check mode), "bf16" or "fp16" (tensor-core path; fp32 master weights)."""
+
+    def __init__(self, model_params, patch, batch, mode="bf16", lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7,
+                 sync_bn=True, process_group=None, weights=None, seed=None):
+        _device.require_cuda()
+        p = dict(model_params)
+        p.setdefault("n_blocks", len(p["n_filters"]))
+        for k, v in (("activation", "lrelu"), ("batch_norm", True), ("kern_size", 3), ("kern_size_upconv", 2)):
+            if p.setdefault(k, v) != v:
+                raise NotImplementedError("training is implemented for %s=%r (the value of every shipped model)" % (k, v))
+        nb = p["n_blocks"]
+        self.params = p
+        self.pools = _spec._pools(p.get("pool_size", 2), nb)
+        self.isconcat = list(p.get("isconcat") or [False] * nb)
+        if any(q not in (1, 2) for q in self.pools):
+            raise NotImplementedError("training supports pool sizes 1 and 2")
+        self.patch = tuple(int(s) for s in patch)
+        self.batch = int(batch)
+        if mode not in ("fp32", "bf16"):
+            raise NotImplementedError("training runs in 'bf16' (tensor cores, fp32 master weights) or 'fp32' (check mode); "
+                                      "fp16 activations would need loss scaling (dL/dlogit ~ 1/n_voxels underflows)")
+        self.mode = mode
+        self.dev = _device.device()
+        self.tdtype = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}[mode]
+        self.te_dtype = {"fp32": _lib.TE_F32, "bf16": _lib.TE_BF16, "fp16": _lib.TE_F16}[mode]
+        self.lr, self.b1, self.b2, self.eps = lr, beta_1, beta_2, epsilon
+        self.sync_bn, self.group = sync_bn, process_group
+        self.step_count = 0
+        self.L = _lib.lib()
+        self.spec = _spec.unet_spec(**{k: p[k] for k in ("n_filters", "n_blocks", "activation", "batch_norm", "kern_size",
+                                                         "kern_size_upconv", "isconcat", "pool_size") if k in p})
+        sizes = [int(np.prod(s)) for _, s in self.spec]
+        self.offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        n_par = int(self.offsets[-1])
+        self.theta = torch.zeros(n_par, dtype=torch.float32, device=self.dev)
+        self.grad = torch.zeros_like(self.theta)
+        self.m = torch.zeros_like(self.theta)
+        self.v = torch.zeros_like(self.theta)
+        self.set_weights(weights if weights is not None else _spec.keras_default_init(self.spec, seed))
+        self._plan()
+
+    # ------------------------------------------------------------------ weights
+    def set_weights(self, weights):
+        if len(weights) != len(self.spec):
+            raise ValueError("expected %d weight arrays, got %d" % (len(self.spec), len(weights)))
+        flat = np.concatenate([np.asarray(w, dtype=np.float32).reshape(-1) for w in weights])
+        if flat.size != self.theta.numel():
+            raise ValueError("weight sizes do not match the model")
+        self.theta.copy_(torch.from_numpy(flat))
+
+    def get_weights(self):
+        flat = self.theta.cpu().numpy()
+        return [flat[self.offsets[i]:self.offsets[i + 1]].reshape(s).copy() for i, (_, s) in enumerate(self.spec)]
+
+    def get_gradients(self):
+        flat = self.grad.cpu().numpy()
+        return [flat[self.offsets[i]:self.offsets[i + 1]].reshape(s).copy() if k not in ("bn_mean", "bn_var") else None
+                for i, (k, s) in enumerate(self.spec)]
+
+    def _w(self, i):
+        return self.theta[self.offsets[i]:self.offsets[i + 1]]
+
+    def _g(self, i):
+        return self.grad[self.offsets[i]:self.offsets[i + 1]]
+
+    # ------------------------------------------------------------------ plan
+    def _plan(self):
+        """Layer list in Keras creation order (= spec order); every entry knows its weight indices,
+        its input activation(s) and owns its output buffers."""
+        p, nb, n = self.params, self.params["n_blocks"], self.batch
+        mk = lambda size, c, grad=True: _Act(n, size, c, self.tdtype, self.dev, self.te_dtype, grad)  # noqa: E731
+        self.inp = mk(self.patch, 1, grad=False)
+        layers, wi = [], 0
+        size, cur = list(self.patch), self.inp
+        skips = []
+
+        def conv(src, src2, cout):
+            nonlocal wi
+            lay = dict(op="conv", w=wi, src=src, src2=src2, cin=src.c + (src2.c if src2 else 0), cout=cout,
+                       y=mk(src.size, cout, grad=False), a=mk(src.size, cout))
+            wi += 6
+            layers.append(lay)
+            return lay["a"]
+
+        for i in range(nb):
+            f = p["n_filters"][i]
+            cur = conv(cur, None, f)
+            cur = conv(cur, None, 2 * f)
+            skips.append(cur)
+            if self.pools[i] > 1:
+                if any(s % 2 for s in size):
+                    raise ValueError("pool size must divide the spatial extent")
+                size = [s // 2 for s in size]
+                out = mk(size, cur.c)
+                layers.append(dict(op="pool", src=cur, a=out))
+                cur = out
+        nf = cur.c
+        cur = conv(cur, None, nf)
+        cur = conv(cur, None, 2 * nf)
+        for i in range(nb - 1, -1, -1):
+            f = p["n_filters"][i]
+            skip = None
+            if self.pools[i] > 1:
+                size = [s * 2 for s in size]
+                up = mk(size, cur.c)
+                layers.append(dict(op="upconv", w=wi, src=cur, a=up))
+                wi += 2
+                cur = up
+                if self.isconcat[i]:
+                    skip = skips[i]
+            cur = conv(cur, skip, 2 * f)
+            cur = conv(cur, None, 2 * f)
+        layers.append(dict(op="head", w=wi, src=cur))
+        wi += 2
+        assert wi == len(self.spec), (wi, len(self.spec))
+        self.layers = layers
+        maxc = max(max(l.get("cout", 1), l.get("cin", 1)) for l in layers)
+        # scratch
+        self.stats = torch.zeros(2 * max(maxc, 1024), dtype=torch.float64, device=self.dev)
+        wpack = max(int(self.L.te_tr_conv3_wpack_bytes(l["cin"], l["cout"])) for l in layers if l["op"] == "conv")
+        wpack = max(wpack, max(int(self.L.te_tr_conv3_wpack_bytes(l["cout"], l["cin"])) for l in layers if l["op"] == "conv"))
+        self.wpack = torch.empty(max(wpack, 16), dtype=torch.uint8, device=self.dev)
+        self.wflip = torch.empty(27 * max(l["cin"] * l["cout"] for l in layers if l["op"] == "conv"), dtype=torch.float32,
+                                 device=self.dev)
+        self.zero_bias = torch.zeros(maxc, dtype=torch.float32, device=self.dev)
+        self.loss = torch.zeros(1, dtype=torch.float64, device=self.dev)
+        self.dl = torch.empty(self.batch * int(np.prod(self.patch)), dtype=torch.float32, device=self.dev)
+        self.labels = torch.empty((self.batch,) + self.patch, dtype=torch.uint8, device=self.dev)
+        for lay in layers:
+            if lay["op"] == "conv":
+                c = lay["cout"]
+                lay["cat"] = mk(lay["src"].size, lay["cin"]) if (lay["src2"] is not None and self.mode == "fp32") else None
+                lay["bn"] = {k: torch.empty(c, dtype=torch.float32, device=self.dev)
+                             for k in ("mean", "rstd", "scale", "shift", "dbeta_n", "dgamma_n", "var")}
+
+    def workspace_bytes(self):
+        tot = 0
+        for lay in self.layers:
+            for k in ("y", "a"):
+                if k in lay:
+                    tot += lay[k].t.numel() * lay[k].t.element_size() * (2 if lay[k].g is not None else 1)
+        return tot
+
+    # ------------------------------------------------------------------ helpers
+    def _call(self, name, *args):
+        _lib.check(getattr(self.L, name)(*args), name)
+
+    def _reduce_stats(self, c2):
+        s = self.stats[:c2]
+        if self.sync_bn:
+            sharding.allreduce_sum_(s, self.group)
+        return s
+
+    # ------------------------------------------------------------------ step
+    def forward_backward(self, x, y):
+        """x: (n,pz,py,px[,1]) float (already rescaled to the network's input range), y: same shape
+        {0,1}.  Leaves the global-batch mean loss in self.loss and the LOCAL gradient contribution
+        in self.grad (sum over ranks = gradient of the global-batch loss).  Returns the loss tensor."""
+        st = _device.stream_ptr()
+        world = sharding.world(self.group)[1] if self.sync_bn else 1
+        tx = _device.to_device(x)
+        ty = _device.to_device(y)
+        if tx.dim() == 5:
+            tx, ty = tx[..., 0], ty[..., 0]
+        if tuple(tx.shape) != (self.batch,) + self.patch:
+            raise ValueError("expected a batch of shape %s, got %s" % ((self.batch,) + self.patch, tuple(tx.shape)))
+        self.inp.t.copy_(tx.reshape(self.inp.t.shape))
+        self.labels.copy_(ty.reshape(self.labels.shape))
+        self.grad.zero_()
+        self.loss.zero_()
+        br = ctypes.byref
+        # ---------------- forward
+        for lay in self.layers:
+            op = lay["op"]
+            if op == "conv":
+                wi, c = lay["w"], lay["cout"]
+                if lay.get("cat") is not None:          # fp32 check mode: the concatenation is materialised
+                    lay["cat"].t.copy_(torch.cat([lay["src"].t, lay["src2"].t], dim=-1))
+                    xin, x2 = lay["cat"], None
+                else:
+                    xin, x2 = lay["src"], (br(lay["src2"].x) if lay["src2"] is not None else None)
+                self._call("te_tr_conv3", br(xin.x), x2, self._w(wi).data_ptr(), self._w(wi + 1).data_ptr(),
+                           br(lay["y"].x), self.wpack.data_ptr(), st)
+                self.stats[:2 * c].zero_()
+                self._call("te_tr_bn_stats", br(lay["y"].x), self.stats.data_ptr(), st)
+                s = self._reduce_stats(2 * c)
+                n_tot = float(lay["y"].nvox * world)
+                bn = lay["bn"]
+                mean = s[:c] / n_tot
+                var = torch.clamp(s[c:2 * c] / n_tot - mean * mean, min=0.0)
+                rstd = torch.rsqrt(var + BN_EPS)
+                gamma, beta = self._w(wi + 2).double(), self._w(wi + 3).double()
+                bn["mean"].copy_(mean); bn["var"].copy_(var); bn["rstd"].copy_(rstd)
+                bn["scale"].copy_(gamma * rstd); bn["shift"].copy_(beta - mean * gamma * rstd)
+                self._call("te_tr_bn_act_fwd", br(lay["y"].x), br(lay["a"].x), bn["scale"].data_ptr(), bn["shift"].data_ptr(),
+                           LRELU_ALPHA, st)
+            elif op == "pool":
+                self._call("te_tr_maxpool_fwd", br(lay["src"].x), br(lay["a"].x), 2, st)
+            elif op == "upconv":
+                wi = lay["w"]
+                self._call("te_tr_upconv_fwd", br(lay["src"].x), self._w(wi).data_ptr(), self._w(wi + 1).data_ptr(),
+                           br(lay["a"].x), 2, LRELU_ALPHA, st)
+            else:
+                wi, src = lay["w"], lay["src"]
+                self.stats[:2 * src.c].zero_()
+                n_tot = float(src.nvox * sharding.world(self.group)[1])
+                self._call("te_tr_head_loss", br(src.x), self._w(wi).data_ptr(), self._w(wi + 1).data_ptr(),
+                           self.labels.data_ptr(), br(src.dx), self.loss.data_ptr(), self.stats.data_ptr(), n_tot,
+                           self.dl.data_ptr(), None, st)
+                self._g(wi).copy_(self.stats[:src.c])
+                self._g(wi + 1).copy_(self.stats[src.c:src.c + 1])
+        # ---------------- backward
+        pending_pool = {}                     # id(skip activation) -> True once the decoder wrote its gradient
+        for lay in reversed(self.layers):
+            op = lay["op"]
+            if op == "head":
+                continue
+            if op == "conv":
+                wi, c, a, yb, bn = lay["w"], lay["cout"], lay["a"], lay["y"], lay["bn"]
+                self.stats[:2 * c].zero_()
+                self._call("te_tr_bn_act_bwd_reduce", br(yb.x), br(a.dx), bn["scale"].data_ptr(), bn["shift"].data_ptr(),
+                           bn["mean"].data_ptr(), bn["rstd"].data_ptr(), LRELU_ALPHA, self.stats.data_ptr(), st)
+                # parameter gradients use the LOCAL sums (the gradient all-reduce adds the ranks up);
+                # the normalisation backward needs the GLOBAL batch sums
+                self._g(wi + 3).copy_(self.stats[:c])
+                self._g(wi + 2).copy_(self.stats[c:2 * c])
+                s = self._reduce_stats(2 * c)
+                n_tot = float(yb.nvox * world)
+                bn["dbeta_n"].copy_(s[:c] / n_tot)
+                bn["dgamma_n"].copy_(s[c:2 * c] / n_tot)
+                # dy overwrites da in place (element-wise, same index)
+                self._call("te_tr_bn_act_bwd_apply", br(yb.x), br(a.dx), br(a.dx), bn["scale"].data_ptr(), bn["shift"].data_ptr(),
+                           bn["mean"].data_ptr(), bn["rstd"].data_ptr(), bn["dbeta_n"].data_ptr(), bn["dgamma_n"].data_ptr(),
+                           LRELU_ALPHA, st)
+                dy = a.dx
+                cin = lay["cin"]
+                self.stats[:2 * c].zero_()
+                if lay.get("cat") is not None:
+                    cat, s1, s2 = lay["cat"], lay["src"], lay["src2"]
+                    self._call("te_tr_conv3_wgrad", br(cat.x), br(dy), self._g(wi).data_ptr(), cin, 0, self.stats.data_ptr(), st)
+                    self._g(wi + 1).copy_(self.stats[:c])
+                    self._call("te_tr_flip_weights", self._w(wi).data_ptr(), cin, c, 0, cin, self.wflip.data_ptr(), st)
+                    self._call("te_tr_conv3", br(dy), None, self.wflip.data_ptr(), self.zero_bias.data_ptr(), br(cat.dx),
+                               self.wpack.data_ptr(), st)
+                    s1.g.copy_(cat.g[..., :s1.c])
+                    s2.g.copy_(cat.g[..., s1.c:])
+                    pending_pool[id(s2)] = True
+                    continue
+                # weight gradients (+ bias gradient through the first call)
+                off = 0
+                for k, src in enumerate([lay["src"], lay["src2"]]):
+                    if src is None:
+                        continue
+                    self._call("te_tr_conv3_wgrad", br(src.x), br(dy), self._g(wi).data_ptr(), cin, off,
+                               self.stats.data_ptr() if k == 0 else None, st)
+                    off += src.c
+                self._g(wi + 1).copy_(self.stats[:c])
+                # data gradients
+                off = 0
+                for src in (lay["src"], lay["src2"]):
+                    if src is None:
+                        continue
+                    if src.g is not None:
+                        self._call("te_tr_flip_weights", self._w(wi).data_ptr(), cin, c, off, src.c, self.wflip.data_ptr(), st)
+                        self._call("te_tr_conv3", br(dy), None, self.wflip.data_ptr(), self.zero_bias.data_ptr(), br(src.dx),
+                                   self.wpack.data_ptr(), st)
+                        pending_pool[id(src)] = True
+                    off += src.c
+            elif op == "pool":
+                src = lay["src"]
+                acc = 1 if pending_pool.get(id(src)) else 0
+                self._call("te_tr_maxpool_bwd", br(src.x), br(lay["a"].dx), br(src.dx), 2, acc, st)
+            elif op == "upconv":
+                wi, src, a = lay["w"], lay["src"], lay["a"]
+                self.stats[:2 * a.c].zero_()
+                self._call("te_tr_upconv_bwd", br(src.x), br(a.x), br(a.dx), self._w(wi).data_ptr(), 2, LRELU_ALPHA,
+                           self._g(wi).data_ptr(), self.stats.data_ptr(), br(src.dx), st)
+                self._g(wi + 1).copy_(self.stats[:a.c])
+        return self.loss
+
+    def apply_gradients(self):
+        """All-reduces the flat gradient buffer over the ranks, applies Keras Adam and updates the BN
+        moving statistics from the (global) batch statistics of the last forward pass."""
+        sharding.allreduce_sum_(self.grad, self.group)
+        self.step_count += 1
+        self._call("te_tr_adam", self.theta.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                   self.theta.numel(), self.lr, self.b1, self.b2, self.eps, self.step_count, 1.0, _device.stream_ptr())
+        for lay in self.layers:
+            if lay["op"] == "conv":
+                wi, bn = lay["w"], lay["bn"]
+                self._w(wi + 4).mul_(BN_MOMENTUM).add_(bn["mean"], alpha=1.0 - BN_MOMENTUM)
+                self._w(wi + 5).mul_(BN_MOMENTUM).add_(bn["var"], alpha=1.0 - BN_MOMENTUM)
+
+    def train_step(self, x, y):
+        """One fit step on a batch; returns the (global-batch mean) loss as a python float."""
+        self.forward_backward(x, y)
+        self.apply_gradients()
+        loss = sharding.allreduce_sum_(self.loss.clone(), self.group)
+        return float(loss.item())

@@ -32,6 +32,15 @@ def main():
     print("forward of %d patches: %.3f ms  (%.1f TFLOP/s effective, %.1f Mvox/s)" %
           (chunk, ms, chunk * net.flops_per_patch / ms / 1e9, chunk * 64 ** 3 / ms / 1e3))
     print("label mean", float(out.float().mean()))
+    if os.environ.get("PROF_LAYERS"):
+        net.set_profiling(True)
+        for _ in range(3):
+            net.unet_forward_into(x, out)
+        torch.cuda.synchronize()
+        for name, kernel, flops, ms_l, cnt in net.layer_times():
+            if cnt:
+                print("  %-18s %-34s %8.1f us  %7.1f TFLOP/s" % (name, kernel, 1e3 * ms_l / cnt, chunk * flops / (ms_l / cnt) / 1e9))
+        net.set_profiling(False)
 
 
 if __name__ == "__main__":
