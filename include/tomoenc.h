@@ -235,10 +235,13 @@ int te_tr_maxpool_bwd(const te_tensor* x, const te_tensor* dpool, const te_tenso
                       void* stream);
 /* a = LeakyReLU(Conv3DTranspose(k 2, strides s)(x) + bias); w: (2,2,2,Cout,Cin). */
 int te_tr_upconv_fwd(const te_tensor* x, const float* w, const float* bias, const te_tensor* a, int32_t stride,
-                     float alpha, void* stream);
-/* da <- dz = da * LeakyReLU'(a); dbias2c[0..C) += sum dz; dw += weight gradient; dx = data gradient (optional). */
+                     float alpha, void* wpack, void* stream);
+/* dz = da * LeakyReLU'(a); dbias2c[0..C) += sum dz; dw += weight gradient; dx = data gradient (optional).
+ * 16-bit tensors: dz is written "space to depth" into dz2 (N, D/2, H/2, W/2, 8 C) and both gradients are
+ * pointwise products on the tensor cores (wpack as above); fp32: da is overwritten with dz, CUDA cores. */
 int te_tr_upconv_bwd(const te_tensor* x, const te_tensor* a, const te_tensor* da, const float* w, int32_t stride,
-                     float alpha, float* dw, double* dbias2c, const te_tensor* dx, void* stream);
+                     float alpha, float* dw, double* dbias2c, const te_tensor* dx, const te_tensor* dz2, void* wpack,
+                     void* stream);
 /* 1x1x1 head + sigmoid + Keras binary cross-entropy (mean over n_total voxels), forward and backward. */
 int te_tr_head_loss(const te_tensor* a, const float* w, const float* b, const uint8_t* y, const te_tensor* da,
                     double* loss, double* dwb2c, double n_total, float* dl, float* probs, void* stream);

@@ -188,6 +188,43 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(TView x, TView dpool, 
   }
 }
 
+// Transposed conv backward on the tensor cores: dz2[v][sub * C + c] = da[2v + sub][c] * lrelu'(a[2v + sub][c])
+// ("space to depth": the 8 sub-positions of a low-resolution voxel become channel groups), so that
+//   dx = pointwise_conv(dz2, w viewed as [8 Cout][Cin])   and   dw = pointwise_wgrad(dz2, x);
+// dbias2[c] += sum dz.  Thread = (low-res voxel, sub, 8-channel group).
+template <typename T>
+__global__ void __launch_bounds__(256) lrelu_bwd_s2d_kernel(TView a, TView da, TView dz2, float alpha, double* dbias2) {
+  const int C = a.C, Dl = a.D / 2, Hl = a.H / 2, Wl = a.W / 2;
+  const long long total = static_cast<long long>(a.N) * Dl * Hl * Wl * 8 * C;
+  long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  stride -= stride % C;
+  const long long start = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (start >= stride) return;
+  const int c = static_cast<int>(start % C);
+  const T* ap = static_cast<const T*>(a.ptr);
+  const T* dp = static_cast<const T*>(da.ptr);
+  T* op = static_cast<T*>(dz2.ptr);
+  float s = 0.f;
+  double ds = 0.0;
+  int cnt = 0;
+  for (long long e = start; e < total; e += stride) {
+    long long t = e / C;
+    const int sub = static_cast<int>(t & 7); t >>= 3;
+    const int x = static_cast<int>(t % Wl); t /= Wl;
+    const int y = static_cast<int>(t % Hl); t /= Hl;
+    const int z = static_cast<int>(t % Dl);
+    const long long n = t / Dl;
+    const long long hv = ((n * a.D + 2 * z + (sub >> 2)) * a.H + 2 * y + ((sub >> 1) & 1)) * a.W + 2 * x + (sub & 1);
+    const float av = ldv<T>(ap + hv * a.ctot + a.coff + c);
+    const float dz = ldv<T>(dp + hv * da.ctot + da.coff + c) * (av > 0.f ? 1.f : alpha);
+    stv<T>(op + (e / (8LL * C)) * dz2.ctot + dz2.coff + sub * C + c, dz);
+    s += dz;
+    if (++cnt == 64) { ds += s; s = 0.f; cnt = 0; }
+  }
+  ds += s;
+  atomicAdd(dbias2 + c, ds);
+}
+
 // Transposed conv (k = 2, stride s) backward, part 1: dz = da * lrelu'(a) in place (a and z have the
 // same sign) and dbias[c] += sum dz.
 template <typename T>
@@ -352,15 +389,20 @@ struct WgParams {
   long long total_tiles;
 };
 
-template <bool FP16>
+// NTAPS = 27: 3x3x3 conv (haloed x box).  NTAPS = 1: pointwise (dw[ci][co] = sum_v x[v][ci] dy[v][co]), used by the
+// transposed-conv backward with x := dz2 (8 Cout channels) and dy := the layer input.
+template <bool FP16, int NTAPS>
 __global__ void __launch_bounds__(256, 1) wgrad_mma_kernel(const WgParams p) {
+  constexpr int HL = NTAPS == 27 ? 1 : 0;
+  constexpr int BXX = 8 + 2 * HL, BYY = 16 + 2 * HL;
+  constexpr int XVOX = (kWgTZ + 2 * HL) * BYY * BXX;
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ci0 = blockIdx.y * 32, co0 = blockIdx.z * 32;
   const int mt = warp & 1, nt = warp >> 1;                // this warp's mma tile: ci [16 mt, +16), co [8 nt, +8)
-  float acc[27][4];
+  float acc[NTAPS][4];
 #pragma unroll
-  for (int t = 0; t < 27; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
+  for (int t = 0; t < NTAPS; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
 
   auto load_tile = [&](long long tile, int stage) {
     long long t = tile;
@@ -370,11 +412,11 @@ __global__ void __launch_bounds__(256, 1) wgrad_mma_kernel(const WgParams p) {
     const long long n = t;
     uint8_t* sx = smem + stage * kWgStage;
     uint8_t* sd = sx + kWgXVox * kWgRow;
-    // x box: (TZ+2, 18, 10) voxels x 32 channels = 4 chunks of 16 B per voxel
-    for (int i = tid; i < kWgXVox * 4; i += 256) {
+    // x box: (TZ+2h, 16+2h, 8+2h) voxels x 32 channels = 4 chunks of 16 B per voxel
+    for (int i = tid; i < XVOX * 4; i += 256) {
       const int vox = i >> 2, ch = i & 3;
-      const int bx = vox % 10, by = (vox / 10) % 18, bz = vox / 180;
-      const int xx = x0 + bx - 1, yy = y0 + by - 1, zz = z0 + bz - 1;
+      const int bx = vox % BXX, by = (vox / BXX) % BYY, bz = vox / (BXX * BYY);
+      const int xx = x0 + bx - HL, yy = y0 + by - HL, zz = z0 + bz - HL;
       const bool ok = xx >= 0 && xx < p.W && yy >= 0 && yy < p.H && zz >= 0 && zz < p.D && ci0 + ch * 8 < p.Ci;
       const long long gv = ((n * p.D + (ok ? zz : 0)) * p.H + (ok ? yy : 0)) * p.W + (ok ? xx : 0);
       cp_async16(sx + vox * kWgRow + ch * 16, p.x + (gv * p.x_ctot + p.x_coff + ci0 + (ok ? ch * 8 : 0)) * 2, ok);
@@ -411,15 +453,15 @@ __global__ void __launch_bounds__(256, 1) wgrad_mma_kernel(const WgParams p) {
         ldmatrix_x2_trans(bfrag, sd + vox * kWgRow + nt * 16);
       }
 #pragma unroll
-      for (int tap = 0; tap < 27; ++tap) {
-        const int dz = tap / 9, dyy = (tap / 3) % 3, dxx = tap % 3;  // +1 biased box offsets
+      for (int tap = 0; tap < NTAPS; ++tap) {
+        const int dz = NTAPS == 27 ? tap / 9 : 0, dyy = NTAPS == 27 ? (tap / 3) % 3 : 0, dxx = NTAPS == 27 ? tap % 3 : 0;  // +1 biased box offsets
         // A fragment (x window): m = ci (16), k = voxel (16): four 8x8 matrices
         //   a0: m 0-7,k 0-7   a1: m 8-15,k 0-7   a2: m 0-7,k 8-15   a3: m 8-15,k 8-15
         // stored [voxel][channel]: matrix rows = voxels (k), 16-byte row chunk = 8 channels (m) -> .trans
         uint32_t afrag[4];
         const int mi = lane >> 3, r = lane & 7;                      // lane supplies row r of matrix mi
         const int kh = mi >> 1, mh = mi & 1;
-        const int vox = ((pz + dz) * 18 + (yr + kh + dyy)) * 10 + (r + dxx);
+        const int vox = ((pz + dz) * BYY + (yr + kh + dyy)) * BXX + (r + dxx);
         ldmatrix_x4_trans(afrag, sx + vox * kWgRow + (mt * 16 + mh * 8) * 2);
         mma16816<FP16>(acc[tap], afrag, bfrag);
       }
@@ -430,7 +472,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_mma_kernel(const WgParams p) {
   // flush: c0,c1 -> (row g, cols 2t, 2t+1); c2,c3 -> (row g + 8)
   const int g = lane >> 2, tq = lane & 3;
 #pragma unroll
-  for (int tap = 0; tap < 27; ++tap) {
+  for (int tap = 0; tap < NTAPS; ++tap) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int ci = ci0 + mt * 16 + g + h * 8;
@@ -532,23 +574,33 @@ __global__ void __launch_bounds__(256) flip_weights_kernel(const float* __restri
   }
 }
 
-// Device-side twin of conv_umma_pack(): fp32 w[tap][cin][cout] (Keras layout) -> swizzled 16-bit slabs.
+// Device-side twin of conv_umma_pack().  ntaps = 27: fp32 w[tap][cin][cout] (Keras Conv3D layout).
+// ntaps = 1, nsub = 1: pointwise conv, w[cin][cout].  ntaps = 1, nsub = 8: transposed conv,
+// w[sub][cout][cin] (Keras Conv3DTranspose layout).  Output: swizzled 16-bit slabs.
 __global__ void __launch_bounds__(256) pack_umma_kernel(const float* __restrict__ w, uint8_t* __restrict__ dst, int Cin, int Cout,
-                                                         int CB, int NT, int fuse, int fp16) {
-  const long long total = 27LL * Cin * Cout;
+                                                         int CB, int NT, int fuse, int fp16, int ntaps, int nsub) {
+  const long long total = static_cast<long long>(ntaps) * nsub * Cin * Cout;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   const int rowb = CB * 2;
   const uint32_t mask = CB == 16 ? 1u : (CB == 32 ? 3u : 7u);
   const int kchunks = Cin / CB;
-  const long long slab = 3LL * NT * rowb;
+  const int taps_g = ntaps == 27 ? 3 : 1, ngroups = ntaps == 27 ? 9 : 1;
+  const long long slab = static_cast<long long>(taps_g) * NT * rowb;
   for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
-    const int cout = static_cast<int>(e % Cout);
-    const int cin = static_cast<int>((e / Cout) % Cin);
-    const int tap = static_cast<int>(e / (static_cast<long long>(Cin) * Cout));
+    int cout, cin, tap = 0, sub = 0;
+    if (nsub == 8) {                       // [sub][cout][cin]
+      cin = static_cast<int>(e % Cin);
+      cout = static_cast<int>((e / Cin) % Cout);
+      sub = static_cast<int>(e / (static_cast<long long>(Cin) * Cout));
+    } else {                               // [tap][cin][cout]
+      cout = static_cast<int>(e % Cout);
+      cin = static_cast<int>((e / Cout) % Cin);
+      tap = static_cast<int>(e / (static_cast<long long>(Cin) * Cout));
+    }
     const int nt = cout / NT, r = cout % NT, kc = cin / CB, kk = cin % CB;
-    int g, t;
-    if (fuse) { g = tap % 9; t = 2 - tap / 9; } else { g = tap / 3; t = tap % 3; }
-    uint8_t* base = dst + ((static_cast<long long>(nt) * kchunks + kc) * 9 + g) * slab;
+    int g = 0, t = 0;
+    if (ntaps == 27) { if (fuse) { g = tap % 9; t = 2 - tap / 9; } else { g = tap / 3; t = tap % 3; } }
+    uint8_t* base = dst + (((static_cast<long long>(nt) * nsub + sub) * kchunks + kc) * ngroups + g) * slab;
     const uint32_t Lo = static_cast<uint32_t>((t * NT + r) * rowb + kk * 2);
     const uint32_t P = Lo ^ (((Lo >> 7) & mask) << 4);
     const float val = w[e];
@@ -572,13 +624,13 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-int make_tmap5(CUtensorMap* tm, const te_tensor& v, const ConvUmmaConfig& cfg) {
+int make_tmap5(CUtensorMap* tm, const te_tensor& v, const ConvUmmaConfig& cfg, int halo = 1) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled is not available"); return TE_ERR_CUDA; }
   cuuint64_t gdim[5] = {(cuuint64_t)v.ctot, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.D, (cuuint64_t)v.N};
   cuuint64_t gstr[4] = {(cuuint64_t)v.ctot * 2, (cuuint64_t)v.W * v.ctot * 2, (cuuint64_t)v.H * v.W * v.ctot * 2,
                         (cuuint64_t)v.D * v.H * v.W * v.ctot * 2};
-  cuuint32_t box[5] = {(cuuint32_t)cfg.CB, 10, 18, (cuuint32_t)(cfg.TZ + 2), 1};
+  cuuint32_t box[5] = {(cuuint32_t)cfg.CB, (cuuint32_t)(8 + 2 * halo), (cuuint32_t)(16 + 2 * halo), (cuuint32_t)(cfg.TZ + 2 * halo), 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   const CUtensorMapSwizzle sw = cfg.CB == 16 ? CU_TENSOR_MAP_SWIZZLE_32B
                                 : (cfg.CB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
@@ -588,6 +640,37 @@ int make_tmap5(CUtensorMap* tm, const te_tensor& v, const ConvUmmaConfig& cfg) {
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return TE_ERR_CUDA; }
   return TE_OK;
 }
+
+// Packs the weights on the device and launches conv_umma_kernel.  ntaps 27: 3x3x3 'same' conv
+// (w[27][Cin][Cout]); ntaps 1, up_stride 0: pointwise conv (w[Cin][Cout]); ntaps 1, up_stride 2:
+// transposed conv k = s = 2 (w[8][Cout][Cin]).
+int umma_conv(const te_tensor& x, const te_tensor* x2, const float* w, const float* bias, const te_tensor& y, void* wpack,
+              const ConvUmmaConfig& cfg, int ntaps, int up_stride, int lrelu, float alpha, cudaStream_t st) {
+  const int Cin = x.C + (x2 ? x2->C : 0), Cout = y.C;
+  const int nsub = up_stride ? 8 : 1;
+  const int fuse = ntaps == 27 && 3 * cfg.NT <= 256;
+  pack_umma_kernel<<<blocks_for(static_cast<long long>(ntaps) * nsub * Cin * Cout, 256), 256, 0, st>>>(
+      w, static_cast<uint8_t*>(wpack), Cin, Cout, cfg.CB, cfg.NT, fuse, x.dtype == TE_F16, ntaps, nsub);
+  TE_LAUNCH_CHECK();
+  ConvUmmaLaunch C{};
+  const int halo = ntaps == 27 ? 1 : 0;
+  int rc = make_tmap5(&C.tmap_in, x, cfg, halo);
+  if (rc != TE_OK) return rc;
+  if (x2) { rc = make_tmap5(&C.tmap_in2, *x2, cfg, halo); if (rc != TE_OK) return rc; } else C.tmap_in2 = C.tmap_in;
+  C.Cin2 = x2 ? x2->C : 0;
+  C.w_packed = wpack; C.bias = bias;
+  C.out = y.ptr; C.out_ctot = y.ctot; C.out_coff = y.coff;
+  C.N = x.N; C.D = x.D; C.H = x.H; C.W = x.W;
+  C.Cin = Cin; C.Cout = Cout; C.ntaps = ntaps; C.up_stride = up_stride; C.act_lrelu = lrelu; C.alpha = alpha;
+  C.fp16 = x.dtype == TE_F16;
+  C.CB = cfg.CB; C.NT = cfg.NT; C.TZ = cfg.TZ;
+  cudaError_t e = conv_umma_launch(C, st);
+  count_launch();
+  if (e != cudaSuccess) { set_error("tensor-core conv launch failed: %s", cudaGetErrorString(e)); return TE_ERR_CUDA; }
+  return TE_OK;
+}
+
+bool dense(const te_tensor& t) { return t.coff == 0 && t.C == t.ctot; }
 
 bool same_grid(const te_tensor& a, const te_tensor& b) {
   return a.N == b.N && a.D == b.D && a.H == b.H && a.W == b.W;
@@ -620,27 +703,7 @@ extern "C" int te_tr_conv3(const te_tensor* x, const te_tensor* x2, const float*
   const bool dense_in = x->coff == 0 && x->C == x->ctot && (!x2 || (x2->coff == 0 && x2->C == x2->ctot));
   const bool umma = x->dtype != TE_F32 && wpack && dense_in && conv_umma_config(Cin, Cout, &cfg) &&
                     (!x2 || (x->C % cfg.CB == 0 && x2->C % cfg.CB == 0));
-  if (umma) {
-    const int fuse = 3 * cfg.NT <= 256;
-    pack_umma_kernel<<<blocks_for(27LL * Cin * Cout, 256), 256, 0, st>>>(w, static_cast<uint8_t*>(wpack), Cin, Cout, cfg.CB,
-                                                                         cfg.NT, fuse, x->dtype == TE_F16);
-    TE_LAUNCH_CHECK();
-    ConvUmmaLaunch C{};
-    int rc = make_tmap5(&C.tmap_in, *x, cfg);
-    if (rc != TE_OK) return rc;
-    if (x2) { rc = make_tmap5(&C.tmap_in2, *x2, cfg); if (rc != TE_OK) return rc; } else C.tmap_in2 = C.tmap_in;
-    C.Cin2 = x2 ? x2->C : 0;
-    C.w_packed = wpack; C.bias = bias;
-    C.out = y->ptr; C.out_ctot = y->ctot; C.out_coff = y->coff;
-    C.N = x->N; C.D = x->D; C.H = x->H; C.W = x->W;
-    C.Cin = Cin; C.Cout = Cout; C.ntaps = 27; C.up_stride = 0; C.act_lrelu = 0; C.alpha = 0.f;
-    C.fp16 = x->dtype == TE_F16;
-    C.CB = cfg.CB; C.NT = cfg.NT; C.TZ = cfg.TZ;
-    cudaError_t e = conv_umma_launch(C, st);
-    count_launch();
-    if (e != cudaSuccess) { set_error("te_tr_conv3: launch failed: %s", cudaGetErrorString(e)); return TE_ERR_CUDA; }
-    return TE_OK;
-  }
+  if (umma) return umma_conv(*x, x2, w, bias, *y, wpack, cfg, 27, 0, 0, 0.f, st);
   TE_CHECK_ARG(!x2, "te_tr_conv3: two-input form needs the tensor-core path (16-bit, dense, channel counts % 16)");
   cudaError_t e = simt_conv3(view_of(*x), view_of(*y), w, bias, 0, 0.f, act_of(x->dtype), st);
   count_launch();
@@ -728,26 +791,102 @@ extern "C" int te_tr_maxpool_bwd(const te_tensor* x, const te_tensor* dpool, con
   return TE_OK;
 }
 
-// a = lrelu(convT_{k=2,stride}(x) + bias); w Keras layout (2,2,2,Cout,Cin) fp32 on the device
+// a = lrelu(convT_{k=2,stride}(x) + bias); w Keras layout (2,2,2,Cout,Cin) fp32 on the device.  16-bit dense
+// tensors with channel counts % 16 and stride 2 run on the tcgen05 kernel (wpack as for te_tr_conv3).
 extern "C" int te_tr_upconv_fwd(const te_tensor* x, const float* w, const float* bias, const te_tensor* a, int32_t stride,
-                                float alpha, void* stream) {
+                                float alpha, void* wpack, void* stream) {
   TE_TR_CHECK_T(x, "te_tr_upconv_fwd"); TE_TR_CHECK_T(a, "te_tr_upconv_fwd");
   TE_CHECK_ARG(w && bias && stride >= 2 && a->D == x->D * stride && a->H == x->H * stride && a->W == x->W * stride &&
                    a->N == x->N && x->dtype == a->dtype, "te_tr_upconv_fwd: bad argument");
-  cudaError_t e = simt_upconv(view_of(*x), view_of(*a), w, bias, stride, 1, alpha, act_of(x->dtype), static_cast<cudaStream_t>(stream));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ConvUmmaConfig cfg;
+  if (x->dtype != TE_F32 && wpack && stride == 2 && dense(*x) && conv_umma_config(x->C, a->C, &cfg))
+    return umma_conv(*x, nullptr, w, bias, *a, wpack, cfg, 1, 2, 1, alpha, st);
+  cudaError_t e = simt_upconv(view_of(*x), view_of(*a), w, bias, stride, 1, alpha, act_of(x->dtype), st);
   count_launch();
   if (e != cudaSuccess) { set_error("te_tr_upconv_fwd: %s", cudaGetErrorString(e)); return TE_ERR_CUDA; }
   return TE_OK;
 }
 
-// da is overwritten with dz = da * lrelu'(a); dbias2c[0..C) += sum dz; dw += wgrad; dx = dgrad (if dx)
+namespace te {
+namespace {
+template <bool FP16, int NTAPS>
+cudaError_t launch_wgrad_mma_t(const WgParams& p, dim3 g, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_mma_kernel<FP16, NTAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  wgrad_mma_kernel<FP16, NTAPS><<<g, 256, kWgSmem, st>>>(p);
+  return cudaGetLastError();
+}
+
+bool wgrad_mma_ok(const te_tensor& x, const te_tensor& dy) {
+  static const bool no_mma = getenv("TOMOENC_NO_MMA_WGRAD") != nullptr;
+  return !no_mma && x.dtype != TE_F32 && x.C % 8 == 0 && dy.C % 8 == 0 && x.ctot % 8 == 0 && dy.ctot % 8 == 0 &&
+         x.coff % 8 == 0 && dy.coff % 8 == 0 && x.C >= 8;
+}
+
+// dw[ntaps][dw_cin][dy.C] += wgrad(x, dy) on mma.sync tiles
+int wgrad_mma(const te_tensor& x, const te_tensor& dy, float* dw, int dw_cin, int ci_off, int ntaps, cudaStream_t st) {
+  WgParams p;
+  p.x = static_cast<const uint8_t*>(x.ptr); p.x_ctot = x.ctot; p.x_coff = x.coff;
+  p.dy = static_cast<const uint8_t*>(dy.ptr); p.dy_ctot = dy.ctot; p.dy_coff = dy.coff;
+  p.dw = dw; p.dw_cin = dw_cin; p.ci_off = ci_off; p.Cout = dy.C;
+  p.Ci = x.C; p.N = x.N; p.D = x.D; p.H = x.H; p.W = x.W;
+  p.tiles_x = (x.W + 7) / 8; p.tiles_y = (x.H + 15) / 16; p.tiles_z = (x.D + kWgTZ - 1) / kWgTZ;
+  p.total_tiles = static_cast<long long>(p.N) * p.tiles_z * p.tiles_y * p.tiles_x;
+  const int cib = (x.C + 31) / 32, cob = (dy.C + 31) / 32;
+  long long gx = (2LL * kNumSMs + cib * cob - 1) / (cib * cob);
+  if (gx < 1) gx = 1;
+  if (gx > p.total_tiles) gx = p.total_tiles;
+  dim3 g(static_cast<unsigned>(gx), cib, cob);
+  const bool fp16 = x.dtype == TE_F16;
+  cudaError_t e = ntaps == 27 ? (fp16 ? launch_wgrad_mma_t<true, 27>(p, g, st) : launch_wgrad_mma_t<false, 27>(p, g, st))
+                              : (fp16 ? launch_wgrad_mma_t<true, 1>(p, g, st) : launch_wgrad_mma_t<false, 1>(p, g, st));
+  count_launch();
+  if (e != cudaSuccess) { set_error("wgrad launch failed: %s", cudaGetErrorString(e)); return TE_ERR_CUDA; }
+  return TE_OK;
+}
+}  // namespace
+}  // namespace te
+
+// Transposed conv backward.  dbias2c[0..C) += sum dz; dw (2,2,2,Cout,Cin) += weight gradient; dx = data gradient
+// (optional).  Tensor-core path (16-bit, dense, channels % 16, dz2 = scratch tensor (N, D/2, H/2, W/2, 8 Cout) of the
+// same dtype, wpack): da is left untouched and dz goes, rearranged, to dz2.  Otherwise (fp32 check mode) da is
+// overwritten with dz in place and CUDA-core kernels are used.
 extern "C" int te_tr_upconv_bwd(const te_tensor* x, const te_tensor* a, const te_tensor* da, const float* w, int32_t stride,
-                                float alpha, float* dw, double* dbias2c, const te_tensor* dx, void* stream) {
+                                float alpha, float* dw, double* dbias2c, const te_tensor* dx, const te_tensor* dz2, void* wpack,
+                                void* stream) {
   TE_TR_CHECK_T(x, "te_tr_upconv_bwd"); TE_TR_CHECK_T(a, "te_tr_upconv_bwd"); TE_TR_CHECK_T(da, "te_tr_upconv_bwd");
   TE_CHECK_ARG(w && dw && dbias2c && stride == 2 && same_grid(*a, *da) && a->C == da->C && x->dtype == a->dtype && a->dtype == da->dtype,
                "te_tr_upconv_bwd: bad argument (stride 2 only)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const TView vx = view_of(*x), va = view_of(*a), vd = view_of(*da);
+  ConvUmmaConfig cfg;
+  const bool tc = a->dtype != TE_F32 && dz2 && dz2->ptr && wpack && dense(*dz2) && dz2->C == 8 * a->C && same_grid(*dz2, *x) &&
+                  dz2->dtype == a->dtype && wgrad_mma_ok(*dz2, *x) && (!dx || (dense(*dx) && conv_umma_config(dz2->C, x->C, &cfg)));
+  if (tc) {
+    const TView vz = view_of(*dz2);
+    int grid = blocks_for(va.voxels() * va.C, 256, 8);
+    if (static_cast<long long>(grid) * 256 < va.C) grid = (va.C + 255) / 256;
+    TE_DISPATCH_T(a->dtype, (lrelu_bwd_s2d_kernel<T><<<grid, 256, 0, st>>>(va, vd, vz, alpha, dbias2c)));
+    TE_LAUNCH_CHECK();
+    // dw[(sub, co)][ci] = sum_v dz2[v][(sub, co)] x[v][ci]
+    int rc = wgrad_mma(*dz2, *x, dw, dz2->C, 0, 1, st);
+    if (rc != TE_OK) return rc;
+    if (dx) {
+      TE_CHECK_ARG(same_grid(*x, *dx) && x->C == dx->C && x->dtype == dx->dtype, "te_tr_upconv_bwd: dx must match x");
+      // dx[v][ci] = sum_(sub, co) dz2[v][(sub, co)] w[(sub, co)][ci]: pointwise conv, w already in [Cin' = 8 Cout][Cout' = Cin] order
+      static float* zero_bias = nullptr;
+      if (!zero_bias) { TE_CUDA(cudaMalloc(&zero_bias, 4096 * sizeof(float))); TE_CUDA(cudaMemset(zero_bias, 0, 4096 * sizeof(float))); }
+      TE_CHECK_ARG(dx->C <= 4096, "te_tr_upconv_bwd: too many channels");
+      rc = umma_conv(*dz2, nullptr, w, zero_bias, *dx, wpack, cfg, 1, 0, 0, 0.f, st);
+      if (rc != TE_OK) return rc;
+    }
+    return TE_OK;
+  }
   int grid = blocks_for(va.voxels() * va.C, 256, 8);
   if (static_cast<long long>(grid) * 256 < va.C) grid = (va.C + 255) / 256;
   TE_DISPATCH_T(a->dtype, (lrelu_bwd_bias_kernel<T><<<grid, 256, 0, st>>>(va, vd, alpha, dbias2c)));
@@ -778,39 +917,15 @@ extern "C" int te_tr_conv3_wgrad(const te_tensor* x, const te_tensor* dy, float*
                "te_tr_conv3_wgrad: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const TView vx = view_of(*x), vd = view_of(*dy);
-  static const bool no_mma = getenv("TOMOENC_NO_MMA_WGRAD") != nullptr;
-  const bool mma = !no_mma && x->dtype != TE_F32 && x->C % 8 == 0 && dy->C % 8 == 0 && x->ctot % 8 == 0 && dy->ctot % 8 == 0 &&
-                   x->coff % 8 == 0 && dy->coff % 8 == 0 && x->C >= 8;
-  if (mma) {
-    WgParams p;
-    p.x = static_cast<const uint8_t*>(x->ptr); p.x_ctot = x->ctot; p.x_coff = x->coff;
-    p.dy = static_cast<const uint8_t*>(dy->ptr); p.dy_ctot = dy->ctot; p.dy_coff = dy->coff;
-    p.dw = dw; p.dw_cin = dw_cin; p.ci_off = ci_off; p.Cout = dy->C;
-    p.Ci = x->C; p.N = x->N; p.D = x->D; p.H = x->H; p.W = x->W;
-    p.tiles_x = (x->W + 7) / 8; p.tiles_y = (x->H + 15) / 16; p.tiles_z = (x->D + kWgTZ - 1) / kWgTZ;
-    p.total_tiles = static_cast<long long>(p.N) * p.tiles_z * p.tiles_y * p.tiles_x;
-    const int cib = (x->C + 31) / 32, cob = (dy->C + 31) / 32;
-    long long gx = (static_cast<long long>(kNumSMs) + cib * cob - 1) / (cib * cob);
-    if (gx < 1) gx = 1;
-    if (gx > p.total_tiles) gx = p.total_tiles;
-    static bool attr[2] = {false, false};
-    const int fp16 = x->dtype == TE_F16;
-    if (!attr[fp16]) {
-      cudaError_t e = fp16 ? cudaFuncSetAttribute(wgrad_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem)
-                           : cudaFuncSetAttribute(wgrad_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem);
-      if (e != cudaSuccess) { set_error("te_tr_conv3_wgrad: %s", cudaGetErrorString(e)); return TE_ERR_CUDA; }
-      attr[fp16] = true;
-    }
-    dim3 g(static_cast<unsigned>(gx), cib, cob);
-    if (fp16) wgrad_mma_kernel<true><<<g, 256, kWgSmem, st>>>(p);
-    else wgrad_mma_kernel<false><<<g, 256, kWgSmem, st>>>(p);
-    TE_LAUNCH_CHECK();
+  if (wgrad_mma_ok(*x, *dy)) {
+    const int rc = wgrad_mma(*x, *dy, dw, dw_cin, ci_off, 27, st);
+    if (rc != TE_OK) return rc;
   } else {
     const long long elems = static_cast<long long>(vx.C) * vd.C;
     const long long nvox = vd.voxels();
-    int splits = static_cast<int>(nvox / 4096);
+    int splits = static_cast<int>(nvox / (elems >= 256 ? 4096 : 512));
     if (splits < 1) splits = 1;
-    if (splits > 256) splits = 256;
+    if (splits > 2048) splits = 2048;
     dim3 g(static_cast<unsigned>((elems + 255) / 256), 27, splits);
     TE_DISPATCH_T(x->dtype, (conv3_wgrad_simt_kernel<T><<<g, 256, 0, st>>>(vx, vd, dw, dw_cin, ci_off, splits)));
     TE_LAUNCH_CHECK();

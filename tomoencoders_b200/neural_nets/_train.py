@@ -179,10 +179,14 @@ class UnetTrainer:
         self.stats = torch.zeros(2 * max(maxc, 1024), dtype=torch.float64, device=self.dev)
         wpack = max(int(self.L.te_tr_conv3_wpack_bytes(l["cin"], l["cout"])) for l in layers if l["op"] == "conv")
         wpack = max(wpack, max(int(self.L.te_tr_conv3_wpack_bytes(l["cout"], l["cin"])) for l in layers if l["op"] == "conv"))
-        self.wpack = torch.empty(max(wpack, 16), dtype=torch.uint8, device=self.dev)
         self.wflip = torch.empty(27 * max(l["cin"] * l["cout"] for l in layers if l["op"] == "conv"), dtype=torch.float32,
                                  device=self.dev)
         self.zero_bias = torch.zeros(maxc, dtype=torch.float32, device=self.dev)
+        ups = [l for l in layers if l["op"] == "upconv"]
+        self.dz2 = torch.empty(max([l["a"].t.numel() for l in ups] + [1]), dtype=self.tdtype, device=self.dev)
+        for l in ups:      # packed-weight scratch must also hold the transposed-conv (8 sub-positions) and pointwise forms
+            wpack = max(wpack, 8 * l["src"].c * l["a"].c * 2)
+        self.wpack = torch.empty(max(wpack, 16), dtype=torch.uint8, device=self.dev)
         self.loss = torch.zeros(1, dtype=torch.float64, device=self.dev)
         self.dl = torch.empty(self.batch * int(np.prod(self.patch)), dtype=torch.float32, device=self.dev)
         self.labels = torch.empty((self.batch,) + self.patch, dtype=torch.uint8, device=self.dev)
@@ -259,7 +263,7 @@ class UnetTrainer:
             elif op == "upconv":
                 wi = lay["w"]
                 self._call("te_tr_upconv_fwd", br(lay["src"].x), self._w(wi).data_ptr(), self._w(wi + 1).data_ptr(),
-                           br(lay["a"].x), 2, LRELU_ALPHA, st)
+                           br(lay["a"].x), 2, LRELU_ALPHA, self.wpack.data_ptr(), st)
             else:
                 wi, src = lay["w"], lay["src"]
                 self.stats[:2 * src.c].zero_()
@@ -333,8 +337,16 @@ class UnetTrainer:
             elif op == "upconv":
                 wi, src, a = lay["w"], lay["src"], lay["a"]
                 self.stats[:2 * a.c].zero_()
+                dz2 = None
+                if self.mode != "fp32":
+                    # scratch: the gradient buffer of a same-resolution activation is large enough and dead by now?
+                    # no -- keep it simple and explicit: one scratch tensor sized for the largest transposed conv
+                    d = TeTensor()
+                    d.ptr, d.dtype, d.ctot, d.coff, d.C = self.dz2.data_ptr(), self.te_dtype, 8 * a.c, 0, 8 * a.c
+                    d.N, (d.D, d.H, d.W) = src.n, src.size
+                    dz2 = br(d)
                 self._call("te_tr_upconv_bwd", br(src.x), br(a.x), br(a.dx), self._w(wi).data_ptr(), 2, LRELU_ALPHA,
-                           self._g(wi).data_ptr(), self.stats.data_ptr(), br(src.dx), st)
+                           self._g(wi).data_ptr(), self.stats.data_ptr(), br(src.dx), dz2, self.wpack.data_ptr(), st)
                 self._g(wi + 1).copy_(self.stats[:a.c])
         return self.loss
 
