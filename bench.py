@@ -330,6 +330,38 @@ def run_ours(args):
     enc_value = world * ENC_PATCHES / (enc_ms / 1e3)
     enc_flops = ae.models["encoder"].net_for((PATCH,) * 3, CHUNK).flops_per_patch
 
+    # ------------------------------------------------------------------ training leg (BASELINE configs[4]): fwd + bwd + Adam,
+    # 64 patch pairs of 64^3 split over the ranks (8 per rank at N = 8; never fewer than 8 per rank here), SyncBN,
+    # one flat gradient all-reduce per step
+    train = None
+    if os.environ.get("TOMOENC_BENCH_TRAIN", "1") != "0":
+        from tomoencoders_b200.neural_nets._train import UnetTrainer
+        del vol, seg
+        torch.cuda.empty_cache()
+        tb = max(8, 64 // world)
+        tr = UnetTrainer(M_A01, (PATCH,) * 3, tb, mode="bf16", seed=13)
+        gx = torch.Generator(device=dev).manual_seed(8 + rank)
+        tx = torch.rand((tb,) + (PATCH,) * 3, generator=gx, device=dev)
+        ty = (torch.rand((tb,) + (PATCH,) * 3, generator=gx, device=dev) < 0.5).to(torch.uint8)
+        for _ in range(2):
+            tr.train_step(tx, ty)
+        barrier()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches_t0 = _lib.lib().te_launch_count()
+        t0e.record()
+        n_tr = max(1, min(args.steps, 3))
+        for _ in range(n_tr):
+            tloss = tr.train_step(tx, ty)
+        t1e.record()
+        barrier()
+        tr_ms = max_over_ranks(t0e.elapsed_time(t1e)) / n_tr
+        train = {"metric": "training patch pairs/sec (U-net M_a01 fwd+bwd+Adam, 64^3 pairs, bf16 activations, fp32 master weights)",
+                 "value": world * tb / (tr_ms / 1e3), "unit": "patch pairs/s", "ms_per_step": tr_ms, "global_batch": world * tb,
+                 "per_rank_batch": tb, "loss": tloss, "tflops_effective_3x_fwd": 3 * world * tb * net.flops_per_patch / (tr_ms / 1e3) / 1e12,
+                 "gpu_launches_per_step": int((_lib.lib().te_launch_count() - launches_t0) / n_tr),
+                 "collectives": "all-reduce(flat fp32 gradient, 4.77 M values) + SyncBN all-reduces of per-channel sums" if world > 1 else "none (1 rank)"}
+        del tr, tx, ty
+
     if rank == 0:
         cpu_v, cpu_dt, cpu_threads = cpu_reference_leg(4)
         flops_patch = net.flops_per_patch
@@ -365,6 +397,7 @@ def run_ours(args):
                        "value": enc_value, "unit": "patches/s", "ms_per_step": enc_ms, "patches_per_rank_per_step": ENC_PATCHES,
                        "tflops_effective": enc_value * enc_flops / 1e12,
                        "collectives": "allreduce(16513 f64 PCA moments) + allgather((n,2) projections)" if world > 1 else "none (1 rank)"},
+            "train": train,
             "cpu_baseline": {"value": cpu_v, "unit": "voxels/s", "cores": cpu_threads, "kind": "port",
                              "sample": "4 x 64^3 tiles: oracle extract + torch-CPU fp32 U-net M_a01 + fill (%.1f s)" % cpu_dt},
         }

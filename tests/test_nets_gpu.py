@@ -164,5 +164,7 @@ def test_predict_patches_argument_checks():
         SurfaceSegmenter(model_initialization="nope")
     y = fe.predict_patches("segmenter", np.zeros((0, 32, 32, 32, 1), np.float32), 2, None)
     assert y.shape == (0, 32, 32, 32, 1)
+    # training exists for the segmenter (tests/test_train_gpu.py); the processors without a trainer say so
+    from tomoencoders_b200.neural_nets import Enhancer_fCNN
     with pytest.raises(NotImplementedError):
-        fe.train(None, None, (32,) * 3, 2, 4, 0.1, False, 0.1, 1)
+        Enhancer_fCNN(model_initialization="define-new", descriptor_tag="t", **SMALL).train(None, None)

@@ -1,11 +1,18 @@
 """``SurfaceSegmenter``: drop-in for /root/reference/tomo_encoders/neural_nets/surface_segmenter.py:36-350
-on the inference path (3-D U-net, clip + rescale + predict + round -> uint8 labels)."""
+(3-D U-net; inference: clip + rescale + predict + round -> uint8 labels; training: random multi-scale
+patch pairs with blank rejection, noise and rot90 augmentation -> Adam / binary cross-entropy fit steps)."""
 import os
+import time
 
 import numpy as np
+import torch
 
+from .. import _device
+from ..structures.patches import Patches
 from .keras_processor import Vox2VoxProcessor_fCNN
 from .Unet3D import build_Unet_3D
+
+MAX_ITERS = 2000                    # surface_segmenter.py:27
 
 
 class SurfaceSegmenter(Vox2VoxProcessor_fCNN):
@@ -37,6 +44,107 @@ class SurfaceSegmenter(Vox2VoxProcessor_fCNN):
     def segment_volume(self, vol, p_grid, chunk_size, min_max=None, out=None):
         """Fused extract -> predict -> fill of a whole volume (see process_volume)."""
         return self.process_volume(vol, p_grid, chunk_size, min_max=min_max, model_key="segmenter", out=out)
+
+    # ------------------------------------------------------------------ training (surface_segmenter.py:43-124, 202-244)
+    def train(self, Xs, Ys, input_size, max_stride, batch_size, cutoff, random_rotate, add_noise, n_epochs,
+              steps_per_epoch=None, mode="bf16", verbose=1):
+        """surface_segmenter.py:43-66.  Xs / Ys: lists of volumes (numpy or torch, host or CUDA) and
+        their ground-truth label volumes.  Keras' ``fit(x=generator, epochs, steps_per_epoch)`` is
+        replaced by UnetTrainer fit steps (Adam defaults, BinaryCrossentropy, BN in training mode,
+        :322-323); the reference's validation_steps are a no-op there (no validation_data) and here.
+        The trained weights (and BN moving statistics) are written back to models["segmenter"]."""
+        from ._train import UnetTrainer
+        model = self.models["segmenter"]
+        dg = self._data_generator(Xs, Ys, batch_size, input_size, max_stride, cutoff, random_rotate, add_noise)
+        tot_steps, val_split = 1000, 0.2
+        if steps_per_epoch is None:
+            steps_per_epoch = int((1 - val_split) * tot_steps // batch_size)
+        trainer = getattr(self, "_trainer", None)
+        if trainer is None or trainer.patch != tuple(input_size) or trainer.batch != batch_size:
+            trainer = UnetTrainer(model.model_params, input_size, batch_size, mode=mode, weights=model.get_weights())
+            self._trainer = trainer
+        else:
+            trainer.set_weights(model.get_weights())
+        t0 = time.time()
+        history = []
+        for epoch in range(n_epochs):
+            losses = []
+            for _ in range(steps_per_epoch):
+                x, y = next(dg)
+                losses.append(trainer.train_step(x, y))
+            history.append(float(np.mean(losses)))
+            if verbose:
+                print("Epoch %d/%d - %d steps - loss: %.4f" % (epoch + 1, n_epochs, steps_per_epoch, history[-1]))
+        model.set_weights(trainer.get_weights())
+        if verbose:
+            print("training time = %.2f seconds" % (time.time() - t0))
+        return history
+
+    def _find_blanks(self, patches, cutoff, Y_gt, input_size):
+        """surface_segmenter.py:75-82: keep patches whose label std exceeds cutoff x the largest std."""
+        assert tuple(Y_gt.shape) == tuple(patches.vol_shape), "volume of Y_gt does not match vol_shape"
+        y_tmp = _device.to_device(patches.extract(Y_gt, input_size)).float()
+        ystd = y_tmp.reshape(len(y_tmp), -1).std(dim=1, unbiased=False)
+        return (ystd > ystd.max() * cutoff).cpu().numpy().astype(bool)
+
+    def get_training_patches(self, vol_shape, batch_size, input_size, max_stride, cutoff, Y_gt):
+        """surface_segmenter.py:85-124: random multi-scale patches ('random': width = stride x input
+        size, stride in [1, max_stride)), rejected when blank, until batch_size survive."""
+        ip, tot_len, patches = 0, 0, None
+        while tot_len < batch_size:
+            assert ip <= MAX_ITERS, "stuck in loop while finding patches to train on"
+            ip += 1
+            p_tmp = Patches(vol_shape, initialize_by="random", min_patch_size=input_size, max_stride=max_stride,
+                            n_points=batch_size)
+            if cutoff > 0.0:
+                cond_list = self._find_blanks(p_tmp, cutoff, Y_gt, input_size)
+            else:
+                cond_list = np.ones(len(p_tmp), dtype=bool)
+            if np.sum(cond_list) > 0:
+                p_tmp = p_tmp.filter_by_condition(cond_list)
+                if patches is None:
+                    patches = p_tmp.copy()
+                else:
+                    patches.append(p_tmp)
+                tot_len = len(patches)        # (the reference only counts after the second round: one extra loop)
+        assert patches is not None, "get_patches() failed to return any patches with selected conditions"
+        return patches.select_random_sample(batch_size)
+
+    def extract_training_patch_pairs(self, X, Y, patches, add_noise, random_rotate, input_size):
+        """keras_processor.py:213-232 on the device: binned gather of x and y, per-patch Gaussian noise
+        with sigma ~ U(0, add_noise), random rot90 about a random axis pair (cubic patches)."""
+        batch_size = len(patches)
+        y = _device.to_device(patches.extract(_device.to_device(Y), input_size))
+        x = _device.to_device(patches.extract(_device.to_device(X), input_size)).float()
+        std_batch = torch.from_numpy(np.random.uniform(0, add_noise, batch_size).astype(np.float32)).to(x.device)
+        x = x + torch.randn_like(x) * std_batch.view(-1, 1, 1, 1)
+        if random_rotate:
+            nrots = np.random.randint(0, 4, batch_size)
+            for ii in range(batch_size):
+                axes = tuple(int(a) for a in np.random.choice([0, 1, 2], size=2, replace=False))
+                if nrots[ii]:
+                    x[ii] = torch.rot90(x[ii], int(nrots[ii]), axes)
+                    y[ii] = torch.rot90(y[ii], int(nrots[ii]), axes)
+        return x.unsqueeze(-1), y.to(torch.uint8).unsqueeze(-1)
+
+    def _data_generator(self, Xs, Ys, batch_size, input_size, max_stride, cutoff, random_rotate, add_noise):
+        """surface_segmenter.py:202-244: yields (x float32 (B,P,P,P,1), y uint8) CUDA tensors."""
+        Xs = [_device.to_device(X) for X in Xs]
+        Ys = [_device.to_device(Y) for Y in Ys]
+        while True:
+            n_vols = len(Xs)
+            idx_vols = np.repeat(np.arange(0, n_vols), int(np.ceil(batch_size / n_vols)))[:batch_size]
+            xy = []
+            for ivol in range(n_vols):
+                Y_gt = Ys[ivol] if len(Ys) > 1 else Ys[0]
+                sub_batch_size = int(np.sum(idx_vols == ivol))
+                if sub_batch_size < 1:
+                    continue
+                patches = self.get_training_patches(tuple(Xs[ivol].shape), sub_batch_size, input_size, max_stride, cutoff, Y_gt)
+                xy.append(self.extract_training_patch_pairs(Xs[ivol], Y_gt, patches, add_noise, random_rotate, input_size))
+            yield torch.cat([a for a, _ in xy], dim=0), torch.cat([b for _, b in xy], dim=0)
+
+    data_generator = _data_generator          # the reference's `train` calls data_generator (quirk Q3)
 
     def random_data_generator(self, batch_size, input_size=(64, 64, 64)):
         """surface_segmenter.py:326-334."""
