@@ -12,6 +12,7 @@
 // normalisation / activation / pooling / loss operators are HBM-bound element-wise kernels.
 #include "conv_umma.cuh"
 #include "layers_simt.cuh"
+#include "sm100_ptx.cuh"
 #include "te_common.cuh"
 
 #include <cstdlib>
@@ -327,6 +328,58 @@ __global__ void __launch_bounds__(256) conv3_wgrad_simt_kernel(TView x, TView dy
   atomicAdd(dw + (static_cast<long long>(tap) * dw_cin + ci_off + ci) * Co + co, acc);
 }
 
+// First layer (Cin = 1): dw[tap][co] += sum_v x[v + tap] dy[v][co].  Thread = one (tap, co) pair; a block
+// stages a (4, 16, 8) voxel tile of dy and the haloed x tile in shared memory as fp32 and walks it.
+template <typename T>
+__global__ void __launch_bounds__(1024) conv3_wgrad_c1_kernel(TView x, TView dy, float* dw, int dw_cin, int ci_off) {
+  constexpr int TZ = 4;
+  extern __shared__ float sh[];
+  float* xs = sh;                         // [TZ + 2][18][10]
+  float* ds = sh + (TZ + 2) * 180;        // [TZ * 128][Cout]
+  const int Co = dy.C;
+  const int tid = threadIdx.x;
+  const bool active = tid < 27 * Co;
+  const int tap = active ? tid / Co : 0, co = active ? tid - tap * Co : 0;
+  const int dz = tap / 9, dyy = (tap / 3) % 3, dxx = tap % 3;            // +1 biased
+  const int tiles_x = (dy.W + 7) / 8, tiles_y = (dy.H + 15) / 16, tiles_z = (dy.D + TZ - 1) / TZ;
+  const long long total = static_cast<long long>(dy.N) * tiles_z * tiles_y * tiles_x;
+  const T* xp = static_cast<const T*>(x.ptr);
+  const T* gp = static_cast<const T*>(dy.ptr);
+  float acc = 0.f;
+  for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    long long t = tile;
+    const int x0 = static_cast<int>(t % tiles_x) * 8; t /= tiles_x;
+    const int y0 = static_cast<int>(t % tiles_y) * 16; t /= tiles_y;
+    const int z0 = static_cast<int>(t % tiles_z) * TZ; t /= tiles_z;
+    const long long n = t;
+    __syncthreads();
+    for (int i = tid; i < (TZ + 2) * 180; i += blockDim.x) {
+      const int bx = i % 10, by = (i / 10) % 18, bz = i / 180;
+      const int xx = x0 + bx - 1, yy = y0 + by - 1, zz = z0 + bz - 1;
+      const bool ok = xx >= 0 && xx < x.W && yy >= 0 && yy < x.H && zz >= 0 && zz < x.D;
+      xs[i] = ok ? ldv<T>(xp + (((n * x.D + zz) * x.H + yy) * x.W + xx) * x.ctot + x.coff) : 0.f;
+    }
+    for (int i = tid; i < TZ * 128 * Co; i += blockDim.x) {
+      const int c = i % Co, v = i / Co;
+      const int bx = v & 7, by = (v >> 3) & 15, bz = v >> 7;
+      const int xx = x0 + bx, yy = y0 + by, zz = z0 + bz;
+      const bool ok = xx < dy.W && yy < dy.H && zz < dy.D;
+      ds[i] = ok ? ldv<T>(gp + (((n * dy.D + zz) * dy.H + yy) * dy.W + xx) * dy.ctot + dy.coff + c) : 0.f;
+    }
+    __syncthreads();
+    if (active) {
+      for (int pz = 0; pz < TZ; ++pz)
+        for (int py = 0; py < 16; ++py) {
+          const float* xr = xs + ((pz + dz) * 18 + py + dyy) * 10 + dxx;
+          const float* dr = ds + ((pz * 16 + py) * 8) * Co + co;
+#pragma unroll
+          for (int px = 0; px < 8; ++px) acc = fmaf(xr[px], dr[px * Co], acc);
+        }
+    }
+  }
+  if (active) atomicAdd(dw + (static_cast<long long>(tap) * dw_cin + ci_off) * Co + co, acc);
+}
+
 // dbias[c] += sum_v dy[v][c]
 template <typename T>
 __global__ void __launch_bounds__(256) channel_sum_kernel(TView dy, double* out2) {
@@ -346,143 +399,142 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(TView dy, double* out2
 // ldmatrix.trans.  Voxel rows are padded to 80 bytes (32 ch x 2 B + 16) to spread the 8 row
 // addresses of an ldmatrix over distinct banks.
 // ------------------------------------------------------------------------------------------------
-constexpr int kWgTZ = 2;
-constexpr int kWgRow = 80;                                           // bytes per voxel row in shared memory
-constexpr int kWgXVox = (kWgTZ + 2) * 18 * 10;                       // haloed x box
-constexpr int kWgDVox = kWgTZ * 16 * 8;                              // dy box
-constexpr int kWgStage = (kWgXVox + kWgDVox) * kWgRow;               // 78 080 B
-constexpr int kWgSmem = 2 * kWgStage;
+constexpr int kWgTZ = 4;
+constexpr int kWgThreads = 288;                                      // 9 warps: one (dz, dy) tap row each
 
-__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
-  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
-  const int sz = valid ? 16 : 0;                                     // src-size 0 -> zero fill
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* p) {
-  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t saddr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
-}
-__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t (&r)[2], const void* p) {
-  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
-  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
 }
 template <bool FP16>
-__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   if constexpr (FP16)
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
   else
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 struct WgParams {
-  const uint8_t* x; int x_ctot, x_coff;       // 16-bit NDHWC
-  const uint8_t* dy; int dy_ctot, dy_coff;
-  float* dw; int dw_cin, ci_off, Cout;        // dw[27][dw_cin][Cout]
-  int Ci, N, D, H, W;
+  float* dw; int dw_cin, ci_off, Cout;        // dw[ntaps][dw_cin][Cout]
+  int Ci, x_coff, dy_coff;
+  int N, D, H, W;
   int tiles_x, tiles_y, tiles_z;
   long long total_tiles;
 };
 
-// NTAPS = 27: 3x3x3 conv (haloed x box).  NTAPS = 1: pointwise (dw[ci][co] = sum_v x[v][ci] dy[v][co]), used by the
-// transposed-conv backward with x := dz2 (8 Cout channels) and dy := the layer input.
+// Shared-memory row (voxel) of 32 channels = 64 bytes, 64-byte TMA swizzle: 16-byte chunk c of voxel
+// row v sits at v * 64 + ((c ^ ((v >> 1) & 3)) << 4) relative to a 512-byte aligned base.  The 8 row
+// addresses of an ldmatrix (8 consecutive voxels, fixed c) then fall into 8 distinct 16-byte bank
+// groups, for any starting voxel.
+__device__ __forceinline__ uint32_t sw64(uint32_t base, int vox, int chunk) {
+  return base + static_cast<uint32_t>(vox) * 64u + (static_cast<uint32_t>(chunk ^ ((vox >> 1) & 3)) << 4);
+}
+
+// NTAPS = 27: 3x3x3 conv (haloed x box); warp w owns the tap row (dz, dy) = (w / 3, w % 3), i.e. the
+// three dx taps, for the whole 32 (ci) x 32 (co) block: 3 x 2 x 4 mma tiles = 96 accumulator registers.
+// NTAPS = 1: pointwise product (transposed-conv backward); the 9 warps split the k-steps.
+// Operands arrive by TMA (one 5-D box per operand and tile, zero-filled outside the patch / beyond the
+// channel count), double-buffered; fragments are fetched with ldmatrix.trans because the GEMM K
+// dimension (voxels) is the slow dimension of both NDHWC operands.
 template <bool FP16, int NTAPS>
-__global__ void __launch_bounds__(256, 1) wgrad_mma_kernel(const WgParams p) {
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_mma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy, const WgParams p) {
   constexpr int HL = NTAPS == 27 ? 1 : 0;
-  constexpr int BXX = 8 + 2 * HL, BYY = 16 + 2 * HL;
-  constexpr int XVOX = (kWgTZ + 2 * HL) * BYY * BXX;
-  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int BXX = 8 + 2 * HL, BYY = 16 + 2 * HL, BZZ = kWgTZ + 2 * HL;
+  constexpr uint32_t X_BYTES = BZZ * BYY * BXX * 64, D_BYTES = kWgTZ * 16 * 8 * 64;
+  constexpr uint32_t X_STAGE = (X_BYTES + 1023) / 1024 * 1024, D_STAGE = (D_BYTES + 1023) / 1024 * 1024;
+  constexpr int TPW = NTAPS == 27 ? 3 : 1;              // taps per warp
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * (X_STAGE + D_STAGE));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ci0 = blockIdx.y * 32, co0 = blockIdx.z * 32;
-  const int mt = warp & 1, nt = warp >> 1;                // this warp's mma tile: ci [16 mt, +16), co [8 nt, +8)
-  float acc[NTAPS][4];
+  if (tid == 0) {
+    mbar_init(full, 1); mbar_init(full + 1, 1);
+    fence_barrier_init();
+    prefetch_tmap(&tmap_x); prefetch_tmap(&tmap_dy);
+  }
+  __syncthreads();
+  float acc[TPW][2][4][4];
 #pragma unroll
-  for (int t = 0; t < NTAPS; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
+  for (int t = 0; t < TPW; ++t)
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int n = 0; n < 4; ++n) { acc[t][m][n][0] = acc[t][m][n][1] = acc[t][m][n][2] = acc[t][m][n][3] = 0.f; }
 
-  auto load_tile = [&](long long tile, int stage) {
+  auto issue = [&](long long tile, int stage) {          // warp 0, warp-uniform; one elected lane issues
     long long t = tile;
     const int x0 = static_cast<int>(t % p.tiles_x) * 8; t /= p.tiles_x;
     const int y0 = static_cast<int>(t % p.tiles_y) * 16; t /= p.tiles_y;
     const int z0 = static_cast<int>(t % p.tiles_z) * kWgTZ; t /= p.tiles_z;
-    const long long n = t;
-    uint8_t* sx = smem + stage * kWgStage;
-    uint8_t* sd = sx + kWgXVox * kWgRow;
-    // x box: (TZ+2h, 16+2h, 8+2h) voxels x 32 channels = 4 chunks of 16 B per voxel
-    for (int i = tid; i < XVOX * 4; i += 256) {
-      const int vox = i >> 2, ch = i & 3;
-      const int bx = vox % BXX, by = (vox / BXX) % BYY, bz = vox / (BXX * BYY);
-      const int xx = x0 + bx - HL, yy = y0 + by - HL, zz = z0 + bz - HL;
-      const bool ok = xx >= 0 && xx < p.W && yy >= 0 && yy < p.H && zz >= 0 && zz < p.D && ci0 + ch * 8 < p.Ci;
-      const long long gv = ((n * p.D + (ok ? zz : 0)) * p.H + (ok ? yy : 0)) * p.W + (ok ? xx : 0);
-      cp_async16(sx + vox * kWgRow + ch * 16, p.x + (gv * p.x_ctot + p.x_coff + ci0 + (ok ? ch * 8 : 0)) * 2, ok);
+    const int n = static_cast<int>(t);
+    if (elect_one()) {
+      mbar_expect_tx(full + stage, X_BYTES + D_BYTES);
+      tma_load_5d(smem + stage * (X_STAGE + D_STAGE), &tmap_x, full + stage, p.x_coff + ci0, x0 - HL, y0 - HL, z0 - HL, n);
+      tma_load_5d(smem + stage * (X_STAGE + D_STAGE) + X_STAGE, &tmap_dy, full + stage, p.dy_coff + co0, x0, y0, z0, n);
     }
-    for (int i = tid; i < kWgDVox * 4; i += 256) {
-      const int vox = i >> 2, ch = i & 3;
-      const int bx = vox & 7, by = (vox >> 3) & 15, bz = vox >> 7;
-      const int xx = x0 + bx, yy = y0 + by, zz = z0 + bz;
-      const bool ok = xx < p.W && yy < p.H && zz < p.D && co0 + ch * 8 < p.Cout;
-      const long long gv = ((n * p.D + (ok ? zz : 0)) * p.H + (ok ? yy : 0)) * p.W + (ok ? xx : 0);
-      cp_async16(sd + vox * kWgRow + ch * 16, p.dy + (gv * p.dy_ctot + p.dy_coff + co0 + (ok ? ch * 8 : 0)) * 2, ok);
-    }
-    cp_async_commit();
+    __syncwarp();
   };
 
   const long long first = blockIdx.x, step = gridDim.x;
   int stage = 0;
-  if (first < p.total_tiles) load_tile(first, 0);
+  uint32_t phases = 0;                                     // bit s = parity of stage s
+  if (warp == 0 && first < p.total_tiles) issue(first, 0);
+  const int wdz = warp / 3, wdy = warp % 3;               // this warp's tap row (NTAPS = 27)
   for (long long tile = first; tile < p.total_tiles; tile += step) {
     const long long next = tile + step;
-    if (next < p.total_tiles) { load_tile(next, stage ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-    __syncthreads();
-    const uint8_t* sx = smem + stage * kWgStage;
-    const uint8_t* sd = sx + kWgXVox * kWgRow;
-    // k-steps: 16 voxels = two x rows (y, y+1) of 8 voxels of one z plane
+    if (warp == 0 && next < p.total_tiles) issue(next, stage ^ 1);
+    mbar_wait(full + stage, (phases >> stage) & 1u);
+    phases ^= 1u << stage;
+    const uint32_t sx = smem_u32(smem + stage * (X_STAGE + D_STAGE));
+    const uint32_t sd = sx + X_STAGE;
+    // k-step = 16 voxels = two x rows (y, y+1) of one z plane
 #pragma unroll 1
-    for (int ks = 0; ks < kWgTZ * 8; ++ks) {
+    for (int ks = (NTAPS == 27 ? 0 : warp); ks < kWgTZ * 8; ks += (NTAPS == 27 ? 1 : 9)) {
       const int pz = ks >> 3, yr = (ks & 7) * 2;
-      // B fragment (dy): k = voxel (16), n = co (8): two 8x8 matrices (k 0-7, k 8-15), rows = voxels
-      uint32_t bfrag[2];
-      {
-        const int r = lane & 15;                                    // lanes 0-15 supply the 16 row addresses
-        const int vox = (pz * 16 + yr + (r >> 3)) * 8 + (r & 7);
-        ldmatrix_x2_trans(bfrag, sd + vox * kWgRow + nt * 16);
-      }
-#pragma unroll
-      for (int tap = 0; tap < NTAPS; ++tap) {
-        const int dz = NTAPS == 27 ? tap / 9 : 0, dyy = NTAPS == 27 ? (tap / 3) % 3 : 0, dxx = NTAPS == 27 ? tap % 3 : 0;  // +1 biased box offsets
-        // A fragment (x window): m = ci (16), k = voxel (16): four 8x8 matrices
-        //   a0: m 0-7,k 0-7   a1: m 8-15,k 0-7   a2: m 0-7,k 8-15   a3: m 8-15,k 8-15
-        // stored [voxel][channel]: matrix rows = voxels (k), 16-byte row chunk = 8 channels (m) -> .trans
-        uint32_t afrag[4];
-        const int mi = lane >> 3, r = lane & 7;                      // lane supplies row r of matrix mi
-        const int kh = mi >> 1, mh = mi & 1;
-        const int vox = ((pz + dz) * BYY + (yr + kh + dyy)) * BXX + (r + dxx);
-        ldmatrix_x4_trans(afrag, sx + vox * kWgRow + (mt * 16 + mh * 8) * 2);
-        mma16816<FP16>(acc[tap], afrag, bfrag);
-      }
-    }
-    __syncthreads();
-    stage ^= 1;
-  }
-  // flush: c0,c1 -> (row g, cols 2t, 2t+1); c2,c3 -> (row g + 8)
-  const int g = lane >> 2, tq = lane & 3;
-#pragma unroll
-  for (int tap = 0; tap < NTAPS; ++tap) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int ci = ci0 + mt * 16 + g + h * 8;
+      const int mi = lane >> 3, r = lane & 7;
+      // B fragments (dy): matrices (k-half kh, chunk c): lane group mi -> kh = mi & 1, chunk = 2 j + (mi >> 1)
+      uint32_t bf[2][4];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const int co = co0 + nt * 8 + tq * 2 + j;
-        if (ci < p.Ci && co < p.Cout)
-          atomicAdd(p.dw + (static_cast<long long>(tap) * p.dw_cin + p.ci_off + ci) * p.Cout + co, acc[tap][h * 2 + j]);
+        const int vox = (pz * 16 + yr + (mi & 1)) * 8 + r;
+        ldmatrix_x4_trans(bf[j], sw64(sd, vox, 2 * j + (mi >> 1)));
+      }
+#pragma unroll
+      for (int t = 0; t < TPW; ++t) {
+        const int dz = NTAPS == 27 ? wdz : 0, dyy = NTAPS == 27 ? wdy : 0, dxx = NTAPS == 27 ? t : 0;   // +HL biased
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          // A fragment (x window): a0: m 0-7,k 0-7  a1: m 8-15,k 0-7  a2: m 0-7,k 8-15  a3: m 8-15,k 8-15
+          uint32_t af[4];
+          const int vox = ((pz + dz) * BYY + (yr + (mi >> 1) + dyy)) * BXX + (r + dxx);
+          ldmatrix_x4_trans(af, sw64(sx, vox, mt * 2 + (mi & 1)));
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) mma16816<FP16>(acc[t][mt][nt], af, bf[nt >> 1][(nt & 1) * 2], bf[nt >> 1][(nt & 1) * 2 + 1]);
+        }
       }
     }
+    __syncthreads();                                       // every warp is done with this stage before it is refilled
+    stage ^= 1;
+  }
+  // flush: c0,c1 -> (row g, cols 2 tq, 2 tq + 1); c2,c3 -> (row g + 8)
+  const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+  for (int t = 0; t < TPW; ++t) {
+    const int tap = NTAPS == 27 ? warp * 3 + t : 0;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int ci = ci0 + mt * 16 + g + (e >> 1) * 8, co = co0 + nt * 8 + tq * 2 + (e & 1);
+          if (ci < p.Ci && co < p.Cout)
+            atomicAdd(p.dw + (static_cast<long long>(tap) * p.dw_cin + p.ci_off + ci) * p.Cout + co, acc[t][mt][nt][e]);
+        }
   }
 }
 
@@ -810,15 +862,17 @@ extern "C" int te_tr_upconv_fwd(const te_tensor* x, const float* w, const float*
 
 namespace te {
 namespace {
+constexpr int kWgSmem = 2 * (((kWgTZ + 2) * 18 * 10 * 64 + 1023) / 1024 * 1024 + kWgTZ * 16 * 8 * 64) + 1024 + 64;
+
 template <bool FP16, int NTAPS>
-cudaError_t launch_wgrad_mma_t(const WgParams& p, dim3 g, cudaStream_t st) {
+cudaError_t launch_wgrad_mma_t(const CUtensorMap& tx, const CUtensorMap& td, const WgParams& p, dim3 g, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_mma_kernel<FP16, NTAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem);
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  wgrad_mma_kernel<FP16, NTAPS><<<g, 256, kWgSmem, st>>>(p);
+  wgrad_mma_kernel<FP16, NTAPS><<<g, kWgThreads, kWgSmem, st>>>(tx, td, p);
   return cudaGetLastError();
 }
 
@@ -828,23 +882,43 @@ bool wgrad_mma_ok(const te_tensor& x, const te_tensor& dy) {
          x.coff % 8 == 0 && dy.coff % 8 == 0 && x.C >= 8;
 }
 
+// 5-D map (C, W, H, D, N) with a box of 32 channels x (8 + 2h) x (16 + 2h) x (TZ + 2h) voxels, 64-byte swizzle
+int make_tmap_wg(CUtensorMap* tm, const te_tensor& v, int halo) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available"); return TE_ERR_CUDA; }
+  cuuint64_t gdim[5] = {(cuuint64_t)v.ctot, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.D, (cuuint64_t)v.N};
+  cuuint64_t gstr[4] = {(cuuint64_t)v.ctot * 2, (cuuint64_t)v.W * v.ctot * 2, (cuuint64_t)v.H * v.W * v.ctot * 2,
+                        (cuuint64_t)v.D * v.H * v.W * v.ctot * 2};
+  cuuint32_t box[5] = {32, (cuuint32_t)(8 + 2 * halo), (cuuint32_t)(16 + 2 * halo), (cuuint32_t)(kWgTZ + 2 * halo), 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, v.dtype == TE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, v.ptr, gdim,
+                   gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return TE_ERR_CUDA; }
+  return TE_OK;
+}
+
 // dw[ntaps][dw_cin][dy.C] += wgrad(x, dy) on mma.sync tiles
 int wgrad_mma(const te_tensor& x, const te_tensor& dy, float* dw, int dw_cin, int ci_off, int ntaps, cudaStream_t st) {
   WgParams p;
-  p.x = static_cast<const uint8_t*>(x.ptr); p.x_ctot = x.ctot; p.x_coff = x.coff;
-  p.dy = static_cast<const uint8_t*>(dy.ptr); p.dy_ctot = dy.ctot; p.dy_coff = dy.coff;
   p.dw = dw; p.dw_cin = dw_cin; p.ci_off = ci_off; p.Cout = dy.C;
-  p.Ci = x.C; p.N = x.N; p.D = x.D; p.H = x.H; p.W = x.W;
+  p.Ci = x.C; p.x_coff = x.coff; p.dy_coff = dy.coff;
+  p.N = x.N; p.D = x.D; p.H = x.H; p.W = x.W;
   p.tiles_x = (x.W + 7) / 8; p.tiles_y = (x.H + 15) / 16; p.tiles_z = (x.D + kWgTZ - 1) / kWgTZ;
   p.total_tiles = static_cast<long long>(p.N) * p.tiles_z * p.tiles_y * p.tiles_x;
+  CUtensorMap tx, td;
+  int rc = make_tmap_wg(&tx, x, ntaps == 27 ? 1 : 0);
+  if (rc != TE_OK) return rc;
+  rc = make_tmap_wg(&td, dy, 0);
+  if (rc != TE_OK) return rc;
   const int cib = (x.C + 31) / 32, cob = (dy.C + 31) / 32;
-  long long gx = (2LL * kNumSMs + cib * cob - 1) / (cib * cob);
+  long long gx = (static_cast<long long>(kNumSMs) + cib * cob - 1) / (cib * cob);
   if (gx < 1) gx = 1;
   if (gx > p.total_tiles) gx = p.total_tiles;
   dim3 g(static_cast<unsigned>(gx), cib, cob);
   const bool fp16 = x.dtype == TE_F16;
-  cudaError_t e = ntaps == 27 ? (fp16 ? launch_wgrad_mma_t<true, 27>(p, g, st) : launch_wgrad_mma_t<false, 27>(p, g, st))
-                              : (fp16 ? launch_wgrad_mma_t<true, 1>(p, g, st) : launch_wgrad_mma_t<false, 1>(p, g, st));
+  cudaError_t e = ntaps == 27 ? (fp16 ? launch_wgrad_mma_t<true, 27>(tx, td, p, g, st) : launch_wgrad_mma_t<false, 27>(tx, td, p, g, st))
+                              : (fp16 ? launch_wgrad_mma_t<true, 1>(tx, td, p, g, st) : launch_wgrad_mma_t<false, 1>(tx, td, p, g, st));
   count_launch();
   if (e != cudaSuccess) { set_error("wgrad launch failed: %s", cudaGetErrorString(e)); return TE_ERR_CUDA; }
   return TE_OK;
@@ -920,6 +994,22 @@ extern "C" int te_tr_conv3_wgrad(const te_tensor* x, const te_tensor* dy, float*
   if (wgrad_mma_ok(*x, *dy)) {
     const int rc = wgrad_mma(*x, *dy, dw, dw_cin, ci_off, 27, st);
     if (rc != TE_OK) return rc;
+  } else if (x->C == 1 && dy->C <= 37) {
+    const int threads = (27 * dy->C + 31) / 32 * 32;
+    const size_t shb = (6 * 180 + 4 * 128 * static_cast<size_t>(dy->C)) * sizeof(float);
+    const long long tiles = static_cast<long long>(vd.N) * ((vd.D + 3) / 4) * ((vd.H + 15) / 16) * ((vd.W + 7) / 8);
+    const int grid = static_cast<int>(tiles < 2LL * kNumSMs ? tiles : 2LL * kNumSMs);
+    if (x->dtype == TE_F32) {
+      TE_CUDA(cudaFuncSetAttribute(conv3_wgrad_c1_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shb)));
+      conv3_wgrad_c1_kernel<float><<<grid, threads, shb, st>>>(vx, vd, dw, dw_cin, ci_off);
+    } else if (x->dtype == TE_F16) {
+      TE_CUDA(cudaFuncSetAttribute(conv3_wgrad_c1_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shb)));
+      conv3_wgrad_c1_kernel<__half><<<grid, threads, shb, st>>>(vx, vd, dw, dw_cin, ci_off);
+    } else {
+      TE_CUDA(cudaFuncSetAttribute(conv3_wgrad_c1_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shb)));
+      conv3_wgrad_c1_kernel<__nv_bfloat16><<<grid, threads, shb, st>>>(vx, vd, dw, dw_cin, ci_off);
+    }
+    TE_LAUNCH_CHECK();
   } else {
     const long long elems = static_cast<long long>(vx.C) * vd.C;
     const long long nvox = vd.voxels();

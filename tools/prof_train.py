@@ -58,6 +58,8 @@ def main():
     for t, name, cnt in sorted(rows, reverse=True):
         print("  %-28s %4d calls %9.2f ms  %5.1f%%" % (name, cnt, t, 100 * t / tot))
     print("  sum of operator times %.1f ms" % tot)
+    for name in ("te_tr_conv3_wgrad", "te_tr_conv3", "te_tr_upconv_bwd"):
+        print("  %s per call (ms, call order):" % name, " ".join("%.2f" % a.elapsed_time(b) for a, b in times[name]))
 
 
 if __name__ == "__main__":
