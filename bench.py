@@ -21,6 +21,11 @@ import time
 
 import numpy as np
 
+# NCCL prints "NCCL version ..." on stdout when NCCL_DEBUG=VERSION (the image default): stdout must carry the
+# JSON line only
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
