@@ -58,12 +58,25 @@ struct KParams {
   float* head_logits;
   uint8_t* pool_out;    // fused MaxPool3D(2) output (nullptr = none)
   int pool_ctot, pool_coff;
+  int reuse_ok;         // host: enough spatial tiles to fill the GPU when the (Cout tile, sub) pairs are looped inside a CTA
 };
 
 struct TileCoord { int ntile, sub, n, z0, y0, x0; };
 
-__device__ __forceinline__ TileCoord decode_tile(const KParams& p, long long t, int TZ) {
+// `reuse` (un-haloed kernels whose channel chunks all fit the input ring): the outer index is the
+// spatial tile, the inner index j enumerates the (Cout tile, sub-position) pairs that share its
+// input boxes.  Otherwise j = 0 and t enumerates everything.
+__device__ __forceinline__ TileCoord decode_tile(const KParams& p, long long t, int TZ, bool reuse = false, int j = 0) {
   TileCoord c;
+  if (reuse) {
+    c.x0 = static_cast<int>(t % p.tiles_x) * 8;  t /= p.tiles_x;
+    c.y0 = static_cast<int>(t % p.tiles_y) * 16; t /= p.tiles_y;
+    c.z0 = static_cast<int>(t % p.tiles_z) * TZ; t /= p.tiles_z;
+    c.n = static_cast<int>(t);
+    c.sub = j % p.nsub;
+    c.ntile = j / p.nsub;
+    return c;
+  }
   c.x0 = static_cast<int>(t % p.tiles_x) * 8;  t /= p.tiles_x;
   c.y0 = static_cast<int>(t % p.tiles_y) * 16; t /= p.tiles_y;
   c.z0 = static_cast<int>(t % p.tiles_z) * TZ; t /= p.tiles_z;
@@ -99,7 +112,7 @@ struct Cfg {
   static constexpr int W_STAGE = ((G * SLAB) + 1023) / 1024 * 1024;
   // input-box ring: the haloed boxes of the 3x3x3 conv are large (2 stages); the un-haloed boxes of
   // the transposed conv are small and each feeds few MMAs, so more of them are kept in flight
-  static constexpr int NUM_A = HALO ? 2 : 4;
+  static constexpr int NUM_A = HALO ? 2 : (A_STAGE <= 16 * 1024 ? 8 : 4);
   // plane-fused MMA schedule (see the UMMA issuer): needs 3 * NT <= 256 result columns per instruction
   static constexpr bool FUSE = HALO && (3 * NT <= 256);
   static constexpr int ACC_COLS = TZ * NT;                              // fp32 columns of one accumulator set
@@ -158,14 +171,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   constexpr uint32_t w_bytes = static_cast<uint32_t>(G) * slab_bytes;     // one stage
   // all the weights of the layer fit the ring: load them once, never release them
   const bool w_resident = p.n_ntiles == 1 && p.nsub == 1 && p.kchunks * NGROUPS <= kNumWStages;
+  // input-box reuse across the (Cout tile, sub-position) pairs of a spatial tile (transposed / pointwise convs):
+  // a transposed conv would otherwise re-read its input 8 times (ncu: 1072 MB for a 134 MB tensor)
+  const bool reuse = !HALO && p.reuse_ok && p.kchunks <= kNumAStages && p.n_ntiles * p.nsub > 1;
+  const int J = reuse ? p.n_ntiles * p.nsub : 1;
+  const long long outer_tiles = reuse ? p.total_tiles / J : p.total_tiles;
 
   if (warp == 0) {
     // ============================== TMA producer ==============================
     // The whole warp runs the (warp-uniform) control flow; one elected lane issues the copies and
     // runs ahead of the MMAs by the depth of the ring.
     uint32_t as = 0, aph = 0;
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(p, tile, TZ);
+    for (long long tile = blockIdx.x; tile < outer_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile, TZ, reuse, 0);
 #pragma unroll 1
       for (int kc = 0; kc < p.kchunks; ++kc) {
         mbar_wait(a_empty + as, aph ^ 1);
@@ -184,20 +202,23 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   } else if (warp == 6) {
     // ============================== weight-slab producer ==============================
     uint32_t ws = 0, wph = 0;
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(p, tile, TZ);
-      const uint8_t* wsrc = p.w_packed + (static_cast<size_t>(tc.ntile) * p.nsub + tc.sub) * p.kchunks * NGROUPS *
-                                             static_cast<size_t>(w_bytes);
-      const int nstages = p.kchunks * NGROUPS;
+    for (long long tile = blockIdx.x; tile < outer_tiles; tile += gridDim.x) {
 #pragma unroll 1
-      for (int g = 0; g < nstages; ++g) {
-        mbar_wait(w_empty + ws, wph ^ 1);
-        if (elect_one()) {
-          mbar_expect_tx(w_full + ws, w_bytes);
-          bulk_load(w_stage + ws * C::W_STAGE, wsrc + static_cast<size_t>(g) * w_bytes, w_bytes, w_full + ws);
+      for (int j = 0; j < J; ++j) {
+        const TileCoord tc = decode_tile(p, tile, TZ, reuse, j);
+        const uint8_t* wsrc = p.w_packed + (static_cast<size_t>(tc.ntile) * p.nsub + tc.sub) * p.kchunks * NGROUPS *
+                                               static_cast<size_t>(w_bytes);
+        const int nstages = p.kchunks * NGROUPS;
+#pragma unroll 1
+        for (int g = 0; g < nstages; ++g) {
+          mbar_wait(w_empty + ws, wph ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(w_full + ws, w_bytes);
+            bulk_load(w_stage + ws * C::W_STAGE, wsrc + static_cast<size_t>(g) * w_bytes, w_bytes, w_full + ws);
+          }
+          __syncwarp();
+          if (++ws == kNumWStages) { ws = 0; wph ^= 1; }
         }
-        __syncwarp();
-        if (++ws == kNumWStages) { ws = 0; wph ^= 1; }
       }
       if (w_resident) break;
     }
@@ -211,14 +232,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     constexpr uint32_t sbo_w = 8u * C::ROWB;
     uint32_t as = 0, aph = 0, ws = 0, wph = 0, ab = 0, abph = 0;
     bool w_ready = false;                       // resident weights: every stage has been waited for once
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (long long tile = blockIdx.x; tile < outer_tiles; tile += gridDim.x) {
+     const uint32_t as0 = as, aph0 = aph;       // ring position of this spatial tile's first input box
+#pragma unroll 1
+     for (int j = 0; j < J; ++j) {
       mbar_wait(acc_empty + ab, abph ^ 1);
       tc_fence_after();
       const uint32_t acc_col = tmem_base + ab * C::ACC_COLS;
       if (w_resident) ws = 0;
+      as = as0; aph = aph0;
 #pragma unroll 1
       for (int kc = 0; kc < p.kchunks; ++kc) {
-        mbar_wait(a_full + as, aph);
+        if (j == 0) mbar_wait(a_full + as, aph);
         const uint64_t adesc0 = make_smem_desc(smem_u32(a_stage + as * C::A_STAGE), 16, sbo_a, C::LAYOUT);
 #pragma unroll 1
         for (int gs = 0; gs < NGROUPS; ++gs) {
@@ -293,8 +318,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
             }
             if (!w_resident) umma_commit(w_empty + ws);   // stage free once these MMAs retire
             if (gs == NGROUPS - 1) {
-              umma_commit(a_empty + as);
-              if (kc == p.kchunks - 1) umma_commit(acc_full + ab);
+              if (!reuse) umma_commit(a_empty + as);
+              if (kc == p.kchunks - 1) {
+                umma_commit(acc_full + ab);
+                if (reuse && j == J - 1) {
+                  // every pair of this spatial tile has been issued: its input boxes are free once
+                  // these MMAs retire (one commit per ring stage it occupied)
+                  uint32_t s2 = as0;
+                  for (int k2 = 0; k2 < p.kchunks; ++k2) {
+                    umma_commit(a_empty + s2);
+                    if (++s2 == kNumAStages) s2 = 0;
+                  }
+                }
+              }
             }
           }
           __syncwarp();
@@ -304,6 +340,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       }
       if (w_resident) w_ready = true;
       if (++ab == 2) { ab = 0; abph ^= 1; }
+     }
     }
   } else {
     // ============================== epilogue warps ==============================
@@ -311,8 +348,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     const int m = q * 32 + lane;                  // accumulator row = voxel (y = m / 8, x = m % 8)
     const int my = m >> 3, mx = m & 7;
     uint32_t ab = 0, abph = 0;
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(p, tile, TZ);
+    for (long long tile = blockIdx.x; tile < outer_tiles; tile += gridDim.x) {
+     for (int j = 0; j < J; ++j) {
+      const TileCoord tc = decode_tile(p, tile, TZ, reuse, j);
       mbar_wait(acc_full + ab, abph);
       tc_fence_after();
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ab * C::ACC_COLS;
@@ -411,6 +449,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + ab);
       if (++ab == 2) { ab = 0; abph ^= 1; }
+     }
     }
   }
 
@@ -464,6 +503,7 @@ KParams make_params(const ConvUmmaLaunch& L) {
   p.pool_out = static_cast<uint8_t*>(L.pool_out);
   p.pool_ctot = L.pool_ctot;
   p.pool_coff = L.pool_coff;
+  p.reuse_ok = !p.halo && p.total_tiles / (static_cast<long long>(p.n_ntiles) * p.nsub) >= kNumSMs ? 1 : 0;
   return p;
 }
 
@@ -530,6 +570,7 @@ int conv_umma_grid(const ConvUmmaLaunch& L) {
 cudaError_t conv_umma_launch(const ConvUmmaLaunch& L, cudaStream_t stream) {
   const KParams p = make_params(L);
   if (p.total_tiles <= 0) return cudaSuccess;
+  // un-haloed kernels may iterate the (Cout tile, sub-position) pairs inside a spatial tile (input reuse)
   const int grid = static_cast<int>(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs);
 #define TE_CONV_CASE(cb, nt, tz)                                                          \
   if (L.CB == cb && L.NT == nt && L.TZ == tz)                                             \
