@@ -1,0 +1,266 @@
+// First layer of every graph (Conv3D(f, 3, 'same') on ONE input channel,
+// /root/reference/tomo_encoders/neural_nets/Unet3D.py:117-122, autoencoders.py:168-173) on the tensor
+// cores.  K = 27 taps is padded to 32: four "builder" warps assemble the im2col operand of one z plane
+// (128 voxels x 32 taps, 64-byte rows, 64-byte swizzle) in shared memory from the haloed single-channel
+// input tile, one warp issues two K = 16 UMMAs per plane into TMEM, four warps run the epilogue
+// (bias + LeakyReLU -> 16-bit NDHWC).  The CUDA-core version of this layer needed 432 FMAs per voxel
+// and was 8 % of a U-net forward / 22 % of an encoder forward for 0.2 % of the FLOPs.
+#include "layers_simt.cuh"
+#include "sm100_ptx.cuh"
+#include "te_common.cuh"
+
+#include <cstdlib>
+
+namespace te {
+namespace {
+
+constexpr int kTZ = 4;                       // z planes per tile
+constexpr int kStagesA = 8;                  // im2col ring: one plane (128 rows x 64 B = 8 KB) per stage (= 2 tiles)
+static_assert(kStagesA == 2 * kTZ, "the builders' closed-form stage index assumes a ring of two tiles");
+constexpr int kThreadsC1 = 448;              // warp 0 UMMA, warp 1 idle, warps 2-5 epilogue, warps 6-13 builders (two groups of 128)
+constexpr int kInTile = (kTZ + 2) * 18 * 10; // haloed input tile (elements)
+
+struct C1Params {
+  const uint16_t* in;       // (N, D, H, W) 16-bit
+  uint8_t* out;             // NDHWC 16-bit
+  int out_ctot, out_coff;
+  const float* w;           // [27][Cout] fp32 (Keras (3,3,3,1,Cout))
+  const float* bias;
+  int N, D, H, W;
+  int tiles_x, tiles_y, tiles_z;
+  long long total_tiles;
+  int lrelu, fp16;
+  float alpha;
+};
+
+__device__ __forceinline__ uint16_t to_bits(float v, int fp16) {
+  if (fp16) { __half h = __float2half_rn(v); return *reinterpret_cast<uint16_t*>(&h); }
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack2f(float a, float b, int fp16) {
+  if (fp16) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int NT>
+__global__ void __launch_bounds__(kThreadsC1, 1) conv1_umma_kernel(const C1Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_stage = smem;                                   // kStagesA x 8 KB
+  uint8_t* b_tile = smem + kStagesA * 8192;                  // NT rows x 64 B (K-major, SW64), 1024-aligned
+  uint16_t* in_tile = reinterpret_cast<uint16_t*>(b_tile + 4096);   // [kInTile]
+  float* s_bias = reinterpret_cast<float*>(b_tile + 4096 + 4096);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_tile + 4096 + 4096 + 512);
+  uint64_t* a_full = bars;                    // [kStagesA], 128 arrivals
+  uint64_t* a_empty = a_full + kStagesA;      // [kStagesA]
+  uint64_t* acc_full = a_empty + kStagesA;    // [2]
+  uint64_t* acc_empty = acc_full + 2;         // [2], 4 arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int TMEM_COLS = 2 * kTZ * NT <= 128 ? 128 : (2 * kTZ * NT <= 256 ? 256 : 512);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStagesA; ++i) { mbar_init(a_full + i, 128); mbar_init(a_empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+    fence_barrier_init();
+  }
+  if (warp == 0) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  // weights: B[n][k] = w[k][n] for k < 27, zero for the 5 padding taps; 64-byte rows, SW64 swizzle
+  for (int i = threadIdx.x; i < NT * 32; i += kThreadsC1) {
+    const int n = i >> 5, k = i & 31;
+    const float v = k < 27 ? __ldg(p.w + k * NT + n) : 0.f;
+    const uint32_t lo = static_cast<uint32_t>(n * 64 + k * 2);
+    *reinterpret_cast<uint16_t*>(b_tile + (lo ^ (((lo >> 7) & 3u) << 4))) = to_bits(v, p.fp16);
+  }
+  for (int i = threadIdx.x; i < NT; i += kThreadsC1) s_bias[i] = __ldg(p.bias + i);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ============================== UMMA issuer ==============================
+    const uint32_t idesc = make_idesc_f16(128, NT, p.fp16 ? 0u : 1u);
+    const uint64_t bdesc = make_smem_desc(smem_u32(b_tile), 16, 512, kLayoutSW64);
+    uint32_t as = 0, aph = 0, ab = 0, abph = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(acc_empty + ab, abph ^ 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int pz = 0; pz < kTZ; ++pz) {
+        mbar_wait(a_full + as, aph);
+        tc_fence_after();
+        const uint64_t adesc = make_smem_desc(smem_u32(a_stage + as * 8192), 16, 512, kLayoutSW64);
+        if (elect_one()) {
+          const uint32_t acc = tmem_base + ab * (kTZ * NT) + pz * NT;
+          umma_ss(acc, adesc, bdesc, idesc, 0u);
+          umma_ss(acc, adesc + 2, bdesc + 2, idesc, 1u);       // second K = 16 step: +32 bytes
+          umma_commit(a_empty + as);
+          if (pz == kTZ - 1) umma_commit(acc_full + ab);
+        }
+        __syncwarp();
+        if (++as == kStagesA) { as = 0; aph ^= 1; }
+      }
+      if (++ab == 2) { ab = 0; abph ^= 1; }
+    }
+  } else if (warp >= 6) {
+    // ============================== im2col builders (2 groups x 128 threads) ==============================
+    // group g builds planes g and g + 2 of every tile; plane pz of the k-th tile of this CTA goes to ring
+    // stage (4 k + pz) % 8.  The haloed input tile of the NEXT tile is prefetched into registers while the
+    // current one is being expanded, so the global-memory latency is off the critical path.
+    const int bt = threadIdx.x - 6 * 32;              // 0..255
+    const int grp = bt >> 7, row = bt & 127;          // row = voxel of the plane
+    const int my = row >> 3, mx = row & 7;
+    constexpr int kPre = (kInTile + 255) / 256;       // input elements per builder thread
+    uint16_t pre[kPre];
+    auto fetch = [&](long long tile) {
+      long long t = tile;
+      const int x0 = static_cast<int>(t % p.tiles_x) * 8; t /= p.tiles_x;
+      const int y0 = static_cast<int>(t % p.tiles_y) * 16; t /= p.tiles_y;
+      const int z0 = static_cast<int>(t % p.tiles_z) * kTZ; t /= p.tiles_z;
+      const long long n = t;
+#pragma unroll
+      for (int j = 0; j < kPre; ++j) {
+        const int i = bt + 256 * j;
+        const int bx = i % 10, by = (i / 10) % 18, bz = i / 180;
+        const int xx = x0 + bx - 1, yy = y0 + by - 1, zz = z0 + bz - 1;
+        const bool ok = i < kInTile && xx >= 0 && xx < p.W && yy >= 0 && yy < p.H && zz >= 0 && zz < p.D;
+        pre[j] = ok ? __ldg(p.in + ((n * p.D + zz) * p.H + yy) * p.W + xx) : static_cast<uint16_t>(0);
+      }
+    };
+    if (static_cast<long long>(blockIdx.x) < p.total_tiles) fetch(blockIdx.x);
+    uint32_t k = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++k) {
+      named_bar_sync(1, 256);                           // previous tile fully expanded by both groups
+#pragma unroll
+      for (int j = 0; j < kPre; ++j) {
+        const int i = bt + 256 * j;
+        if (i < kInTile) in_tile[i] = pre[j];
+      }
+      named_bar_sync(1, 256);
+      if (tile + gridDim.x < p.total_tiles) fetch(tile + gridDim.x);
+#pragma unroll 1
+      for (int pz = grp; pz < kTZ; pz += 2) {
+        // row = 27 taps (dz, dy, dx) of voxel (pz, my, mx), 5 zeros: 16 packed 32-bit words
+        uint32_t wv[16];
+        uint16_t v[32];
+#pragma unroll
+        for (int tp = 0; tp < 27; ++tp) {
+          const int dz = tp / 9, dy = (tp / 3) % 3, dx = tp % 3;
+          v[tp] = in_tile[((pz + dz) * 18 + my + dy) * 10 + mx + dx];
+        }
+#pragma unroll
+        for (int tp = 27; tp < 32; ++tp) v[tp] = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) wv[j] = static_cast<uint32_t>(v[2 * j]) | (static_cast<uint32_t>(v[2 * j + 1]) << 16);
+        const uint32_t as = ((k & 1u) << 2) + pz, aph = (k >> 1) & 1u;
+        mbar_wait(a_empty + as, aph ^ 1);
+        uint8_t* dst = a_stage + as * 8192 + row * 64;
+        const int sw = (row >> 1) & 3;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(dst + ((c ^ sw) << 4)) = make_uint4(wv[4 * c], wv[4 * c + 1], wv[4 * c + 2], wv[4 * c + 3]);
+        fence_proxy_async_smem();                       // generic-proxy writes -> visible to the UMMA (async proxy)
+        mbar_arrive(a_full + as);
+      }
+    }
+  } else if (warp >= 2) {
+    // ============================== epilogue warps ==============================
+    const int q = warp & 3;
+    const int m = q * 32 + lane, my = m >> 3, mx = m & 7;
+    uint32_t ab = 0, abph = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      long long t = tile;
+      const int x0 = static_cast<int>(t % p.tiles_x) * 8; t /= p.tiles_x;
+      const int y0 = static_cast<int>(t % p.tiles_y) * 16; t /= p.tiles_y;
+      const int z0 = static_cast<int>(t % p.tiles_z) * kTZ; t /= p.tiles_z;
+      const long long n = t;
+      mbar_wait(acc_full + ab, abph);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ab * (kTZ * NT);
+      const int iy = y0 + my, ix = x0 + mx;
+#pragma unroll 1
+      for (int pz = 0; pz < kTZ; pz += 2) {
+#pragma unroll
+        for (int c0 = 0; c0 < NT; c0 += 16) {
+          uint32_t r0[16], r1[16];
+          tmem_ld16(tbase + pz * NT + c0, r0);
+          tmem_ld16(tbase + (pz + 1) * NT + c0, r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int iz = z0 + pz + h;
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float x = __uint_as_float(h ? r1[j] : r0[j]) + s_bias[c0 + j];
+              if (p.lrelu) x = x > 0.f ? x : p.alpha * x;
+              v[j] = x;
+            }
+            if (iz < p.D && iy < p.H && ix < p.W) {
+              const long long ov = ((n * p.D + iz) * p.H + iy) * p.W + ix;
+              uint4* dst = reinterpret_cast<uint4*>(p.out + (ov * p.out_ctot + p.out_coff + c0) * 2);
+              dst[0] = make_uint4(pack2f(v[0], v[1], p.fp16), pack2f(v[2], v[3], p.fp16), pack2f(v[4], v[5], p.fp16),
+                                  pack2f(v[6], v[7], p.fp16));
+              dst[1] = make_uint4(pack2f(v[8], v[9], p.fp16), pack2f(v[10], v[11], p.fp16), pack2f(v[12], v[13], p.fp16),
+                                  pack2f(v[14], v[15], p.fp16));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + ab);
+      if (++ab == 2) { ab = 0; abph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+constexpr int kSmemC1 = kStagesA * 8192 + 4096 + 4096 + 512 + 512 + 1024;
+
+template <int NT>
+cudaError_t launch_nt(const C1Params& p, int grid, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv1_umma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemC1);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  conv1_umma_kernel<NT><<<grid, kThreadsC1, kSmemC1, st>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+// Returns true when the layer was taken (Cin = 1, 16-bit activations, Cout in {16, 32, 64}); *err = launch status.
+bool conv1_umma_try(const TView& in, const TView& out, const float* w, const float* bias, int lrelu, float alpha, int act_type,
+                    cudaStream_t st, cudaError_t* err) {
+  static const bool off = getenv("TOMOENC_NO_C1_UMMA") != nullptr;
+  if (off || in.C != 1 || in.ctot != 1 || act_type == ACT_F32) return false;
+  if (out.C != 16 && out.C != 32 && out.C != 64) return false;
+  if (out.ctot % 8 != 0 || out.coff % 8 != 0 || kInTile * 2 > 4096) return false;
+  C1Params p;
+  p.in = static_cast<const uint16_t*>(in.ptr);
+  p.out = static_cast<uint8_t*>(out.ptr);
+  p.out_ctot = out.ctot; p.out_coff = out.coff;
+  p.w = w; p.bias = bias;
+  p.N = in.N; p.D = in.D; p.H = in.H; p.W = in.W;
+  p.tiles_x = (in.W + 7) / 8; p.tiles_y = (in.H + 15) / 16; p.tiles_z = (in.D + kTZ - 1) / kTZ;
+  p.total_tiles = static_cast<long long>(in.N) * p.tiles_z * p.tiles_y * p.tiles_x;
+  p.lrelu = lrelu; p.alpha = alpha; p.fp16 = act_type == ACT_F16;
+  if (p.total_tiles <= 0) { *err = cudaSuccess; return true; }
+  const int grid = static_cast<int>(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs);
+  *err = out.C == 16 ? launch_nt<16>(p, grid, st) : (out.C == 32 ? launch_nt<32>(p, grid, st) : launch_nt<64>(p, grid, st));
+  return true;
+}
+
+}  // namespace te

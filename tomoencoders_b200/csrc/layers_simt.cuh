@@ -19,6 +19,9 @@ enum ActType { ACT_F32 = 0, ACT_BF16 = 1, ACT_F16 = 2 };
 // 3x3x3 'same' conv, w = [27][Cin][Cout] fp32 (Keras layout, BN folded), fp32 accumulation.
 cudaError_t simt_conv3(const TView& in, const TView& out, const float* w, const float* bias, int lrelu, float alpha,
                        int act_type, cudaStream_t st);
+// Tensor-core version of the Cin = 1 first layer (conv1_umma.cu); returns false when it does not apply.
+bool conv1_umma_try(const TView& in, const TView& out, const float* w, const float* bias, int lrelu, float alpha, int act_type,
+                    cudaStream_t st, cudaError_t* err);
 // transposed conv k=2, stride s ('same': output = s x input; gaps get bias only), w = [8][Cout][Cin].
 cudaError_t simt_upconv(const TView& in, const TView& out, const float* w, const float* bias, int stride, int lrelu,
                         float alpha, int act_type, cudaStream_t st);
