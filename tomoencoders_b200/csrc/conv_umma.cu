@@ -25,6 +25,7 @@
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include <vector>
 
 namespace te {
@@ -58,10 +59,19 @@ struct KParams {
   float* head_logits;
   uint8_t* pool_out;    // fused MaxPool3D(2) output (nullptr = none)
   int pool_ctot, pool_coff;
+  int tma_out;          // un-haloed kernels: epilogue writes through the output tensor maps
   int reuse_ok;         // host: enough spatial tiles to fill the GPU when the (Cout tile, sub) pairs are looped inside a CTA
 };
 
 struct TileCoord { int ntile, sub, n, z0, y0, x0; };
+struct OutMaps { CUtensorMap m[8]; };
+
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
 
 // `reuse` (un-haloed kernels whose channel chunks all fit the input ring): the outer index is the
 // spatial tile, the inner index j enumerates the (Cout tile, sub-position) pairs that share its
@@ -86,6 +96,13 @@ __device__ __forceinline__ TileCoord decode_tile(const KParams& p, long long t, 
   c.sub = static_cast<int>(t % p.nsub);        t /= p.nsub;
   c.ntile = static_cast<int>(t);
   return c;
+}
+
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_le1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all_groups() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_barrier(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 __device__ __forceinline__ uint32_t pack2(float a, float b, int fp16) {
@@ -120,17 +137,26 @@ struct Cfg {
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
                                    : TMEM_COLS_RAW <= 256 ? 256 : 512;
   static_assert(TMEM_COLS_RAW <= 512, "accumulators do not fit TMEM");
-  static constexpr int W_ROOM = 227 * 1024 - 2048 - NUM_A * A_STAGE;
+  static constexpr int W_ROOM = 227 * 1024 - 2048 - NUM_A * A_STAGE - (HALO ? 0 : 2 * 2 * 128 * (NT < 64 ? NT : 64) * 2);
   static constexpr int NUM_W = W_ROOM / W_STAGE >= 4 ? 4 : W_ROOM / W_STAGE;
   static_assert(NUM_W >= 2, "weight ring needs two stages");
-  static constexpr int SMEM_BYTES = NUM_A * A_STAGE + NUM_W * W_STAGE + 1024 /*barriers*/ + 1024 /*align*/;
+  // the un-haloed kernels (transposed / pointwise convs: 8 x more output per input voxel, few MMAs) are
+  // epilogue-bound (ncu: tensor pipe 6 %, DRAM 29 % on dec0.upconv), so they run two groups of four
+  // epilogue warps, each taking half of the tile's z planes
+  static constexpr int EPI_GROUPS = HALO ? 1 : 2;
+  static constexpr int THREADS = kThreads + (EPI_GROUPS - 1) * 128;
+  // TMA-store staging of the un-haloed kernels: per epilogue group two buffers of 128 voxels x OUT_BOX channels
+  static constexpr int OUT_BOX = NT < 64 ? NT : 64;
+  static constexpr int STG_BUF = 128 * OUT_BOX * 2;
+  static constexpr int STG_BYTES = HALO ? 0 : EPI_GROUPS * 2 * STG_BUF;
+  static constexpr int SMEM_BYTES = STG_BYTES + NUM_A * A_STAGE + NUM_W * W_STAGE + 1024 /*barriers*/ + 1024 /*align*/;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
 };
 
 template <int CB, int NT, int TZ, int HALO>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__((Cfg<CB, NT, TZ, HALO>::THREADS), 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_in2,
-                 const KParams p) {
+                 const __grid_constant__ OutMaps omaps, const KParams p) {
   using C = Cfg<CB, NT, TZ, HALO>;
   constexpr int kNumAStages = C::NUM_A;
   constexpr int BX = 8 + 2 * HALO, BY = 16 + 2 * HALO, BZ = TZ + 2 * HALO;   // input box (voxels)
@@ -150,13 +176,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   uint64_t* acc_full = w_empty + kNumWStages;    // [2]
   uint64_t* acc_empty = acc_full + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint8_t* stg = reinterpret_cast<uint8_t*>(bars) + 1024;    // [EPI_GROUPS][2][STG_BUF], 1024-aligned (un-haloed kernels)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kNumAStages; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
     for (int i = 0; i < kNumWStages; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4 * C::EPI_GROUPS); }
     fence_barrier_init();
     prefetch_tmap(&tmap_in);
   }
@@ -345,6 +372,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   } else {
     // ============================== epilogue warps ==============================
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int eg = warp >= 7 ? 1 : 0;             // epilogue group (warps 2-5 / 7-10): its share of the z planes
+    constexpr int PZ_PER_GROUP = TZ / C::EPI_GROUPS;
     const int m = q * 32 + lane;                  // accumulator row = voxel (y = m / 8, x = m % 8)
     const int my = m >> 3, mx = m & 7;
     uint32_t ab = 0, abph = 0;
@@ -357,11 +386,65 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       const int iy = tc.y0 + my, ix = tc.x0 + mx;
       const float* bias = p.bias + tc.ntile * NT;
       static_assert(TZ % 2 == 0, "the epilogue walks the z planes of a tile in pairs");
-      {
+      bool done_by_tma = false;
+      if constexpr (!HALO) {
+        if (p.tma_out) {
+          // TMEM -> registers -> bias / LeakyReLU -> swizzled staging buffer -> ONE TMA box store per plane and
+          // 64-channel group.  (Per-thread 16-byte stores touch 32 different 128-byte lines per instruction;
+          // the L1 store path, shared by all warps of the SM, was the bound of these kernels.)
+          constexpr int OB = C::OUT_BOX, ROWB_O = OB * 2;      // channels and bytes per staged voxel row
+          constexpr uint32_t SWM = ROWB_O == 128 ? 7u : (ROWB_O == 64 ? 3u : 1u);
+          uint8_t* my_stg = stg + eg * 2 * C::STG_BUF;
+          const bool issuer = (warp == (eg ? 7 : 2));
+          uint32_t it = 0;
+#pragma unroll 1
+          for (int pz = eg * PZ_PER_GROUP; pz < (eg + 1) * PZ_PER_GROUP; ++pz) {
+#pragma unroll 1
+            for (int cg = 0; cg < NT; cg += OB, ++it) {
+              uint8_t* buf = my_stg + (it & 1) * C::STG_BUF;
+              // the store issued two rounds ago from this buffer must have finished reading it
+              if (issuer) { if (elect_one()) bulk_wait_read_le1(); __syncwarp(); }
+              named_barrier(1 + eg, 128);
+#pragma unroll
+              for (int c0 = 0; c0 < OB; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(tbase + pz * NT + cg + c0, r);
+                tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int j2 = 0; j2 < 16; ++j2) {
+                  float x = __uint_as_float(r[j2]) + __ldg(bias + cg + c0 + j2);
+                  if (p.act_lrelu) x = x > 0.f ? x : p.alpha * x;
+                  v[j2] = x;
+                }
+                // row m of the box, 16-byte chunks (c0 / 8) and (c0 / 8 + 1), swizzled like the TMA expects
+                const uint32_t rowoff = static_cast<uint32_t>(m) * ROWB_O;
+                const uint32_t ch0 = static_cast<uint32_t>(c0 >> 3);
+                const uint32_t sw = (rowoff >> 7) & SWM;
+                *reinterpret_cast<uint4*>(buf + rowoff + (((ch0) ^ sw) << 4)) =
+                    make_uint4(pack2(v[0], v[1], p.fp16), pack2(v[2], v[3], p.fp16), pack2(v[4], v[5], p.fp16), pack2(v[6], v[7], p.fp16));
+                *reinterpret_cast<uint4*>(buf + rowoff + (((ch0 + 1) ^ sw) << 4)) =
+                    make_uint4(pack2(v[8], v[9], p.fp16), pack2(v[10], v[11], p.fp16), pack2(v[12], v[13], p.fp16), pack2(v[14], v[15], p.fp16));
+              }
+              fence_proxy_async_smem();
+              named_barrier(1 + eg, 128);
+              if (issuer) {
+                if (elect_one()) {
+                  tma_store_5d(&omaps.m[tc.sub], buf, tc.ntile * NT + cg, tc.x0, tc.y0, tc.z0 + pz, tc.n);
+                  bulk_commit_group();
+                }
+                __syncwarp();
+              }
+            }
+          }
+          done_by_tma = true;
+        }
+      }
+      if (!done_by_tma) {
         // one z plane at a time: a voxel's channels are written back to back (interleaving the
         // stores of two planes measured 10-50 % slower on the store-bound layers)
 #pragma unroll 1
-        for (int pz = 0; pz < TZ; ++pz) {
+        for (int pz = eg * PZ_PER_GROUP; pz < (eg + 1) * PZ_PER_GROUP; ++pz) {
           const int iz = tc.z0 + pz;
           const bool valid = iz < p.D && iy < p.H && ix < p.W;
           long long ovox;
@@ -453,6 +536,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     }
   }
 
+  if constexpr (!HALO) {
+    if (p.tma_out && (warp == 2 || warp == 7)) {
+      if (elect_one()) bulk_wait_all_groups();
+      __syncwarp();
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -468,7 +557,9 @@ cudaError_t launch_cfg(const ConvUmmaLaunch& L, const KParams& p, int grid, cuda
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  conv_umma_kernel<CB, NT, TZ, HALO><<<grid, kThreads, C::SMEM_BYTES, stream>>>(L.tmap_in, L.tmap_in2, p);
+  OutMaps om;
+  for (int i = 0; i < 8; ++i) om.m[i] = L.tmap_out[i];
+  conv_umma_kernel<CB, NT, TZ, HALO><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(L.tmap_in, L.tmap_in2, om, p);
   return cudaGetLastError();
 }
 
@@ -503,6 +594,7 @@ KParams make_params(const ConvUmmaLaunch& L) {
   p.pool_out = static_cast<uint8_t*>(L.pool_out);
   p.pool_ctot = L.pool_ctot;
   p.pool_coff = L.pool_coff;
+  p.tma_out = (!p.halo && L.use_tma_out && L.out != nullptr) ? 1 : 0;
   p.reuse_ok = !p.halo && p.total_tiles / (static_cast<long long>(p.n_ntiles) * p.nsub) >= kNumSMs ? 1 : 0;
   return p;
 }
@@ -560,6 +652,51 @@ void conv_umma_pack(const float* w, int Cin, int Cout, int ntaps, int nsub, cons
                 *reinterpret_cast<uint16_t*>(base + P) = bits;
               }
         }
+}
+
+namespace {
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn2 get_encode2() {
+  static EncodeTiledFn2 fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult q;
+    void* p = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess) fn = (EncodeTiledFn2)p;
+  }
+  return fn;
+}
+}  // namespace
+
+void conv_umma_make_out_maps(ConvUmmaLaunch* L) {
+  L->use_tma_out = 0;
+  static const bool off = getenv("TOMOENC_NO_TMA_EPILOGUE") != nullptr;
+  if (off || L->ntaps == 27 || L->out == nullptr) return;
+  if (L->out_ctot % 8 != 0 || L->out_coff % 8 != 0 || L->NT % 16 != 0) return;
+  EncodeTiledFn2 enc = get_encode2();
+  if (!enc) return;
+  const int s = L->up_stride ? L->up_stride : 1;
+  const int nsub = L->up_stride ? 8 : 1;
+  const long long D2 = static_cast<long long>(L->D) * s, H2 = static_cast<long long>(L->H) * s, W2 = static_cast<long long>(L->W) * s;
+  const long long ct = L->out_ctot;
+  const int ob = L->NT < 64 ? L->NT : 64;
+  const CUtensorMapSwizzle sw = ob * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : (ob * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  for (int sub = 0; sub < nsub; ++sub) {
+    const int a = (sub >> 2) & 1, b = (sub >> 1) & 1, c = sub & 1;
+    uint8_t* base = static_cast<uint8_t*>(L->out) + ((((L->up_stride ? a : 0) * H2 + (L->up_stride ? b : 0)) * W2 + (L->up_stride ? c : 0)) * ct + L->out_coff) * 2;
+    cuuint64_t gdim[5] = {(cuuint64_t)L->Cout, (cuuint64_t)L->W, (cuuint64_t)L->H, (cuuint64_t)L->D, (cuuint64_t)L->N};
+    cuuint64_t gstr[4] = {(cuuint64_t)(s * ct * 2), (cuuint64_t)(s * W2 * ct * 2), (cuuint64_t)(s * H2 * W2 * ct * 2),
+                          (cuuint64_t)(D2 * H2 * W2 * ct * 2)};
+    cuuint32_t box[5] = {(cuuint32_t)ob, 8, 16, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (enc(&L->tmap_out[sub], L->fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, gdim, gstr, box,
+            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return;
+  }
+  for (int sub = nsub; sub < 8; ++sub) L->tmap_out[sub] = L->tmap_out[0];
+  L->use_tma_out = 1;
 }
 
 int conv_umma_grid(const ConvUmmaLaunch& L) {

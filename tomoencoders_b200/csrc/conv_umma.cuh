@@ -35,7 +35,16 @@ struct ConvUmmaLaunch {
   int pool_ctot, pool_coff;
   // kernel configuration chosen by conv_umma_config()
   int CB, NT, TZ;
+  // un-haloed kernels (transposed / pointwise convs): output through TMA box stores.  tmap_out[sub] is a
+  // 5-D map (C, W, H, D, N) of the output voxels this sub-position writes (for a transposed conv: every
+  // second voxel, base shifted by the sub-position), box (min(NT, 64), 8, 16, 1, 1), swizzle = box row
+  // bytes.  Built by conv_umma_make_out_maps(); ignored when use_tma_out == 0.
+  CUtensorMap tmap_out[8];
+  int use_tma_out;
 };
+// Fills L.tmap_out / L.use_tma_out from L.out, L.out_ctot, L.out_coff, L.N/D/H/W, L.Cout, L.up_stride, L.NT,
+// L.fp16 (un-haloed launches only; leaves use_tma_out = 0 when the layout does not qualify).
+void conv_umma_make_out_maps(ConvUmmaLaunch* L);
 
 struct ConvUmmaConfig { int CB, NT, TZ; };
 // Picks (channel chunk, Cout tile, z planes per tile) for a layer; returns false if unsupported.

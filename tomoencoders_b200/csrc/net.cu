@@ -53,6 +53,8 @@ struct Layer {
   bool skip = false;         // layer folded into its predecessor (the fused head)
   ConvUmmaConfig cfg{};
   CUtensorMap tmap{}, tmap2{};
+  CUtensorMap omaps[8]{};    // output tensor maps of the un-haloed kernels (TMA-store epilogue), built per batch size
+  int omaps_n = -1, omaps_ok = 0;
   double flops = 0.0;
   float head_b = 0.f;
   // optional per-layer timing (te_net_set_profiling): event pairs recorded around every launch
@@ -644,6 +646,17 @@ int run_layers(te_net* net, int n, const HeadOut& ho, cudaStream_t st) {
             if (dbg & 1) C.out = nullptr;
             if (dbg & 2) C.pool_out = nullptr;
           }
+          if (C.ntaps == 1) {
+            if (L.omaps_n != n) {
+              conv_umma_make_out_maps(&C);
+              for (int k = 0; k < 8; ++k) L.omaps[k] = C.tmap_out[k];
+              L.omaps_ok = C.use_tma_out;
+              L.omaps_n = n;
+            } else {
+              for (int k = 0; k < 8; ++k) C.tmap_out[k] = L.omaps[k];
+              C.use_tma_out = L.omaps_ok;
+            }
+          }
           e = conv_umma_launch(C, st);
           count_launch();
         } else if (L.op == OP_CONV3) {
@@ -791,6 +804,8 @@ extern "C" int te_net_layer_kernel(const te_net* net, int i, char* buf, int bufl
   const Layer& L = net->layers[i];
   if (L.skip) snprintf(buf, buflen, "fused into previous layer");
   else if (L.use_umma) snprintf(buf, buflen, "conv_umma_kernel<%d,%d,%d>%s", L.cfg.CB, L.cfg.NT, L.cfg.TZ, L.fused_head ? "+head" : "");
+  else if (L.op == OP_CONV3 && L.Cin == 1 && net->act_type != ACT_F32 && (L.Cout == 16 || L.Cout == 32 || L.Cout == 64))
+    snprintf(buf, buflen, "conv1_umma_kernel<%d>", L.Cout);
   else {
     static const char* names[] = {"conv3_kernel", "upconv_kernel", "maxpool_kernel", "head_kernel", "dense_kernel"};
     snprintf(buf, buflen, "%s", names[L.op]);
