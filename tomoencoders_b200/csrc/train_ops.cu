@@ -151,6 +151,209 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(TView y, TView da
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// 8-channel vectorised versions (16-bit tensors, C a power-of-two multiple of 8 up to 256, 16-byte aligned
+// channel slices): one 128-bit access per tensor and voxel; per-channel sums are reduced across the warp
+// (lanes with the same channel group), across the block in shared memory, then 2C atomics per block.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void load8v(const T* p, float (&f)[8]) {
+  const uint4 r = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if constexpr (std::is_same<T, __half>::value) {
+      const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+      f[2 * j] = v.x; f[2 * j + 1] = v.y;
+    } else {
+      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+      f[2 * j] = v.x; f[2 * j + 1] = v.y;
+    }
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store8v(T* p, const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if constexpr (std::is_same<T, __half>::value) { __half2 h = __floats2half2_rn(f[2 * j], f[2 * j + 1]); w[j] = *reinterpret_cast<uint32_t*>(&h); }
+    else { __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]); w[j] = *reinterpret_cast<uint32_t*>(&h); }
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// out[c] += sum a, out[C + c] += sum b with (a[8], b[8]) = f(voxel, first channel of the group); `items` work items,
+// item -> (voxel index passed to f) is the identity: the caller decodes it.
+template <typename F>
+__device__ __forceinline__ void reduce2_v8(int C, long long items, double* out, F f) {
+  __shared__ float red[8][2][256];
+  const int G = C >> 3;
+  const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int g = static_cast<int>(t % G);
+  const long long istride = nthreads / G;
+  float sa[8], sb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sa[j] = sb[j] = 0.f;
+  for (long long it = t / G; it < items; it += istride) {
+    float a[8], b[8];
+    f(it, g * 8, a, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sa[j] += a[j]; sb[j] += b[j]; }
+  }
+  for (int off = 16; off >= G; off >>= 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sa[j] += __shfl_xor_sync(0xffffffffu, sa[j], off);
+      sb[j] += __shfl_xor_sync(0xffffffffu, sb[j], off);
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < G) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { red[warp][0][lane * 8 + j] = sa[j]; red[warp][1][lane * 8 + j] = sb[j]; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    const int which = i / C, c = i - which * C;
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += red[w][which][c];
+    atomicAdd(out + which * C + c, static_cast<double>(tot));
+  }
+}
+
+bool v8_ok(const te_tensor& t) {
+  const int G = t.C >> 3;
+  return t.dtype != TE_F32 && t.C % 8 == 0 && t.C <= 256 && G >= 1 && (G & (G - 1)) == 0 && G <= 32 && t.ctot % 8 == 0 && t.coff % 8 == 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_stats_v8_kernel(TView y, double* stats) {
+  const T* p = static_cast<const T*>(y.ptr);
+  reduce2_v8(y.C, y.voxels(), stats, [&](long long vox, int c0, float (&a)[8], float (&b)[8]) {
+    load8v<T>(p + vox * y.ctot + y.coff + c0, a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = a[j] * a[j];
+  });
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_act_fwd_v8_kernel(TView y, TView a, const float* __restrict__ scale,
+                                                             const float* __restrict__ shift, float alpha) {
+  const int G = y.C >> 3;
+  const long long total = y.voxels() * G;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const T* yp = static_cast<const T*>(y.ptr);
+  T* ap = static_cast<T*>(a.ptr);
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const long long vox = e / G;
+    const int c0 = static_cast<int>(e - vox * G) * 8;
+    float f[8];
+    load8v<T>(yp + vox * y.ctot + y.coff + c0, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float z = fmaf(scale[c0 + j], f[j], shift[c0 + j]);
+      f[j] = z > 0.f ? z : alpha * z;
+    }
+    store8v<T>(ap + vox * a.ctot + a.coff + c0, f);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_act_bwd_reduce_v8_kernel(TView y, TView da, const float* __restrict__ scale,
+                                                                    const float* __restrict__ shift, const float* __restrict__ mean,
+                                                                    const float* __restrict__ rstd, float alpha, double* red) {
+  const T* yp = static_cast<const T*>(y.ptr);
+  const T* dp = static_cast<const T*>(da.ptr);
+  reduce2_v8(y.C, y.voxels(), red, [&](long long vox, int c0, float (&a)[8], float (&b)[8]) {
+    float yv[8], d[8];
+    load8v<T>(yp + vox * y.ctot + y.coff + c0, yv);
+    load8v<T>(dp + vox * da.ctot + da.coff + c0, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float z = fmaf(scale[c0 + j], yv[j], shift[c0 + j]);
+      const float dz = d[j] * (z > 0.f ? 1.f : alpha);
+      a[j] = dz;
+      b[j] = dz * (yv[j] - mean[c0 + j]) * rstd[c0 + j];
+    }
+  });
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_act_bwd_apply_v8_kernel(TView y, TView da, TView dy, const float* __restrict__ scale,
+                                                                   const float* __restrict__ shift, const float* __restrict__ mean,
+                                                                   const float* __restrict__ rstd, const float* __restrict__ dbeta_n,
+                                                                   const float* __restrict__ dgamma_n, float alpha) {
+  const int G = y.C >> 3;
+  const long long total = y.voxels() * G;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const T* yp = static_cast<const T*>(y.ptr);
+  const T* dp = static_cast<const T*>(da.ptr);
+  T* op = static_cast<T*>(dy.ptr);
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const long long vox = e / G;
+    const int c0 = static_cast<int>(e - vox * G) * 8;
+    float yv[8], d[8];
+    load8v<T>(yp + vox * y.ctot + y.coff + c0, yv);
+    load8v<T>(dp + vox * da.ctot + da.coff + c0, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float z = fmaf(scale[c0 + j], yv[j], shift[c0 + j]);
+      const float dz = d[j] * (z > 0.f ? 1.f : alpha);
+      const float xhat = (yv[j] - mean[c0 + j]) * rstd[c0 + j];
+      d[j] = scale[c0 + j] * (dz - dbeta_n[c0 + j] - xhat * dgamma_n[c0 + j]);
+    }
+    store8v<T>(op + vox * dy.ctot + dy.coff + c0, d);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) channel_sum_v8_kernel(TView dy, double* out2) {
+  const T* p = static_cast<const T*>(dy.ptr);
+  reduce2_v8(dy.C, dy.voxels(), out2, [&](long long vox, int c0, float (&a)[8], float (&b)[8]) {
+    load8v<T>(p + vox * dy.ctot + dy.coff + c0, a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = 0.f;
+  });
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) head_wgrad_v8_kernel(TView a, const float* __restrict__ dl, double* dwb2c) {
+  const T* p = static_cast<const T*>(a.ptr);
+  reduce2_v8(a.C, a.voxels(), dwb2c, [&](long long vox, int c0, float (&s0)[8], float (&s1)[8]) {
+    const float d = dl[vox];
+    load8v<T>(p + vox * a.ctot + a.coff + c0, s0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s0[j] *= d; s1[j] = d; }
+  });
+}
+
+// space-to-depth transposed-conv backward, vectorised: item = (low-res voxel, sub-position)
+template <typename T>
+__global__ void __launch_bounds__(256) lrelu_bwd_s2d_v8_kernel(TView a, TView da, TView dz2, float alpha, double* dbias2) {
+  const int C = a.C, Dl = a.D / 2, Hl = a.H / 2, Wl = a.W / 2;
+  const T* ap = static_cast<const T*>(a.ptr);
+  const T* dp = static_cast<const T*>(da.ptr);
+  T* op = static_cast<T*>(dz2.ptr);
+  reduce2_v8(C, static_cast<long long>(a.N) * Dl * Hl * Wl * 8, dbias2, [&](long long item, int c0, float (&s0)[8], float (&s1)[8]) {
+    long long t = item;
+    const int sub = static_cast<int>(t & 7); t >>= 3;
+    const long long lv = t;
+    const int x = static_cast<int>(t % Wl); t /= Wl;
+    const int y = static_cast<int>(t % Hl); t /= Hl;
+    const int z = static_cast<int>(t % Dl);
+    const long long n = t / Dl;
+    const long long hv = ((n * a.D + 2 * z + (sub >> 2)) * a.H + 2 * y + ((sub >> 1) & 1)) * a.W + 2 * x + (sub & 1);
+    float av[8];
+    load8v<T>(ap + hv * a.ctot + a.coff + c0, av);
+    load8v<T>(dp + hv * da.ctot + da.coff + c0, s0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s0[j] *= (av[j] > 0.f ? 1.f : alpha); s1[j] = 0.f; }
+    store8v<T>(op + lv * dz2.ctot + dz2.coff + sub * C + c0, s0);
+  });
+}
+
 // MaxPool3D(p) backward: the gradient of a pooled voxel goes to the FIRST window element (z, y, x
 // scan order) equal to the maximum (torch / TF argmax convention); every input voxel is written.
 // accumulate = 1 adds to dx (the skip connection already deposited its gradient there).
@@ -778,6 +981,13 @@ extern "C" int te_tr_bn_stats(const te_tensor* y, double* stats2c, void* stream)
   const TView v = view_of(*y);
   int grid = blocks_for(v.voxels() * v.C, 256, 8);
   if (static_cast<long long>(grid) * 256 < v.C) grid = (v.C + 255) / 256;
+  if (v8_ok(*y)) {
+    const int g8 = blocks_for(v.voxels() * (v.C >> 3), 256, 8);
+    if (y->dtype == TE_F16) bn_stats_v8_kernel<__half><<<g8, 256, 0, static_cast<cudaStream_t>(stream)>>>(v, stats2c);
+    else bn_stats_v8_kernel<__nv_bfloat16><<<g8, 256, 0, static_cast<cudaStream_t>(stream)>>>(v, stats2c);
+    TE_LAUNCH_CHECK();
+    return TE_OK;
+  }
   TE_DISPATCH_T(y->dtype, (bn_stats_kernel<T><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(v, stats2c)));
   TE_LAUNCH_CHECK();
   return TE_OK;
@@ -788,6 +998,13 @@ extern "C" int te_tr_bn_act_fwd(const te_tensor* y, const te_tensor* a, const fl
   TE_TR_CHECK_T(y, "te_tr_bn_act_fwd"); TE_TR_CHECK_T(a, "te_tr_bn_act_fwd");
   TE_CHECK_ARG(scale && shift && same_grid(*y, *a) && y->C == a->C && y->dtype == a->dtype, "te_tr_bn_act_fwd: bad argument");
   const TView vy = view_of(*y), va = view_of(*a);
+  if (v8_ok(*y) && v8_ok(*a)) {
+    const int g8 = blocks_for(vy.voxels() * (vy.C >> 3), 256);
+    if (y->dtype == TE_F16) bn_act_fwd_v8_kernel<__half><<<g8, 256, 0, static_cast<cudaStream_t>(stream)>>>(vy, va, scale, shift, alpha);
+    else bn_act_fwd_v8_kernel<__nv_bfloat16><<<g8, 256, 0, static_cast<cudaStream_t>(stream)>>>(vy, va, scale, shift, alpha);
+    TE_LAUNCH_CHECK();
+    return TE_OK;
+  }
   TE_DISPATCH_T(y->dtype, (bn_act_fwd_kernel<T><<<blocks_for(vy.voxels() * vy.C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
                               vy, va, scale, shift, alpha)));
   TE_LAUNCH_CHECK();
@@ -800,6 +1017,14 @@ extern "C" int te_tr_bn_act_bwd_reduce(const te_tensor* y, const te_tensor* da, 
   TE_CHECK_ARG(scale && shift && mean && rstd && red2c && same_grid(*y, *da) && y->C == da->C && y->dtype == da->dtype,
                "te_tr_bn_act_bwd_reduce: bad argument");
   const TView vy = view_of(*y), vd = view_of(*da);
+  if (v8_ok(*y) && v8_ok(*da)) {
+    const int g8 = blocks_for(vy.voxels() * (vy.C >> 3), 256, 8);
+    cudaStream_t st8 = static_cast<cudaStream_t>(stream);
+    if (y->dtype == TE_F16) bn_act_bwd_reduce_v8_kernel<__half><<<g8, 256, 0, st8>>>(vy, vd, scale, shift, mean, rstd, alpha, red2c);
+    else bn_act_bwd_reduce_v8_kernel<__nv_bfloat16><<<g8, 256, 0, st8>>>(vy, vd, scale, shift, mean, rstd, alpha, red2c);
+    TE_LAUNCH_CHECK();
+    return TE_OK;
+  }
   int grid = blocks_for(vy.voxels() * vy.C, 256, 8);
   if (static_cast<long long>(grid) * 256 < vy.C) grid = (vy.C + 255) / 256;
   TE_DISPATCH_T(y->dtype, (bn_act_bwd_reduce_kernel<T><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -816,6 +1041,14 @@ extern "C" int te_tr_bn_act_bwd_apply(const te_tensor* y, const te_tensor* da, c
                    y->C == da->C && y->C == dy->C && y->dtype == da->dtype && y->dtype == dy->dtype,
                "te_tr_bn_act_bwd_apply: bad argument");
   const TView vy = view_of(*y), vd = view_of(*da), vo = view_of(*dy);
+  if (v8_ok(*y) && v8_ok(*da) && v8_ok(*dy)) {
+    const int g8 = blocks_for(vy.voxels() * (vy.C >> 3), 256);
+    cudaStream_t st8 = static_cast<cudaStream_t>(stream);
+    if (y->dtype == TE_F16) bn_act_bwd_apply_v8_kernel<__half><<<g8, 256, 0, st8>>>(vy, vd, vo, scale, shift, mean, rstd, dbeta_n, dgamma_n, alpha);
+    else bn_act_bwd_apply_v8_kernel<__nv_bfloat16><<<g8, 256, 0, st8>>>(vy, vd, vo, scale, shift, mean, rstd, dbeta_n, dgamma_n, alpha);
+    TE_LAUNCH_CHECK();
+    return TE_OK;
+  }
   TE_DISPATCH_T(y->dtype, (bn_act_bwd_apply_kernel<T><<<blocks_for(vy.voxels() * vy.C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
                               vy, vd, vo, scale, shift, mean, rstd, dbeta_n, dgamma_n, alpha)));
   TE_LAUNCH_CHECK();
@@ -946,7 +1179,13 @@ extern "C" int te_tr_upconv_bwd(const te_tensor* x, const te_tensor* a, const te
     const TView vz = view_of(*dz2);
     int grid = blocks_for(va.voxels() * va.C, 256, 8);
     if (static_cast<long long>(grid) * 256 < va.C) grid = (va.C + 255) / 256;
-    TE_DISPATCH_T(a->dtype, (lrelu_bwd_s2d_kernel<T><<<grid, 256, 0, st>>>(va, vd, vz, alpha, dbias2c)));
+    if (v8_ok(*a) && v8_ok(*da) && dz2->ctot % 8 == 0) {
+      const int g8 = blocks_for(va.voxels() * (va.C >> 3), 256, 8);
+      if (a->dtype == TE_F16) lrelu_bwd_s2d_v8_kernel<__half><<<g8, 256, 0, st>>>(va, vd, vz, alpha, dbias2c);
+      else lrelu_bwd_s2d_v8_kernel<__nv_bfloat16><<<g8, 256, 0, st>>>(va, vd, vz, alpha, dbias2c);
+    } else {
+      TE_DISPATCH_T(a->dtype, (lrelu_bwd_s2d_kernel<T><<<grid, 256, 0, st>>>(va, vd, vz, alpha, dbias2c)));
+    }
     TE_LAUNCH_CHECK();
     // dw[(sub, co)][ci] = sum_v dz2[v][(sub, co)] x[v][ci]
     int rc = wgrad_mma(*dz2, *x, dw, dz2->C, 0, 1, st);
@@ -1024,7 +1263,13 @@ extern "C" int te_tr_conv3_wgrad(const te_tensor* x, const te_tensor* dy, float*
   if (dbias2c) {
     int grid = blocks_for(vd.voxels() * vd.C, 256, 8);
     if (static_cast<long long>(grid) * 256 < vd.C) grid = (vd.C + 255) / 256;
-    TE_DISPATCH_T(dy->dtype, (channel_sum_kernel<T><<<grid, 256, 0, st>>>(vd, dbias2c)));
+    if (v8_ok(*dy)) {
+      const int g8 = blocks_for(vd.voxels() * (vd.C >> 3), 256, 8);
+      if (dy->dtype == TE_F16) channel_sum_v8_kernel<__half><<<g8, 256, 0, st>>>(vd, dbias2c);
+      else channel_sum_v8_kernel<__nv_bfloat16><<<g8, 256, 0, st>>>(vd, dbias2c);
+    } else {
+      TE_DISPATCH_T(dy->dtype, (channel_sum_kernel<T><<<grid, 256, 0, st>>>(vd, dbias2c)));
+    }
     TE_LAUNCH_CHECK();
   }
   return TE_OK;
@@ -1045,7 +1290,13 @@ extern "C" int te_tr_head_loss(const te_tensor* a, const float* w, const float* 
   TE_LAUNCH_CHECK();
   int grid = blocks_for(va.voxels() * va.C, 256, 8);
   if (static_cast<long long>(grid) * 256 < va.C) grid = (va.C + 255) / 256;
-  TE_DISPATCH_T(a->dtype, (head_wgrad_kernel<T><<<grid, 256, 0, st>>>(va, dl, dwb2c)));
+  if (v8_ok(*a)) {
+    const int g8 = blocks_for(va.voxels() * (va.C >> 3), 256, 8);
+    if (a->dtype == TE_F16) head_wgrad_v8_kernel<__half><<<g8, 256, 0, st>>>(va, dl, dwb2c);
+    else head_wgrad_v8_kernel<__nv_bfloat16><<<g8, 256, 0, st>>>(va, dl, dwb2c);
+  } else {
+    TE_DISPATCH_T(a->dtype, (head_wgrad_kernel<T><<<grid, 256, 0, st>>>(va, dl, dwb2c)));
+  }
   TE_LAUNCH_CHECK();
   return TE_OK;
 }
