@@ -240,8 +240,20 @@ def run_ours(args):
     else:
         tf_peak, peak_src, hbm_peak = 1400.0, "fallback (B200_PROFILING.md sustained)", 6650.0
     achieved = dom["flops"] / (dom["ms"] / 1e3) / 1e12
+    # DRAM traffic per launch of the dominant kernel: ncu --set full capture committed under profiles/ (one launch of
+    # every layer at this very shape: 32 x 64^3 patches), averaged over the layers this kernel instantiation runs
+    traffic, traffic_note = None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if os.path.isfile(tpath) and CHUNK == 32:
+        tj = json.load(open(tpath))["layers"]
+        got = [tj[l]["dram_read_bytes"] + tj[l]["dram_write_bytes"] for l in dom["layers"] if l in tj]
+        if got:
+            traffic = sum(got) / len(got)
+            traffic_note = "mean dram read+write bytes per launch over %s (profiles/traffic_r01.json, ncu --set full)" % \
+                ", ".join(l for l in dom["layers"] if l in tj)
     roofline = {"bound": "tensor", "kernel": dom_name, "layers": dom["layers"], "achieved": achieved, "peak": tf_peak,
-                "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None, "peak_source": peak_src,
+                "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": traffic, "traffic_note": traffic_note,
+                "peak_source": peak_src,
                 "launches_per_step": dom["launches"], "avg_launch_ms": dom["ms"] / dom["launches"],
                 "share_of_step": dom["ms"] / tot_ms}
     all_tc_flops = sum(k["flops"] for n_, k in by_kernel.items() if n_.startswith("conv_umma"))
