@@ -38,6 +38,8 @@ VOL = (512, 512, 512)
 PATCH = 64
 CHUNK = 32
 ENC_PATCHES = 4096          # 64^3 patches encoded per rank per step in the "encode" leg
+CPU_TILES = 12              # bounded CPU sample of the same workload (10-30 s on the box's host cores)
+ENC_CHUNK = 128             # patches per encoder launch (the encoder keeps only pooled tensors: 128 patches = 1.3 GB)
 METRIC = "voxels/sec segmented (3-D U-net M_a01, 64^3 tiles of a 512^3 fp16 volume per GPU)"
 
 
@@ -329,7 +331,7 @@ def run_ours(args):
     # ------------------------------------------------------------------ encode + PCA leg (patches/s)
     def enc_step():
         pca = LatentPCA(2)
-        ae.embed_volume(vol, enc_patches, CHUNK, min_max=min_max, out=lat)
+        ae.embed_volume(vol, enc_patches, ENC_CHUNK, min_max=min_max, out=lat)
         pca.partial_fit(lat)
         pca.finalize()                      # all-reduce of the moments when world > 1
         return pca.transform_all_gather(lat)
@@ -345,7 +347,7 @@ def run_ours(args):
     barrier()
     enc_ms = max_over_ranks(c0.elapsed_time(c1)) / n_enc_steps
     enc_value = world * ENC_PATCHES / (enc_ms / 1e3)
-    enc_flops = ae.models["encoder"].net_for((PATCH,) * 3, CHUNK).flops_per_patch
+    enc_flops = ae.models["encoder"].net_for((PATCH,) * 3, ENC_CHUNK).flops_per_patch
 
     # ------------------------------------------------------------------ training leg (BASELINE configs[4]): fwd + bwd + Adam,
     # 64 patch pairs of 64^3 split over the ranks (8 per rank at N = 8; never fewer than 8 per rank here), SyncBN,
@@ -380,7 +382,7 @@ def run_ours(args):
         del tr, tx, ty
 
     if rank == 0:
-        cpu_v, cpu_dt, cpu_threads = cpu_reference_leg(4)
+        cpu_v, cpu_dt, cpu_threads = cpu_reference_leg(CPU_TILES)
         flops_patch = net.flops_per_patch
         line = {
             "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
@@ -411,12 +413,12 @@ def run_ours(args):
                             "(read+write 537 MB), te_gather_norm (fused clip/rescale, the product path), te_scatter of the "
                             "uint8 mask (read+write 268 MB); *_api = the same through Grid.extract / fill_patches_in_volume"},
             "encode": {"metric": "64^3 patches/sec encoded + PCA-projected (encoder [16,32,64], latent 128)",
-                       "value": enc_value, "unit": "patches/s", "ms_per_step": enc_ms, "patches_per_rank_per_step": ENC_PATCHES,
+                       "value": enc_value, "unit": "patches/s", "ms_per_step": enc_ms, "patches_per_rank_per_step": ENC_PATCHES, "chunk": ENC_CHUNK,
                        "tflops_effective": enc_value * enc_flops / 1e12,
                        "collectives": "allreduce(16513 f64 PCA moments) + allgather((n,2) projections)" if world > 1 else "none (1 rank)"},
             "train": train,
             "cpu_baseline": {"value": cpu_v, "unit": "voxels/s", "cores": cpu_threads, "kind": "port",
-                             "sample": "4 x 64^3 tiles: oracle extract + torch-CPU fp32 U-net M_a01 + fill (%.1f s)" % cpu_dt},
+                             "sample": "%d x 64^3 tiles: oracle extract + torch-CPU fp32 U-net M_a01 + fill (%.1f s)" % (CPU_TILES, cpu_dt)},
         }
         print(json.dumps(line))
     if world > 1:

@@ -257,24 +257,108 @@ template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256) dense_kernel(const TIn* __restrict__ x, long long n, int nin, int nout,
                                                      const float* __restrict__ w, const float* __restrict__ b, int lrelu,
                                                      float alpha, TOut* __restrict__ out) {
-  __shared__ float part[8][32];
+  // block = 8 rows x 32 outputs; its 8 warps split the input range; every weight fetched (coalesced over
+  // the lanes) feeds 8 independent accumulators, and the loop is unrolled 4 x for memory-level parallelism
+  constexpr int R = 8;
+  __shared__ float part[8][R][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = blockIdx.y;
+  const long long row0 = static_cast<long long>(blockIdx.y) * R;
   const int j = blockIdx.x * 32 + lane;
   const int chunk = (nin + 7) / 8;
   const int i0 = warp * chunk, i1 = min(nin, i0 + chunk);
-  float acc = 0.f;
-  if (j < nout) {
-    const TIn* xr = x + row * nin;
-    for (int i = i0; i < i1; ++i) acc = fmaf(ld<TIn>(xr + i), w[static_cast<long long>(i) * nout + j], acc);
+  float acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = 0.f;
+  const int jj = j < nout ? j : nout - 1;
+  int i = i0;
+  for (; i + 4 <= i1; i += 4) {
+    float wv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) wv[u] = __ldg(w + static_cast<long long>(i + u) * nout + jj);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (row0 + r < n) {
+        const TIn* xr = x + (row0 + r) * nin + i;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[r] = fmaf(ld<TIn>(xr + u), wv[u], acc[r]);
+      }
+    }
   }
-  part[warp][lane] = acc;
+  for (; i < i1; ++i) {
+    const float wv = __ldg(w + static_cast<long long>(i) * nout + jj);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (row0 + r < n) acc[r] = fmaf(ld<TIn>(x + (row0 + r) * nin + i), wv, acc[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) part[warp][r][lane] = acc[r];
   __syncthreads();
-  if (warp == 0 && j < nout) {
-    float s = b[j];
-    for (int k = 0; k < 8; ++k) s += part[k][lane];
-    if (lrelu) s = s > 0.f ? s : alpha * s;
-    st<TOut>(out + row * nout + j, s);
+  if (warp < R && j < nout && row0 + warp < n) {
+    float sum = b[j];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum += part[k][warp][lane];
+    if (lrelu) sum = sum > 0.f ? sum : alpha * sum;
+    st<TOut>(out + (row0 + warp) * nout + j, sum);
+  }
+}
+
+// Split-K variant for long input vectors (the 8192 -> 128 layer behind Flatten): grid.z blocks share the
+// input range and add their partial sums into a zeroed fp32 scratch; dense_finish applies bias / activation.
+template <typename TIn>
+__global__ void __launch_bounds__(256) dense_splitk_kernel(const TIn* __restrict__ x, long long n, int nin, int nout,
+                                                            const float* __restrict__ w, float* __restrict__ acc_out, int kper) {
+  constexpr int R = 8;
+  __shared__ float part[8][R][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row0 = static_cast<long long>(blockIdx.y) * R;
+  const int j = blockIdx.x * 32 + lane;
+  const int k0 = blockIdx.z * kper, k1 = min(nin, k0 + kper);
+  const int chunk = (k1 - k0 + 7) / 8;
+  const int i0 = k0 + warp * chunk, i1 = min(k1, i0 + chunk);
+  float acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = 0.f;
+  const int jj = j < nout ? j : nout - 1;
+  int i = i0;
+  for (; i + 8 <= i1; i += 8) {
+    float wv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) wv[u] = __ldg(w + static_cast<long long>(i + u) * nout + jj);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (row0 + r < n) {
+        const TIn* xr = x + (row0 + r) * nin + i;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[r] = fmaf(ld<TIn>(xr + u), wv[u], acc[r]);
+      }
+    }
+  }
+  for (; i < i1; ++i) {
+    const float wv = __ldg(w + static_cast<long long>(i) * nout + jj);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (row0 + r < n) acc[r] = fmaf(ld<TIn>(x + (row0 + r) * nin + i), wv, acc[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) part[warp][r][lane] = acc[r];
+  __syncthreads();
+  if (warp < R && j < nout && row0 + warp < n) {
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum += part[k][warp][lane];
+    atomicAdd(acc_out + (row0 + warp) * nout + j, sum);
+  }
+}
+
+template <typename TOut>
+__global__ void __launch_bounds__(256) dense_finish_kernel(const float* __restrict__ acc, const float* __restrict__ b, long long n,
+                                                            int nout, int lrelu, float alpha, TOut* __restrict__ out) {
+  const long long total = n * nout;
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float sum = acc[e] + b[e % nout];
+    if (lrelu) sum = sum > 0.f ? sum : alpha * sum;
+    st<TOut>(out + e, sum);
   }
 }
 
@@ -361,9 +445,25 @@ cudaError_t simt_head(const TView& in, const float* w, float b, uint8_t* labels,
 }
 
 cudaError_t simt_dense(const void* x, int in_type, long long n, int nin, int nout, const float* w, const float* b,
-                       int lrelu, float alpha, void* out, int out_type, cudaStream_t st) {
+                       int lrelu, float alpha, void* out, int out_type, cudaStream_t st, float* acc_scratch) {
   if (n <= 0) return cudaSuccess;
-  dim3 grid((nout + 31) / 32, static_cast<unsigned>(n));
+  if (acc_scratch != nullptr && nin >= 2048) {
+    const int kper = 512, ks = (nin + kper - 1) / kper;
+    cudaError_t e = cudaMemsetAsync(acc_scratch, 0, static_cast<size_t>(n) * nout * sizeof(float), st);
+    if (e != cudaSuccess) return e;
+    dim3 g3((nout + 31) / 32, static_cast<unsigned>((n + 7) / 8), ks);
+    if (in_type == ACT_F32) dense_splitk_kernel<float><<<g3, 256, 0, st>>>(static_cast<const float*>(x), n, nin, nout, w, acc_scratch, kper);
+    else if (in_type == ACT_BF16) dense_splitk_kernel<__nv_bfloat16><<<g3, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), n, nin, nout, w, acc_scratch, kper);
+    else dense_splitk_kernel<__half><<<g3, 256, 0, st>>>(static_cast<const __half*>(x), n, nin, nout, w, acc_scratch, kper);
+    count_launch();
+    const int gf = blocks_for(n * nout, 256);
+    if (out_type == ACT_F32) dense_finish_kernel<float><<<gf, 256, 0, st>>>(acc_scratch, b, n, nout, lrelu, alpha, static_cast<float*>(out));
+    else if (out_type == ACT_BF16) dense_finish_kernel<__nv_bfloat16><<<gf, 256, 0, st>>>(acc_scratch, b, n, nout, lrelu, alpha, static_cast<__nv_bfloat16*>(out));
+    else dense_finish_kernel<__half><<<gf, 256, 0, st>>>(acc_scratch, b, n, nout, lrelu, alpha, static_cast<__half*>(out));
+    count_launch();
+    return cudaGetLastError();
+  }
+  dim3 grid((nout + 31) / 32, static_cast<unsigned>((n + 7) / 8));
 #define TE_DENSE(TI, TO) \
   dense_kernel<TI, TO><<<grid, 256, 0, st>>>(static_cast<const TI*>(x), n, nin, nout, w, b, lrelu, alpha, static_cast<TO*>(out))
   if (in_type == ACT_F32 && out_type == ACT_F32) TE_DENSE(float, float);

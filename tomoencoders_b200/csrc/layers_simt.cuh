@@ -31,9 +31,10 @@ cudaError_t simt_maxpool(const TView& in, const TView& out, int pool, int act_ty
 cudaError_t simt_head(const TView& in, const float* w, float b, uint8_t* labels, float* probs, float* logits,
                       int act_type, cudaStream_t st);
 // dense: out[n][j] = act(sum_i x[n][i] w[i][j] + b[j]); x is the flattened NDHWC tensor of `in_type`;
-// out_type selects the element type of out (dense row-major (N, nout)).
+// out_type selects the element type of out (dense row-major (N, nout)).  acc_scratch (optional, n * nout fp32):
+// enables the split-K path for long input vectors.
 cudaError_t simt_dense(const void* x, int in_type, long long n, int nin, int nout, const float* w, const float* b,
-                       int lrelu, float alpha, void* out, int out_type, cudaStream_t st);
+                       int lrelu, float alpha, void* out, int out_type, cudaStream_t st, float* acc_scratch = nullptr);
 // view -> dense fp32 NDHWC copy (test hook).
 cudaError_t simt_to_f32(const TView& in, float* out, int act_type, cudaStream_t st);
 // dense fp32 -> activation type (decoder input etc.)

@@ -80,6 +80,7 @@ struct te_net {
   int last_n = 0;
   bool profiling = false;
   float* d_dense_tmp[2] = {nullptr, nullptr};
+  float* d_dense_acc = nullptr;     // split-K accumulation scratch of the dense layers
   te::TView input{};                // network input view (C = 1)
 };
 
@@ -385,6 +386,7 @@ void free_net(te_net* net) {
     if (L.d_wpacked) cudaFree(L.d_wpacked);
   }
   for (int i = 0; i < 2; ++i) if (net->d_dense_tmp[i]) cudaFree(net->d_dense_tmp[i]);
+  if (net->d_dense_acc) cudaFree(net->d_dense_acc);
   delete net;
 }
 
@@ -487,6 +489,11 @@ extern "C" int te_net_create(const te_net_desc* desc, te_net** out) {
         return TE_ERR_CUDA;
       }
       net->workspace_bytes += static_cast<long long>(desc->max_batch) * maxh * 4;
+    }
+    if (cudaMalloc(&net->d_dense_acc, static_cast<size_t>(desc->max_batch) * maxh * sizeof(float)) != cudaSuccess) {
+      set_error("te_net_create: out of device memory");
+      free_net(net);
+      return TE_ERR_CUDA;
     }
   }
   *out = net;
@@ -675,7 +682,7 @@ int run_layers(te_net* net, int n, const HeadOut& ho, cudaStream_t st) {
         const void* src = L.dense_in ? L.dense_in : dense_src;
         const int src_type = L.dense_in ? L.dense_in_type : dense_src_type;
         void* dst = L.dense_out ? L.dense_out : static_cast<void*>(net->d_dense_tmp[tmp_idx]);
-        e = simt_dense(src, src_type, n, L.nin, L.nout, L.d_w, L.d_bias, L.lrelu, alpha, dst, L.dense_out_type, st);
+        e = simt_dense(src, src_type, n, L.nin, L.nout, L.d_w, L.d_bias, L.lrelu, alpha, dst, L.dense_out_type, st, net->d_dense_acc);
         dense_src = dst;
         dense_src_type = L.dense_out_type;
         tmp_idx ^= 1;
