@@ -38,7 +38,7 @@ VOL = (512, 512, 512)
 PATCH = 64
 CHUNK = 32
 ENC_PATCHES = 4096          # 64^3 patches encoded per rank per step in the "encode" leg
-CPU_TILES = 12              # bounded CPU sample of the same workload (10-30 s on the box's host cores)
+CPU_TILES = 48              # bounded CPU sample of the same workload (10-30 s on the box's host cores)
 ENC_CHUNK = 128             # patches per encoder launch (the encoder keeps only pooled tensors: 128 patches = 1.3 GB)
 METRIC = "voxels/sec segmented (3-D U-net M_a01, 64^3 tiles of a 512^3 fp16 volume per GPU)"
 

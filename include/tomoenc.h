@@ -245,6 +245,15 @@ int te_tr_upconv_bwd(const te_tensor* x, const te_tensor* a, const te_tensor* da
 /* 1x1x1 head + sigmoid + Keras binary cross-entropy (mean over n_total voxels), forward and backward. */
 int te_tr_head_loss(const te_tensor* a, const float* w, const float* b, const uint8_t* y, const te_tensor* da,
                     double* loss, double* dwb2c, double n_total, float* dl, float* probs, void* stream);
+/* Dense layers and loss of the autoencoder training step (RegularizedAutoencoder.train_step,
+ * neural_nets/autoencoders.py:498-526; hidden_layer :60-91).  Dense activations are fp32 (N, n) row-major. */
+int te_tr_dense_fwd(const float* x, int64_t n, int32_t nin, int32_t nout, const float* w, const float* bias, float* y,
+                    void* stream);
+int te_tr_dense_bwd(const float* x, const float* dy, int64_t n, int32_t nin, int32_t nout, const float* w, float* dw,
+                    double* dbias2c, float* dx, void* stream);
+/* 1x1x1 head + sigmoid + mean squared error + weight * KL(target || p); loss3 += {total, mse, kl}. */
+int te_tr_head_ae_loss(const te_tensor* a, const float* w, const float* b, const void* target, const te_tensor* da,
+                       double* loss3, double* dwb2c, double n_total, float weight, float* dl, float* probs, void* stream);
 /* Keras Adam on a flat parameter buffer; g is multiplied by grad_scale first (1 / world size after an all-reduce). */
 int te_tr_adam(float* w, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                int64_t step, float grad_scale, void* stream);

@@ -16,7 +16,7 @@ import torch.nn.functional as F
 from . import nets_torch as O
 
 BN_MOMENTUM = 0.9
-TRAINABLE = ("conv_k", "conv_b", "convT_k", "convT_b", "bn_gamma", "bn_beta")
+TRAINABLE = ("conv_k", "conv_b", "convT_k", "convT_b", "dense_k", "dense_b", "bn_gamma", "bn_beta")
 
 
 class _WT(O._W):
@@ -118,3 +118,38 @@ def unet_train_step(x, y, weights, opt, dtype=torch.float64, **model_params):
     for i, v in new_moving.items():
         new_w[i] = v
     return loss, [np.asarray(w, dtype=np.float32) for w in new_w], grads
+
+
+def keras_mse_kl(x, p, weight):
+    """RegularizedAutoencoder.train_step (autoencoders.py:498-526): mean(mse(x, p)) + weight * mean(kl_divergence(x, p)),
+    Keras' kl_divergence clips both arguments to [1e-7, 1] and sums y_true * log(y_true / y_pred) over the channel axis."""
+    eps = 1e-7
+    mse = ((x - p) ** 2).mean()
+    yt, yp = torch.clamp(x, eps, 1.0), torch.clamp(p, eps, 1.0)
+    kl = (yt * torch.log(yt / yp)).mean()
+    return mse + weight * kl, mse, kl
+
+
+def cae_loss_and_grads(x, weights_enc, weights_dec, model_size, weight=1.0 / 250.0, dtype=torch.float64, **model_params):
+    """x (N,D,H,W,1) in [0,1].  Returns (total, mse, kl, grads_enc + grads_dec (Keras order; None for moving statistics),
+    new_moving {index in the concatenated list: array})."""
+    spec_e, flatten_shape, preflatten = O.encoder_spec(model_size, **model_params)
+    spec_d = O.decoder_spec(model_size, **model_params)
+    W = _WT(list(weights_enc) + list(weights_dec), list(spec_e) + list(spec_d), dtype)
+    old_bn = O._bn
+    O._bn = _bn_train
+    try:
+        t = torch.from_numpy(np.ascontiguousarray(x)).to(dtype).permute(0, 4, 1, 2, 3)
+        z, _, _ = O.encoder_graph(t, W, **model_params)
+        assert W.i == len(spec_e)
+        p = O.decoder_graph(z, W, flatten_shape, preflatten, **model_params)
+    finally:
+        O._bn = old_bn
+    total, mse, kl = keras_mse_kl(t, p, weight)
+    total.backward()
+    grads = []
+    for i, kind in enumerate(W.kinds):
+        leaf = W.leaves[i]
+        grads.append(leaf.grad.detach().numpy().astype(np.float64) if kind in TRAINABLE and leaf.grad is not None else None)
+    new_moving = {i: v.numpy().astype(np.float64) for i, v in W.new_moving.items()}
+    return float(total.item()), float(mse.item()), float(kl.item()), grads, new_moving

@@ -141,6 +141,9 @@ _SIGNATURES = {
     "te_tr_upconv_fwd": (ctypes.c_int, [_TP, _P, _P, _TP, _I32, _F, _P, _P]),
     "te_tr_upconv_bwd": (ctypes.c_int, [_TP, _TP, _TP, _P, _I32, _F, _P, _P, _TP, _TP, _P, _P]),
     "te_tr_head_loss": (ctypes.c_int, [_TP, _P, _P, _P, _TP, _P, _P, _D, _P, _P, _P]),
+    "te_tr_dense_fwd": (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _P, _P, _P]),
+    "te_tr_dense_bwd": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P]),
+    "te_tr_head_ae_loss": (ctypes.c_int, [_TP, _P, _P, _P, _TP, _P, _P, _D, _F, _P, _P, _P]),
     "te_tr_adam": (ctypes.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I64, _F, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -800,6 +800,92 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(TView a, const float* _
   });
 }
 
+// ------------------------------------------------------------------------------------------------
+// Autoencoder loss (RegularizedAutoencoder.train_step, /root/reference/tomo_encoders/neural_nets/autoencoders.py:498-526):
+//   logit = a . w + b ; p = sigmoid(logit)
+//   total = mean((x - p)^2) + weight * mean(KL(x || p)),  KL = clip(x, eps, 1) * log(clip(x, eps, 1) / clip(p, eps, 1))
+// (keras.losses.mean_squared_error / kl_divergence over the single channel, eps = 1e-7).  loss3 += {total, mse, kl}.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) head_ae_loss_kernel(TView a, const float* __restrict__ w, const float* __restrict__ b,
+                                                            const T* __restrict__ target, TView da, double* loss3, float inv_n,
+                                                            float weight, float* __restrict__ dl_out, float* probs) {
+  const int C = a.C;
+  const long long nvox = a.voxels();
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const T* ap = static_cast<const T*>(a.ptr);
+  T* dp = static_cast<T*>(da.ptr);
+  extern __shared__ float sw[];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const float bias = b[0];
+  double s_mse = 0.0, s_kl = 0.0;
+  for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < nvox; v += stride) {
+    const T* row = ap + v * a.ctot + a.coff;
+    float logit = bias;
+    for (int c = 0; c < C; ++c) logit = fmaf(ldv<T>(row + c), sw[c], logit);
+    const float pr = 1.f / (1.f + expf(-logit));
+    if (probs) probs[v] = pr;
+    const float xt = ldv<T>(target + v);
+    const float eps = 1e-7f;
+    const float yt = fminf(fmaxf(xt, eps), 1.f), yp = fminf(fmaxf(pr, eps), 1.f);
+    const float diff = xt - pr;
+    s_mse += diff * diff;
+    s_kl += yt * logf(yt / yp);
+    float dldp = -2.f * diff;
+    if (pr > eps && pr < 1.f) dldp += weight * (-yt / yp);
+    const float dl = dldp * pr * (1.f - pr) * inv_n;
+    dl_out[v] = dl;
+    T* drow = dp + v * da.ctot + da.coff;
+    for (int c = 0; c < C; ++c) stv<T>(drow + c, dl * sw[c]);
+  }
+  __shared__ double sl[2][8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s_mse += __shfl_xor_sync(0xffffffffu, s_mse, o); s_kl += __shfl_xor_sync(0xffffffffu, s_kl, o); }
+  if ((threadIdx.x & 31) == 0) { sl[0][threadIdx.x >> 5] = s_mse; sl[1][threadIdx.x >> 5] = s_kl; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = 0.0, k = 0.0;
+    for (int i = 0; i < 8; ++i) { m += sl[0][i]; k += sl[1][i]; }
+    atomicAdd(loss3, (m + weight * k) * inv_n);
+    atomicAdd(loss3 + 1, m * inv_n);
+    atomicAdd(loss3 + 2, k * inv_n);
+  }
+}
+
+// Dense layer backward (fp32, small): dw[i][j] += sum_n x[n][i] dy[n][j]; db2[j] += sum_n dy[n][j]; dx[n][i] = sum_j dy[n][j] w[i][j]
+__global__ void __launch_bounds__(256) dense_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, long long n, int nin,
+                                                           int nout, float* __restrict__ dw, double* __restrict__ db2) {
+  const long long total = static_cast<long long>(nin) * nout;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int j = static_cast<int>(e % nout);
+    const long long i = e / nout;
+    float acc = 0.f;
+    for (long long r = 0; r < n; ++r) acc = fmaf(x[r * nin + i], dy[r * nout + j], acc);
+    dw[e] += acc;
+    if (i == 0) {
+      float sb = 0.f;
+      for (long long r = 0; r < n; ++r) sb += dy[r * nout + j];
+      atomicAdd(db2 + j, static_cast<double>(sb));
+    }
+  }
+}
+__global__ void __launch_bounds__(256) dense_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, long long n, int nin,
+                                                           int nout, float* __restrict__ dx) {
+  // one warp per (row, input index): lanes split the output range (coalesced reads of w[i][:]), shuffle reduction
+  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (long long e = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; e < n * nin; e += warps) {
+    const long long r = e / nin, i = e - r * nin;
+    float acc = 0.f;
+    for (int j = lane; j < nout; j += 32) acc = fmaf(dy[r * nout + j], w[i * nout + j], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) dx[e] = acc;
+  }
+}
+
 // Keras Adam: lr_t = lr sqrt(1 - b2^t) / (1 - b1^t); theta -= lr_t m / (sqrt(v) + eps)
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, long long n, float lr_t, float b1, float b2,
@@ -977,7 +1063,7 @@ extern "C" int te_tr_flip_weights(const float* w, int32_t Cin, int32_t Cout, int
 
 extern "C" int te_tr_bn_stats(const te_tensor* y, double* stats2c, void* stream) {
   TE_TR_CHECK_T(y, "te_tr_bn_stats");
-  TE_CHECK_ARG(stats2c && y->C <= 4096, "te_tr_bn_stats: bad argument");
+  TE_CHECK_ARG(stats2c && y->C <= (1 << 20), "te_tr_bn_stats: bad argument");
   const TView v = view_of(*y);
   int grid = blocks_for(v.voxels() * v.C, 256, 8);
   if (static_cast<long long>(grid) * 256 < v.C) grid = (v.C + 255) / 256;
@@ -1309,6 +1395,54 @@ extern "C" int te_tr_adam(float* w, const float* g, float* m, float* v, int64_t 
                       (1.0 - pow(static_cast<double>(beta1), static_cast<double>(step)));
   adam_kernel<<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(w, g, m, v, n, static_cast<float>(lr_t), beta1, beta2,
                                                                                   eps, grad_scale);
+  TE_LAUNCH_CHECK();
+  return TE_OK;
+}
+
+// ---- dense layers of the autoencoder (fp32 activations: these tensors are a few KB per sample)
+extern "C" int te_tr_dense_fwd(const float* x, int64_t n, int32_t nin, int32_t nout, const float* w, const float* bias, float* y,
+                               void* stream) {
+  TE_CHECK_ARG(x && w && bias && y && n >= 0 && nin > 0 && nout > 0, "te_tr_dense_fwd: bad argument");
+  cudaError_t e = simt_dense(x, ACT_F32, n, nin, nout, w, bias, 0, 0.f, y, ACT_F32, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) { set_error("te_tr_dense_fwd: %s", cudaGetErrorString(e)); return TE_ERR_CUDA; }
+  return TE_OK;
+}
+
+extern "C" int te_tr_dense_bwd(const float* x, const float* dy, int64_t n, int32_t nin, int32_t nout, const float* w, float* dw,
+                               double* dbias2c, float* dx, void* stream) {
+  TE_CHECK_ARG(x && dy && w && dw && dbias2c && n >= 0 && nin > 0 && nout > 0, "te_tr_dense_bwd: bad argument");
+  if (n == 0) return TE_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dense_wgrad_kernel<<<blocks_for(static_cast<long long>(nin) * nout, 256), 256, 0, st>>>(x, dy, n, nin, nout, dw, dbias2c);
+  TE_LAUNCH_CHECK();
+  if (dx) {
+    dense_dgrad_kernel<<<blocks_for(n * nin * 32, 256), 256, 0, st>>>(dy, w, n, nin, nout, dx);
+    TE_LAUNCH_CHECK();
+  }
+  return TE_OK;
+}
+
+// loss3 (double [3], accumulated) = {total, mse, kl}; dwb2c as for te_tr_head_loss; target: (n_voxels) of a's dtype
+extern "C" int te_tr_head_ae_loss(const te_tensor* a, const float* w, const float* b, const void* target, const te_tensor* da,
+                                  double* loss3, double* dwb2c, double n_total, float weight, float* dl, float* probs, void* stream) {
+  TE_TR_CHECK_T(a, "te_tr_head_ae_loss"); TE_TR_CHECK_T(da, "te_tr_head_ae_loss");
+  TE_CHECK_ARG(w && b && target && loss3 && dwb2c && dl && n_total > 0 && same_grid(*a, *da) && a->C == da->C && a->dtype == da->dtype &&
+                   a->C <= 1024, "te_tr_head_ae_loss: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const TView va = view_of(*a), vd = view_of(*da);
+  const size_t sh = static_cast<size_t>(a->C) * sizeof(float);
+  TE_DISPATCH_T(a->dtype, (head_ae_loss_kernel<T><<<blocks_for(va.voxels(), 256, 8), 256, sh, st>>>(
+                              va, w, b, static_cast<const T*>(target), vd, loss3, static_cast<float>(1.0 / n_total), weight, dl, probs)));
+  TE_LAUNCH_CHECK();
+  if (v8_ok(*a)) {
+    const int g8 = blocks_for(va.voxels() * (va.C >> 3), 256, 8);
+    if (a->dtype == TE_F16) head_wgrad_v8_kernel<__half><<<g8, 256, 0, st>>>(va, dl, dwb2c);
+    else head_wgrad_v8_kernel<__nv_bfloat16><<<g8, 256, 0, st>>>(va, dl, dwb2c);
+  } else {
+    int grid = blocks_for(va.voxels() * va.C, 256, 8);
+    if (static_cast<long long>(grid) * 256 < va.C) grid = (va.C + 255) / 256;
+    TE_DISPATCH_T(a->dtype, (head_wgrad_kernel<T><<<grid, 256, 0, st>>>(va, dl, dwb2c)));
+  }
   TE_LAUNCH_CHECK();
   return TE_OK;
 }

@@ -55,6 +55,34 @@ class _Act:
         return self.n * int(np.prod(self.size))
 
 
+class _Vec:
+    """A (N, n) fp32 activation of the dense part of the autoencoder (+ its gradient), described to the
+    operators as an (N, 1, 1, 1, n) tensor."""
+
+    def __init__(self, n, c, device, need_grad=True):
+        self.n, self.c, self.size = n, c, (1, 1, 1)
+        self.t = torch.empty((n, c), dtype=torch.float32, device=device)
+        self.g = torch.empty_like(self.t) if need_grad else None
+
+    def _desc(self, t):
+        d = TeTensor()
+        d.ptr, d.dtype, d.ctot, d.coff, d.C = t.data_ptr(), _lib.TE_F32, self.c, 0, self.c
+        d.N, d.D, d.H, d.W = self.n, 1, 1, 1
+        return d
+
+    @property
+    def x(self):
+        return self._desc(self.t)
+
+    @property
+    def dx(self):
+        return self._desc(self.g)
+
+    @property
+    def nvox(self):
+        return self.n
+
+
 class UnetTrainer:
     """Owns the weights of one U-net and runs fit steps on batches of (x, y) patch pairs.
 
@@ -87,8 +115,7 @@ class UnetTrainer:
         self.sync_bn, self.group = sync_bn, process_group
         self.step_count = 0
         self.L = _lib.lib()
-        self.spec = _spec.unet_spec(**{k: p[k] for k in ("n_filters", "n_blocks", "activation", "batch_norm", "kern_size",
-                                                         "kern_size_upconv", "isconcat", "pool_size") if k in p})
+        self.spec = self._make_spec(p)
         sizes = [int(np.prod(s)) for _, s in self.spec]
         self.offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
         n_par = int(self.offsets[-1])
@@ -98,6 +125,10 @@ class UnetTrainer:
         self.v = torch.zeros_like(self.theta)
         self.set_weights(weights if weights is not None else _spec.keras_default_init(self.spec, seed))
         self._plan()
+
+    def _make_spec(self, p):
+        return _spec.unet_spec(**{k: p[k] for k in ("n_filters", "n_blocks", "activation", "batch_norm", "kern_size",
+                                                    "kern_size_upconv", "isconcat", "pool_size") if k in p})
 
     # ------------------------------------------------------------------ weights
     def set_weights(self, weights):
@@ -174,7 +205,12 @@ class UnetTrainer:
         wi += 2
         assert wi == len(self.spec), (wi, len(self.spec))
         self.layers = layers
-        maxc = max(max(l.get("cout", 1), l.get("cin", 1)) for l in layers)
+        self._alloc_scratch()
+
+    def _alloc_scratch(self):
+        layers = self.layers
+        maxc = max(max(l.get("cout", 1), l.get("cin", 1)) for l in layers if l["op"] != "dense")
+        maxc = max([maxc] + [l["cout"] for l in layers if l["op"] == "dense"])
         # scratch
         self.stats = torch.zeros(2 * max(maxc, 1024), dtype=torch.float64, device=self.dev)
         wpack = max(int(self.L.te_tr_conv3_wpack_bytes(l["cin"], l["cout"])) for l in layers if l["op"] == "conv")
@@ -190,10 +226,13 @@ class UnetTrainer:
         self.loss = torch.zeros(1, dtype=torch.float64, device=self.dev)
         self.dl = torch.empty(self.batch * int(np.prod(self.patch)), dtype=torch.float32, device=self.dev)
         self.labels = torch.empty((self.batch,) + self.patch, dtype=torch.uint8, device=self.dev)
+        self.loss3 = torch.zeros(3, dtype=torch.float64, device=self.dev)
+        mk = lambda size, c, grad=True: _Act(self.batch, size, c, self.tdtype, self.dev, self.te_dtype, grad)  # noqa: E731
         for lay in layers:
-            if lay["op"] == "conv":
+            if lay["op"] in ("conv", "dense"):
                 c = lay["cout"]
-                lay["cat"] = mk(lay["src"].size, lay["cin"]) if (lay["src2"] is not None and self.mode == "fp32") else None
+                if lay["op"] == "conv":
+                    lay["cat"] = mk(lay["src"].size, lay["cin"]) if (lay["src2"] is not None and self.mode == "fp32") else None
                 lay["bn"] = {k: torch.empty(c, dtype=torch.float32, device=self.dev)
                              for k in ("mean", "rstd", "scale", "shift", "dbeta_n", "dgamma_n", "var")}
 
@@ -215,21 +254,57 @@ class UnetTrainer:
             sharding.allreduce_sum_(s, self.group)
         return s
 
+    # ------------------------------------------------------------------ BN + LeakyReLU helpers (conv and dense layers)
+    def _bn_forward(self, y_desc, a_desc, c, nvox, wi, bn, world, st):
+        br = ctypes.byref
+        self.stats[:2 * c].zero_()
+        self._call("te_tr_bn_stats", br(y_desc), self.stats.data_ptr(), st)
+        s = self._reduce_stats(2 * c)
+        n_tot = float(nvox * world)
+        mean = s[:c] / n_tot
+        var = torch.clamp(s[c:2 * c] / n_tot - mean * mean, min=0.0)
+        rstd = torch.rsqrt(var + BN_EPS)
+        gamma, beta = self._w(wi + 2).double(), self._w(wi + 3).double()
+        bn["mean"].copy_(mean); bn["var"].copy_(var); bn["rstd"].copy_(rstd)
+        bn["scale"].copy_(gamma * rstd); bn["shift"].copy_(beta - mean * gamma * rstd)
+        self._call("te_tr_bn_act_fwd", br(y_desc), br(a_desc), bn["scale"].data_ptr(), bn["shift"].data_ptr(), LRELU_ALPHA, st)
+
+    def _bn_backward(self, y_desc, da_desc, c, nvox, wi, bn, world, st):
+        """da -> dy in place; parameter gradients use the LOCAL sums (the gradient all-reduce adds the
+        ranks up), the normalisation backward the GLOBAL batch sums."""
+        br = ctypes.byref
+        self.stats[:2 * c].zero_()
+        self._call("te_tr_bn_act_bwd_reduce", br(y_desc), br(da_desc), bn["scale"].data_ptr(), bn["shift"].data_ptr(),
+                   bn["mean"].data_ptr(), bn["rstd"].data_ptr(), LRELU_ALPHA, self.stats.data_ptr(), st)
+        self._g(wi + 3).copy_(self.stats[:c])
+        self._g(wi + 2).copy_(self.stats[c:2 * c])
+        s = self._reduce_stats(2 * c)
+        n_tot = float(nvox * world)
+        bn["dbeta_n"].copy_(s[:c] / n_tot)
+        bn["dgamma_n"].copy_(s[c:2 * c] / n_tot)
+        self._call("te_tr_bn_act_bwd_apply", br(y_desc), br(da_desc), br(da_desc), bn["scale"].data_ptr(), bn["shift"].data_ptr(),
+                   bn["mean"].data_ptr(), bn["rstd"].data_ptr(), bn["dbeta_n"].data_ptr(), bn["dgamma_n"].data_ptr(),
+                   LRELU_ALPHA, st)
+
     # ------------------------------------------------------------------ step
-    def forward_backward(self, x, y):
+    def forward_backward(self, x, y=None):
         """x: (n,pz,py,px[,1]) float (already rescaled to the network's input range), y: same shape
-        {0,1}.  Leaves the global-batch mean loss in self.loss and the LOCAL gradient contribution
-        in self.grad (sum over ranks = gradient of the global-batch loss).  Returns the loss tensor."""
+        {0,1} (segmenter; the autoencoder reconstructs x).  Leaves the global-batch mean loss in
+        self.loss and the LOCAL gradient contribution in self.grad (sum over ranks = gradient of the
+        global-batch loss).  Returns the loss tensor."""
         st = _device.stream_ptr()
         world = sharding.world(self.group)[1] if self.sync_bn else 1
         tx = _device.to_device(x)
-        ty = _device.to_device(y)
         if tx.dim() == 5:
-            tx, ty = tx[..., 0], ty[..., 0]
+            tx = tx[..., 0]
         if tuple(tx.shape) != (self.batch,) + self.patch:
             raise ValueError("expected a batch of shape %s, got %s" % ((self.batch,) + self.patch, tuple(tx.shape)))
         self.inp.t.copy_(tx.reshape(self.inp.t.shape))
-        self.labels.copy_(ty.reshape(self.labels.shape))
+        if y is not None:
+            ty = _device.to_device(y)
+            if ty.dim() == 5:
+                ty = ty[..., 0]
+            self.labels.copy_(ty.reshape(self.labels.shape))
         self.grad.zero_()
         self.loss.zero_()
         br = ctypes.byref
@@ -245,26 +320,23 @@ class UnetTrainer:
                     xin, x2 = lay["src"], (br(lay["src2"].x) if lay["src2"] is not None else None)
                 self._call("te_tr_conv3", br(xin.x), x2, self._w(wi).data_ptr(), self._w(wi + 1).data_ptr(),
                            br(lay["y"].x), self.wpack.data_ptr(), st)
-                self.stats[:2 * c].zero_()
-                self._call("te_tr_bn_stats", br(lay["y"].x), self.stats.data_ptr(), st)
-                s = self._reduce_stats(2 * c)
-                n_tot = float(lay["y"].nvox * world)
-                bn = lay["bn"]
-                mean = s[:c] / n_tot
-                var = torch.clamp(s[c:2 * c] / n_tot - mean * mean, min=0.0)
-                rstd = torch.rsqrt(var + BN_EPS)
-                gamma, beta = self._w(wi + 2).double(), self._w(wi + 3).double()
-                bn["mean"].copy_(mean); bn["var"].copy_(var); bn["rstd"].copy_(rstd)
-                bn["scale"].copy_(gamma * rstd); bn["shift"].copy_(beta - mean * gamma * rstd)
-                self._call("te_tr_bn_act_fwd", br(lay["y"].x), br(lay["a"].x), bn["scale"].data_ptr(), bn["shift"].data_ptr(),
-                           LRELU_ALPHA, st)
+                self._bn_forward(lay["y"].x, lay["a"].x, c, lay["y"].nvox, wi, lay["bn"], world, st)
             elif op == "pool":
                 self._call("te_tr_maxpool_fwd", br(lay["src"].x), br(lay["a"].x), 2, st)
             elif op == "upconv":
                 wi = lay["w"]
                 self._call("te_tr_upconv_fwd", br(lay["src"].x), self._w(wi).data_ptr(), self._w(wi + 1).data_ptr(),
                            br(lay["a"].x), 2, LRELU_ALPHA, self.wpack.data_ptr(), st)
-            else:
+            elif op == "flatten":                      # Keras Flatten of NDHWC = the memory order; dense layers run in fp32
+                lay["a"].t.copy_(lay["src"].t.reshape(self.batch, -1))
+            elif op == "dense":
+                wi, c, src = lay["w"], lay["cout"], lay["src"]
+                self._call("te_tr_dense_fwd", src.t.data_ptr(), self.batch, lay["cin"], c, self._w(wi).data_ptr(),
+                           self._w(wi + 1).data_ptr(), lay["y"].t.data_ptr(), st)
+                self._bn_forward(lay["y"].x, lay["a"].x, c, self.batch, wi, lay["bn"], world, st)
+            elif op == "reshape":
+                lay["a"].t.copy_(lay["src"].t.reshape(lay["a"].t.shape))
+            elif op == "head":
                 wi, src = lay["w"], lay["src"]
                 self.stats[:2 * src.c].zero_()
                 n_tot = float(src.nvox * sharding.world(self.group)[1])
@@ -273,29 +345,28 @@ class UnetTrainer:
                            self.dl.data_ptr(), None, st)
                 self._g(wi).copy_(self.stats[:src.c])
                 self._g(wi + 1).copy_(self.stats[src.c:src.c + 1])
+            elif op == "head_ae":
+                wi, src = lay["w"], lay["src"]
+                self.stats[:2 * src.c].zero_()
+                self.loss3.zero_()
+                n_tot = float(src.nvox * sharding.world(self.group)[1])
+                self._call("te_tr_head_ae_loss", br(src.x), self._w(wi).data_ptr(), self._w(wi + 1).data_ptr(),
+                           self.inp.t.data_ptr(), br(src.dx), self.loss3.data_ptr(), self.stats.data_ptr(), n_tot,
+                           float(self.reg_weight), self.dl.data_ptr(), None, st)
+                self.loss.copy_(self.loss3[:1])
+                self._g(wi).copy_(self.stats[:src.c])
+                self._g(wi + 1).copy_(self.stats[src.c:src.c + 1])
+            else:
+                raise ValueError(op)
         # ---------------- backward
         pending_pool = {}                     # id(skip activation) -> True once the decoder wrote its gradient
         for lay in reversed(self.layers):
             op = lay["op"]
-            if op == "head":
+            if op in ("head", "head_ae"):
                 continue
             if op == "conv":
                 wi, c, a, yb, bn = lay["w"], lay["cout"], lay["a"], lay["y"], lay["bn"]
-                self.stats[:2 * c].zero_()
-                self._call("te_tr_bn_act_bwd_reduce", br(yb.x), br(a.dx), bn["scale"].data_ptr(), bn["shift"].data_ptr(),
-                           bn["mean"].data_ptr(), bn["rstd"].data_ptr(), LRELU_ALPHA, self.stats.data_ptr(), st)
-                # parameter gradients use the LOCAL sums (the gradient all-reduce adds the ranks up);
-                # the normalisation backward needs the GLOBAL batch sums
-                self._g(wi + 3).copy_(self.stats[:c])
-                self._g(wi + 2).copy_(self.stats[c:2 * c])
-                s = self._reduce_stats(2 * c)
-                n_tot = float(yb.nvox * world)
-                bn["dbeta_n"].copy_(s[:c] / n_tot)
-                bn["dgamma_n"].copy_(s[c:2 * c] / n_tot)
-                # dy overwrites da in place (element-wise, same index)
-                self._call("te_tr_bn_act_bwd_apply", br(yb.x), br(a.dx), br(a.dx), bn["scale"].data_ptr(), bn["shift"].data_ptr(),
-                           bn["mean"].data_ptr(), bn["rstd"].data_ptr(), bn["dbeta_n"].data_ptr(), bn["dgamma_n"].data_ptr(),
-                           LRELU_ALPHA, st)
+                self._bn_backward(yb.x, a.dx, c, yb.nvox, wi, bn, world, st)
                 dy = a.dx
                 cin = lay["cin"]
                 self.stats[:2 * c].zero_()
@@ -339,8 +410,6 @@ class UnetTrainer:
                 self.stats[:2 * a.c].zero_()
                 dz2 = None
                 if self.mode != "fp32":
-                    # scratch: the gradient buffer of a same-resolution activation is large enough and dead by now?
-                    # no -- keep it simple and explicit: one scratch tensor sized for the largest transposed conv
                     d = TeTensor()
                     d.ptr, d.dtype, d.ctot, d.coff, d.C = self.dz2.data_ptr(), self.te_dtype, 8 * a.c, 0, 8 * a.c
                     d.N, (d.D, d.H, d.W) = src.n, src.size
@@ -348,6 +417,17 @@ class UnetTrainer:
                 self._call("te_tr_upconv_bwd", br(src.x), br(a.x), br(a.dx), self._w(wi).data_ptr(), 2, LRELU_ALPHA,
                            self._g(wi).data_ptr(), self.stats.data_ptr(), br(src.dx), dz2, self.wpack.data_ptr(), st)
                 self._g(wi + 1).copy_(self.stats[:a.c])
+            elif op == "flatten":
+                lay["src"].g.copy_(lay["a"].g.reshape(lay["src"].g.shape))
+            elif op == "dense":
+                wi, c, src, a, yb = lay["w"], lay["cout"], lay["src"], lay["a"], lay["y"]
+                self._bn_backward(yb.x, a.dx, c, self.batch, wi, lay["bn"], world, st)
+                self.stats[:2 * c].zero_()
+                self._call("te_tr_dense_bwd", src.t.data_ptr(), a.g.data_ptr(), self.batch, lay["cin"], c, self._w(wi).data_ptr(),
+                           self._g(wi).data_ptr(), self.stats.data_ptr(), src.g.data_ptr() if src.g is not None else None, st)
+                self._g(wi + 1).copy_(self.stats[:c])
+            elif op == "reshape":
+                lay["src"].g.copy_(lay["a"].g.reshape(lay["src"].g.shape))
         return self.loss
 
     def apply_gradients(self):
@@ -358,14 +438,131 @@ class UnetTrainer:
         self._call("te_tr_adam", self.theta.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                    self.theta.numel(), self.lr, self.b1, self.b2, self.eps, self.step_count, 1.0, _device.stream_ptr())
         for lay in self.layers:
-            if lay["op"] == "conv":
+            if lay["op"] in ("conv", "dense"):
                 wi, bn = lay["w"], lay["bn"]
                 self._w(wi + 4).mul_(BN_MOMENTUM).add_(bn["mean"], alpha=1.0 - BN_MOMENTUM)
                 self._w(wi + 5).mul_(BN_MOMENTUM).add_(bn["var"], alpha=1.0 - BN_MOMENTUM)
 
-    def train_step(self, x, y):
+    def train_step(self, x, y=None):
         """One fit step on a batch; returns the (global-batch mean) loss as a python float."""
         self.forward_backward(x, y)
         self.apply_gradients()
         loss = sharding.allreduce_sum_(self.loss.clone(), self.group)
         return float(loss.item())
+
+
+class CAETrainer(UnetTrainer):
+    """Fit steps of the convolutional autoencoder (``SelfSupervisedCAE.train``,
+    /root/reference/tomo_encoders/neural_nets/autoencoders.py:674-718; custom step
+    ``RegularizedAutoencoder.train_step`` :498-526): encoder ``build_encoder_r`` (:246-347) -> decoder
+    ``build_decoder_r`` (:350-447), loss = mean squared error + weight * KL(x || decoded) (weight 1/250),
+    Adam.  The flat weight buffer holds the encoder's arrays followed by the decoder's, both in Keras
+    order.  Conv layers as in UnetTrainer; the dense layers (a few KB per sample) run in fp32."""
+
+    def __init__(self, model_params, model_size, batch, reg_weight=1.0 / 250.0, regularization_type="kl", **kwargs):
+        if regularization_type != "kl":
+            raise NotImplementedError("only the 'kl' regularisation (the reference's default) is implemented")
+        self.reg_weight = float(reg_weight)
+        super().__init__(model_params, model_size, batch, **kwargs)
+
+    def _spec_params(self, p):
+        keys = ("n_filters", "n_blocks", "activation", "batch_norm", "kern_size", "kern_size_upconv", "hidden_units",
+                "pool_size", "POOL_FLAG")
+        return {k: p[k] for k in keys if k in p}
+
+    def _make_spec(self, p):
+        if "hidden_units" not in p:
+            raise ValueError("hidden_units is required")
+        if any(q != 2 for q in self.pools):
+            raise NotImplementedError("autoencoder training supports pool size 2")
+        enc = _spec.encoder_spec(self.patch, **self._spec_params(p))
+        dec = _spec.decoder_spec(self.patch, **self._spec_params(p))
+        self.n_enc = len(enc)
+        return enc + dec
+
+    def _plan(self):
+        p, nb, n = self.params, self.params["n_blocks"], self.batch
+        mk = lambda size, c, grad=True: _Act(n, size, c, self.tdtype, self.dev, self.te_dtype, grad)  # noqa: E731
+        hidden = [int(h) for h in p["hidden_units"]]
+        pool_flag = bool(p.get("POOL_FLAG", True))
+        self.inp = mk(self.patch, 1, grad=False)
+        layers, wi = [], 0
+        size, cur = list(self.patch), self.inp
+
+        def conv(src, cout):
+            nonlocal wi
+            lay = dict(op="conv", w=wi, src=src, src2=None, cin=src.c, cout=cout, y=mk(src.size, cout, grad=False),
+                       a=mk(src.size, cout))
+            wi += 6
+            layers.append(lay)
+            return lay["a"]
+
+        def pool(src):
+            nonlocal size
+            if any(s % 2 for s in size):
+                raise ValueError("pool size must divide the spatial extent")
+            size = [s // 2 for s in size]
+            out = mk(size, src.c)
+            layers.append(dict(op="pool", src=src, a=out))
+            return out
+
+        def dense(src, cout):
+            nonlocal wi
+            lay = dict(op="dense", w=wi, src=src, cin=src.c, cout=cout, y=_Vec(n, cout, self.dev, need_grad=False),
+                       a=_Vec(n, cout, self.dev))
+            wi += 6
+            layers.append(lay)
+            return lay["a"]
+
+        def upconv(src):
+            nonlocal wi, size
+            size = [s * 2 for s in size]
+            up = mk(size, src.c)
+            layers.append(dict(op="upconv", w=wi, src=src, a=up))
+            wi += 2
+            return up
+
+        # ---- encoder (autoencoders.py:297-345)
+        for i in range(nb):
+            f = p["n_filters"][i]
+            cur = conv(cur, f)
+            cur = conv(cur, 2 * f)
+            cur = pool(cur)
+        if pool_flag:
+            cur = pool(cur)
+        pre_size, pre_c = list(size), cur.c
+        flat = _Vec(n, pre_c * int(np.prod(size)), self.dev)
+        layers.append(dict(op="flatten", src=cur, a=flat))
+        vec = flat
+        for h in hidden:
+            vec = dense(vec, h)
+        self.latent_layer = layers[-1]
+        assert wi == self.n_enc, (wi, self.n_enc)
+        # ---- decoder (autoencoders.py:407-447)
+        for h in hidden[::-1][1:]:
+            vec = dense(vec, h)
+        vec = dense(vec, flat.c)
+        cur = mk(pre_size, pre_c)
+        layers.append(dict(op="reshape", src=vec, a=cur))
+        size = list(pre_size)
+        if pool_flag:
+            cur = upconv(cur)
+        for i in range(nb - 1, -1, -1):
+            f = p["n_filters"][i]
+            cur = upconv(cur)
+            cur = conv(cur, f)
+            cur = conv(cur, f)
+        layers.append(dict(op="head_ae", w=wi, src=cur))
+        wi += 2
+        assert wi == len(self.spec), (wi, len(self.spec))
+        self.layers = layers
+        self._alloc_scratch()
+
+    def get_model_weights(self):
+        """(encoder weights, decoder weights), each in Keras get_weights() order."""
+        w = self.get_weights()
+        return w[:self.n_enc], w[self.n_enc:]
+
+    def losses(self):
+        """(total, pixel mse, KL) of the last step, local share of the global-batch means."""
+        return tuple(float(v) for v in self.loss3.cpu())

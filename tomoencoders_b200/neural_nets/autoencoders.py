@@ -65,6 +65,69 @@ class SelfSupervisedCAE(EmbeddingLearner):
                            max_stride=max_stride, n_points=batch_size)
         raise ValueError("sampling method not supported")
 
+    # ------------------------------------------------------------------ training (autoencoders.py:604-718)
+    def extract_training_sub_volumes(self, X, patches, add_noise, random_rotate):
+        """autoencoders.py:640-655 on the device (add_noise is accepted and, as in the reference, unused)."""
+        batch_size = len(patches)
+        x = _device.to_device(patches.extract(_device.to_device(X), self.model_size)).float()
+        if random_rotate:
+            nrots = np.random.randint(0, 4, batch_size)
+            for ii in range(batch_size):
+                axes = tuple(int(a) for a in np.random.choice([0, 1, 2], size=2, replace=False))
+                if nrots[ii]:
+                    x[ii] = torch.rot90(x[ii], int(nrots[ii]), axes)
+        return x.unsqueeze(-1)
+
+    def data_generator(self, Xs, batch_size, sampling_method, max_stride=1, random_rotate=False, add_noise=0.1):
+        """autoencoders.py:604-638: yields (B,P,P,P,1) float32 CUDA tensors."""
+        Xs = [_device.to_device(X) for X in Xs]
+        while True:
+            n_vols = len(Xs)
+            idx_vols = np.repeat(np.arange(0, n_vols), int(np.ceil(batch_size / n_vols)))[:batch_size]
+            x = []
+            for ivol in range(n_vols):
+                nsub = int(np.sum(idx_vols == ivol))
+                if nsub < 1:
+                    continue
+                patches = self.get_patches(tuple(Xs[ivol].shape), sampling_method, nsub, max_stride=max_stride)
+                x.append(self.extract_training_sub_volumes(Xs[ivol], patches, add_noise, random_rotate))
+            yield torch.cat(x, dim=0)
+
+    def train(self, vols, batch_size=10, sampling_method="random-fixed-width", n_epochs=10, random_rotate=True,
+              add_noise=0.1, max_stride=1, normalize_sampling_factor=2, steps_per_epoch=None, mode="bf16", verbose=1):
+        """autoencoders.py:674-718: RegularizedAutoencoder(encoder, decoder, weight 1/250, 'kl') compiled with Adam and
+        fitted on generated batches; here CAETrainer fit steps.  The volumes are expected in the network's input range
+        [0, 1] (the reference leaves normalisation to its data loader, :683).  The trained weights are written back to
+        models["encoder"] / models["decoder"]; returns the per-epoch mean of the total loss."""
+        from ._train import CAETrainer
+        enc, dec = self.models["encoder"], self.models["decoder"]
+        dg = self.data_generator(vols, batch_size, sampling_method, max_stride=max_stride, random_rotate=random_rotate,
+                                 add_noise=add_noise)
+        tot_steps, val_split = 500, 0.2
+        if steps_per_epoch is None:
+            steps_per_epoch = int((1 - val_split) * tot_steps // batch_size)
+        trainer = getattr(self, "_trainer", None)
+        if trainer is None or trainer.batch != batch_size:
+            trainer = CAETrainer(enc.model_params, self.model_size, batch_size, mode=mode,
+                                 weights=enc.get_weights() + dec.get_weights())
+            self._trainer = trainer
+        else:
+            trainer.set_weights(enc.get_weights() + dec.get_weights())
+        t0 = time.time()
+        history = []
+        for epoch in range(n_epochs):
+            losses = [trainer.train_step(next(dg)) for _ in range(steps_per_epoch)]
+            history.append(float(np.mean(losses)))
+            if verbose:
+                print("Epoch %d/%d - %d steps - loss: %.5f" % (epoch + 1, n_epochs, steps_per_epoch, history[-1]))
+        we, wd = trainer.get_model_weights()
+        enc.set_weights(we)
+        dec.set_weights(wd)
+        self.models["autoencoder"] = "trained"       # the reference stores the fitted RegularizedAutoencoder here
+        if verbose:
+            print("training time = %.2f seconds" % (time.time() - t0))
+        return history
+
     def predict_embeddings(self, x, chunk_size, min_max=None, TIMEIT=False):
         """autoencoders.py:729-777: x (nb,pz,py,px,1) -> (nb, latent) float32 (rescale, no clip)."""
         assert x.ndim == 5, "x must be 5-dimensional (batch_size, nz, ny, nx, 1)."
