@@ -100,6 +100,7 @@ __device__ __forceinline__ TileCoord decode_tile(const KParams& p, long long t, 
 
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_le1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all_groups() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void named_barrier(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -137,18 +138,25 @@ struct Cfg {
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
                                    : TMEM_COLS_RAW <= 256 ? 256 : 512;
   static_assert(TMEM_COLS_RAW <= 512, "accumulators do not fit TMEM");
-  static constexpr int W_ROOM = 227 * 1024 - 2048 - NUM_A * A_STAGE - (HALO ? 0 : 2 * 2 * 128 * (NT < 64 ? NT : 64) * 2);
-  static constexpr int NUM_W = W_ROOM / W_STAGE >= 4 ? 4 : W_ROOM / W_STAGE;
-  static_assert(NUM_W >= 2, "weight ring needs two stages");
   // the un-haloed kernels (transposed / pointwise convs: 8 x more output per input voxel, few MMAs) are
   // epilogue-bound (ncu: tensor pipe 6 %, DRAM 29 % on dec0.upconv), so they run two groups of four
   // epilogue warps, each taking half of the tile's z planes
-  static constexpr int EPI_GROUPS = HALO ? 1 : 2;
+  // ... and so are the thin haloed layers (NT <= 32 with one or two channel chunks: ~1.5 k cycles of epilogue per
+  // plane against ~0.6 k of UMMAs per plane and chunk)
+  static constexpr int EPI_GROUPS = (HALO && NT > 32) ? 1 : 2;
   static constexpr int THREADS = kThreads + (EPI_GROUPS - 1) * 128;
-  // TMA-store staging of the un-haloed kernels: per epilogue group two buffers of 128 voxels x OUT_BOX channels
+  // TMA-store epilogue: per epilogue group STG_NBUF staging buffers of 128 voxels x OUT_BOX channels.  The weight
+  // ring gives up a stage where that is what it takes to fit at least one buffer per group.
   static constexpr int OUT_BOX = NT < 64 ? NT : 64;
   static constexpr int STG_BUF = 128 * OUT_BOX * 2;
-  static constexpr int STG_BYTES = HALO ? 0 : EPI_GROUPS * 2 * STG_BUF;
+  static constexpr int ROOM0 = 227 * 1024 - 2048 - NUM_A * A_STAGE;
+  static constexpr int W_FIT2 = (ROOM0 - EPI_GROUPS * 2 * STG_BUF) / W_STAGE;   // with double-buffered staging
+  static constexpr int W_FIT1 = (ROOM0 - EPI_GROUPS * STG_BUF) / W_STAGE;       // with single-buffered staging
+  static constexpr int STG_NBUF = W_FIT2 >= 2 ? 2 : 1;
+  static constexpr int W_FIT = STG_NBUF == 2 ? W_FIT2 : W_FIT1;
+  static constexpr int NUM_W = W_FIT >= 4 ? 4 : W_FIT;
+  static_assert(NUM_W >= 2, "weight ring needs two stages");
+  static constexpr int STG_BYTES = EPI_GROUPS * STG_NBUF * STG_BUF;
   static constexpr int SMEM_BYTES = STG_BYTES + NUM_A * A_STAGE + NUM_W * W_STAGE + 1024 /*barriers*/ + 1024 /*align*/;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
 };
@@ -176,7 +184,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   uint64_t* acc_full = w_empty + kNumWStages;    // [2]
   uint64_t* acc_empty = acc_full + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  uint8_t* stg = reinterpret_cast<uint8_t*>(bars) + 1024;    // [EPI_GROUPS][2][STG_BUF], 1024-aligned (un-haloed kernels)
+  uint8_t* stg = reinterpret_cast<uint8_t*>(bars) + 1024;    // [EPI_GROUPS][STG_NBUF][STG_BUF], 1024-aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -387,23 +395,27 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       const float* bias = p.bias + tc.ntile * NT;
       static_assert(TZ % 2 == 0, "the epilogue walks the z planes of a tile in pairs");
       bool done_by_tma = false;
-      if constexpr (!HALO) {
+      {
         if (p.tma_out) {
           // TMEM -> registers -> bias / LeakyReLU -> swizzled staging buffer -> ONE TMA box store per plane and
           // 64-channel group.  (Per-thread 16-byte stores touch 32 different 128-byte lines per instruction;
           // the L1 store path, shared by all warps of the SM, was the bound of these kernels.)
           constexpr int OB = C::OUT_BOX, ROWB_O = OB * 2;      // channels and bytes per staged voxel row
           constexpr uint32_t SWM = ROWB_O == 128 ? 7u : (ROWB_O == 64 ? 3u : 1u);
-          uint8_t* my_stg = stg + eg * 2 * C::STG_BUF;
+          uint8_t* my_stg = stg + eg * C::STG_NBUF * C::STG_BUF;
           const bool issuer = (warp == (eg ? 7 : 2));
           uint32_t it = 0;
 #pragma unroll 1
           for (int pz = eg * PZ_PER_GROUP; pz < (eg + 1) * PZ_PER_GROUP; ++pz) {
 #pragma unroll 1
             for (int cg = 0; cg < NT; cg += OB, ++it) {
-              uint8_t* buf = my_stg + (it & 1) * C::STG_BUF;
-              // the store issued two rounds ago from this buffer must have finished reading it
-              if (issuer) { if (elect_one()) bulk_wait_read_le1(); __syncwarp(); }
+              uint8_t* buf = my_stg + (C::STG_NBUF == 2 ? (it & 1) : 0) * C::STG_BUF;
+              // the store issued from this buffer (two rounds ago, or the previous one with a single buffer) must have
+              // finished reading it
+              if (issuer) {
+                if (elect_one()) { if (C::STG_NBUF == 2) bulk_wait_read_le1(); else bulk_wait_read_0(); }
+                __syncwarp();
+              }
               named_barrier(1 + eg, 128);
 #pragma unroll
               for (int c0 = 0; c0 < OB; c0 += 16) {
@@ -494,8 +506,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         // the full-resolution stores above stay one voxel row at a time.  max over the z pair
         // (two accumulator planes of the same thread), the x pair (lane ^ 1) and the y pair
         // (lane ^ 8); extents are even, so the partners of a valid even voxel are valid too.
+        static_assert(PZ_PER_GROUP % 2 == 0 || HALO == 0, "the fused pool walks the planes of a group in pairs");
 #pragma unroll 1
-        for (int pz = 0; pz < TZ; pz += 2) {
+        for (int pz = eg * PZ_PER_GROUP; pz < (eg + 1) * PZ_PER_GROUP; pz += 2) {
           const int iz = tc.z0 + pz;
           const bool valid = iz < p.D && iy < p.H && ix < p.W && ((mx | my) & 1) == 0;
           const long long pvox = ((static_cast<long long>(tc.n) * (p.D >> 1) + (iz >> 1)) * (p.H >> 1) + (iy >> 1)) *
@@ -536,11 +549,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     }
   }
 
-  if constexpr (!HALO) {
-    if (p.tma_out && (warp == 2 || warp == 7)) {
-      if (elect_one()) bulk_wait_all_groups();
-      __syncwarp();
-    }
+  if (p.tma_out && (warp == 2 || (C::EPI_GROUPS == 2 && warp == 7))) {
+    if (elect_one()) bulk_wait_all_groups();
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -594,7 +605,7 @@ KParams make_params(const ConvUmmaLaunch& L) {
   p.pool_out = static_cast<uint8_t*>(L.pool_out);
   p.pool_ctot = L.pool_ctot;
   p.pool_coff = L.pool_coff;
-  p.tma_out = (!p.halo && L.use_tma_out && L.out != nullptr) ? 1 : 0;
+  p.tma_out = (L.use_tma_out && L.out != nullptr) ? 1 : 0;
   p.reuse_ok = !p.halo && p.total_tiles / (static_cast<long long>(p.n_ntiles) * p.nsub) >= kNumSMs ? 1 : 0;
   return p;
 }
@@ -677,7 +688,8 @@ EncodeTiledFn2 get_encode2() {
 void conv_umma_make_out_maps(ConvUmmaLaunch* L) {
   L->use_tma_out = 0;
   static const bool off = getenv("TOMOENC_NO_TMA_EPILOGUE") != nullptr;
-  if (off || L->ntaps == 27 || L->out == nullptr) return;
+  static const bool off_halo = getenv("TOMOENC_NO_TMA_EPILOGUE_CONV") != nullptr;
+  if (off || (off_halo && L->ntaps == 27) || L->out == nullptr) return;
   if (L->out_ctot % 8 != 0 || L->out_coff % 8 != 0 || L->NT % 16 != 0) return;
   EncodeTiledFn2 enc = get_encode2();
   if (!enc) return;

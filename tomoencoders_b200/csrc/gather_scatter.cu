@@ -217,10 +217,11 @@ __global__ void __launch_bounds__(256) gather_norm_kernel(GatherParams p, NormPa
                       ((static_cast<long long>(z0) + static_cast<long long>(iz0) * b) * p.Y + y0) * p.X + x0;
     const long long row_pitch = static_cast<long long>(b) * p.X, plane_pitch = static_cast<long long>(b) * p.Y * p.X;
     TOut* dst0 = reinterpret_cast<TOut*>(p.out) + u * static_cast<long long>(items_per_unit) * 8;
-    for (int it0 = threadIdx.x; it0 < items_per_unit; it0 += 2 * 256) {
-      float f[2][8];
+    constexpr int U = 4;                 // independent items (128-bit loads) in flight per thread
+    for (int it0 = threadIdx.x; it0 < items_per_unit; it0 += U * 256) {
+      float f[U][8];
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
+      for (int k = 0; k < U; ++k) {
         const int it = it0 + k * 256;
         if (it < items_per_unit) {
           const int pl = it / items_per_plane, r = it - pl * items_per_plane;
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(256) gather_norm_kernel(GatherParams p, NormPa
         }
       }
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
+      for (int k = 0; k < U; ++k) {
         const int it = it0 + k * 256;
         if (it >= items_per_unit) continue;
         if (q.rescale) {

@@ -653,7 +653,7 @@ int run_layers(te_net* net, int n, const HeadOut& ho, cudaStream_t st) {
             if (dbg & 1) C.out = nullptr;
             if (dbg & 2) C.pool_out = nullptr;
           }
-          if (C.ntaps == 1) {
+          if (C.out != nullptr) {
             if (L.omaps_n != n) {
               conv_umma_make_out_maps(&C);
               for (int k = 0; k < 8; ++k) L.omaps[k] = C.tmap_out[k];

@@ -1005,7 +1005,7 @@ int umma_conv(const te_tensor& x, const te_tensor* x2, const float* w, const flo
   C.Cin = Cin; C.Cout = Cout; C.ntaps = ntaps; C.up_stride = up_stride; C.act_lrelu = lrelu; C.alpha = alpha;
   C.fp16 = x.dtype == TE_F16;
   C.CB = cfg.CB; C.NT = cfg.NT; C.TZ = cfg.TZ;
-  if (ntaps == 1) conv_umma_make_out_maps(&C);
+  conv_umma_make_out_maps(&C);
   cudaError_t e = conv_umma_launch(C, st);
   count_launch();
   if (e != cudaSuccess) { set_error("tensor-core conv launch failed: %s", cudaGetErrorString(e)); return TE_ERR_CUDA; }
