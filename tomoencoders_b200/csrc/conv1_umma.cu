@@ -14,9 +14,9 @@
 namespace te {
 namespace {
 
-constexpr int kTZ = 4;                       // z planes per tile
-constexpr int kStagesA = 8;                  // im2col ring: one plane (128 rows x 64 B = 8 KB) per stage (= 2 tiles)
-static_assert(kStagesA == 2 * kTZ, "the builders' closed-form stage index assumes a ring of two tiles");
+constexpr int kTZ = 8;                       // z planes per tile (TMEM: 2 x 8 x Cout columns -> Cout <= 32)
+constexpr int kStagesA = kTZ;                // im2col ring: one plane (128 rows x 64 B = 8 KB) per stage; plane pz of
+                                             // the k-th tile of a CTA uses stage pz with phase parity k & 1
 constexpr int kThreadsC1 = 448;              // warp 0 UMMA, warp 1 idle, warps 2-5 epilogue, warps 6-13 builders (two groups of 128)
 constexpr int kInTile = (kTZ + 2) * 18 * 10; // haloed input tile (elements)
 
@@ -145,21 +145,31 @@ __global__ void __launch_bounds__(kThreadsC1, 1) conv1_umma_kernel(const C1Param
       }
       named_bar_sync(1, 256);
       if (tile + gridDim.x < p.total_tiles) fetch(tile + gridDim.x);
-#pragma unroll 1
-      for (int pz = grp; pz < kTZ; pz += 2) {
+      // group g expands planes [g kTZ/2, (g + 1) kTZ/2) one after the other and keeps the 3 x 3 in-plane
+      // neighbourhoods of the last two input planes in registers: 9 shared-memory loads per output plane
+      // instead of 27
+      constexpr int PPG = kTZ / 2;
+      const int pz0 = grp * PPG;
+      uint16_t nb[3][9];
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int t9 = 0; t9 < 9; ++t9) nb[q][t9] = in_tile[((pz0 + q) * 18 + my + t9 / 3) * 10 + mx + t9 % 3];
+#pragma unroll
+      for (int pp = 0; pp < PPG; ++pp) {
+        const int pz = pz0 + pp;
+#pragma unroll
+        for (int t9 = 0; t9 < 9; ++t9) nb[2][t9] = in_tile[((pz + 2) * 18 + my + t9 / 3) * 10 + mx + t9 % 3];
         // row = 27 taps (dz, dy, dx) of voxel (pz, my, mx), 5 zeros: 16 packed 32-bit words
-        uint32_t wv[16];
         uint16_t v[32];
 #pragma unroll
-        for (int tp = 0; tp < 27; ++tp) {
-          const int dz = tp / 9, dy = (tp / 3) % 3, dx = tp % 3;
-          v[tp] = in_tile[((pz + dz) * 18 + my + dy) * 10 + mx + dx];
-        }
+        for (int tp = 0; tp < 27; ++tp) v[tp] = nb[tp / 9][tp % 9];
 #pragma unroll
         for (int tp = 27; tp < 32; ++tp) v[tp] = 0;
+        uint32_t wv[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) wv[j] = static_cast<uint32_t>(v[2 * j]) | (static_cast<uint32_t>(v[2 * j + 1]) << 16);
-        const uint32_t as = ((k & 1u) << 2) + pz, aph = (k >> 1) & 1u;
+        const uint32_t as = pz, aph = k & 1u;
         mbar_wait(a_empty + as, aph ^ 1);
         uint8_t* dst = a_stage + as * 8192 + row * 64;
         const int sw = (row >> 1) & 3;
@@ -168,6 +178,8 @@ __global__ void __launch_bounds__(kThreadsC1, 1) conv1_umma_kernel(const C1Param
           *reinterpret_cast<uint4*>(dst + ((c ^ sw) << 4)) = make_uint4(wv[4 * c], wv[4 * c + 1], wv[4 * c + 2], wv[4 * c + 3]);
         fence_proxy_async_smem();                       // generic-proxy writes -> visible to the UMMA (async proxy)
         mbar_arrive(a_full + as);
+#pragma unroll
+        for (int t9 = 0; t9 < 9; ++t9) { nb[0][t9] = nb[1][t9]; nb[1][t9] = nb[2][t9]; }
       }
     }
   } else if (warp >= 2) {
@@ -241,12 +253,12 @@ cudaError_t launch_nt(const C1Params& p, int grid, cudaStream_t st) {
 
 }  // namespace
 
-// Returns true when the layer was taken (Cin = 1, 16-bit activations, Cout in {16, 32, 64}); *err = launch status.
+// Returns true when the layer was taken (Cin = 1, 16-bit activations, Cout in {16, 32}); *err = launch status.
 bool conv1_umma_try(const TView& in, const TView& out, const float* w, const float* bias, int lrelu, float alpha, int act_type,
                     cudaStream_t st, cudaError_t* err) {
   static const bool off = getenv("TOMOENC_NO_C1_UMMA") != nullptr;
   if (off || in.C != 1 || in.ctot != 1 || act_type == ACT_F32) return false;
-  if (out.C != 16 && out.C != 32 && out.C != 64) return false;
+  if (out.C != 16 && out.C != 32) return false;             // TMEM: 2 x kTZ x Cout <= 512 columns
   if (out.ctot % 8 != 0 || out.coff % 8 != 0 || kInTile * 2 > 4096) return false;
   C1Params p;
   p.in = static_cast<const uint16_t*>(in.ptr);
@@ -259,7 +271,7 @@ bool conv1_umma_try(const TView& in, const TView& out, const float* w, const flo
   p.lrelu = lrelu; p.alpha = alpha; p.fp16 = act_type == ACT_F16;
   if (p.total_tiles <= 0) { *err = cudaSuccess; return true; }
   const int grid = static_cast<int>(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs);
-  *err = out.C == 16 ? launch_nt<16>(p, grid, st) : (out.C == 32 ? launch_nt<32>(p, grid, st) : launch_nt<64>(p, grid, st));
+  *err = out.C == 16 ? launch_nt<16>(p, grid, st) : launch_nt<32>(p, grid, st);
   return true;
 }
 

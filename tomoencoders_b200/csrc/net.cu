@@ -811,7 +811,7 @@ extern "C" int te_net_layer_kernel(const te_net* net, int i, char* buf, int bufl
   const Layer& L = net->layers[i];
   if (L.skip) snprintf(buf, buflen, "fused into previous layer");
   else if (L.use_umma) snprintf(buf, buflen, "conv_umma_kernel<%d,%d,%d>%s", L.cfg.CB, L.cfg.NT, L.cfg.TZ, L.fused_head ? "+head" : "");
-  else if (L.op == OP_CONV3 && L.Cin == 1 && net->act_type != ACT_F32 && (L.Cout == 16 || L.Cout == 32 || L.Cout == 64))
+  else if (L.op == OP_CONV3 && L.Cin == 1 && net->act_type != ACT_F32 && (L.Cout == 16 || L.Cout == 32))
     snprintf(buf, buflen, "conv1_umma_kernel<%d>", L.Cout);
   else {
     static const char* names[] = {"conv3_kernel", "upconv_kernel", "maxpool_kernel", "head_kernel", "dense_kernel"};
