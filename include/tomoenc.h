@@ -98,6 +98,52 @@ int te_minmax_strided(const void* vol, int vol_dtype, const int64_t vol_shape[3]
                       float* out2, float* scratch, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Volume normalisation / contrast / masking -- the calls every user of the path makes right before
+ * (and after) it (misc/voxel_processing.py).  Views are described by up to
+ * four extents (outer -> inner) and strides in ELEMENTS, so the sub-sampled views the reference
+ * builds by slicing (vol[::s, ::s, ::s], vol[:, ::s, ::s, ::s]) are read in place.
+ */
+
+/* min / max of a strided view (first half of np.histogram's range search, modified_autocontrast
+ * misc/voxel_processing.py:160-204).  out2 = device float[2]; scratch = device float[2 * 1024]. */
+int te_minmax_nd(const void* data, int dtype, const int64_t shape[4], const int64_t strides[4],
+                 float* out2, float* scratch, void* stream);
+
+/* np.histogram(view, bins = edges) (misc/voxel_processing.py:189): counts[i] = #{edges[i] <= a <
+ * edges[i+1]}, last bin closed; edges = device double[nbins + 1], monotone (the host passes numpy's
+ * own np.linspace edges in the bin dtype numpy would choose); counts = device uint64[nbins], zeroed
+ * by the call.  nbins <= 1024.  Bit-exact against numpy. */
+int te_histogram_nd(const void* data, int dtype, const int64_t shape[4], const int64_t strides[4],
+                    const double* edges, int32_t nbins, unsigned long long* counts, void* stream);
+
+/* out = (in - lo) / denom, fp32 round-to-nearest subtract and divide (bit-exact against numpy float32
+ * arithmetic).  Replaces _rescale_data (misc/voxel_processing.py:81-89) on device arrays and the
+ * per-chunk body of normalize_volume_gpu (:207-253); denom = max - min + 1e-12 is formed by the host
+ * in float32.  out_dtype in {TE_F32, TE_F16}; in == out allowed for equal element sizes; both
+ * buffers 16-byte aligned. */
+int te_rescale(const void* in, int in_dtype, void* out, int out_dtype, int64_t n, float lo, float denom,
+               void* stream);
+
+/* edge_map (misc/voxel_processing.py:106-122): out[z,y,x] = 1 where any in-bounds 6-neighbour of
+ * Y[z,y,x] holds a different value (bit pattern), else 0.  out = uint8 / bool volume. */
+int te_edge_map(const void* Y, int elem_size, const int64_t shape[3], uint8_t* out, void* stream);
+
+/* cylindrical_mask (misc/voxel_processing.py:124-140), in place: vol[z,y,x] = value wherever
+ * NOT ((y - n//2)^2 + (x - n//2)^2 < rad^2), rad = int(mask_fac * n / 2) computed by the host, n =
+ * shape[1] = shape[2].  value_bits = the mask value already cast to the element type. */
+int te_cylindrical_mask(void* vol, int elem_size, const int64_t shape[3], int64_t rad, uint32_t value_bits,
+                        void* stream);
+
+/* get_values_cyl_mask (misc/voxel_processing.py:142-157): vol[cyl > 0] in C order.  The inside set of
+ * row y is the interval [x_lo[y], x_hi[y]); row_off[y] = number of inside voxels of rows < y of one
+ * slice, per_slice = total per slice (device int32[n], int32[n], int64[n]; built by the host from
+ * rad).  strides in elements (sub-sampled views are read in place).  out holds shape[0] * per_slice
+ * elements. */
+int te_cyl_values(const void* vol, int elem_size, const int64_t shape[3], const int64_t strides[3],
+                  const int32_t* x_lo, const int32_t* x_hi, const int64_t* row_off, int64_t per_slice,
+                  void* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Convolutional networks.  One handle = one Keras model of the reference:
  *   kind "unet"    build_Unet_3D            (neural_nets/Unet3D.py:199-291)       -> segmenter / enhancer
  *   kind "encoder" build_encoder_r          (neural_nets/autoencoders.py:246-347) -> latent vectors

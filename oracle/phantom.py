@@ -30,3 +30,23 @@ def random_points(vol_shape, patch, n, seed):
     """semantics of structures/patches.py:379 (high exclusive): corner in [0, vol - patch)."""
     g = np.random.default_rng(seed)
     return np.stack([g.integers(0, vol_shape[a] - patch, n) for a in range(3)], axis=1).astype(np.uint32)
+
+
+def cosine_volume(shape, dtype, seed):
+    """Smooth seeded volume with a skewed histogram (separable cosines + noise); inputs of
+    tests/golden/voxel_golden.npz."""
+    g = np.random.default_rng(seed)
+    z, y, x = np.meshgrid(*[np.arange(s, dtype=np.float64) for s in shape], indexing="ij")
+    v = np.cos(z / 5.0) * np.cos(y / 7.0) + np.sin(x / 3.0) ** 2 + 0.3 * g.standard_normal(shape)
+    v = (v - v.min()) / (v.max() - v.min())
+    if np.dtype(dtype) == np.uint8:
+        return (v * 255).astype(np.uint8)
+    if np.dtype(dtype) == np.uint16:
+        return (v * 40000 + 1000).astype(np.uint16)
+    return (v * 3.0 - 1.0).astype(dtype)
+
+
+def cosine_labels(shape, seed):
+    g = np.random.default_rng(seed)
+    z, y, x = np.meshgrid(*[np.arange(s, dtype=np.float64) for s in shape], indexing="ij")
+    return (np.cos(z / 4.0) + np.cos(y / 5.0) + np.cos(x / 6.0) + 0.2 * g.standard_normal(shape)) > 0.3

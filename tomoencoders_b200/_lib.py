@@ -45,17 +45,35 @@ def _stale():
 
 def build_library(force=False, verbose=False):
     """Compiles csrc/*.cu for sm_100a into tomoencoders_b200/libtomoenc.so (nvcc cross-compiles
-    without a GPU).  Returns the library path."""
+    without a GPU): one object per source (only stale ones are recompiled, in parallel) under
+    tomoencoders_b200/_build/, then one link.  Returns the library path."""
     if not force and not _stale():
         return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "nvcc")
+    obj_dir = os.path.join(_HERE, "_build")
+    os.makedirs(obj_dir, exist_ok=True)
+    headers = glob.glob(os.path.join(CSRC, "*.cuh")) + [HEADER]
+    t_hdr = max(os.path.getmtime(h) for h in headers)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    jobs, objs = [], []
+    for src in sources():
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or not os.path.isfile(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), t_hdr):
+            jobs.append([nvcc] + flags + ["-c", "-o", obj, src])
+
+    def run(cmd):
+        if verbose:
+            print(" ".join(cmd))
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise TomoEncError("nvcc failed:\n%s\n%s" % (r.stdout, r.stderr))
+
+    with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
+        list(ex.map(run, jobs))
     tmp = LIB_PATH + ".tmp.%d" % os.getpid()
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp] + sources()
-    if verbose:
-        print(" ".join(cmd))
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise TomoEncError("nvcc failed:\n%s\n%s" % (r.stdout, r.stderr))
+    run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp] + objs)
     os.replace(tmp, LIB_PATH)
     return LIB_PATH
 
@@ -108,6 +126,12 @@ _SIGNATURES = {
     "te_scatter": (ctypes.c_int, [_P, ctypes.c_int, _P, _I64, ctypes.POINTER(_I32), _P,
                                   ctypes.POINTER(_I64), _P, ctypes.c_int, _P]),
     "te_minmax_strided": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_I64), ctypes.c_int, _P, _P, _P]),
+    "te_minmax_nd": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_I64), ctypes.POINTER(_I64), _P, _P, _P]),
+    "te_histogram_nd": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_I64), ctypes.POINTER(_I64), _P, _I32, _P, _P]),
+    "te_rescale": (ctypes.c_int, [_P, ctypes.c_int, _P, ctypes.c_int, _I64, _F, _F, _P]),
+    "te_edge_map": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_I64), _P, _P]),
+    "te_cylindrical_mask": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_I64), _I64, ctypes.c_uint32, _P]),
+    "te_cyl_values": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_I64), ctypes.POINTER(_I64), _P, _P, _P, _I64, _P, _P]),
     "te_net_weight_count": (_I64, [ctypes.POINTER(NetDesc)]),
     "te_net_create": (ctypes.c_int, [ctypes.POINTER(NetDesc), ctypes.POINTER(_P)]),
     "te_net_set_weights": (ctypes.c_int, [_P, _P, _I64]),

@@ -182,6 +182,142 @@ __global__ void __launch_bounds__(1024) pca_solve_kernel(const double* __restric
   }
 }
 
+// Fast path (d <= 128): the same parallel-ordered cyclic Jacobi with the matrix resident in shared
+// memory (row pitch m + 1 doubles, m = d rounded up to even; the dummy row / column of an odd d stays
+// zero and only ever sees identity rotations).  A round is ONE phase: thread-owned 2 x 2 blocks
+// (pair i) x (pair j) take the column rotation of pair j and the row rotation of pair i together
+// (A <- J^T A J touches each block exactly once), and the eigenvector matrix is kept transposed in
+// `work` so that its update is a coalesced two-row rotation.  Two barriers per round instead of
+// three, no strided global traffic: 56.7 ms -> well under 2 ms for d = 128.
+__global__ void __launch_bounds__(1024) pca_solve_smem_kernel(const double* __restrict__ moments, int d, int k,
+                                                               double* __restrict__ mean, double* __restrict__ comps,
+                                                               double* __restrict__ evar, double* __restrict__ work) {
+  extern __shared__ double As[];          // m x (m + 1)
+  double* VT = work;                      // d x d, row e = eigenvector e
+  __shared__ double cs[64], sn[64];
+  __shared__ int pp[64], qq[64];
+  __shared__ int order[128];
+  __shared__ double red[32];
+  __shared__ int done;
+  __shared__ double flip;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int m = (d + 1) / 2 * 2, half = m / 2, pitch = m + 1;
+  const double cnt = moments[0];
+  const double* s1 = moments + 1;
+  const double* s2 = moments + 1 + d;
+  for (int j = tid; j < d; j += nt) mean[j] = s1[j] / cnt;
+  __syncthreads();
+  for (int e = tid; e < m * m; e += nt) {
+    const int i = e / m, j = e % m;
+    double a = 0.0;
+    if (i < d && j < d) {
+      const double s = 0.5 * (s2[i * d + j] + s2[j * d + i]);
+      a = (s - cnt * mean[i] * mean[j]) / (cnt - 1.0);
+    }
+    As[i * pitch + j] = a;
+  }
+  for (int e = tid; e < d * d; e += nt) VT[e] = (e / d == e % d) ? 1.0 : 0.0;
+  __syncthreads();
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = 0.0, dg = 0.0;
+    for (int e = tid; e < m * m; e += nt) {
+      const int i = e / m, j = e % m;
+      const double a = As[i * pitch + j];
+      if (i == j) dg += a * a; else off += a * a;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      off += __shfl_xor_sync(0xffffffffu, off, o);
+      dg += __shfl_xor_sync(0xffffffffu, dg, o);
+    }
+    // deterministic two-level reduction (no atomics: every launch takes the same number of sweeps)
+    if ((tid & 31) == 0) red[tid >> 5] = off;
+    __syncthreads();
+    if (tid == 0) { double t = 0.0; for (int w = 0; w < (nt >> 5); ++w) t += red[w]; red[0] = t; }
+    __syncthreads();
+    const double off_all = red[0];
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = dg;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < (nt >> 5); ++w) t += red[w];
+      done = off_all <= 1e-26 * (t + 1e-300) ? 1 : 0;
+    }
+    __syncthreads();
+    if (done) break;
+    for (int round = 0; round < m - 1; ++round) {
+      if (tid < half) {
+        // circle method: player m-1 fixed, the others rotate
+        const int t = tid;
+        int a = t == 0 ? m - 1 : (round + t) % (m - 1);
+        int b = t == 0 ? round % (m - 1) : (round + (m - 1) - t) % (m - 1);
+        const int p = a < b ? a : b, q = a < b ? b : a;
+        double c = 1.0, s = 0.0;
+        const double apq = As[p * pitch + q];
+        if (q < d && fabs(apq) > 1e-300) {
+          const double tau = (As[q * pitch + q] - As[p * pitch + p]) / (2.0 * apq);
+          const double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          c = 1.0 / sqrt(1.0 + tt * tt);
+          s = tt * c;
+        }
+        pp[t] = p; qq[t] = q; cs[t] = c; sn[t] = s;
+      }
+      __syncthreads();
+      for (int blk = tid; blk < half * half; blk += nt) {
+        const int ti = blk / half, tj = blk - ti * half;
+        const int p1 = pp[ti], q1 = qq[ti], p2 = pp[tj], q2 = qq[tj];
+        const double c1 = cs[ti], s1r = sn[ti], c2 = cs[tj], s2r = sn[tj];
+        double* rp = As + p1 * pitch;
+        double* rq = As + q1 * pitch;
+        const double app = rp[p2], apq = rp[q2], aqp = rq[p2], aqq = rq[q2];
+        // columns (pair j): [x_p, x_q] <- [c x_p - s x_q, s x_p + c x_q]
+        const double bpp = c2 * app - s2r * apq, bpq = s2r * app + c2 * apq;
+        const double bqp = c2 * aqp - s2r * aqq, bqq = s2r * aqp + c2 * aqq;
+        // rows (pair i)
+        rp[p2] = c1 * bpp - s1r * bqp;
+        rq[p2] = s1r * bpp + c1 * bqp;
+        rp[q2] = c1 * bpq - s1r * bqq;
+        rq[q2] = s1r * bpq + c1 * bqq;
+      }
+      for (int e = tid; e < half * d; e += nt) {
+        const int t = e / d, j = e - t * d;
+        const int p = pp[t], q = qq[t];
+        if (q >= d) continue;
+        const double c = cs[t], s = sn[t];
+        const double vp = VT[p * d + j], vq = VT[q * d + j];
+        VT[p * d + j] = c * vp - s * vq;
+        VT[q * d + j] = s * vp + c * vq;
+      }
+      __syncthreads();
+    }
+  }
+  // top-k eigenpairs, descending; sign: largest-|v| entry positive (sklearn svd_flip, u_based_decision=False)
+  if (tid == 0) {
+    for (int i = 0; i < d; ++i) order[i] = i;
+    for (int c = 0; c < k; ++c) {
+      int best = c;
+      for (int i = c + 1; i < d; ++i)
+        if (As[order[i] * pitch + order[i]] > As[order[best] * pitch + order[best]]) best = i;
+      const int tmp = order[c]; order[c] = order[best]; order[best] = tmp;
+    }
+  }
+  __syncthreads();
+  for (int c = 0; c < k; ++c) {
+    const int col = order[c];
+    if (tid == 0) {
+      int jm = 0;
+      double vm = -1.0;
+      for (int j = 0; j < d; ++j) { const double a = fabs(VT[col * d + j]); if (a > vm) { vm = a; jm = j; } }
+      flip = VT[col * d + jm] < 0.0 ? -1.0 : 1.0;
+      evar[c] = As[col * pitch + col];
+    }
+    __syncthreads();
+    for (int j = tid; j < d; j += nt) comps[c * d + j] = flip * VT[col * d + j];
+    __syncthreads();
+  }
+}
+
 // one warp per row
 __global__ void __launch_bounds__(256) pca_project_kernel(const float* __restrict__ h, long long n, int d,
                                                           const double* __restrict__ mean,
@@ -227,8 +363,20 @@ extern "C" int te_pca_solve(const double* moments, int32_t d, int32_t k, double*
   TE_CHECK_ARG(moments && mean && components && explained_variance && work, "te_pca_solve: null pointer");
   TE_CHECK_ARG(d >= 1 && d <= 256, "te_pca_solve: d must be in [1, 256]");
   TE_CHECK_ARG(k >= 1 && k <= d, "te_pca_solve: k must be in [1, d]");
-  pca_solve_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(moments, d, k, mean, components,
-                                                                      explained_variance, work);
+  if (d <= 128) {
+    const int m = (d + 1) / 2 * 2;
+    const size_t smem = static_cast<size_t>(m) * (m + 1) * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+      TE_CUDA(cudaFuncSetAttribute(pca_solve_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 129 * 8));
+      attr_set = true;
+    }
+    pca_solve_smem_kernel<<<1, 1024, smem, static_cast<cudaStream_t>(stream)>>>(moments, d, k, mean, components,
+                                                                                 explained_variance, work);
+  } else {
+    pca_solve_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(moments, d, k, mean, components,
+                                                                        explained_variance, work);
+  }
   TE_LAUNCH_CHECK();
   return TE_OK;
 }
