@@ -36,8 +36,8 @@ struct GatherParams {
 // patch (>= 1024 16-byte items when the patch is large enough), so that the per-unit index
 // arithmetic (64-bit, coordinates from global memory) is amortised and every thread has several
 // independent items; everything inside a unit is 32-bit.
-static int planes_per_unit(int pz, int items_per_plane) {
-  int ppu = (1024 + items_per_plane - 1) / items_per_plane;
+static int planes_per_unit(int pz, int items_per_plane, int target_items = 1024) {
+  int ppu = (target_items + items_per_plane - 1) / items_per_plane;
   if (ppu > pz) ppu = pz;
   if (ppu < 1) ppu = 1;
   while (pz % ppu) --ppu;
@@ -163,37 +163,84 @@ struct NormParams {
   float lo, hi, inv;   // inv = 1 / (hi - lo + 1e-12) evaluated in fp32 as a division below
 };
 
+// 8 consecutive elements (8 * sizeof(TIn) contiguous bytes at an arbitrary alignment) as raw 32-bit words:
+// the loads of several items are issued back to back and converted only when they are consumed.
+template <typename TIn> struct Raw8 { uint32_t w[2 * sizeof(TIn)]; };
+
 template <typename TIn>
-__device__ __forceinline__ void load8(const TIn* src, uint32_t b, float (&f)[8]) {
-  if (b == 1) {
-    // unbinned: 8 consecutive elements = 8 * sizeof(TIn) contiguous bytes at an arbitrary alignment
-    const uint8_t* s8 = reinterpret_cast<const uint8_t*>(src);
-    if constexpr (sizeof(TIn) == 1) {
-      const uintptr_t a = reinterpret_cast<uintptr_t>(s8);
-      const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
-      const uint32_t sh = (static_cast<uint32_t>(a) & 3u) * 8u;
-      uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);
-      if (sh) { const uint32_t w2 = __ldg(w + 2); w0 = __funnelshift_r(w0, w1, sh); w1 = __funnelshift_r(w1, w2, sh); }
-      const uint32_t ww[2] = {w0, w1};
+__device__ __forceinline__ void load8_raw(const TIn* src, Raw8<TIn>& r) {
+  const uint8_t* s8 = reinterpret_cast<const uint8_t*>(src);
+  if constexpr (sizeof(TIn) == 1) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(s8);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+    const uint32_t sh = (static_cast<uint32_t>(a) & 3u) * 8u;
+    uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);
+    if (sh) { const uint32_t w2 = __ldg(w + 2); w0 = __funnelshift_r(w0, w1, sh); w1 = __funnelshift_r(w1, w2, sh); }
+    r.w[0] = w0; r.w[1] = w1;
+  } else if constexpr (sizeof(TIn) == 2) {
+    const uint4 raw = load16_unaligned(s8);
+    r.w[0] = raw.x; r.w[1] = raw.y; r.w[2] = raw.z; r.w[3] = raw.w;
+  } else {
+    const uint4 r0 = load16_unaligned(s8), r1 = load16_unaligned(s8 + 16);
+    r.w[0] = r0.x; r.w[1] = r0.y; r.w[2] = r0.z; r.w[3] = r0.w;
+    r.w[4] = r1.x; r.w[5] = r1.y; r.w[6] = r1.z; r.w[7] = r1.w;
+  }
+}
+
+template <typename TIn>
+__device__ __forceinline__ void convert8(const Raw8<TIn>& r, float (&f)[8]) {
+  if constexpr (sizeof(TIn) == 1) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] = static_cast<float>((ww[e >> 2] >> ((e & 3) * 8)) & 0xffu);
-    } else if constexpr (sizeof(TIn) == 2) {
-      const uint4 raw = load16_unaligned(s8);
-      const uint32_t ww[4] = {raw.x, raw.y, raw.z, raw.w};
+    for (int e = 0; e < 8; ++e) f[e] = static_cast<float>((r.w[e >> 2] >> ((e & 3) * 8)) & 0xffu);
+  } else if constexpr (sizeof(TIn) == 2) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const uint16_t h = static_cast<uint16_t>(ww[e >> 1] >> ((e & 1) * 16));
-        if constexpr (std::is_same<TIn, __half>::value) f[e] = __half2float(__ushort_as_half(h));
-        else f[e] = static_cast<float>(h);
-      }
-    } else {
-      const uint4 r0 = load16_unaligned(s8), r1 = load16_unaligned(s8 + 16);
-      f[0] = __uint_as_float(r0.x); f[1] = __uint_as_float(r0.y); f[2] = __uint_as_float(r0.z); f[3] = __uint_as_float(r0.w);
-      f[4] = __uint_as_float(r1.x); f[5] = __uint_as_float(r1.y); f[6] = __uint_as_float(r1.z); f[7] = __uint_as_float(r1.w);
+    for (int e = 0; e < 8; ++e) {
+      const uint16_t h = static_cast<uint16_t>(r.w[e >> 1] >> ((e & 1) * 16));
+      if constexpr (std::is_same<TIn, __half>::value) f[e] = __half2float(__ushort_as_half(h));
+      else f[e] = static_cast<float>(h);
     }
   } else {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) f[e] = to_f32<TIn>(src[static_cast<long long>(e) * b]);
+    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r.w[e]);
+  }
+}
+
+// binned (decimated) patches: element xi of the row comes from x0 + xi * b
+template <typename TIn>
+__device__ __forceinline__ void load8_binned(const TIn* src, uint32_t b, float (&f)[8]) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) f[e] = to_f32<TIn>(src[static_cast<long long>(e) * b]);
+}
+
+template <typename TOut>
+__device__ __forceinline__ void norm_store8(float (&f)[8], const struct NormParams& q, float denom, float inv, TOut* o) {
+  if (q.rescale) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = f[e];
+      if (q.do_clip) v = fminf(fmaxf(v, q.lo), q.hi);
+      // fp32 output (check mode): IEEE division like the reference; 16-bit outputs: the
+      // quotient is rounded to 8 / 11 significant bits anyway, so multiply by the reciprocal
+      if constexpr (sizeof(TOut) == 4) f[e] = (v - q.lo) / denom;
+      else f[e] = (v - q.lo) * inv;
+    }
+  }
+  if constexpr (sizeof(TOut) == 4) {
+    reinterpret_cast<float4*>(o)[0] = make_float4(f[0], f[1], f[2], f[3]);
+    reinterpret_cast<float4*>(o)[1] = make_float4(f[4], f[5], f[6], f[7]);
+  } else {
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if constexpr (std::is_same<TOut, __nv_bfloat16>::value) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+        w[e] = *reinterpret_cast<uint32_t*>(&h);
+      } else {
+        __half2 h = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+        w[e] = *reinterpret_cast<uint32_t*>(&h);
+      }
+    }
+    stg_cs_u4(o, make_uint4(w[0], w[1], w[2], w[3]));
   }
 }
 
@@ -207,6 +254,7 @@ __global__ void __launch_bounds__(256) gather_norm_kernel(GatherParams p, NormPa
   const int items_per_unit = p.ppu * items_per_plane;
   const float denom = q.hi - q.lo + 1e-12f;
   const float inv = 1.0f / denom;
+  constexpr int U = sizeof(TIn) == 4 ? 4 : 8;   // independent items (raw loads) in flight per thread
   for (long long u = blockIdx.x; u < units; u += gridDim.x) {
     const long long i = u / upp;
     const int iz0 = static_cast<int>(u - i * upp) * p.ppu;
@@ -217,51 +265,34 @@ __global__ void __launch_bounds__(256) gather_norm_kernel(GatherParams p, NormPa
                       ((static_cast<long long>(z0) + static_cast<long long>(iz0) * b) * p.Y + y0) * p.X + x0;
     const long long row_pitch = static_cast<long long>(b) * p.X, plane_pitch = static_cast<long long>(b) * p.Y * p.X;
     TOut* dst0 = reinterpret_cast<TOut*>(p.out) + u * static_cast<long long>(items_per_unit) * 8;
-    constexpr int U = 4;                 // independent items (128-bit loads) in flight per thread
-    for (int it0 = threadIdx.x; it0 < items_per_unit; it0 += U * 256) {
-      float f[U][8];
+    if (b == 1) {
+      for (int it0 = threadIdx.x; it0 < items_per_unit; it0 += U * 256) {
+        Raw8<TIn> raw[U];
 #pragma unroll
-      for (int k = 0; k < U; ++k) {
-        const int it = it0 + k * 256;
-        if (it < items_per_unit) {
-          const int pl = it / items_per_plane, r = it - pl * items_per_plane;
-          const int iy = r / groups_per_row, gx = r - iy * groups_per_row;
-          load8<TIn>(src0 + pl * plane_pitch + iy * row_pitch + static_cast<long long>(gx) * 8 * b, b, f[k]);
+        for (int k = 0; k < U; ++k) {
+          const int it = it0 + k * 256;
+          if (it < items_per_unit) {
+            const int pl = it / items_per_plane, r = it - pl * items_per_plane;
+            const int iy = r / groups_per_row, gx = r - iy * groups_per_row;
+            load8_raw<TIn>(src0 + pl * plane_pitch + iy * row_pitch + gx * 8, raw[k]);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+          const int it = it0 + k * 256;
+          if (it >= items_per_unit) continue;
+          float f[8];
+          convert8<TIn>(raw[k], f);
+          norm_store8<TOut>(f, q, denom, inv, dst0 + static_cast<long long>(it) * 8);
         }
       }
-#pragma unroll
-      for (int k = 0; k < U; ++k) {
-        const int it = it0 + k * 256;
-        if (it >= items_per_unit) continue;
-        if (q.rescale) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float v = f[k][e];
-            if (q.do_clip) v = fminf(fmaxf(v, q.lo), q.hi);
-            // fp32 output (check mode): IEEE division like the reference; 16-bit outputs: the
-            // quotient is rounded to 8 / 11 significant bits anyway, so multiply by the reciprocal
-            if constexpr (sizeof(TOut) == 4) f[k][e] = (v - q.lo) / denom;
-            else f[k][e] = (v - q.lo) * inv;
-          }
-        }
-        TOut* o = dst0 + static_cast<long long>(it) * 8;
-        if constexpr (sizeof(TOut) == 4) {
-          reinterpret_cast<float4*>(o)[0] = make_float4(f[k][0], f[k][1], f[k][2], f[k][3]);
-          reinterpret_cast<float4*>(o)[1] = make_float4(f[k][4], f[k][5], f[k][6], f[k][7]);
-        } else {
-          uint32_t w[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if constexpr (std::is_same<TOut, __nv_bfloat16>::value) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(f[k][2 * e], f[k][2 * e + 1]);
-              w[e] = *reinterpret_cast<uint32_t*>(&h);
-            } else {
-              __half2 h = __floats2half2_rn(f[k][2 * e], f[k][2 * e + 1]);
-              w[e] = *reinterpret_cast<uint32_t*>(&h);
-            }
-          }
-          *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
+    } else {
+      for (int it = threadIdx.x; it < items_per_unit; it += 256) {
+        const int pl = it / items_per_plane, r = it - pl * items_per_plane;
+        const int iy = r / groups_per_row, gx = r - iy * groups_per_row;
+        float f[8];
+        load8_binned<TIn>(src0 + pl * plane_pitch + iy * row_pitch + static_cast<long long>(gx) * 8 * b, b, f);
+        norm_store8<TOut>(f, q, denom, inv, dst0 + static_cast<long long>(it) * 8);
       }
     }
   }
@@ -478,7 +509,7 @@ extern "C" int te_gather(const void* vol, int elem_size, const int64_t vol_shape
 template <typename TIn>
 static int launch_gather_norm(const GatherParams& p, const NormParams& q, int out_dtype, cudaStream_t st) {
   GatherParams pp = p;
-  pp.ppu = planes_per_unit(p.pz, p.py * (p.px / 8));
+  pp.ppu = planes_per_unit(p.pz, p.py * (p.px / 8), sizeof(TIn) == 4 ? 1024 : 2048);
   const int grid = grid_for(p.n * (p.pz / pp.ppu), 1, 8);
   if (out_dtype == TE_BF16) gather_norm_kernel<TIn, __nv_bfloat16><<<grid, 256, 0, st>>>(pp, q);
   else if (out_dtype == TE_F16) gather_norm_kernel<TIn, __half><<<grid, 256, 0, st>>>(pp, q);

@@ -17,6 +17,12 @@ namespace {
 constexpr int kSeg = 4096;       // elements of the innermost dimension one block takes at a time
 constexpr int kMaxBins = 1024;
 
+// short rows: a block takes this many consecutive rows at a time (>= one per warp, >= 4 * kSeg elements)
+__host__ __device__ inline int rows_per_unit(long long n3) {
+  const long long r = (4LL * kSeg) / (n3 > 0 ? n3 : 1);
+  return static_cast<int>(r < 8 ? 8 : r);
+}
+
 struct View4 {
   const uint8_t* base;
   long long n[4];    // logical extents (outer -> inner)
@@ -29,34 +35,62 @@ template <> __device__ __forceinline__ float elem_f32<uint16_t>(uint16_t v) { re
 template <> __device__ __forceinline__ float elem_f32<__half>(__half v) { return __half2float(v); }
 template <> __device__ __forceinline__ float elem_f32<float>(float v) { return v; }
 
-// Calls f(value as fp32) for every element of the view.  A block takes units = (row, segment of kSeg
-// innermost elements); VEC = true reads 16 bytes per thread (innermost stride 1, 16-byte aligned rows).
+// Calls f(value as fp32) for every element of the view.  Long rows (n[3] >= kSeg): a block takes one
+// (row, segment of kSeg elements) at a time, all threads striding the segment.  Short rows: a block
+// takes kSeg / n[3] consecutive rows, one warp per row, so that every lane has work whatever the row
+// length (a 64^3 patch row is 64 elements).  VEC = true reads 16 bytes per lane (innermost stride 1,
+// 16-byte aligned rows).
+template <typename T, bool VEC, typename F>
+__device__ __forceinline__ void for_each_in_row(const T* rp, long long sx, int len, int first, int step, F&& f) {
+  constexpr int EPV = 16 / sizeof(T);
+  if (VEC) {
+    const int nvec = len / EPV;
+    for (int c = first; c < nvec; c += step) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(rp) + c);
+      const T* e = reinterpret_cast<const T*>(&q);
+#pragma unroll
+      for (int i = 0; i < EPV; ++i) f(elem_f32<T>(e[i]));
+    }
+    for (int x = nvec * EPV + first; x < len; x += step) f(elem_f32<T>(rp[x]));
+  } else {
+    for (int x = first; x < len; x += step) f(elem_f32<T>(rp[x * sx]));
+  }
+}
+
 template <typename T, bool VEC, typename F>
 __device__ __forceinline__ void for_each_elem(const View4& v, F&& f) {
-  const long long segs = (v.n[3] + kSeg - 1) / kSeg;
   const long long rows = v.n[0] * v.n[1] * v.n[2];
-  const long long units = rows * segs;
-  constexpr int EPV = 16 / sizeof(T);
-  for (long long u = blockIdx.x; u < units; u += gridDim.x) {
-    const long long row = u / segs, seg = u - row * segs;
-    const long long i2 = row % v.n[2], t = row / v.n[2];
-    const long long i1 = t % v.n[1], i0 = t / v.n[1];
-    const T* rp = reinterpret_cast<const T*>(v.base) + i0 * v.st[0] + i1 * v.st[1] + i2 * v.st[2];
-    const long long x0 = seg * kSeg;
-    const int len = static_cast<int>(v.n[3] - x0 < kSeg ? v.n[3] - x0 : kSeg);
-    if (VEC) {
-      const T* sp = rp + x0;                       // x0 * sizeof(T) is a multiple of 16
-      const int nvec = len / EPV;
-      for (int c = threadIdx.x; c < nvec; c += blockDim.x) {
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(sp) + c);
-        const T* e = reinterpret_cast<const T*>(&q);
-#pragma unroll
-        for (int i = 0; i < EPV; ++i) f(elem_f32<T>(e[i]));
+  const T* base = reinterpret_cast<const T*>(v.base);
+  if (v.n[3] >= kSeg) {
+    const long long segs = (v.n[3] + kSeg - 1) / kSeg;
+    const long long units = rows * segs;
+    for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+      const long long row = u / segs, seg = u - row * segs;
+      const long long i2 = row % v.n[2], t = row / v.n[2];
+      const long long i1 = t % v.n[1], i0 = t / v.n[1];
+      const long long x0 = seg * kSeg;                 // x0 * sizeof(T) is a multiple of 16
+      const int len = static_cast<int>(v.n[3] - x0 < kSeg ? v.n[3] - x0 : kSeg);
+      const T* rp = base + i0 * v.st[0] + i1 * v.st[1] + i2 * v.st[2] + x0 * v.st[3];
+      for_each_in_row<T, VEC>(rp, v.st[3], len, threadIdx.x, blockDim.x, f);
+    }
+  } else {
+    const int rpu = rows_per_unit(v.n[3]);
+    const long long units = (rows + rpu - 1) / rpu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int len = static_cast<int>(v.n[3]);
+    for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+      const long long r0 = u * rpu;
+      const long long r1 = r0 + rpu < rows ? r0 + rpu : rows;
+      long long row = r0 + warp;
+      if (row >= r1) continue;
+      long long i2 = row % v.n[2], t = row / v.n[2];
+      long long i1 = t % v.n[1], i0 = t / v.n[1];
+      for (; row < r1; row += nwarps) {
+        const T* rp = base + i0 * v.st[0] + i1 * v.st[1] + i2 * v.st[2];
+        for_each_in_row<T, VEC>(rp, v.st[3], len, lane, 32, f);
+        i2 += nwarps;                                  // advance the row index with carries (no division)
+        while (i2 >= v.n[2]) { i2 -= v.n[2]; if (++i1 >= v.n[1]) { i1 = 0; ++i0; } }
       }
-      for (int x = nvec * EPV + threadIdx.x; x < len; x += blockDim.x) f(elem_f32<T>(sp[x]));
-    } else {
-      const long long sx = v.st[3];
-      for (int x = threadIdx.x; x < len; x += blockDim.x) f(elem_f32<T>(rp[(x0 + x) * sx]));
     }
   }
 }
@@ -111,15 +145,24 @@ __global__ void __launch_bounds__(256) histogram_nd_kernel(View4 v, const double
   const float e0f = static_cast<float>(e0);
   const float scale = eN > e0 ? static_cast<float>(nbins / (eN - e0)) : 0.f;
   unsigned int* mine = hist + (threadIdx.x >> 5) * nbins;
+  // neighbouring voxels of a tomogram mostly fall into the same bin: a thread keeps the bin of its previous
+  // element and a run count, and touches shared memory only when the bin changes
+  int cur = -1;
+  unsigned int run = 0;
+  double clo = 0.0, chi = 0.0;
   for_each_elem<T, VEC>(v, [&](float af) {
     const double a = static_cast<double>(af);          // every supported element type is exact in fp32
+    if (cur >= 0 && a >= clo && a < chi) { ++run; return; }
     if (!(a >= e0 && a <= eN)) return;
     int i = static_cast<int>((af - e0f) * scale);      // estimate; the comparisons below decide
     i = i < 0 ? 0 : (i > nbins - 1 ? nbins - 1 : i);
     while (i > 0 && a < ed[i]) --i;
     while (i < nbins - 1 && a >= ed[i + 1]) ++i;
-    atomicAdd(mine + i, 1u);
+    if (i == cur) { ++run; return; }                   // closed last bin: a == eN
+    if (run) atomicAdd(mine + cur, run);
+    cur = i; run = 1; clo = ed[i]; chi = ed[i + 1];
   });
+  if (run) atomicAdd(mine + cur, run);
   __syncthreads();
   for (int i = threadIdx.x; i < nbins; i += blockDim.x) {
     unsigned long long s = 0;
@@ -162,53 +205,64 @@ __global__ void __launch_bounds__(256) rescale_kernel(const TIn* in, TOut* out, 
 // out[z,y,x] = 1 when any in-bounds 6-neighbour holds a different value (bit pattern), else 0.
 // Vector kernel: a thread owns 16 bytes of a row; x neighbours come from funnel shifts of the
 // adjacent 32-bit words, comparisons are SIMD-in-register (__vcmpne4 / __vcmpne2 / !=).
-template <int EB> __device__ __forceinline__ uint32_t ne_mask(uint32_t a, uint32_t b);   // 0xff.. per differing element
-template <> __device__ __forceinline__ uint32_t ne_mask<1>(uint32_t a, uint32_t b) { return __vcmpne4(a, b); }
-template <> __device__ __forceinline__ uint32_t ne_mask<2>(uint32_t a, uint32_t b) { return __vcmpne2(a, b); }
-template <> __device__ __forceinline__ uint32_t ne_mask<4>(uint32_t a, uint32_t b) { return a != b ? 0xffffffffu : 0u; }
+// per-element "is non-zero" of a 32-bit word holding 4 / 2 / 1 elements -> 1 in the lowest bit of each element
+template <int EB> __device__ __forceinline__ uint32_t nonzero_elems(uint32_t d);
+template <> __device__ __forceinline__ uint32_t nonzero_elems<1>(uint32_t d) {
+  return ((((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d) >> 7) & 0x01010101u;
+}
+template <> __device__ __forceinline__ uint32_t nonzero_elems<2>(uint32_t d) {
+  return ((((d & 0x7fff7fffu) + 0x7fff7fffu) | d) >> 15) & 0x00010001u;
+}
+template <> __device__ __forceinline__ uint32_t nonzero_elems<4>(uint32_t d) { return d != 0u ? 1u : 0u; }
 
+// A block takes 8 consecutive rows (one warp per row: the y neighbours of a row are read by the adjacent
+// warps of the same block and hit L1, the z neighbours hit L2); a lane takes 16 bytes of the row at a time.
 template <int EB>
 __global__ void __launch_bounds__(256) edge_map_vec_kernel(const uint8_t* __restrict__ Y, long long Z, long long Yn,
                                                            long long row_bytes, uint8_t* __restrict__ out) {
-  const long long cpr = row_bytes / 16;                      // chunks per row
-  const long long total = Z * Yn * cpr;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; g < total; g += stride) {
-    const long long c = g % cpr, row = g / cpr;
+  const int cpr = static_cast<int>(row_bytes / 16);          // chunks per row
+  const long long rows = Z * Yn;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long row = static_cast<long long>(blockIdx.x) * 8 + warp; row < rows; row += static_cast<long long>(gridDim.x) * 8) {
     const long long y = row % Yn, z = row / Yn;
-    const uint8_t* p = Y + row * row_bytes + c * 16;
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
-    const uint4 ym = y > 0 ? __ldg(reinterpret_cast<const uint4*>(p - row_bytes)) : q;
-    const uint4 yp = y + 1 < Yn ? __ldg(reinterpret_cast<const uint4*>(p + row_bytes)) : q;
-    const uint4 zm = z > 0 ? __ldg(reinterpret_cast<const uint4*>(p - Yn * row_bytes)) : q;
-    const uint4 zp = z + 1 < Z ? __ldg(reinterpret_cast<const uint4*>(p + Yn * row_bytes)) : q;
-    // word before / after the chunk; at the row ends replicate the border element (no difference)
-    const uint32_t prev = c > 0 ? __ldg(reinterpret_cast<const uint32_t*>(p) - 1)
-                                : (EB == 4 ? q.x : q.x << (32 - 8 * EB));
-    const uint32_t next = c + 1 < cpr ? __ldg(reinterpret_cast<const uint32_t*>(p) + 4)
-                                      : (EB == 4 ? q.w : q.w >> (32 - 8 * EB));
-    const uint32_t w[6] = {prev, q.x, q.y, q.z, q.w, next};
-    const uint32_t a[4] = {ym.x, ym.y, ym.z, ym.w}, b[4] = {yp.x, yp.y, yp.z, yp.w};
-    const uint32_t d[4] = {zm.x, zm.y, zm.z, zm.w}, e[4] = {zp.x, zp.y, zp.z, zp.w};
-    uint32_t m[4];
+    const uint8_t* rp = Y + row * row_bytes;
+    const bool has_ym = y > 0, has_yp = y + 1 < Yn, has_zm = z > 0, has_zp = z + 1 < Z;
+    const long long plane = Yn * row_bytes;
+    uint8_t* orow = out + row * (row_bytes / EB);
+    for (int c = lane; c < cpr; c += 32) {
+      const uint8_t* p = rp + c * 16;
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+      const uint4 ym = has_ym ? __ldg(reinterpret_cast<const uint4*>(p - row_bytes)) : q;
+      const uint4 yp = has_yp ? __ldg(reinterpret_cast<const uint4*>(p + row_bytes)) : q;
+      const uint4 zm = has_zm ? __ldg(reinterpret_cast<const uint4*>(p - plane)) : q;
+      const uint4 zp = has_zp ? __ldg(reinterpret_cast<const uint4*>(p + plane)) : q;
+      // word before / after the chunk; at the row ends replicate the border element (no difference)
+      const uint32_t prev = c > 0 ? __ldg(reinterpret_cast<const uint32_t*>(p) - 1)
+                                  : (EB == 4 ? q.x : q.x << (32 - 8 * EB));
+      const uint32_t next = c + 1 < cpr ? __ldg(reinterpret_cast<const uint32_t*>(p) + 4)
+                                        : (EB == 4 ? q.w : q.w >> (32 - 8 * EB));
+      const uint32_t w[6] = {prev, q.x, q.y, q.z, q.w, next};
+      const uint32_t a[4] = {ym.x, ym.y, ym.z, ym.w}, b[4] = {yp.x, yp.y, yp.z, yp.w};
+      const uint32_t d[4] = {zm.x, zm.y, zm.z, zm.w}, e[4] = {zp.x, zp.y, zp.z, zp.w};
+      uint32_t m[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t cur = w[i + 1];
-      const uint32_t left = EB == 4 ? w[i] : __funnelshift_l(w[i], cur, 8 * EB);      // element x-1 under element x
-      const uint32_t right = EB == 4 ? w[i + 2] : __funnelshift_r(cur, w[i + 2], 8 * EB);
-      m[i] = ne_mask<EB>(cur, left) | ne_mask<EB>(cur, right) | ne_mask<EB>(cur, a[i]) | ne_mask<EB>(cur, b[i]) |
-             ne_mask<EB>(cur, d[i]) | ne_mask<EB>(cur, e[i]);
-    }
-    uint8_t* o = out + (row * row_bytes + c * 16) / EB;
-    if (EB == 1) {
-      *reinterpret_cast<uint4*>(o) = make_uint4(m[0] & 0x01010101u, m[1] & 0x01010101u, m[2] & 0x01010101u, m[3] & 0x01010101u);
-    } else if (EB == 2) {
-      // 8 elements -> 8 bytes
-      uint32_t lo = (m[0] & 1u) | ((m[0] >> 8) & 0x100u) | ((m[1] & 1u) << 16) | ((m[1] << 8) & 0x01000000u);
-      uint32_t hi = (m[2] & 1u) | ((m[2] >> 8) & 0x100u) | ((m[3] & 1u) << 16) | ((m[3] << 8) & 0x01000000u);
-      *reinterpret_cast<uint2*>(o) = make_uint2(lo, hi);
-    } else {
-      *reinterpret_cast<uint32_t*>(o) = (m[0] & 1u) | ((m[1] & 1u) << 8) | ((m[2] & 1u) << 16) | ((m[3] & 1u) << 24);
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t cur = w[i + 1];
+        const uint32_t left = EB == 4 ? w[i] : __funnelshift_l(w[i], cur, 8 * EB);      // element x-1 under element x
+        const uint32_t right = EB == 4 ? w[i + 2] : __funnelshift_r(cur, w[i + 2], 8 * EB);
+        const uint32_t diff = (cur ^ left) | (cur ^ right) | (cur ^ a[i]) | (cur ^ b[i]) | (cur ^ d[i]) | (cur ^ e[i]);
+        m[i] = nonzero_elems<EB>(diff);
+      }
+      uint8_t* o = orow + c * (16 / EB);
+      if (EB == 1) {
+        *reinterpret_cast<uint4*>(o) = make_uint4(m[0], m[1], m[2], m[3]);
+      } else if (EB == 2) {
+        // 8 elements -> 8 bytes (element flags sit at bits 0 and 16 of each word)
+        *reinterpret_cast<uint2*>(o) = make_uint2((m[0] & 1u) | ((m[0] >> 8) & 0x100u) | ((m[1] & 1u) << 16) | ((m[1] << 8) & 0x01000000u),
+                                                  (m[2] & 1u) | ((m[2] >> 8) & 0x100u) | ((m[3] & 1u) << 16) | ((m[3] << 8) & 0x01000000u));
+      } else {
+        *reinterpret_cast<uint32_t*>(o) = m[0] | (m[1] << 8) | (m[2] << 16) | (m[3] << 24);
+      }
     }
   }
 }
@@ -235,38 +289,48 @@ __global__ void __launch_bounds__(256) edge_map_scalar_kernel(const T* __restric
 
 // ---- cylindrical mask -----------------------------------------------------------------------------
 // inside(y, x) = (y - n//2)^2 + (x - n//2)^2 < rad^2 (rad > 0), n = shape[1] = shape[2].
-__device__ __forceinline__ bool cyl_inside(long long y, long long x, long long half, long long rad) {
-  const long long yy = y - half, xx = x - half;
-  return rad > 0 && yy * yy + xx * xx < rad * rad;
-}
 
+// A warp takes one row: the inside interval [lo, hi) is found analytically (float sqrt + integer fix-up) and
+// only the outside voxels are written (the inside ones are never touched: HBM traffic = bytes written).
 template <typename T>
 __global__ void __launch_bounds__(256) cyl_mask_kernel(T* __restrict__ vol, long long Z, long long n, long long rad, T val) {
   constexpr int V = 16 / sizeof(T);
   const long long half = n / 2;
-  const long long cpr = (n + V - 1) / V;
-  const long long total = Z * n * cpr;
+  const long long rows = Z * n;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool vec_ok = (n % V) == 0 && (reinterpret_cast<uintptr_t>(vol) & 15) == 0;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  T fill[V];
+  alignas(16) T fill[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) fill[i] = val;
-  for (long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; g < total; g += stride) {
-    const long long c = g % cpr, row = g / cpr;
+  for (long long row = static_cast<long long>(blockIdx.x) * 8 + warp; row < rows; row += static_cast<long long>(gridDim.x) * 8) {
     const long long y = row % n;
-    const long long x0 = c * V;
-    const long long x1 = x0 + V < n ? x0 + V : n;
-    // the inside set of a row is one interval around the centre: a chunk is uniform when both ends agree and
-    // (for "outside") it does not straddle the centre column
-    const bool in0 = cyl_inside(y, x0, half, rad), in1 = cyl_inside(y, x1 - 1, half, rad);
-    T* p = vol + row * n + x0;
-    if (in0 && in1) continue;
-    const bool straddles = x0 <= half && half < x1;
-    if (!in0 && !in1 && !straddles && vec_ok) {
-      *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(fill);
-    } else {
-      for (long long x = x0; x < x1; ++x)
-        if (!cyl_inside(y, x, half, rad)) p[x - x0] = val;
+    const long long yy = y - half;
+    long long lo = 0, hi = 0;                                   // empty interval: everything outside
+    const long long rem = rad > 0 ? rad * rad - yy * yy : 0;    // inside iff xx^2 < rem
+    if (rem > 0) {
+      long long w = static_cast<long long>(sqrt(static_cast<double>(rem)));      // largest w with w^2 <= rem (after fix-up)
+      while (w * w > rem) --w;
+      while ((w + 1) * (w + 1) <= rem) ++w;
+      const long long wi = w * w == rem ? w - 1 : w;            // largest |xx| strictly inside
+      lo = half - wi < 0 ? 0 : half - wi;
+      hi = half + wi + 1 > n ? n : half + wi + 1;
+    }
+    T* rp = vol + row * n;
+    // two outside runs: [0, lo) and [hi, n)
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      const long long a = side == 0 ? 0 : hi, b = side == 0 ? lo : n;
+      if (a >= b) continue;
+      if (vec_ok) {
+        const long long va = (a + V - 1) / V * V, vb = b / V * V;      // aligned core
+        if (va < vb) {
+          for (long long x = a + lane; x < va; x += 32) rp[x] = val;
+          for (long long x = va + lane * V; x < vb; x += 32 * V) *reinterpret_cast<uint4*>(rp + x) = *reinterpret_cast<const uint4*>(fill);
+          for (long long x = vb + lane; x < b; x += 32) rp[x] = val;
+          continue;
+        }
+      }
+      for (long long x = a + lane; x < b; x += 32) rp[x] = val;
     }
   }
 }
@@ -314,7 +378,11 @@ static bool make_view(View4& v, const void* data, int dtype, const int64_t shape
 }
 
 static long long view_units(const View4& v) {
-  return v.n[0] * v.n[1] * v.n[2] * ((v.n[3] + kSeg - 1) / kSeg);
+  const long long rows = v.n[0] * v.n[1] * v.n[2];
+  if (v.n[3] >= kSeg) return rows * ((v.n[3] + kSeg - 1) / kSeg);
+  if (v.n[3] == 0) return 0;
+  const int rpu = rows_per_unit(v.n[3]);
+  return (rows + rpu - 1) / rpu;
 }
 
 }  // namespace
@@ -400,7 +468,7 @@ extern "C" int te_edge_map(const void* Y, int elem_size, const int64_t shape[3],
   const bool vec = row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   if (vec) {
-    const int blocks = blocks_for(total * elem_size / 16, 256);
+    const int blocks = blocks_for(static_cast<long long>(shape[0]) * shape[1], 8, 16);
     const uint8_t* y8 = static_cast<const uint8_t*>(Y);
     if (elem_size == 1) edge_map_vec_kernel<1><<<blocks, 256, 0, st>>>(y8, shape[0], shape[1], row_bytes, out);
     else if (elem_size == 2) edge_map_vec_kernel<2><<<blocks, 256, 0, st>>>(y8, shape[0], shape[1], row_bytes, out);
@@ -424,7 +492,7 @@ extern "C" int te_cylindrical_mask(void* vol, int elem_size, const int64_t shape
   if (total == 0) return TE_OK;
   TE_CHECK_ARG(vol, "te_cylindrical_mask: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int blocks = blocks_for(total * elem_size / 16 + 1, 256);
+  const int blocks = blocks_for(static_cast<long long>(shape[0]) * shape[1], 8, 16);
   if (elem_size == 1) cyl_mask_kernel<uint8_t><<<blocks, 256, 0, st>>>(static_cast<uint8_t*>(vol), shape[0], shape[1], rad, static_cast<uint8_t>(value_bits));
   else if (elem_size == 2) cyl_mask_kernel<uint16_t><<<blocks, 256, 0, st>>>(static_cast<uint16_t*>(vol), shape[0], shape[1], rad, static_cast<uint16_t>(value_bits));
   else cyl_mask_kernel<uint32_t><<<blocks, 256, 0, st>>>(static_cast<uint32_t*>(vol), shape[0], shape[1], rad, value_bits);
