@@ -99,14 +99,14 @@ def test_one_rank_share_of_1m_patches_encode_and_pca(big_volume):
     _need(20)
     fe = SelfSupervisedCAE(model_initialization="define-new", model_size=(64, 64, 64), descriptor_tag="t",
                            mode="fp16", **ENC)
-    fe.models["encoder"].set_weights(OW.draw(O.encoder_spec((64, 64, 64), **ENC), 12))
+    fe.models["encoder"].set_weights(OW.draw(O.encoder_spec((64, 64, 64), **ENC)[0], 12))
     np.random.seed(7)
     p = Patches((N,) * 3, "random-fixed-width", patch_size=(64,) * 3, n_points=1_000_000)
     a, b = sharding.shard_range(len(p), 3, 8)
     assert b - a == 125_000
-    mine = p.select_by_indices(np.arange(a, a + 16_384))              # bounded: 16 384 of the 125 000
+    mine = p.select_by_indices(np.arange(a, b))                       # rank 3 of 8: 125 000 patches
     h = fe.embed_volume(big_volume, mine, 128, min_max=(0.0, 255.0))
-    assert h.shape == (16_384, 128) and h.dtype == torch.float32 and bool(torch.isfinite(h).all())
+    assert h.shape == (125_000, 128) and h.dtype == torch.float32 and bool(torch.isfinite(h).all())
     idx = np.random.default_rng(1).choice(len(mine), 96, replace=False)
     sub = mine.select_by_indices(idx)
     x = sub.extract(big_volume, (64, 64, 64))
@@ -116,7 +116,7 @@ def test_one_rank_share_of_1m_patches_encode_and_pca(big_volume):
     pca = LatentPCA(n_components=2)
     z = pca.fit_transform(h)
     z = torch.as_tensor(z).double().cpu()
-    assert z.shape == (16_384, 2)
+    assert z.shape == (125_000, 2)
     scale = float(z.std(dim=0)[0])
     assert float(z.mean(dim=0).abs().max()) < 1e-3 * scale
     c = (z.T @ z) / len(z)
