@@ -19,6 +19,8 @@
 #include <type_traits>
 
 namespace te {
+bool wgrad_umma_ok(const te_tensor& x, const te_tensor& dy);                                                    // wgrad_umma.cu
+int wgrad_umma(const te_tensor& x, const te_tensor& dy, float* dw, int dw_cin, int ci_off, cudaStream_t st);
 namespace {
 
 template <typename T> __device__ __forceinline__ float ldv(const T* p);
@@ -1317,7 +1319,10 @@ extern "C" int te_tr_conv3_wgrad(const te_tensor* x, const te_tensor* dy, float*
                "te_tr_conv3_wgrad: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const TView vx = view_of(*x), vd = view_of(*dy);
-  if (wgrad_mma_ok(*x, *dy)) {
+  if (te::wgrad_umma_ok(*x, *dy)) {
+    const int rc = te::wgrad_umma(*x, *dy, dw, dw_cin, ci_off, st);
+    if (rc != TE_OK) return rc;
+  } else if (wgrad_mma_ok(*x, *dy)) {
     const int rc = wgrad_mma(*x, *dy, dw, dw_cin, ci_off, 27, st);
     if (rc != TE_OK) return rc;
   } else if (x->C == 1 && dy->C <= 37) {
