@@ -82,3 +82,77 @@ def test_wgrad_operator_random_values_close_to_fp32():
                                             _device.stream_ptr()), "te_tr_conv3_wgrad")
     ref = _reference(x.float(), dy.float()).reshape(27, 32, 64)
     assert float((dw - ref).norm() / ref.norm()) < 1e-5
+
+
+def test_first_layer_wgrad_is_exact_on_integer_inputs():
+    """Cin = 1 (register-tiled CUDA-core kernel): ragged 20 x 24 x 12 grid, Cout = 16, bf16 and fp16."""
+    dev = _device.device()
+    for dtype in (torch.bfloat16, torch.float16):
+        g = torch.Generator(device=dev).manual_seed(11)
+        x = torch.randint(-3, 4, (2, 20, 24, 12, 1), device=dev, generator=g).to(dtype)
+        dy = torch.randint(-2, 3, (2, 20, 24, 12, 16), device=dev, generator=g).to(dtype)
+        dw = torch.zeros((27, 1, 16), device=dev)
+        tx, td = _view(x, 0, 1), _view(dy, 0, 16)
+        _lib.check(_lib.lib().te_tr_conv3_wgrad(ctypes.byref(tx), ctypes.byref(td), dw.data_ptr(), 1, 0, None,
+                                                _device.stream_ptr()), "te_tr_conv3_wgrad")
+        ref = _reference(x.float(), dy.float()).reshape(27, 1, 16)
+        assert torch.equal(dw, ref), float((dw - ref).abs().max())
+
+
+@pytest.mark.parametrize("accumulate", [0, 1])
+def test_maxpool_backward_vectorised_equals_scalar_kernel(accumulate):
+    """The 8-channel kernel (16-bit tensors) against the scalar kernel (the same values as fp32 tensors):
+    same first-argmax tie rule, so the gradients are identical, ties included (values on a coarse grid)."""
+    dev = _device.device()
+    g = torch.Generator(device=dev).manual_seed(5)
+    x32 = torch.randint(-8, 9, (2, 8, 12, 16, 32), device=dev, generator=g).float() * 0.25
+    gp32 = torch.randint(-8, 9, (2, 4, 6, 8, 32), device=dev, generator=g).float() * 0.5
+    dx0 = torch.randint(-4, 5, x32.shape, device=dev, generator=g).float()
+    outs = []
+    for dt in (torch.float32, torch.bfloat16):
+        x, gp, dx = x32.to(dt), gp32.to(dt), dx0.to(dt).clone()
+        tx, tg, tdx = _view(x, 0, 32), _view(gp, 0, 32), _view(dx, 0, 32)
+        _lib.check(_lib.lib().te_tr_maxpool_bwd(ctypes.byref(tx), ctypes.byref(tg), ctypes.byref(tdx), 2, accumulate,
+                                                _device.stream_ptr()), "te_tr_maxpool_bwd")
+        outs.append(dx.float())
+    assert torch.equal(outs[0], outs[1])
+    # and against torch autograd where the window maximum is unique
+    xx = x32.permute(0, 4, 1, 2, 3).contiguous().requires_grad_(True)
+    torch.nn.functional.max_pool3d(xx, 2).backward(gp32.permute(0, 4, 1, 2, 3).contiguous())
+    ref = xx.grad.permute(0, 2, 3, 4, 1) + (dx0 if accumulate else 0)
+    w = x32.reshape(2, 4, 2, 6, 2, 8, 2, 32).permute(0, 1, 3, 5, 7, 2, 4, 6).reshape(2, 4, 6, 8, 32, 8)
+    top2 = w.topk(2, dim=-1).values
+    unique = (top2[..., 0] > top2[..., 1])
+    unique = unique[:, :, None, :, None, :, None, :].expand(2, 4, 2, 6, 2, 8, 2, 32).reshape(2, 8, 12, 16, 32)
+    assert torch.equal(outs[1][unique], ref[unique])
+
+
+def test_fused_head_loss_matches_unfused_fp32_path():
+    """te_tr_head_loss on bf16 tensors (one fused 128-bit-vectorised pass) against the fp32 tensors path."""
+    dev = _device.device()
+    g = torch.Generator(device=dev).manual_seed(9)
+    shape = (2, 16, 16, 24, 32)
+    a16 = torch.randn(shape, device=dev, generator=g).to(torch.bfloat16)
+    w = torch.randn(32, device=dev, generator=g) * 0.3
+    b = torch.tensor([0.1], device=dev)
+    y = (torch.rand(shape[:-1], device=dev, generator=g) < 0.4).to(torch.uint8)
+    nvox = y.numel()
+    res = []
+    for dt in (torch.float32, torch.bfloat16):
+        a = a16.to(dt)
+        da = torch.zeros_like(a)
+        loss = torch.zeros(1, dtype=torch.float64, device=dev)
+        dwb = torch.zeros(64, dtype=torch.float64, device=dev)
+        dl = torch.zeros(nvox, device=dev)
+        probs = torch.zeros(nvox, device=dev)
+        ta, tda = _view(a, 0, 32), _view(da, 0, 32)
+        _lib.check(_lib.lib().te_tr_head_loss(ctypes.byref(ta), w.data_ptr(), b.data_ptr(), y.data_ptr(), ctypes.byref(tda),
+                                              loss.data_ptr(), dwb.data_ptr(), float(nvox), dl.data_ptr(), probs.data_ptr(),
+                                              _device.stream_ptr()), "te_tr_head_loss")
+        res.append((float(loss), dwb.clone(), dl.clone(), probs.clone(), da.float()))
+    (l0, d0, dl0, p0, da0), (l1, d1, dl1, p1, da1) = res
+    assert abs(l0 - l1) < 1e-6 * abs(l0)
+    torch.testing.assert_close(d1[:33], d0[:33], rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(dl1, dl0, rtol=1e-5, atol=1e-12)
+    torch.testing.assert_close(p1, p0, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(da1, da0, rtol=2 ** -7, atol=1e-12)       # da is stored in bf16

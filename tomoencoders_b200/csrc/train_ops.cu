@@ -358,6 +358,57 @@ __global__ void __launch_bounds__(256) lrelu_bwd_s2d_v8_kernel(TView a, TView da
 
 // MaxPool3D(p) backward: the gradient of a pooled voxel goes to the FIRST window element (z, y, x
 // scan order) equal to the maximum (torch / TF argmax convention); every input voxel is written.
+// MaxPool3D(2) backward, 8 channels per thread: the eight window positions are loaded as 128-bit rows (all
+// in flight), first-argmax per channel (Keras / TF tie rule of the scalar kernel below), eight 128-bit stores.
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool2_bwd_v8_kernel(TView x, TView dpool, TView dx, int accumulate) {
+  const int G = x.C >> 3;
+  const int Do = x.D / 2, Ho = x.H / 2, Wo = x.W / 2;
+  const long long total = static_cast<long long>(x.N) * Do * Ho * Wo * G;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const T* xp = static_cast<const T*>(x.ptr);
+  const T* gp = static_cast<const T*>(dpool.ptr);
+  T* op = static_cast<T*>(dx.ptr);
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int c0 = static_cast<int>(e % G) * 8;
+    long long t = e / G;
+    const int ox = static_cast<int>(t % Wo); t /= Wo;
+    const int oy = static_cast<int>(t % Ho); t /= Ho;
+    const int oz = static_cast<int>(t % Do);
+    const long long n = t / Do;
+    float v[8][8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const long long vox = ((n * x.D + oz * 2 + (k >> 2)) * x.H + oy * 2 + ((k >> 1) & 1)) * x.W + ox * 2 + (k & 1);
+      load8v<T>(xp + vox * x.ctot + x.coff + c0, v[k]);
+    }
+    float g[8];
+    load8v<T>(gp + (((n * Do + oz) * Ho + oy) * Wo + ox) * dpool.ctot + dpool.coff + c0, g);
+    int arg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float best = -INFINITY;
+      arg[j] = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (v[k][j] > best) { best = v[k][j]; arg[j] = k; }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const long long vox = ((n * x.D + oz * 2 + (k >> 2)) * x.H + oy * 2 + ((k >> 1) & 1)) * x.W + ox * 2 + (k & 1);
+      T* dst = op + vox * dx.ctot + dx.coff + c0;
+      float o[8];
+      if (accumulate) load8v<T>(dst, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float add = arg[j] == k ? g[j] : 0.f;
+        o[j] = accumulate ? o[j] + add : add;
+      }
+      store8v<T>(dst, o);
+    }
+  }
+}
+
 // accumulate = 1 adds to dx (the skip connection already deposited its gradient there).
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(TView x, TView dpool, TView dx, int p, int accumulate) {
@@ -585,6 +636,102 @@ __global__ void __launch_bounds__(1024) conv3_wgrad_c1_kernel(TView x, TView dy,
   if (active) atomicAdd(dw + (static_cast<long long>(tap) * dw_cin + ci_off) * Co + co, acc);
 }
 
+// First layer, register-tiled (Cout = 8 or 16, 16-bit tensors).  Warp = (ty tap row, group of 4 output channels):
+// 9 taps (tz, tx) x 4 channels = 36 accumulators per lane; the 32 lanes split the voxels of a (8, 16, 8) tile as
+// (4 y rows, 8 x) and walk z with a sliding 3 x 3 window of x values, so one voxel costs 3 scalar + 1 128-bit
+// shared loads for 36 FMAs (the kernel above: 16 loads per 8 FMAs).  Row pitch 40 floats = 8 banks per y row and a
+// voxel-major float4 layout of dy keep every load conflict-free.  Lanes are reduced with shuffles at the very end.
+template <typename T>
+__global__ void __launch_bounds__(384, 2) conv3_wgrad_c1_tiled_kernel(TView x, TView dy, float* dw, int dw_cin, int ci_off) {
+  constexpr int TZ = 8, XP = 40, NVOX = TZ * 128;
+  extern __shared__ __align__(16) float sh[];
+  float* xs = sh;                                                  // [TZ + 2][18][XP]
+  float4* ds = reinterpret_cast<float4*>(sh + (TZ + 2) * 18 * XP);  // [Co / 4][NVOX]
+  const int Co = dy.C, CG = Co >> 2, H8 = Co >> 3;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nwarps_active = 3 * CG;
+  const int tg = warp % 3, cg = warp / 3;
+  const int px = lane & 7, pyq = lane >> 3;
+  const int tiles_x = (dy.W + 7) / 8, tiles_y = (dy.H + 15) / 16, tiles_z = (dy.D + TZ - 1) / TZ;
+  const long long total = static_cast<long long>(dy.N) * tiles_z * tiles_y * tiles_x;
+  const T* xp = static_cast<const T*>(x.ptr);
+  const T* gp = static_cast<const T*>(dy.ptr);
+  float acc[3][3][4];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) acc[a][b][0] = acc[a][b][1] = acc[a][b][2] = acc[a][b][3] = 0.f;
+  for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    long long t = tile;
+    const int x0 = static_cast<int>(t % tiles_x) * 8; t /= tiles_x;
+    const int y0 = static_cast<int>(t % tiles_y) * 16; t /= tiles_y;
+    const int z0 = static_cast<int>(t % tiles_z) * TZ; t /= tiles_z;
+    const long long n = t;
+    __syncthreads();
+    for (int i = tid; i < (TZ + 2) * 180; i += blockDim.x) {
+      const int bx = i % 10, by = (i / 10) % 18, bz = i / 180;
+      const int xx = x0 + bx - 1, yy = y0 + by - 1, zz = z0 + bz - 1;
+      const bool ok = xx >= 0 && xx < x.W && yy >= 0 && yy < x.H && zz >= 0 && zz < x.D;
+      xs[(bz * 18 + by) * XP + bx] = ok ? ldv<T>(xp + (((n * x.D + zz) * x.H + yy) * x.W + xx) * x.ctot + x.coff) : 0.f;
+    }
+    for (int i = tid; i < NVOX * H8; i += blockDim.x) {
+      const int h = i % H8, v = i / H8;
+      const int bx = v & 7, by = (v >> 3) & 15, bz = v >> 7;
+      const int xx = x0 + bx, yy = y0 + by, zz = z0 + bz;
+      float f[8];
+      if (xx < dy.W && yy < dy.H && zz < dy.D) load8v<T>(gp + (((n * dy.D + zz) * dy.H + yy) * dy.W + xx) * dy.ctot + dy.coff + h * 8, f);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = 0.f;
+      }
+      ds[(2 * h) * NVOX + v] = make_float4(f[0], f[1], f[2], f[3]);
+      ds[(2 * h + 1) * NVOX + v] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    __syncthreads();
+    if (warp < nwarps_active) {
+#pragma unroll 1
+      for (int pyb = 0; pyb < 4; ++pyb) {
+        const int py = pyb * 4 + pyq;
+        const float* xr = xs + (py + tg) * XP + px;
+        float w0[3], w1[3], w2[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { w0[d] = xr[d]; w1[d] = xr[18 * XP + d]; }
+        const float4* dr = ds + cg * NVOX + py * 8 + px;
+#pragma unroll
+        for (int pz = 0; pz < TZ; ++pz) {
+#pragma unroll
+          for (int d = 0; d < 3; ++d) w2[d] = xr[(pz + 2) * 18 * XP + d];
+          const float4 g = dr[pz * 128];
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            acc[0][d][0] = fmaf(w0[d], g.x, acc[0][d][0]); acc[0][d][1] = fmaf(w0[d], g.y, acc[0][d][1]);
+            acc[0][d][2] = fmaf(w0[d], g.z, acc[0][d][2]); acc[0][d][3] = fmaf(w0[d], g.w, acc[0][d][3]);
+            acc[1][d][0] = fmaf(w1[d], g.x, acc[1][d][0]); acc[1][d][1] = fmaf(w1[d], g.y, acc[1][d][1]);
+            acc[1][d][2] = fmaf(w1[d], g.z, acc[1][d][2]); acc[1][d][3] = fmaf(w1[d], g.w, acc[1][d][3]);
+            acc[2][d][0] = fmaf(w2[d], g.x, acc[2][d][0]); acc[2][d][1] = fmaf(w2[d], g.y, acc[2][d][1]);
+            acc[2][d][2] = fmaf(w2[d], g.z, acc[2][d][2]); acc[2][d][3] = fmaf(w2[d], g.w, acc[2][d][3]);
+          }
+#pragma unroll
+          for (int d = 0; d < 3; ++d) { w0[d] = w1[d]; w1[d] = w2[d]; }
+        }
+      }
+    }
+  }
+  if (warp < nwarps_active) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float v = acc[a][b][c];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == 0) atomicAdd(dw + (static_cast<long long>((a * 3 + tg) * 3 + b) * dw_cin + ci_off) * Co + cg * 4 + c, v);
+        }
+  }
+}
+
 // dbias[c] += sum_v dy[v][c]
 template <typename T>
 __global__ void __launch_bounds__(256) channel_sum_kernel(TView dy, double* out2) {
@@ -785,6 +932,83 @@ __global__ void __launch_bounds__(256) head_loss_kernel(TView a, const float* __
   for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
   if ((threadIdx.x & 31) == 0) sl[threadIdx.x >> 5] = lsum;
   __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < 8; ++i) tot += sl[i];
+    atomicAdd(loss, tot * inv_n);
+  }
+}
+
+// Fused, vectorised head: G = C / 8 lanes share a voxel (one 128-bit load of `a` and one 128-bit store of `da`
+// per lane, logit reduced with shuffles), and the head's weight / bias gradient (sum_v a[v][c] dl[v], sum_v dl[v])
+// is accumulated in the same pass, so `a` is read once and dl never re-read.
+template <typename T>
+__global__ void __launch_bounds__(256) head_loss_v8_kernel(TView a, const float* __restrict__ w, const float* __restrict__ b,
+                                                            const uint8_t* __restrict__ y, TView da, double* loss, double* dwb2c,
+                                                            float inv_n, float* __restrict__ dl_out, float* probs) {
+  __shared__ float red[8][264];
+  __shared__ double sl[8];
+  const int C = a.C, G = C >> 3;
+  const long long nvox = a.voxels();
+  const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int g = static_cast<int>(t % G);
+  const long long istride = nthreads / G;
+  const T* ap = static_cast<const T*>(a.ptr);
+  T* dp = static_cast<T*>(da.ptr);
+  float wr[8], sa[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { wr[j] = w[g * 8 + j]; sa[j] = 0.f; }
+  const float bias = b[0];
+  float lsum = 0.f, dsum = 0.f;
+  for (long long v = t / G; v < nvox; v += istride) {
+    float f[8];
+    load8v<T>(ap + v * a.ctot + a.coff + g * 8, f);
+    float part = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part = fmaf(f[j], wr[j], part);
+    for (int off = G >> 1; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+    const float logit = part + bias;
+    const float pr = 1.f / (1.f + expf(-logit));
+    const float yt = static_cast<float>(y[v]);
+    const float eps = 1e-7f;
+    const float pc = fminf(fmaxf(pr, eps), 1.f - eps);
+    const float dldp = (pr > eps && pr < 1.f - eps) ? -(yt / (pc + eps) - (1.f - yt) / (1.f - pc + eps)) : 0.f;
+    const float dl = dldp * pr * (1.f - pr) * inv_n;
+    if (g == 0) {
+      if (probs) probs[v] = pr;
+      dl_out[v] = dl;
+      lsum += -(yt * logf(pc + eps) + (1.f - yt) * logf(1.f - pc + eps));
+      dsum += dl;
+    }
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o[j] = dl * wr[j]; sa[j] = fmaf(f[j], dl, sa[j]); }
+    store8v<T>(dp + v * da.ctot + da.coff + g * 8, o);
+  }
+  for (int off = 16; off >= G; off >>= 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sa[j] += __shfl_xor_sync(0xffffffffu, sa[j], off);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
+    dsum += __shfl_xor_sync(0xffffffffu, dsum, off);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < G) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = sa[j];
+  }
+  if (lane == 0) { red[warp][256] = dsum; sl[warp] = static_cast<double>(lsum); }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    float tot = 0.f, dtot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { tot += red[k][i]; dtot += red[k][256]; }
+    atomicAdd(dwb2c + i, static_cast<double>(tot));
+    atomicAdd(dwb2c + C + i, static_cast<double>(dtot));
+  }
   if (threadIdx.x == 0) {
     double tot = 0.0;
     for (int i = 0; i < 8; ++i) tot += sl[i];
@@ -1159,6 +1383,13 @@ extern "C" int te_tr_maxpool_bwd(const te_tensor* x, const te_tensor* dpool, con
   TE_CHECK_ARG(pool >= 1 && same_grid(*x, *dx) && x->C == dx->C && x->C == dpool->C && x->dtype == dx->dtype &&
                    x->dtype == dpool->dtype, "te_tr_maxpool_bwd: bad argument");
   const TView vx = view_of(*x), vg = view_of(*dpool), vd = view_of(*dx);
+  if (pool == 2 && v8_ok(*x) && v8_ok(*dpool) && v8_ok(*dx) && x->D % 2 == 0 && x->H % 2 == 0 && x->W % 2 == 0) {
+    const int grid = blocks_for(vg.voxels() * (vg.C >> 3), 256, 8);
+    if (x->dtype == TE_F16) maxpool2_bwd_v8_kernel<__half><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(vx, vg, vd, accumulate);
+    else maxpool2_bwd_v8_kernel<__nv_bfloat16><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(vx, vg, vd, accumulate);
+    TE_LAUNCH_CHECK();
+    return TE_OK;
+  }
   TE_DISPATCH_T(x->dtype, (maxpool_bwd_kernel<T><<<blocks_for(vg.voxels() * vg.C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
                               vx, vg, vd, pool, accumulate)));
   TE_LAUNCH_CHECK();
@@ -1325,6 +1556,18 @@ extern "C" int te_tr_conv3_wgrad(const te_tensor* x, const te_tensor* dy, float*
   } else if (wgrad_mma_ok(*x, *dy)) {
     const int rc = wgrad_mma(*x, *dy, dw, dw_cin, ci_off, 27, st);
     if (rc != TE_OK) return rc;
+  } else if (x->C == 1 && x->dtype != TE_F32 && (dy->C == 8 || dy->C == 16) && dy->ctot % 8 == 0 && dy->coff % 8 == 0) {
+    const size_t shb = (10 * 18 * 40 + 1024 * static_cast<size_t>(dy->C)) * sizeof(float);
+    const long long tiles = static_cast<long long>(vd.N) * ((vd.D + 7) / 8) * ((vd.H + 15) / 16) * ((vd.W + 7) / 8);
+    const int grid = static_cast<int>(tiles < 2LL * kNumSMs ? tiles : 2LL * kNumSMs);
+    if (x->dtype == TE_F16) {
+      TE_CUDA(cudaFuncSetAttribute(conv3_wgrad_c1_tiled_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shb)));
+      conv3_wgrad_c1_tiled_kernel<__half><<<grid, 384, shb, st>>>(vx, vd, dw, dw_cin, ci_off);
+    } else {
+      TE_CUDA(cudaFuncSetAttribute(conv3_wgrad_c1_tiled_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shb)));
+      conv3_wgrad_c1_tiled_kernel<__nv_bfloat16><<<grid, 384, shb, st>>>(vx, vd, dw, dw_cin, ci_off);
+    }
+    TE_LAUNCH_CHECK();
   } else if (x->C == 1 && dy->C <= 37) {
     const int threads = (27 * dy->C + 31) / 32 * 32;
     const size_t shb = (6 * 180 + 4 * 128 * static_cast<size_t>(dy->C)) * sizeof(float);
@@ -1375,6 +1618,14 @@ extern "C" int te_tr_head_loss(const te_tensor* a, const float* w, const float* 
                    a->C <= 1024, "te_tr_head_loss: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const TView va = view_of(*a), vd = view_of(*da);
+  if (v8_ok(*a) && v8_ok(*da)) {
+    const int g8 = blocks_for(va.voxels() * (va.C >> 3), 256, 4);
+    const float inv = static_cast<float>(1.0 / n_total);
+    if (a->dtype == TE_F16) head_loss_v8_kernel<__half><<<g8, 256, 0, st>>>(va, w, b, y, vd, loss, dwb2c, inv, dl, probs);
+    else head_loss_v8_kernel<__nv_bfloat16><<<g8, 256, 0, st>>>(va, w, b, y, vd, loss, dwb2c, inv, dl, probs);
+    TE_LAUNCH_CHECK();
+    return TE_OK;
+  }
   const size_t sh = static_cast<size_t>(a->C) * sizeof(float);
   TE_DISPATCH_T(a->dtype, (head_loss_kernel<T><<<blocks_for(va.voxels(), 256, 8), 256, sh, st>>>(
                               va, w, b, y, vd, loss, static_cast<float>(1.0 / n_total), dl, probs)));
