@@ -300,6 +300,17 @@ int te_tr_dense_bwd(const float* x, const float* dy, int64_t n, int32_t nin, int
 /* 1x1x1 head + sigmoid + mean squared error + weight * KL(target || p); loss3 += {total, mse, kl}. */
 int te_tr_head_ae_loss(const te_tensor* a, const float* w, const float* b, const void* target, const te_tensor* da,
                        double* loss3, double* dwb2c, double n_total, float weight, float* dl, float* probs, void* stream);
+/* BatchNormalization bookkeeping between the reduction kernels and the element-wise kernels, one launch each.
+ * te_tr_bn_finalize: stats2c = [sum y (C), sum y^2 (C)] over n_total voxels (all ranks) -> batch mean / biased variance,
+ * rstd = rsqrt(var + eps), scale = gamma * rstd, shift = beta - mean * scale; stats2c is zeroed.
+ * te_tr_bn_bwd_finalize: stats2c = [sum dz (C), sum dz * xhat (C)] (global); the parameter gradients g_beta / g_gamma
+ * take the LOCAL sums (stats2c_local, NULL = same buffer), dbeta_n / dgamma_n the global means; stats2c is zeroed.
+ * te_tr_take_stats: dst[i] = (float) stats[i] for i < n (dst may be NULL), then stats[0, n_zero) = 0. */
+int te_tr_bn_finalize(double* stats2c, int32_t C, double n_total, const float* gamma, const float* beta, float eps,
+                      float* mean, float* var, float* rstd, float* scale, float* shift, void* stream);
+int te_tr_bn_bwd_finalize(double* stats2c, const double* stats2c_local, int32_t C, double n_total, float* g_beta,
+                          float* g_gamma, float* dbeta_n, float* dgamma_n, void* stream);
+int te_tr_take_stats(double* stats, int32_t n, int32_t n_zero, float* dst, void* stream);
 /* Keras Adam on a flat parameter buffer; g is multiplied by grad_scale first (1 / world size after an all-reduce). */
 int te_tr_adam(float* w, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                int64_t step, float grad_scale, void* stream);

@@ -168,6 +168,9 @@ _SIGNATURES = {
     "te_tr_dense_fwd": (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _P, _P, _P]),
     "te_tr_dense_bwd": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P]),
     "te_tr_head_ae_loss": (ctypes.c_int, [_TP, _P, _P, _P, _TP, _P, _P, _D, _F, _P, _P, _P]),
+    "te_tr_bn_finalize": (ctypes.c_int, [_P, _I32, _D, _P, _P, _F, _P, _P, _P, _P, _P, _P]),
+    "te_tr_bn_bwd_finalize": (ctypes.c_int, [_P, _P, _I32, _D, _P, _P, _P, _P, _P]),
+    "te_tr_take_stats": (ctypes.c_int, [_P, _I32, _I32, _P, _P]),
     "te_tr_adam": (ctypes.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I64, _F, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -1643,6 +1643,70 @@ extern "C" int te_tr_head_loss(const te_tensor* a, const float* w, const float* 
   return TE_OK;
 }
 
+// ---- small per-layer "finalize" steps of the BatchNormalization forward / backward: one launch instead of a dozen
+// element-wise host-framework kernels over C values.  Each consumes the fp64 sums left in `stats` by the reduction
+// kernel (after the optional SyncBN all-reduce) and ZEROES them, so the buffer is ready for its next user.
+namespace te {
+namespace {
+__global__ void bn_finalize_kernel(double* stats, int C, double inv_n, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float eps, float* mean, float* var, float* rstd, float* scale, float* shift) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+    const double m = stats[c] * inv_n;
+    double v = stats[C + c] * inv_n - m * m;
+    if (v < 0.0) v = 0.0;
+    const float vf = static_cast<float>(v);
+    const double r = 1.0 / sqrt(v + static_cast<double>(eps));
+    const double gr = static_cast<double>(gamma[c]) * r;
+    mean[c] = static_cast<float>(m); var[c] = vf; rstd[c] = static_cast<float>(r);
+    scale[c] = static_cast<float>(gr); shift[c] = static_cast<float>(static_cast<double>(beta[c]) - m * gr);
+    stats[c] = 0.0; stats[C + c] = 0.0;
+  }
+}
+__global__ void bn_bwd_finalize_kernel(double* stats, const double* stats_local, int C, double inv_n, float* g_beta, float* g_gamma,
+                                       float* dbeta_n, float* dgamma_n) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+    const double sb = stats[c], sg = stats[C + c];
+    const double lb = stats_local ? stats_local[c] : sb, lg = stats_local ? stats_local[C + c] : sg;
+    g_beta[c] = static_cast<float>(lb); g_gamma[c] = static_cast<float>(lg);
+    dbeta_n[c] = static_cast<float>(sb * inv_n); dgamma_n[c] = static_cast<float>(sg * inv_n);
+    stats[c] = 0.0; stats[C + c] = 0.0;
+  }
+}
+__global__ void take_stats_kernel(double* stats, int n, int n_zero, float* dst) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_zero; i += gridDim.x * blockDim.x) {
+    if (i < n && dst) dst[i] = static_cast<float>(stats[i]);
+    stats[i] = 0.0;
+  }
+}
+}  // namespace
+}  // namespace te
+
+extern "C" int te_tr_bn_finalize(double* stats2c, int32_t C, double n_total, const float* gamma, const float* beta, float eps,
+                                 float* mean, float* var, float* rstd, float* scale, float* shift, void* stream) {
+  TE_CHECK_ARG(stats2c && C > 0 && n_total > 0 && gamma && beta && mean && var && rstd && scale && shift, "te_tr_bn_finalize: bad argument");
+  te::bn_finalize_kernel<<<(C + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(stats2c, C, 1.0 / n_total, gamma, beta, eps, mean,
+                                                                                       var, rstd, scale, shift);
+  TE_LAUNCH_CHECK();
+  return TE_OK;
+}
+
+extern "C" int te_tr_bn_bwd_finalize(double* stats2c, const double* stats2c_local, int32_t C, double n_total, float* g_beta,
+                                     float* g_gamma, float* dbeta_n, float* dgamma_n, void* stream) {
+  TE_CHECK_ARG(stats2c && C > 0 && n_total > 0 && g_beta && g_gamma && dbeta_n && dgamma_n, "te_tr_bn_bwd_finalize: bad argument");
+  te::bn_bwd_finalize_kernel<<<(C + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(stats2c, stats2c_local, C, 1.0 / n_total,
+                                                                                           g_beta, g_gamma, dbeta_n, dgamma_n);
+  TE_LAUNCH_CHECK();
+  return TE_OK;
+}
+
+extern "C" int te_tr_take_stats(double* stats, int32_t n, int32_t n_zero, float* dst, void* stream) {
+  TE_CHECK_ARG(stats && n >= 0 && n_zero >= n, "te_tr_take_stats: bad argument");
+  if (n_zero == 0) return TE_OK;
+  te::take_stats_kernel<<<(n_zero + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(stats, n, n_zero, dst);
+  TE_LAUNCH_CHECK();
+  return TE_OK;
+}
+
 extern "C" int te_tr_adam(float* w, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                           int64_t step, float grad_scale, void* stream) {
   TE_CHECK_ARG(w && g && m && v && n >= 0 && step >= 1, "te_tr_adam: bad argument");

@@ -12,6 +12,7 @@ that the data-parallel exchange is a single all-reduce; BN batch statistics are 
 (``sync_bn``), which reproduces the reference's single-device batch semantics on any number of GPUs.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -212,6 +213,8 @@ class UnetTrainer:
         maxc = max(max(l.get("cout", 1), l.get("cin", 1)) for l in layers if l["op"] != "dense")
         maxc = max([maxc] + [l["cout"] for l in layers if l["op"] == "dense"])
         # scratch
+        self.bstat = torch.zeros_like(self.theta)
+        self.mov_mask = torch.zeros_like(self.theta)
         self.stats = torch.zeros(2 * max(maxc, 1024), dtype=torch.float64, device=self.dev)
         wpack = max(int(self.L.te_tr_conv3_wpack_bytes(l["cin"], l["cout"])) for l in layers if l["op"] == "conv")
         wpack = max(wpack, max(int(self.L.te_tr_conv3_wpack_bytes(l["cout"], l["cin"])) for l in layers if l["op"] == "conv"))
@@ -234,7 +237,11 @@ class UnetTrainer:
                 if lay["op"] == "conv":
                     lay["cat"] = mk(lay["src"].size, lay["cin"]) if (lay["src2"] is not None and self.mode == "fp32") else None
                 lay["bn"] = {k: torch.empty(c, dtype=torch.float32, device=self.dev)
-                             for k in ("mean", "rstd", "scale", "shift", "dbeta_n", "dgamma_n", "var")}
+                             for k in ("rstd", "scale", "shift", "dbeta_n", "dgamma_n")}
+                wi = lay["w"]
+                lay["bn"]["mean"] = self.bstat[self.offsets[wi + 4]:self.offsets[wi + 5]]
+                lay["bn"]["var"] = self.bstat[self.offsets[wi + 5]:self.offsets[wi + 6]]
+                self.mov_mask[self.offsets[wi + 4]:self.offsets[wi + 6]] = 1.0
 
     def workspace_bytes(self):
         tot = 0
@@ -256,35 +263,35 @@ class UnetTrainer:
 
     # ------------------------------------------------------------------ BN + LeakyReLU helpers (conv and dense layers)
     def _bn_forward(self, y_desc, a_desc, c, nvox, wi, bn, world, st):
+        """self.stats is all zero on entry and on exit (every consumer kernel re-zeroes what it read)."""
         br = ctypes.byref
-        self.stats[:2 * c].zero_()
         self._call("te_tr_bn_stats", br(y_desc), self.stats.data_ptr(), st)
-        s = self._reduce_stats(2 * c)
-        n_tot = float(nvox * world)
-        mean = s[:c] / n_tot
-        var = torch.clamp(s[c:2 * c] / n_tot - mean * mean, min=0.0)
-        rstd = torch.rsqrt(var + BN_EPS)
-        gamma, beta = self._w(wi + 2).double(), self._w(wi + 3).double()
-        bn["mean"].copy_(mean); bn["var"].copy_(var); bn["rstd"].copy_(rstd)
-        bn["scale"].copy_(gamma * rstd); bn["shift"].copy_(beta - mean * gamma * rstd)
+        self._reduce_stats(2 * c)
+        self._call("te_tr_bn_finalize", self.stats.data_ptr(), c, float(nvox * world), self._w(wi + 2).data_ptr(),
+                   self._w(wi + 3).data_ptr(), BN_EPS, bn["mean"].data_ptr(), bn["var"].data_ptr(), bn["rstd"].data_ptr(),
+                   bn["scale"].data_ptr(), bn["shift"].data_ptr(), st)
         self._call("te_tr_bn_act_fwd", br(y_desc), br(a_desc), bn["scale"].data_ptr(), bn["shift"].data_ptr(), LRELU_ALPHA, st)
 
     def _bn_backward(self, y_desc, da_desc, c, nvox, wi, bn, world, st):
         """da -> dy in place; parameter gradients use the LOCAL sums (the gradient all-reduce adds the
         ranks up), the normalisation backward the GLOBAL batch sums."""
         br = ctypes.byref
-        self.stats[:2 * c].zero_()
         self._call("te_tr_bn_act_bwd_reduce", br(y_desc), br(da_desc), bn["scale"].data_ptr(), bn["shift"].data_ptr(),
                    bn["mean"].data_ptr(), bn["rstd"].data_ptr(), LRELU_ALPHA, self.stats.data_ptr(), st)
-        self._g(wi + 3).copy_(self.stats[:c])
-        self._g(wi + 2).copy_(self.stats[c:2 * c])
-        s = self._reduce_stats(2 * c)
-        n_tot = float(nvox * world)
-        bn["dbeta_n"].copy_(s[:c] / n_tot)
-        bn["dgamma_n"].copy_(s[c:2 * c] / n_tot)
+        local = None
+        if self.sync_bn and world > 1:
+            local = self.stats[:2 * c].clone()
+            self._reduce_stats(2 * c)
+        self._call("te_tr_bn_bwd_finalize", self.stats.data_ptr(), None if local is None else local.data_ptr(), c,
+                   float(nvox * world), self._g(wi + 3).data_ptr(), self._g(wi + 2).data_ptr(), bn["dbeta_n"].data_ptr(),
+                   bn["dgamma_n"].data_ptr(), st)
         self._call("te_tr_bn_act_bwd_apply", br(y_desc), br(da_desc), br(da_desc), bn["scale"].data_ptr(), bn["shift"].data_ptr(),
                    bn["mean"].data_ptr(), bn["rstd"].data_ptr(), bn["dbeta_n"].data_ptr(), bn["dgamma_n"].data_ptr(),
                    LRELU_ALPHA, st)
+
+    def _take(self, n, n_zero, dst, st):
+        """dst[:n] = stats[:n] (fp64 -> fp32), stats[:n_zero] = 0."""
+        self._call("te_tr_take_stats", self.stats.data_ptr(), n, n_zero, dst.data_ptr(), st)
 
     # ------------------------------------------------------------------ step
     def forward_backward(self, x, y=None):
@@ -292,8 +299,10 @@ class UnetTrainer:
         {0,1} (segmenter; the autoencoder reconstructs x).  Leaves the global-batch mean loss in
         self.loss and the LOCAL gradient contribution in self.grad (sum over ranks = gradient of the
         global-batch loss).  Returns the loss tensor."""
-        st = _device.stream_ptr()
-        world = sharding.world(self.group)[1] if self.sync_bn else 1
+        self._load_batch(x, y)
+        return self._run()
+
+    def _load_batch(self, x, y=None):
         tx = _device.to_device(x)
         if tx.dim() == 5:
             tx = tx[..., 0]
@@ -305,6 +314,12 @@ class UnetTrainer:
             if ty.dim() == 5:
                 ty = ty[..., 0]
             self.labels.copy_(ty.reshape(self.labels.shape))
+
+    def _run(self):
+        """Forward + backward on the batch held in self.inp / self.labels: only stream-ordered work on static buffers
+        (C-ABI launches, a few torch element-wise ops, the SyncBN all-reduces), so it can be captured in a CUDA graph."""
+        st = _device.stream_ptr()
+        world = sharding.world(self.group)[1] if self.sync_bn else 1
         self.grad.zero_()
         self.loss.zero_()
         br = ctypes.byref
@@ -338,24 +353,20 @@ class UnetTrainer:
                 lay["a"].t.copy_(lay["src"].t.reshape(lay["a"].t.shape))
             elif op == "head":
                 wi, src = lay["w"], lay["src"]
-                self.stats[:2 * src.c].zero_()
                 n_tot = float(src.nvox * sharding.world(self.group)[1])
                 self._call("te_tr_head_loss", br(src.x), self._w(wi).data_ptr(), self._w(wi + 1).data_ptr(),
                            self.labels.data_ptr(), br(src.dx), self.loss.data_ptr(), self.stats.data_ptr(), n_tot,
                            self.dl.data_ptr(), None, st)
-                self._g(wi).copy_(self.stats[:src.c])
-                self._g(wi + 1).copy_(self.stats[src.c:src.c + 1])
+                self._take(src.c + 1, 2 * src.c, self._g(wi), st)       # head kernel (C) and bias (1) are adjacent in the flat buffer
             elif op == "head_ae":
                 wi, src = lay["w"], lay["src"]
-                self.stats[:2 * src.c].zero_()
                 self.loss3.zero_()
                 n_tot = float(src.nvox * sharding.world(self.group)[1])
                 self._call("te_tr_head_ae_loss", br(src.x), self._w(wi).data_ptr(), self._w(wi + 1).data_ptr(),
                            self.inp.t.data_ptr(), br(src.dx), self.loss3.data_ptr(), self.stats.data_ptr(), n_tot,
                            float(self.reg_weight), self.dl.data_ptr(), None, st)
                 self.loss.copy_(self.loss3[:1])
-                self._g(wi).copy_(self.stats[:src.c])
-                self._g(wi + 1).copy_(self.stats[src.c:src.c + 1])
+                self._take(src.c + 1, 2 * src.c, self._g(wi), st)
             else:
                 raise ValueError(op)
         # ---------------- backward
@@ -369,11 +380,10 @@ class UnetTrainer:
                 self._bn_backward(yb.x, a.dx, c, yb.nvox, wi, bn, world, st)
                 dy = a.dx
                 cin = lay["cin"]
-                self.stats[:2 * c].zero_()
                 if lay.get("cat") is not None:
                     cat, s1, s2 = lay["cat"], lay["src"], lay["src2"]
                     self._call("te_tr_conv3_wgrad", br(cat.x), br(dy), self._g(wi).data_ptr(), cin, 0, self.stats.data_ptr(), st)
-                    self._g(wi + 1).copy_(self.stats[:c])
+                    self._take(c, 2 * c, self._g(wi + 1), st)
                     self._call("te_tr_flip_weights", self._w(wi).data_ptr(), cin, c, 0, cin, self.wflip.data_ptr(), st)
                     self._call("te_tr_conv3", br(dy), None, self.wflip.data_ptr(), self.zero_bias.data_ptr(), br(cat.dx),
                                self.wpack.data_ptr(), st)
@@ -389,7 +399,7 @@ class UnetTrainer:
                     self._call("te_tr_conv3_wgrad", br(src.x), br(dy), self._g(wi).data_ptr(), cin, off,
                                self.stats.data_ptr() if k == 0 else None, st)
                     off += src.c
-                self._g(wi + 1).copy_(self.stats[:c])
+                self._take(c, 2 * c, self._g(wi + 1), st)
                 # data gradients
                 off = 0
                 for src in (lay["src"], lay["src2"]):
@@ -407,7 +417,6 @@ class UnetTrainer:
                 self._call("te_tr_maxpool_bwd", br(src.x), br(lay["a"].dx), br(src.dx), 2, acc, st)
             elif op == "upconv":
                 wi, src, a = lay["w"], lay["src"], lay["a"]
-                self.stats[:2 * a.c].zero_()
                 dz2 = None
                 if self.mode != "fp32":
                     d = TeTensor()
@@ -416,37 +425,73 @@ class UnetTrainer:
                     dz2 = br(d)
                 self._call("te_tr_upconv_bwd", br(src.x), br(a.x), br(a.dx), self._w(wi).data_ptr(), 2, LRELU_ALPHA,
                            self._g(wi).data_ptr(), self.stats.data_ptr(), br(src.dx), dz2, self.wpack.data_ptr(), st)
-                self._g(wi + 1).copy_(self.stats[:a.c])
+                self._take(a.c, 2 * a.c, self._g(wi + 1), st)
             elif op == "flatten":
                 lay["src"].g.copy_(lay["a"].g.reshape(lay["src"].g.shape))
             elif op == "dense":
                 wi, c, src, a, yb = lay["w"], lay["cout"], lay["src"], lay["a"], lay["y"]
                 self._bn_backward(yb.x, a.dx, c, self.batch, wi, lay["bn"], world, st)
-                self.stats[:2 * c].zero_()
                 self._call("te_tr_dense_bwd", src.t.data_ptr(), a.g.data_ptr(), self.batch, lay["cin"], c, self._w(wi).data_ptr(),
                            self._g(wi).data_ptr(), self.stats.data_ptr(), src.g.data_ptr() if src.g is not None else None, st)
-                self._g(wi + 1).copy_(self.stats[:c])
+                self._take(c, 2 * c, self._g(wi + 1), st)
             elif op == "reshape":
                 lay["src"].g.copy_(lay["a"].g.reshape(lay["src"].g.shape))
         return self.loss
 
-    def apply_gradients(self):
-        """All-reduces the flat gradient buffer over the ranks, applies Keras Adam and updates the BN
-        moving statistics from the (global) batch statistics of the last forward pass."""
+    def _post_backward(self):
+        """Gradient all-reduce over the ranks + BN moving statistics from the (global) batch statistics of the last
+        forward pass (graph-capturable: no host-side state)."""
         sharding.allreduce_sum_(self.grad, self.group)
+        # moving = moving * momentum + batch * (1 - momentum) for every BN layer at once: the batch statistics live in
+        # a buffer laid out like theta (bn["mean"] / bn["var"] are views into it), mov_mask selects those entries
+        self.theta.addcmul_(self.mov_mask, self.bstat - self.theta, value=1.0 - BN_MOMENTUM)
+
+    def _adam(self):
         self.step_count += 1
         self._call("te_tr_adam", self.theta.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                    self.theta.numel(), self.lr, self.b1, self.b2, self.eps, self.step_count, 1.0, _device.stream_ptr())
-        for lay in self.layers:
-            if lay["op"] in ("conv", "dense"):
-                wi, bn = lay["w"], lay["bn"]
-                self._w(wi + 4).mul_(BN_MOMENTUM).add_(bn["mean"], alpha=1.0 - BN_MOMENTUM)
-                self._w(wi + 5).mul_(BN_MOMENTUM).add_(bn["var"], alpha=1.0 - BN_MOMENTUM)
+
+    def apply_gradients(self):
+        """All-reduces the flat gradient buffer over the ranks, updates the BN moving statistics and applies Keras
+        Adam (whose update of the moving-statistics entries is exactly zero: their gradient is)."""
+        self._post_backward()
+        self._adam()
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the fit step
+    def _graph_wanted(self):
+        """TOMOENC_TRAIN_GRAPH: "0" never, "1" (default) single-process jobs, "2" also with SyncBN / gradient
+        all-reduces inside the captured region (NCCL collectives are capturable)."""
+        flag = os.environ.get("TOMOENC_TRAIN_GRAPH", "1")
+        if flag == "0" or self.mode == "fp32":
+            return False
+        return sharding.world(self.group)[1] == 1 or flag == "2"
+
+    def _capture(self):
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._run()
+            self._post_backward()
+        self._graph = g
 
     def train_step(self, x, y=None):
-        """One fit step on a batch; returns the (global-batch mean) loss as a python float."""
-        self.forward_backward(x, y)
-        self.apply_gradients()
+        """One fit step on a batch; returns the (global-batch mean) loss as a python float.  After two eager steps
+        (allocations, kernel attributes, communicators) the ~250 launches of forward + backward + all-reduces are
+        replayed as ONE CUDA graph; Adam (host-side step count) stays outside."""
+        self._load_batch(x, y)
+        if not self._graph_wanted():
+            self._run()
+            self.apply_gradients()
+        else:
+            if getattr(self, "_graph", None) is None and getattr(self, "_eager_steps", 0) >= 2:
+                self._capture()
+            if getattr(self, "_graph", None) is not None:
+                self._graph.replay()
+                self._adam()
+            else:
+                self._eager_steps = getattr(self, "_eager_steps", 0) + 1
+                self._run()
+                self.apply_gradients()
         loss = sharding.allreduce_sum_(self.loss.clone(), self.group)
         return float(loss.item())
 

@@ -21,7 +21,7 @@ def main():
     g = np.random.default_rng(0)
     x = torch.from_numpy(g.uniform(0, 1, (batch,) + (size,) * 3).astype(np.float32)).cuda()
     y = (x > 0.5).to(torch.uint8)
-    for _ in range(2):
+    for _ in range(4):                      # two eager steps, the graph capture, one replay
         loss = tr.train_step(x, y)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -34,7 +34,7 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     flops = 3 * 122.23e9 * batch * (size / 64) ** 3
-    print("train step, batch %d x %d^3: %.1f ms (host wall %.1f ms)  loss %.4f  ~%.0f TFLOP/s (3 x fwd FLOPs)  workspace %.2f GB" %
+    print(("train step [%s], batch" % ("graph replay" if getattr(tr, "_graph", None) is not None else "eager")) + " %d x %d^3: %.1f ms (host wall %.1f ms)  loss %.4f  ~%.0f TFLOP/s (3 x fwd FLOPs)  workspace %.2f GB" %
           (batch, size, ms, 1e3 * (time.perf_counter() - t0) / n, loss, flops / ms / 1e9, tr.workspace_bytes() / 1e9))
     # per-operator breakdown
     times = OrderedDict()
@@ -47,6 +47,7 @@ def main():
         b.record()
         times.setdefault(name, []).append((a, b))
     tr._call = timed
+    os.environ["TOMOENC_TRAIN_GRAPH"] = "0"        # the per-operator breakdown needs the eager path
     tr.train_step(x, y)
     torch.cuda.synchronize()
     tot = 0.0
