@@ -21,10 +21,17 @@ import time
 
 import numpy as np
 
-# NCCL prints "NCCL version ..." on stdout when NCCL_DEBUG=VERSION (the image default): stdout must carry the
-# JSON line only
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout must carry the JSON line only, but NCCL writes "NCCL version ..." to file descriptor 1 from C: keep a private
+# duplicate of the real stdout for the JSON line and point descriptor 1 at stderr for everything else
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+sys.stdout.flush()
+os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -147,7 +154,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_ours(args):
@@ -362,7 +369,7 @@ def run_ours(args):
         gx = torch.Generator(device=dev).manual_seed(8 + rank)
         tx = torch.rand((tb,) + (PATCH,) * 3, generator=gx, device=dev)
         ty = (torch.rand((tb,) + (PATCH,) * 3, generator=gx, device=dev) < 0.5).to(torch.uint8)
-        for _ in range(2):
+        for _ in range(4):                  # two eager steps, the CUDA-graph capture, one replay
             tr.train_step(tx, ty)
         barrier()
         t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -377,7 +384,8 @@ def run_ours(args):
         train = {"metric": "training patch pairs/sec (U-net M_a01 fwd+bwd+Adam, 64^3 pairs, bf16 activations, fp32 master weights)",
                  "value": world * tb / (tr_ms / 1e3), "unit": "patch pairs/s", "ms_per_step": tr_ms, "global_batch": world * tb,
                  "per_rank_batch": tb, "loss": tloss, "tflops_effective_3x_fwd": 3 * world * tb * net.flops_per_patch / (tr_ms / 1e3) / 1e12,
-                 "gpu_launches_per_step": int((_lib.lib().te_launch_count() - launches_t0) / n_tr),
+                 "gpu_launches_per_step": int((_lib.lib().te_launch_count() - launches_t0) / n_tr) + tr.graph_launches,
+                 "cuda_graph": tr.graph_launches > 0,
                  "collectives": "all-reduce(flat fp32 gradient, 4.77 M values) + SyncBN all-reduces of per-channel sums" if world > 1 else "none (1 rank)"}
         del tr, tx, ty
 
@@ -420,7 +428,7 @@ def run_ours(args):
             "cpu_baseline": {"value": cpu_v, "unit": "voxels/s", "cores": cpu_threads, "kind": "port",
                              "sample": "%d x 64^3 tiles: oracle extract + torch-CPU fp32 U-net M_a01 + fill (%.1f s)" % (CPU_TILES, cpu_dt)},
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
