@@ -271,10 +271,12 @@ int te_tr_bn_act_fwd(const te_tensor* y, const te_tensor* a, const float* scale,
 /* red2c (double [2C]) += [sum dz, sum dz * xhat], dz = da * LeakyReLU'(z). */
 int te_tr_bn_act_bwd_reduce(const te_tensor* y, const te_tensor* da, const float* scale, const float* shift,
                             const float* mean, const float* rstd, float alpha, double* red2c, void* stream);
-/* dy = scale * (dz - dbeta_n - xhat * dgamma_n), dbeta_n = sum dz / n, dgamma_n = sum dz xhat / n. */
+/* dy = scale * (dz - dbeta_n - xhat * dgamma_n), dbeta_n = sum dz / n, dgamma_n = sum dz xhat / n (dy may be da).
+ * dsum2c (double [2C], optional): [0, C) += sum_v dy -- the bias gradient of the convolution that feeds this
+ * BatchNormalization, taken from the values in flight instead of by another pass over dy. */
 int te_tr_bn_act_bwd_apply(const te_tensor* y, const te_tensor* da, const te_tensor* dy, const float* scale,
                            const float* shift, const float* mean, const float* rstd, const float* dbeta_n,
-                           const float* dgamma_n, float alpha, void* stream);
+                           const float* dgamma_n, float alpha, double* dsum2c, void* stream);
 int te_tr_maxpool_fwd(const te_tensor* x, const te_tensor* out, int32_t pool, void* stream);
 /* dx (+)= gradient routed to the first maximum of every window. */
 int te_tr_maxpool_bwd(const te_tensor* x, const te_tensor* dpool, const te_tensor* dx, int32_t pool, int32_t accumulate,

@@ -159,7 +159,7 @@ _SIGNATURES = {
     "te_tr_bn_stats": (ctypes.c_int, [_TP, _P, _P]),
     "te_tr_bn_act_fwd": (ctypes.c_int, [_TP, _TP, _P, _P, _F, _P]),
     "te_tr_bn_act_bwd_reduce": (ctypes.c_int, [_TP, _TP, _P, _P, _P, _P, _F, _P, _P]),
-    "te_tr_bn_act_bwd_apply": (ctypes.c_int, [_TP, _TP, _TP, _P, _P, _P, _P, _P, _P, _F, _P]),
+    "te_tr_bn_act_bwd_apply": (ctypes.c_int, [_TP, _TP, _TP, _P, _P, _P, _P, _P, _P, _F, _P, _P]),
     "te_tr_maxpool_fwd": (ctypes.c_int, [_TP, _TP, _I32, _P]),
     "te_tr_maxpool_bwd": (ctypes.c_int, [_TP, _TP, _TP, _I32, _I32, _P]),
     "te_tr_upconv_fwd": (ctypes.c_int, [_TP, _P, _P, _TP, _I32, _F, _P, _P]),

@@ -173,6 +173,15 @@ __device__ __forceinline__ void load8v(const T* p, float (&f)[8]) {
     }
   }
 }
+// r[j] = f[j] rounded to T (what store8v writes)
+template <typename T>
+__device__ __forceinline__ void load8r(const float (&f)[8], float (&r)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if constexpr (std::is_same<T, __half>::value) r[j] = __half2float(__float2half_rn(f[j]));
+    else r[j] = __bfloat162float(__float2bfloat16_rn(f[j]));
+  }
+}
 template <typename T>
 __device__ __forceinline__ void store8v(T* p, const float (&f)[8]) {
   uint32_t w[4];
@@ -197,7 +206,17 @@ __device__ __forceinline__ void reduce2_v8(int C, long long items, double* out, 
   float sa[8], sb[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) sa[j] = sb[j] = 0.f;
-  for (long long it = t / G; it < items; it += istride) {
+  long long it = t / G;
+  for (; it + 3 * istride < items; it += 4 * istride) {          // four independent items: their loads are issued together
+    float a[4][8], b[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) f(it + u * istride, g * 8, a[u], b[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sa[j] += a[u][j]; sb[j] += b[u][j]; }
+  }
+  for (; it < items; it += istride) {
     float a[8], b[8];
     f(it, g * 8, a, b);
 #pragma unroll
@@ -262,51 +281,84 @@ __global__ void __launch_bounds__(256) bn_act_fwd_v8_kernel(TView y, TView a, co
   }
 }
 
+// The channel group of a thread is fixed over its whole loop (the thread stride is a multiple of the group count), so the
+// per-channel constants are hoisted into registers once.
 template <typename T>
 __global__ void __launch_bounds__(256) bn_act_bwd_reduce_v8_kernel(TView y, TView da, const float* __restrict__ scale,
                                                                     const float* __restrict__ shift, const float* __restrict__ mean,
                                                                     const float* __restrict__ rstd, float alpha, double* red) {
   const T* yp = static_cast<const T*>(y.ptr);
   const T* dp = static_cast<const T*>(da.ptr);
+  const int G = y.C >> 3;
+  const int cg = static_cast<int>((static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) % G) * 8;
+  float sc[8], sh[8], mu[8], rs[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = scale[cg + j]; sh[j] = shift[cg + j]; mu[j] = mean[cg + j]; rs[j] = rstd[cg + j]; }
   reduce2_v8(y.C, y.voxels(), red, [&](long long vox, int c0, float (&a)[8], float (&b)[8]) {
     float yv[8], d[8];
     load8v<T>(yp + vox * y.ctot + y.coff + c0, yv);
     load8v<T>(dp + vox * da.ctot + da.coff + c0, d);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float z = fmaf(scale[c0 + j], yv[j], shift[c0 + j]);
+      const float z = fmaf(sc[j], yv[j], sh[j]);
       const float dz = d[j] * (z > 0.f ? 1.f : alpha);
       a[j] = dz;
-      b[j] = dz * (yv[j] - mean[c0 + j]) * rstd[c0 + j];
+      b[j] = dz * (yv[j] - mu[j]) * rs[j];
     }
   });
 }
 
+// dy = scale * (dz - dbeta_n - xhat * dgamma_n), possibly in place (dy == da); dsum2c (optional): [0, C) += sum_v dy, the
+// gradient of the bias of the convolution feeding this BatchNormalization (analytically zero; Keras computes it, so it is
+// produced here from the values already in registers instead of by another pass over dy).
 template <typename T>
 __global__ void __launch_bounds__(256) bn_act_bwd_apply_v8_kernel(TView y, TView da, TView dy, const float* __restrict__ scale,
                                                                    const float* __restrict__ shift, const float* __restrict__ mean,
                                                                    const float* __restrict__ rstd, const float* __restrict__ dbeta_n,
-                                                                   const float* __restrict__ dgamma_n, float alpha) {
-  const int G = y.C >> 3;
-  const long long total = y.voxels() * G;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+                                                                   const float* __restrict__ dgamma_n, float alpha, double* dsum2c) {
   const T* yp = static_cast<const T*>(y.ptr);
   const T* dp = static_cast<const T*>(da.ptr);
   T* op = static_cast<T*>(dy.ptr);
-  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
-    const long long vox = e / G;
-    const int c0 = static_cast<int>(e - vox * G) * 8;
+  const int G = y.C >> 3;
+  const int cg = static_cast<int>((static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) % G) * 8;
+  float sc[8], sh[8], mu[8], rs[8], db[8], dg[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = scale[cg + j]; sh[j] = shift[cg + j]; mu[j] = mean[cg + j]; rs[j] = rstd[cg + j];
+    db[j] = dbeta_n[cg + j]; dg[j] = dgamma_n[cg + j];
+  }
+  // reduce2_v8 hands four independent items per iteration to the functor calls; each call loads, computes and stores its own
+  // voxel row (a thread never touches another thread's rows, so the in-place update is safe)
+  auto body = [&](long long vox, int c0, float (&a)[8], float (&b)[8]) {
     float yv[8], d[8];
     load8v<T>(yp + vox * y.ctot + y.coff + c0, yv);
     load8v<T>(dp + vox * da.ctot + da.coff + c0, d);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float z = fmaf(scale[c0 + j], yv[j], shift[c0 + j]);
+      const float z = fmaf(sc[j], yv[j], sh[j]);
       const float dz = d[j] * (z > 0.f ? 1.f : alpha);
-      const float xhat = (yv[j] - mean[c0 + j]) * rstd[c0 + j];
-      d[j] = scale[c0 + j] * (dz - dbeta_n[c0 + j] - xhat * dgamma_n[c0 + j]);
+      const float xhat = (yv[j] - mu[j]) * rs[j];
+      d[j] = sc[j] * (dz - db[j] - xhat * dg[j]);
     }
     store8v<T>(op + vox * dy.ctot + dy.coff + c0, d);
+    if (dsum2c) {
+      float r[8];
+      load8r<T>(d, r);                      // the values as stored (rounded to the tensor dtype)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a[j] = r[j]; b[j] = 0.f; }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a[j] = 0.f; b[j] = 0.f; }
+    }
+  };
+  if (dsum2c) {
+    reduce2_v8(y.C, y.voxels(), dsum2c, body);
+  } else {
+    const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+    const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long items = y.voxels(), istride = nthreads / G;
+    float a[8], b[8];
+    for (long long it = t / G; it < items; it += istride) body(it, cg, a, b);
   }
 }
 
@@ -1347,23 +1399,29 @@ extern "C" int te_tr_bn_act_bwd_reduce(const te_tensor* y, const te_tensor* da, 
 
 extern "C" int te_tr_bn_act_bwd_apply(const te_tensor* y, const te_tensor* da, const te_tensor* dy, const float* scale,
                                       const float* shift, const float* mean, const float* rstd, const float* dbeta_n,
-                                      const float* dgamma_n, float alpha, void* stream) {
+                                      const float* dgamma_n, float alpha, double* dsum2c, void* stream) {
   TE_TR_CHECK_T(y, "te_tr_bn_act_bwd_apply"); TE_TR_CHECK_T(da, "te_tr_bn_act_bwd_apply"); TE_TR_CHECK_T(dy, "te_tr_bn_act_bwd_apply");
   TE_CHECK_ARG(scale && shift && mean && rstd && dbeta_n && dgamma_n && same_grid(*y, *da) && same_grid(*y, *dy) &&
                    y->C == da->C && y->C == dy->C && y->dtype == da->dtype && y->dtype == dy->dtype,
                "te_tr_bn_act_bwd_apply: bad argument");
   const TView vy = view_of(*y), vd = view_of(*da), vo = view_of(*dy);
+  cudaStream_t st8 = static_cast<cudaStream_t>(stream);
   if (v8_ok(*y) && v8_ok(*da) && v8_ok(*dy)) {
-    const int g8 = blocks_for(vy.voxels() * (vy.C >> 3), 256);
-    cudaStream_t st8 = static_cast<cudaStream_t>(stream);
-    if (y->dtype == TE_F16) bn_act_bwd_apply_v8_kernel<__half><<<g8, 256, 0, st8>>>(vy, vd, vo, scale, shift, mean, rstd, dbeta_n, dgamma_n, alpha);
-    else bn_act_bwd_apply_v8_kernel<__nv_bfloat16><<<g8, 256, 0, st8>>>(vy, vd, vo, scale, shift, mean, rstd, dbeta_n, dgamma_n, alpha);
+    const int g8 = blocks_for(vy.voxels() * (vy.C >> 3), 256, 8);
+    if (y->dtype == TE_F16) bn_act_bwd_apply_v8_kernel<__half><<<g8, 256, 0, st8>>>(vy, vd, vo, scale, shift, mean, rstd, dbeta_n, dgamma_n, alpha, dsum2c);
+    else bn_act_bwd_apply_v8_kernel<__nv_bfloat16><<<g8, 256, 0, st8>>>(vy, vd, vo, scale, shift, mean, rstd, dbeta_n, dgamma_n, alpha, dsum2c);
     TE_LAUNCH_CHECK();
     return TE_OK;
   }
-  TE_DISPATCH_T(y->dtype, (bn_act_bwd_apply_kernel<T><<<blocks_for(vy.voxels() * vy.C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  TE_DISPATCH_T(y->dtype, (bn_act_bwd_apply_kernel<T><<<blocks_for(vy.voxels() * vy.C, 256), 256, 0, st8>>>(
                               vy, vd, vo, scale, shift, mean, rstd, dbeta_n, dgamma_n, alpha)));
   TE_LAUNCH_CHECK();
+  if (dsum2c) {
+    int grid = blocks_for(vo.voxels() * vo.C, 256, 8);
+    if (static_cast<long long>(grid) * 256 < vo.C) grid = (vo.C + 255) / 256;
+    TE_DISPATCH_T(dy->dtype, (channel_sum_kernel<T><<<grid, 256, 0, st8>>>(vo, dsum2c)));
+    TE_LAUNCH_CHECK();
+  }
   return TE_OK;
 }
 

@@ -20,8 +20,8 @@
 // Work unit = (patch, z segment of up to 16 planes, 16 x 8 column); a CTA owns one (CB input
 // channels) x (32 output channels) block of all 27 taps for the whole launch: 9 CB TMEM columns of
 // fp32 accumulators, flushed ONCE with coalesced atomics.  Warp 0 = TMA producer (X planes and dY
-// planes in two rings; TMA zero fill supplies the per-patch "same" padding), warp 1 = UMMA issuer,
-// warps 2-5 = epilogue.
+// planes in two rings; TMA zero fill supplies the per-patch "same" padding), warps 1-3 = UMMA issuers
+// (one tz tap each), warps 4-7 = epilogue.
 #include <cuda.h>
 
 #include "sm100_ptx.cuh"
@@ -46,9 +46,9 @@ EncodeTiledFn get_encode() {
 
 constexpr int kZS = 16;              // planes per z segment
 constexpr int kXE = 11;              // x extent of the dY box: 8 + 3 shifts
-constexpr int kNXS = 6, kNYS = 3;    // ring depths (X planes / dY planes)
+constexpr int kNXS = 10, kNYS = 6;   // ring depths (X planes / dY planes): ~5 planes of prefetch
 constexpr uint32_t kYBytes = 16 * kXE * 64;      // 11264: multiple of the 512-byte swizzle repeat
-constexpr int kThreads = 192;
+constexpr int kThreads = 256;             // warp 0 producer, warps 1-3 UMMA issuers (one tz tap each), warps 4-7 epilogue
 
 struct WuParams {
   float* dw; int dw_cin, ci_off, Cout;
@@ -80,9 +80,9 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const int cic = pair % p.nci, coc = pair / p.nci;
 
   if (tid == 0) {
-    for (int i = 0; i < kNXS; ++i) { mbar_init(x_full + i, 1); mbar_init(x_empty + i, 1); }
-    for (int i = 0; i < kNYS; ++i) { mbar_init(y_full + i, 1); mbar_init(y_empty + i, 1); }
-    mbar_init(acc_full, 1);
+    for (int i = 0; i < kNXS; ++i) { mbar_init(x_full + i, 1); mbar_init(x_empty + i, 3); }
+    for (int i = 0; i < kNYS; ++i) { mbar_init(y_full + i, 1); mbar_init(y_empty + i, 3); }
+    mbar_init(acc_full, 3);
     fence_barrier_init();
     prefetch_tmap(&tmap_x); prefetch_tmap(&tmap_dy);
   }
@@ -121,39 +121,42 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ UMMA issuer
-    const uint32_t idesc = make_idesc_f16(128, 3 * CB, p.fmt) | (1u << 15) | (1u << 16);     // A and B MN-major
+  } else if (warp <= 3) {
+    // ------------------------------------------------------------------ UMMA issuers: warp 1 + tz owns the tap plane tz
+    // (its own accumulator, TMEM columns [tz * 3 CB, (tz + 1) * 3 CB)).  One issuer would stall at every plane boundary:
+    // the descriptors live in uniform registers, and rewriting them for the next plane waits until the queued UMMAs have
+    // read them, i.e. the issue queue drains (measured: tensor pipe busy 66 % of the time).  Three issuers keep the queue
+    // fed from two warps while the third turns around.  A ring slot is free once all three have committed (count 3).
+    const int dz = warp - 1;
+    const uint32_t idesc = make_idesc_f16(128, 3 * CB, p.fmt & 1u) | (1u << 15) | (1u << 16);     // A and B MN-major
     const uint64_t da0 = make_smem_desc(smem_u32(ys), 64, kXE * 64, kLayoutSW64, 0);
     const uint64_t db0 = make_smem_desc(smem_u32(xs), 8 * ROWB, 8 * ROWB, BLAYOUT, 0);
+    const uint32_t acc = tmem + dz * 3 * CB;
     uint32_t xc = 0, yc = 0;             // xc = ring count of plane pi = 0 of the current unit
     bool fresh = true;
     for (long long u = first; u < p.units && group < p.ngroups; u += step) {
       for (int zi = 0; zi < p.zs; ++zi) {
-        const int need_lo = zi == 0 ? 0 : zi + 2;
-        for (int pi = need_lo; pi <= zi + 2; ++pi) {
-          const uint32_t c = xc + pi;
-          mbar_wait(x_full + c % kNXS, (c / kNXS) & 1u);
-        }
+        const uint32_t c = xc + zi + dz;                 // the X plane this warp multiplies
+        mbar_wait(x_full + c % kNXS, (c / kNXS) & 1u);
         const uint32_t q = yc % kNYS;
         mbar_wait(y_full + q, (yc / kNYS) & 1u);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t da = da0 + static_cast<uint64_t>((q * kYBytes) >> 4);
+          const uint64_t db = db0 + static_cast<uint64_t>(((c % kNXS) * XSLOT) >> 4);
 #pragma unroll
-          for (int dz = 0; dz < 3; ++dz) {
-            const uint32_t sx = (xc + zi + dz) % kNXS;
-            const uint64_t db = db0 + static_cast<uint64_t>((sx * XSLOT) >> 4);
-#pragma unroll
-            for (int s = 0; s < 8; ++s)
-              umma_ss(tmem + dz * 3 * CB, da + static_cast<uint64_t>((s * 2 * kXE * 64) >> 4),
-                      db + static_cast<uint64_t>((s * 16 * ROWB) >> 4), idesc, (fresh && s == 0) ? 0u : 1u);
-          }
+          for (int s = 0; s < 8; ++s)
+            umma_ss(acc, da + static_cast<uint64_t>((s * 2 * kXE * 64) >> 4), db + static_cast<uint64_t>((s * 16 * ROWB) >> 4), idesc,
+                    (fresh && s == 0) ? 0u : 1u);
           umma_commit(y_empty + q);
-          umma_commit(x_empty + (xc + zi) % kNXS);
-          if (zi == p.zs - 1) {
-            umma_commit(x_empty + (xc + zi + 1) % kNXS);
-            umma_commit(x_empty + (xc + zi + 2) % kNXS);
+          // plane pi is used by the steps zi = pi - tz: this warp is done with plane c; it also stands in for the uses that
+          // never happen at the ends of the unit (plane 0 is only used by tz 0, plane 1 by tz 0 and 1, ...)
+          umma_commit(x_empty + c % kNXS);
+          if (zi == 0) {                                   // planes below this warp's first one
+            for (int k = 0; k < dz; ++k) umma_commit(x_empty + (xc + k) % kNXS);
+          }
+          if (zi == p.zs - 1) {                            // planes above this warp's last one
+            for (int k = dz + 1; k < 3; ++k) umma_commit(x_empty + (xc + zi + k) % kNXS);
           }
         }
         __syncwarp();
@@ -169,7 +172,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     mbar_wait(acc_full, 0);
     tc_fence_after();
     const int lg = warp & 3;             // TMEM lane group of this warp = x-shift atom j
-    if (lg < 3) {
+    if (lg < 3 && p.fmt < 2) {
       const int tx = 2 - lg;
       const int co = coc * 32 + lane;
 #pragma unroll 1
@@ -247,6 +250,7 @@ int wgrad_umma(const te_tensor& x, const te_tensor& dy, float* dw, int dw_cin, i
   if (ng > p.units) ng = p.units;
   p.ngroups = static_cast<int>(ng);
   p.fmt = x.dtype == TE_F16 ? 0u : 1u;
+  if (getenv("TOMOENC_WGRAD_NOEPI")) p.fmt |= 2u;   // experiment
   CUtensorMap tx, td;
   int rc = make_tmap_plane(&tx, x, cb, 8, 18);
   if (rc != TE_OK) return rc;

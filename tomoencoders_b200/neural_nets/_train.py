@@ -288,7 +288,8 @@ class UnetTrainer:
                    bn["dgamma_n"].data_ptr(), st)
         self._call("te_tr_bn_act_bwd_apply", br(y_desc), br(da_desc), br(da_desc), bn["scale"].data_ptr(), bn["shift"].data_ptr(),
                    bn["mean"].data_ptr(), bn["rstd"].data_ptr(), bn["dbeta_n"].data_ptr(), bn["dgamma_n"].data_ptr(),
-                   LRELU_ALPHA, st)
+                   LRELU_ALPHA, self.stats.data_ptr(), st)
+        self._take(c, 2 * c, self._g(wi + 1), st)       # bias gradient of the conv / dense layer in front of the BN
 
     def _take(self, n, n_zero, dst, st):
         """dst[:n] = stats[:n] (fp64 -> fp32), stats[:n_zero] = 0."""
@@ -383,8 +384,7 @@ class UnetTrainer:
                 cin = lay["cin"]
                 if lay.get("cat") is not None:
                     cat, s1, s2 = lay["cat"], lay["src"], lay["src2"]
-                    self._call("te_tr_conv3_wgrad", br(cat.x), br(dy), self._g(wi).data_ptr(), cin, 0, self.stats.data_ptr(), st)
-                    self._take(c, 2 * c, self._g(wi + 1), st)
+                    self._call("te_tr_conv3_wgrad", br(cat.x), br(dy), self._g(wi).data_ptr(), cin, 0, None, st)
                     self._call("te_tr_flip_weights", self._w(wi).data_ptr(), cin, c, 0, cin, self.wflip.data_ptr(), st)
                     self._call("te_tr_conv3", br(dy), None, self.wflip.data_ptr(), self.zero_bias.data_ptr(), br(cat.dx),
                                self.wpack.data_ptr(), st)
@@ -397,10 +397,8 @@ class UnetTrainer:
                 for k, src in enumerate([lay["src"], lay["src2"]]):
                     if src is None:
                         continue
-                    self._call("te_tr_conv3_wgrad", br(src.x), br(dy), self._g(wi).data_ptr(), cin, off,
-                               self.stats.data_ptr() if k == 0 else None, st)
+                    self._call("te_tr_conv3_wgrad", br(src.x), br(dy), self._g(wi).data_ptr(), cin, off, None, st)
                     off += src.c
-                self._take(c, 2 * c, self._g(wi + 1), st)
                 # data gradients
                 off = 0
                 for src in (lay["src"], lay["src2"]):

@@ -99,6 +99,60 @@ __global__ void __launch_bounds__(128, 1) probe(P p, const __half* __restrict__ 
   if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
+
+// ------------------------------------------------------------------------------------------ issue rate
+// cycles per UMMA (M 128, N 3 cb, K 16) with the product kernel's operand layouts: 8 k-steps x 3 accumulators per
+// "plane", back to back from one thread, commit at the end.
+struct PerfP { int cb; int a_mn, b_mn; int iters; };
+__global__ void __launch_bounds__(128, 1) perf(PerfP p, long long* cycles) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* A = smem;                       // 16 KB
+  uint8_t* B = smem + 16384;               // 3 x 9216
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 16384 + 3 * 9216 + 1024);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (uint32_t i = tid; i < (16384 + 3 * 9216) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp == 1) {
+    const uint32_t rowB = p.cb * 2;
+    const uint32_t blay = p.cb == 32 ? kLayoutSW64 : kLayoutSW32;
+    uint32_t idesc = make_idesc_f16(128, 3 * p.cb, 1);
+    uint64_t da0, db0;
+    uint32_t a_step, b_step;
+    if (p.a_mn) { idesc |= 1u << 15; da0 = make_smem_desc(smem_u32(A), 64, XE * 64, kLayoutSW64, 0); a_step = (2 * XE * 64) >> 4; }
+    else { da0 = make_smem_desc(smem_u32(A), 16, 8 * 64, kLayoutSW64, 0); a_step = 2; }       // K-major 128 rows x 64 B, k-step = +32 B
+    if (p.b_mn) { idesc |= 1u << 16; db0 = make_smem_desc(smem_u32(B), 8 * rowB, 8 * rowB, blay, 0); b_step = (16 * rowB) >> 4; }
+    else { db0 = make_smem_desc(smem_u32(B), 16, 8 * 64, kLayoutSW64, 0); b_step = 2; }
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < p.iters; ++it) {
+      if (elect_one()) {
+#pragma unroll
+        for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+          for (int s = 0; s < 8; ++s)
+            umma_ss(tmem + dz * 3 * p.cb, da0 + (uint64_t)((s & (p.a_mn ? 7 : 1)) * a_step),
+                    db0 + (uint64_t)(((dz * 9216) >> 4) + (s & (p.b_mn ? 7 : 1)) * b_step), idesc, 1);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(bar);
+    mbar_wait(bar, 0);
+    long long t1 = clock64();
+    if ((tid & 31) == 0) cycles[0] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 int main() {
   std::vector<__half> ha(A_ROWS * 32), hb(B_ROWS * 32);
   std::vector<float> fa(ha.size()), fb(hb.size());
@@ -145,5 +199,18 @@ int main() {
           if (!swap) bad_total += bad;
         }
   printf("canonical descriptors: %s\n", bad_total == 0 ? "ALL MATCH" : "MISMATCH");
+  long long* dcyc;
+  CK(cudaMalloc(&dcyc, 16));
+  CK(cudaFuncSetAttribute(perf, cudaFuncAttributeMaxDynamicSharedMemorySize, 50 * 1024));
+  for (int cb : {32, 16})
+    for (int mode = 0; mode < 4; ++mode) {
+      PerfP pp{cb, mode & 1, (mode >> 1) & 1, 2000};
+      perf<<<1, 128, 50 * 1024>>>(pp, dcyc);
+      CK(cudaDeviceSynchronize());
+      long long c;
+      CK(cudaMemcpy(&c, dcyc, 8, cudaMemcpyDeviceToHost));
+      printf("issue rate N=%3d A %s B %s: %.1f cycles / UMMA\n", 3 * cb, pp.a_mn ? "MN-major" : "K-major ", pp.b_mn ? "MN-major" : "K-major ",
+             (double)c / (2000.0 * 24));
+    }
   return 0;
 }
