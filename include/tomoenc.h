@@ -317,6 +317,31 @@ int te_tr_take_stats(double* stats, int32_t n, int32_t n_zero, float* dst, void*
 int te_tr_adam(float* w, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                int64_t step, float grad_scale, void* stream);
 
+/* ---- post-stitch labelling: replaces cupyx.scipy.ndimage.label and
+ * scipy.ndimage.find_objects as used by /root/reference/tomo_encoders/tasks/digital_zoom.py:41-43 and
+ * structures/voids.py:188-303, 356-373.  All pointers are device pointers.
+ *
+ * te_label: connected components of the non-zero voxels of vol (u8 / u16 / f16 / f32), connectivity 6 (scipy's default
+ * structure) or 26 (np.ones((3,3,3))); labels (int32, same shape) = 0 for background, 1..n numbered in C order of each
+ * component's first voxel (scipy.ndimage.label's numbering); *n_labels (device int64) = n.  workspace: device scratch of
+ * te_label_workspace_bytes(nvox) bytes.  Up to 2^31 - 1 voxels. */
+int64_t te_label_workspace_bytes(int64_t nvox);
+int te_label(const void* vol, int vol_dtype, const int64_t vol_shape[3], int connectivity, int32_t* labels,
+             int64_t* n_labels, void* workspace, void* stream);
+/* find_objects + sizes: bbox6[i] = {z0, y0, x0, z1, y1, x1} (stops exclusive) and sizes[i] = voxel count of label i + 1. */
+int te_label_stats(const int32_t* labels, const int64_t vol_shape[3], int64_t n_labels, int32_t* bbox6, int64_t* sizes,
+                   void* stream);
+/* out[offsets[i] + local C-order index] = (labels[voxel of box i] == ids[i]) for n boxes (the x_voids of
+ * Voids.count_voids); max_box_voxels = the largest box (sizes the launch). */
+int te_label_crop_masks(const int32_t* labels, const int64_t vol_shape[3], const int32_t* boxes6, const int32_t* ids,
+                        int64_t n, const int64_t* offsets, int64_t max_box_voxels, uint8_t* out, void* stream);
+/* vol[box i] = mask i for i = 0..n-1 in order (numpy slice assignment semantics: later boxes overwrite earlier ones);
+ * owner: device scratch of 4 bytes per voxel of vol. */
+int te_paint_boxes(const uint8_t* masks, const int64_t* offsets, const int32_t* boxes6, int64_t n, int64_t max_box_voxels,
+                   uint8_t* vol, const int64_t vol_shape[3], uint32_t* owner, void* stream);
+/* flags[tile] = 1 iff any voxel of the width^3 tile of Grid(vol_shape, width) is non-zero (tiles in Grid.points order). */
+int te_tile_any(const void* vol, int elem_size, const int64_t vol_shape[3], int32_t width, uint8_t* flags, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,8 +41,12 @@ def _install_stubs():
     k.layers = lay
 
 
+_VOID_STUBS = ("cupyx", "cupyx.scipy", "cupyx.scipy.ndimage", "tifffile", "skimage", "skimage.measure", "tomo_encoders",
+               "tomo_encoders.misc", "tomo_encoders.misc.voxel_processing", "tomo_encoders.misc.ellipse_rad_max")
+
+
 def _remove_stubs():
-    for name in ("cupy", "h5py", "tensorflow", "tensorflow.keras", "tensorflow.keras.layers"):
+    for name in ("cupy", "h5py", "tensorflow", "tensorflow.keras", "tensorflow.keras.layers") + _VOID_STUBS:
         m = sys.modules.get(name)
         if m is not None and getattr(m, "__tomoenc_stub__", False):
             del sys.modules[name]
@@ -70,6 +74,18 @@ def load():
         ns.RefPatches = _load("tomo_encoders/structures/patches.py", "_ref_patches").Patches
         ns.RefGrid = _load("tomo_encoders/structures/grid.py", "_ref_grid").Grid
         ns.ref_voxel = _load("tomo_encoders/misc/voxel_processing.py", "_ref_voxel")
+        # structures/voids.py (count_voids / import_from_grid / export_grid): its module-level imports of cupyx, tifffile,
+        # skimage and of the tomo_encoders package itself are satisfied by stubs that hand it the reference's own Grid
+        from scipy.ndimage import label as _label_np
+        _stub("cupyx"); _stub("cupyx.scipy"); _stub("cupyx.scipy.ndimage", label=_label_np)
+        _stub("tifffile", imsave=None, imread=None)
+        _stub("skimage"); _stub("skimage.measure", marching_cubes=None)
+        _stub("tomo_encoders", Grid=ns.RefGrid)
+        _stub("tomo_encoders.misc")
+        _stub("tomo_encoders.misc.voxel_processing", TimerGPU=getattr(ns.ref_voxel, "TimerGPU", None),
+              TimerCPU=getattr(ns.ref_voxel, "TimerCPU", None))
+        _stub("tomo_encoders.misc.ellipse_rad_max", get_all_max_ellip_rad=None)
+        ns.RefVoids = _load("tomo_encoders/structures/voids.py", "_ref_voids").Voids
     finally:
         _remove_stubs()
     _cache["ns"] = ns

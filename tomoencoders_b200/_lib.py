@@ -171,6 +171,12 @@ _SIGNATURES = {
     "te_tr_bn_finalize": (ctypes.c_int, [_P, _I32, _D, _P, _P, _F, _P, _P, _P, _P, _P, _P]),
     "te_tr_bn_bwd_finalize": (ctypes.c_int, [_P, _P, _I32, _D, _P, _P, _P, _P, _P]),
     "te_tr_take_stats": (ctypes.c_int, [_P, _I32, _I32, _P, _P]),
+    "te_label_workspace_bytes": (_I64, [_I64]),
+    "te_label": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_I64), ctypes.c_int, _P, _P, _P, _P]),
+    "te_label_stats": (ctypes.c_int, [_P, ctypes.POINTER(_I64), _I64, _P, _P, _P]),
+    "te_label_crop_masks": (ctypes.c_int, [_P, ctypes.POINTER(_I64), _P, _P, _I64, _P, _I64, _P, _P]),
+    "te_paint_boxes": (ctypes.c_int, [_P, _P, _P, _I64, _I64, _P, ctypes.POINTER(_I64), _P, _P]),
+    "te_tile_any": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_I64), _I32, _P, _P]),
     "te_tr_adam": (ctypes.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I64, _F, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

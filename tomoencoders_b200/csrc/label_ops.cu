@@ -1,0 +1,408 @@
+// Post-stitch labelling: connected components of the segmented mask, per-component
+// bounding boxes / sizes, component masks, and the sparse tile selection that feeds the next (finer) pass of the path.
+// Replaces cupyx.scipy.ndimage.label / scipy.ndimage.find_objects as used by the reference
+// (/root/reference/tomo_encoders/tasks/digital_zoom.py:41-43, structures/voids.py:188-303, 356-373).
+//
+// Labelling = lock-free union-find over the voxel lattice (HBM-bound integer work, no tensor cores):
+//   init      parent[v] = v for foreground voxels, -1 for background
+//   merge     every foreground voxel is united with its foreground neighbours of smaller linear index (13 of the 26
+//             neighbours, 3 of the 6); the union always hangs the larger root under the smaller one (atomicMin), so the root
+//             of a component is its FIRST voxel in C order
+//   compress  parent[v] = root(v)
+//   number    roots are numbered 1..n in C order by a block-wise prefix sum -> scipy.ndimage.label's numbering
+// int32 indices: volumes up to 2^31 - 1 voxels (the reference labels binned maps; 1024^3 fits).
+#include "te_common.cuh"
+
+namespace te {
+namespace {
+
+constexpr int kScanItems = 4096;            // voxels per block in the numbering passes (256 threads x 16)
+
+struct Dim3 { int Z, Y, X; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) label_init_kernel(const T* __restrict__ vol, int* __restrict__ parent, long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    parent[i] = vol[i] != T(0) ? static_cast<int>(i) : -1;
+}
+
+__device__ __forceinline__ int uf_find(const int* parent, int x) {
+  const volatile int* vp = parent;          // other threads re-parent roots concurrently: always re-read
+  int p = vp[x];
+  while (p != x) { x = p; p = vp[x]; }
+  return x;
+}
+__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
+  while (true) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    if (a < b) { const int t = a; a = b; b = t; }          // a > b: hang a under b
+    const int old = atomicMin(parent + a, b);
+    if (old == a) return;                                    // a was still a root: linked
+    a = old;                                                 // somebody re-parented a meanwhile: retry from there
+  }
+}
+
+// thread = one voxel; 26-connectivity: the 13 neighbours (dz, dy, dx) lexicographically below (0, 0, 0)
+template <int CONN>
+__global__ void __launch_bounds__(256) label_merge_kernel(int* parent, Dim3 d) {
+  const long long n = static_cast<long long>(d.Z) * d.Y * d.X;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (parent[i] < 0) continue;
+    const int x = static_cast<int>(i % d.X);
+    const long long t = i / d.X;
+    const int y = static_cast<int>(t % d.Y), z = static_cast<int>(t / d.Y);
+    if (CONN == 6) {
+      if (x > 0 && parent[i - 1] >= 0) uf_union(parent, static_cast<int>(i), static_cast<int>(i - 1));
+      if (y > 0 && parent[i - d.X] >= 0) uf_union(parent, static_cast<int>(i), static_cast<int>(i - d.X));
+      if (z > 0 && parent[i - static_cast<long long>(d.Y) * d.X] >= 0)
+        uf_union(parent, static_cast<int>(i), static_cast<int>(i - static_cast<long long>(d.Y) * d.X));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 13; ++k) {
+        const int dz = k < 9 ? -1 : 0;
+        const int dy = k < 9 ? k / 3 - 1 : (k < 12 ? -1 : 0);
+        const int dx = k < 9 ? k % 3 - 1 : (k < 12 ? k - 10 : -1);
+        const int zz = z + dz, yy = y + dy, xx = x + dx;
+        if (zz < 0 || yy < 0 || yy >= d.Y || xx < 0 || xx >= d.X) continue;
+        const long long j = (static_cast<long long>(zz) * d.Y + yy) * d.X + xx;
+        if (parent[j] >= 0) uf_union(parent, static_cast<int>(i), static_cast<int>(j));
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) label_compress_kernel(int* parent, long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    if (parent[i] >= 0) parent[i] = uf_find(parent, static_cast<int>(i));
+}
+
+// block b owns voxels [b * kScanItems, (b + 1) * kScanItems); thread t owns 16 consecutive ones
+__device__ __forceinline__ int count_roots16(const int* parent, long long base, long long n) {
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const long long i = base + k;
+    c += (i < n && parent[i] == static_cast<int>(i)) ? 1 : 0;
+  }
+  return c;
+}
+__global__ void __launch_bounds__(256) label_count_kernel(const int* __restrict__ parent, long long n, int* __restrict__ counts) {
+  __shared__ int ws[8];
+  int c = count_roots16(parent, static_cast<long long>(blockIdx.x) * kScanItems + threadIdx.x * 16, n);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int w = 0; w < 8; ++w) tot += ws[w];
+    counts[blockIdx.x] = tot;
+  }
+}
+// exclusive scan of the block counts in place (one CTA walks the array with a running carry); n_labels = total
+__global__ void __launch_bounds__(1024) label_scan_kernel(int* counts, int nblocks, long long* n_labels) {
+  __shared__ int ws[32];
+  __shared__ int carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < nblocks; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < nblocks ? counts[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((threadIdx.x & 31) >= o) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = ws[threadIdx.x];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, o);
+        if (threadIdx.x >= o) w += t;
+      }
+      ws[threadIdx.x] = w;
+    }
+    __syncthreads();
+    const int warp_off = (threadIdx.x >> 5) ? ws[(threadIdx.x >> 5) - 1] : 0;
+    const int carry = carry_s;
+    if (i < nblocks) counts[i] = carry + warp_off + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + warp_off + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_labels = carry_s;
+}
+// roots get their rank (1-based, C order)
+__global__ void __launch_bounds__(256) label_rank_kernel(const int* __restrict__ parent, long long n, const int* __restrict__ offsets,
+                                                          int* __restrict__ labels) {
+  __shared__ int ws[8];
+  const long long base = static_cast<long long>(blockIdx.x) * kScanItems + threadIdx.x * 16;
+  const int c = count_roots16(parent, base, n);
+  int incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((threadIdx.x & 31) >= o) incl += t;
+  }
+  if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  int off = offsets[blockIdx.x] + incl - c;
+  for (int w = 0; w < (threadIdx.x >> 5); ++w) off += ws[w];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const long long i = base + k;
+    if (i < n && parent[i] == static_cast<int>(i)) labels[i] = ++off;
+  }
+}
+// everything else reads its root's rank
+__global__ void __launch_bounds__(256) label_assign_kernel(const int* __restrict__ parent, long long n, int* __restrict__ labels) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int p = parent[i];
+    if (p < 0) labels[i] = 0;
+    else if (p != static_cast<int>(i)) labels[i] = labels[p];       // roots were written by the rank kernel of an earlier launch
+  }
+}
+
+// ---- per-label bounding boxes (find_objects) and voxel counts.  A thread walks 32 consecutive x of one row and flushes a
+// run of equal labels with one set of atomics (components are mostly runs along x).
+__global__ void __launch_bounds__(256) bbox_init_kernel(int* bbox, long long* sizes, long long n_labels) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_labels; i += stride) {
+    bbox[6 * i + 0] = bbox[6 * i + 1] = bbox[6 * i + 2] = 0x7fffffff;
+    bbox[6 * i + 3] = bbox[6 * i + 4] = bbox[6 * i + 5] = 0;
+    sizes[i] = 0;
+  }
+}
+__device__ __forceinline__ void bbox_flush(int* bbox, long long* sizes, int lab, int z, int y, int x0, int x1) {
+  int* b = bbox + 6LL * (lab - 1);
+  atomicMin(b + 0, z); atomicMin(b + 1, y); atomicMin(b + 2, x0);
+  atomicMax(b + 3, z + 1); atomicMax(b + 4, y + 1); atomicMax(b + 5, x1 + 1);
+  atomicAdd(reinterpret_cast<unsigned long long*>(sizes + (lab - 1)), static_cast<unsigned long long>(x1 - x0 + 1));
+}
+__global__ void __launch_bounds__(256) bbox_kernel(const int* __restrict__ labels, Dim3 d, long long n_labels, int* bbox, long long* sizes) {
+  const int segs = (d.X + 31) / 32;
+  const long long items = static_cast<long long>(d.Z) * d.Y * segs;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long it = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; it < items; it += stride) {
+    const int sg = static_cast<int>(it % segs);
+    const long long row = it / segs;
+    const int y = static_cast<int>(row % d.Y), z = static_cast<int>(row / d.Y);
+    const int xa = sg * 32, xb = min(d.X, xa + 32);
+    const int* r = labels + row * d.X;
+    int cur = 0, x0 = 0;
+    for (int x = xa; x < xb; ++x) {
+      const int l = r[x];
+      if (l != cur) {
+        if (cur > 0 && cur <= n_labels) bbox_flush(bbox, sizes, cur, z, y, x0, x - 1);
+        cur = l; x0 = x;
+      }
+    }
+    if (cur > 0 && cur <= n_labels) bbox_flush(bbox, sizes, cur, z, y, x0, xb - 1);
+  }
+}
+
+// ---- component masks: out[offsets[i] + local] = labels[box_i voxel] == ids[i]   (x_voids of Voids.count_voids)
+__global__ void __launch_bounds__(256) crop_masks_kernel(const int* __restrict__ labels, Dim3 d, const int* __restrict__ boxes,
+                                                          const int* __restrict__ ids, const long long* __restrict__ offsets,
+                                                          uint8_t* __restrict__ out) {
+  const int i = blockIdx.y;
+  const int* b = boxes + 6 * i;
+  const int wz = b[3] - b[0], wy = b[4] - b[1], wx = b[5] - b[2];
+  const long long nv = static_cast<long long>(wz) * wy * wx;
+  const int id = ids[i];
+  uint8_t* o = out + offsets[i];
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < nv; e += stride) {
+    const int x = static_cast<int>(e % wx);
+    const long long t = e / wx;
+    const int y = static_cast<int>(t % wy), z = static_cast<int>(t / wy);
+    o[e] = labels[(static_cast<long long>(b[0] + z) * d.Y + b[1] + y) * d.X + b[2] + x] == id ? 1 : 0;
+  }
+}
+
+// ---- V[box_i] = mask_i for i = 0..n-1 IN ORDER (numpy slice assignment: a later box overwrites an earlier one, zeros
+// included).  Pass 0: owner[v] = max over boxes covering v of (i + 1); pass 1: the owner writes.
+template <int PASS>
+__global__ void __launch_bounds__(256) paint_boxes_kernel(const uint8_t* __restrict__ masks, const long long* __restrict__ offsets,
+                                                           const int* __restrict__ boxes, Dim3 d, uint8_t* vol, unsigned* owner) {
+  const int i = blockIdx.y;
+  const int* b = boxes + 6 * i;
+  const int wz = b[3] - b[0], wy = b[4] - b[1], wx = b[5] - b[2];
+  const long long nv = static_cast<long long>(wz) * wy * wx;
+  const uint8_t* m = masks + offsets[i];
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < nv; e += stride) {
+    const int x = static_cast<int>(e % wx);
+    const long long t = e / wx;
+    const int y = static_cast<int>(t % wy), z = static_cast<int>(t / wy);
+    const long long v = (static_cast<long long>(b[0] + z) * d.Y + b[1] + y) * d.X + b[2] + x;
+    if (PASS == 0) atomicMax(owner + v, static_cast<unsigned>(i + 1));
+    else if (owner[v] == static_cast<unsigned>(i + 1)) vol[v] = m[e];
+  }
+}
+
+// ---- flags[tile] = 1 if any voxel of the wd^3 tile of the regular grid is non-zero (tiles z-major, like Grid.points)
+template <int ES>
+__global__ void __launch_bounds__(256) tile_any_kernel(const uint8_t* __restrict__ vol, Dim3 d, int wd, uint8_t* flags) {
+  const int ty = d.Y / wd, tx = d.X / wd, tz = d.Z / wd;
+  const long long n = static_cast<long long>(d.Z) * d.Y * d.X;
+  const long long items = (n * ES + 15) / 16;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const bool vec = (reinterpret_cast<uintptr_t>(vol) & 15) == 0;
+  for (long long it = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; it < items; it += stride) {
+    const long long e0 = it * (16 / ES);
+    const int cnt = static_cast<int>(min(static_cast<long long>(16 / ES), n - e0));
+    bool any = false;
+    if (vec && cnt == 16 / ES) {
+      const uint4 w = *reinterpret_cast<const uint4*>(vol + it * 16);
+      any = (w.x | w.y | w.z | w.w) != 0;
+    } else {
+      for (int k = 0; k < cnt * ES; ++k) any |= vol[e0 * ES + k] != 0;
+    }
+    if (!any) continue;
+    for (int k = 0; k < cnt; ++k) {
+      bool nz = false;
+      for (int bb = 0; bb < ES; ++bb) nz |= vol[(e0 + k) * ES + bb] != 0;
+      if (!nz) continue;
+      const long long e = e0 + k;
+      const int x = static_cast<int>(e % d.X);
+      const long long t = e / d.X;
+      const int y = static_cast<int>(t % d.Y), z = static_cast<int>(t / d.Y);
+      const int a = z / wd, b = y / wd, c = x / wd;
+      if (a < tz && b < ty && c < tx) flags[(static_cast<long long>(a) * ty + b) * tx + c] = 1;
+    }
+  }
+}
+
+inline int grid_for(long long items, int threads) {
+  long long b = (items + threads - 1) / threads;
+  const long long cap = static_cast<long long>(kNumSMs) * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+}  // namespace
+}  // namespace te
+
+using namespace te;
+
+extern "C" int64_t te_label_workspace_bytes(int64_t nvox) {
+  if (nvox < 0) return 0;
+  return nvox * 4 + ((nvox + kScanItems - 1) / kScanItems + 1) * 4 + 256;
+}
+
+extern "C" int te_label(const void* vol, int vol_dtype, const int64_t vol_shape[3], int connectivity, int32_t* labels,
+                        int64_t* n_labels, void* workspace, void* stream) {
+  TE_CHECK_ARG(vol_shape[0] >= 0 && vol_shape[1] >= 0 && vol_shape[2] >= 0, "te_label: negative shape");
+  const long long n = static_cast<long long>(vol_shape[0]) * vol_shape[1] * vol_shape[2];
+  TE_CHECK_ARG(n < 2147483647LL, "te_label: volumes of up to 2^31 - 1 voxels are supported");
+  TE_CHECK_ARG(connectivity == 6 || connectivity == 26, "te_label: connectivity must be 6 (faces) or 26 (faces, edges, corners)");
+  TE_CHECK_ARG(n_labels, "te_label: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n == 0) { TE_CUDA(cudaMemsetAsync(n_labels, 0, 8, st)); return TE_OK; }
+  TE_CHECK_ARG(vol && labels && workspace, "te_label: null pointer");
+  const int es = dtype_size(vol_dtype);
+  TE_CHECK_ARG(es == 1 || es == 2 || es == 4, "te_label: unsupported vol_dtype %d", vol_dtype);
+  int* parent = static_cast<int*>(workspace);
+  int* counts = parent + n;
+  const Dim3 d{static_cast<int>(vol_shape[0]), static_cast<int>(vol_shape[1]), static_cast<int>(vol_shape[2])};
+  const int g = grid_for(n, 256);
+  // non-zero test on the raw bits (-0.0 would count as foreground; masks and label images never hold it)
+  if (es == 1) label_init_kernel<uint8_t><<<g, 256, 0, st>>>(static_cast<const uint8_t*>(vol), parent, n);
+  else if (es == 2) label_init_kernel<uint16_t><<<g, 256, 0, st>>>(static_cast<const uint16_t*>(vol), parent, n);
+  else label_init_kernel<uint32_t><<<g, 256, 0, st>>>(static_cast<const uint32_t*>(vol), parent, n);
+  TE_LAUNCH_CHECK();
+  if (connectivity == 6) label_merge_kernel<6><<<g, 256, 0, st>>>(parent, d);
+  else label_merge_kernel<26><<<g, 256, 0, st>>>(parent, d);
+  TE_LAUNCH_CHECK();
+  label_compress_kernel<<<g, 256, 0, st>>>(parent, n);
+  TE_LAUNCH_CHECK();
+  const int nblocks = static_cast<int>((n + kScanItems - 1) / kScanItems);
+  label_count_kernel<<<nblocks, 256, 0, st>>>(parent, n, counts);
+  TE_LAUNCH_CHECK();
+  label_scan_kernel<<<1, 1024, 0, st>>>(counts, nblocks, reinterpret_cast<long long*>(n_labels));
+  TE_LAUNCH_CHECK();
+  label_rank_kernel<<<nblocks, 256, 0, st>>>(parent, n, counts, labels);
+  TE_LAUNCH_CHECK();
+  label_assign_kernel<<<g, 256, 0, st>>>(parent, n, labels);
+  TE_LAUNCH_CHECK();
+  return TE_OK;
+}
+
+extern "C" int te_label_stats(const int32_t* labels, const int64_t vol_shape[3], int64_t n_labels, int32_t* bbox6, int64_t* sizes,
+                              void* stream) {
+  TE_CHECK_ARG(n_labels >= 0, "te_label_stats: n_labels < 0");
+  if (n_labels == 0) return TE_OK;
+  TE_CHECK_ARG(labels && bbox6 && sizes, "te_label_stats: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Dim3 d{static_cast<int>(vol_shape[0]), static_cast<int>(vol_shape[1]), static_cast<int>(vol_shape[2])};
+  bbox_init_kernel<<<grid_for(n_labels, 256), 256, 0, st>>>(bbox6, reinterpret_cast<long long*>(sizes), n_labels);
+  TE_LAUNCH_CHECK();
+  const long long items = static_cast<long long>(d.Z) * d.Y * ((d.X + 31) / 32);
+  if (items > 0) {
+    bbox_kernel<<<grid_for(items, 256), 256, 0, st>>>(labels, d, n_labels, bbox6, reinterpret_cast<long long*>(sizes));
+    TE_LAUNCH_CHECK();
+  }
+  return TE_OK;
+}
+
+extern "C" int te_label_crop_masks(const int32_t* labels, const int64_t vol_shape[3], const int32_t* boxes6, const int32_t* ids,
+                                   int64_t n, const int64_t* offsets, int64_t max_box_voxels, uint8_t* out, void* stream) {
+  TE_CHECK_ARG(n >= 0 && n <= 65535 * 1LL, "te_label_crop_masks: n must be in [0, 65535] per call");
+  if (n == 0 || max_box_voxels <= 0) return TE_OK;
+  TE_CHECK_ARG(labels && boxes6 && ids && offsets && out, "te_label_crop_masks: null pointer");
+  const Dim3 d{static_cast<int>(vol_shape[0]), static_cast<int>(vol_shape[1]), static_cast<int>(vol_shape[2])};
+  long long gx = (max_box_voxels + 255) / 256;
+  if (gx > 256) gx = 256;
+  crop_masks_kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      labels, d, boxes6, ids, reinterpret_cast<const long long*>(offsets), out);
+  TE_LAUNCH_CHECK();
+  return TE_OK;
+}
+
+extern "C" int te_paint_boxes(const uint8_t* masks, const int64_t* offsets, const int32_t* boxes6, int64_t n, int64_t max_box_voxels,
+                              uint8_t* vol, const int64_t vol_shape[3], uint32_t* owner, void* stream) {
+  TE_CHECK_ARG(n >= 0 && n <= 65535 * 1LL, "te_paint_boxes: n must be in [0, 65535] per call");
+  if (n == 0 || max_box_voxels <= 0) return TE_OK;
+  TE_CHECK_ARG(masks && offsets && boxes6 && vol && owner, "te_paint_boxes: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Dim3 d{static_cast<int>(vol_shape[0]), static_cast<int>(vol_shape[1]), static_cast<int>(vol_shape[2])};
+  const long long nvox = static_cast<long long>(d.Z) * d.Y * d.X;
+  TE_CUDA(cudaMemsetAsync(owner, 0, static_cast<size_t>(nvox) * 4, st));
+  long long gx = (max_box_voxels + 255) / 256;
+  if (gx > 256) gx = 256;
+  const dim3 g(static_cast<unsigned>(gx), static_cast<unsigned>(n));
+  paint_boxes_kernel<0><<<g, 256, 0, st>>>(masks, reinterpret_cast<const long long*>(offsets), boxes6, d, vol, owner);
+  TE_LAUNCH_CHECK();
+  paint_boxes_kernel<1><<<g, 256, 0, st>>>(masks, reinterpret_cast<const long long*>(offsets), boxes6, d, vol, owner);
+  TE_LAUNCH_CHECK();
+  return TE_OK;
+}
+
+extern "C" int te_tile_any(const void* vol, int elem_size, const int64_t vol_shape[3], int32_t width, uint8_t* flags, void* stream) {
+  TE_CHECK_ARG(elem_size == 1 || elem_size == 2 || elem_size == 4, "te_tile_any: elem_size must be 1, 2 or 4");
+  TE_CHECK_ARG(width > 0, "te_tile_any: width must be positive");
+  const Dim3 d{static_cast<int>(vol_shape[0]), static_cast<int>(vol_shape[1]), static_cast<int>(vol_shape[2])};
+  const long long ntiles = static_cast<long long>(d.Z / width) * (d.Y / width) * (d.X / width);
+  const long long n = static_cast<long long>(d.Z) * d.Y * d.X;
+  if (ntiles == 0 || n == 0) return TE_OK;
+  TE_CHECK_ARG(vol && flags, "te_tile_any: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TE_CUDA(cudaMemsetAsync(flags, 0, static_cast<size_t>(ntiles), st));
+  const long long items = (n * elem_size + 15) / 16;
+  const uint8_t* v = static_cast<const uint8_t*>(vol);
+  if (elem_size == 1) tile_any_kernel<1><<<grid_for(items, 256), 256, 0, st>>>(v, d, width, flags);
+  else if (elem_size == 2) tile_any_kernel<2><<<grid_for(items, 256), 256, 0, st>>>(v, d, width, flags);
+  else tile_any_kernel<4><<<grid_for(items, 256), 256, 0, st>>>(v, d, width, flags);
+  TE_LAUNCH_CHECK();
+  return TE_OK;
+}
