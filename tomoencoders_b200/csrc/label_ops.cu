@@ -20,17 +20,40 @@ constexpr int kScanItems = 4096;            // voxels per block in the numbering
 
 struct Dim3 { int Z, Y, X; };
 
+// item = 32 consecutive x of one row (one warp): a foreground voxel starts under the first voxel of its run inside the
+// 32-group (ballot + bit scan, no atomics), so the merge pass only has to stitch runs together
 template <typename T>
-__global__ void __launch_bounds__(256) label_init_kernel(const T* __restrict__ vol, int* __restrict__ parent, long long n) {
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
-    parent[i] = vol[i] != T(0) ? static_cast<int>(i) : -1;
+__global__ void __launch_bounds__(256) label_init_kernel(const T* __restrict__ vol, int* __restrict__ parent, Dim3 d) {
+  const int segs = (d.X + 31) / 32;
+  const long long items = static_cast<long long>(d.Z) * d.Y * segs;
+  const int lane = threadIdx.x & 31;
+  const long long wstride = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long it = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; it < items; it += wstride) {
+    const int sg = static_cast<int>(it % segs);
+    const long long row = it / segs;
+    const int x = sg * 32 + lane;
+    const long long i = row * d.X + x;
+    const bool fg = x < d.X && vol[i] != T(0);
+    const unsigned m = __ballot_sync(0xffffffffu, fg);
+    if (x < d.X) {
+      const unsigned below = ~m & ((1u << lane) - 1u);               // background voxels to my left inside the group
+      const int start = below ? 32 - __clz(below) : 0;
+      parent[i] = fg ? static_cast<int>(row * d.X + sg * 32 + start) : -1;
+    }
+  }
 }
 
-__device__ __forceinline__ int uf_find(const int* parent, int x) {
-  const volatile int* vp = parent;          // other threads re-parent roots concurrently: always re-read
+// Plain (L1-cached) loads on purpose: a stale parent is still an older ancestor, a stale "root" is caught by the atomicMin
+// of uf_union (performed on the live value in L2, its return value is fresh), and every step moves to a smaller index, so
+// the walk terminates; the hot roots of big components are then served by L1 instead of hammering one L2 line.
+__device__ __forceinline__ int uf_find(int* parent, int x) {
+  int* vp = parent;
   int p = vp[x];
-  while (p != x) { x = p; p = vp[x]; }
+  while (p != x) {
+    const int g = vp[p];
+    if (g != p) vp[x] = g;                  // path halving: any ancestor is a valid parent (values only ever decrease)
+    x = p; p = g;
+  }
   return x;
 }
 __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
@@ -45,40 +68,56 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
   }
 }
 
-// thread = one voxel; 26-connectivity: the 13 neighbours (dz, dy, dx) lexicographically below (0, 0, 0)
+// thread = one voxel.  Neighbour rows above / behind: (dz, dy) in {(-1,-1), (-1,0), (-1,1), (0,-1)} with dx in {-1,0,1}
+// (26-connectivity) or (-1,0), (0,-1) with dx = 0 (6-connectivity); the x neighbour only matters across 32-groups.
+// A union (i, j) is skipped when it is implied by others: j's left neighbour also touches i (same run of row'), or both
+// left neighbours are foreground (the pair (i-1, j-1) makes the same link; induction on x).
 template <int CONN>
 __global__ void __launch_bounds__(256) label_merge_kernel(int* parent, Dim3 d) {
   const long long n = static_cast<long long>(d.Z) * d.Y * d.X;
+  const long long plane = static_cast<long long>(d.Y) * d.X;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     if (parent[i] < 0) continue;
     const int x = static_cast<int>(i % d.X);
     const long long t = i / d.X;
     const int y = static_cast<int>(t % d.Y), z = static_cast<int>(t / d.Y);
-    if (CONN == 6) {
-      if (x > 0 && parent[i - 1] >= 0) uf_union(parent, static_cast<int>(i), static_cast<int>(i - 1));
-      if (y > 0 && parent[i - d.X] >= 0) uf_union(parent, static_cast<int>(i), static_cast<int>(i - d.X));
-      if (z > 0 && parent[i - static_cast<long long>(d.Y) * d.X] >= 0)
-        uf_union(parent, static_cast<int>(i), static_cast<int>(i - static_cast<long long>(d.Y) * d.X));
-    } else {
+    const bool left = x > 0 && parent[i - 1] >= 0;
+    if (left && (x & 31) == 0) uf_union(parent, static_cast<int>(i), static_cast<int>(i - 1));
 #pragma unroll
-      for (int k = 0; k < 13; ++k) {
-        const int dz = k < 9 ? -1 : 0;
-        const int dy = k < 9 ? k / 3 - 1 : (k < 12 ? -1 : 0);
-        const int dx = k < 9 ? k % 3 - 1 : (k < 12 ? k - 10 : -1);
-        const int zz = z + dz, yy = y + dy, xx = x + dx;
-        if (zz < 0 || yy < 0 || yy >= d.Y || xx < 0 || xx >= d.X) continue;
-        const long long j = (static_cast<long long>(zz) * d.Y + yy) * d.X + xx;
-        if (parent[j] >= 0) uf_union(parent, static_cast<int>(i), static_cast<int>(j));
+    for (int r = 0; r < 4; ++r) {
+      const int dz = r < 3 ? -1 : 0, dy = r < 3 ? r - 1 : -1;
+      if (CONN == 6 && !((dz == -1 && dy == 0) || (dz == 0 && dy == -1))) continue;
+      const int zz = z + dz, yy = y + dy;
+      if (zz < 0 || yy < 0 || yy >= d.Y) continue;
+      const long long jb = i + dz * plane + static_cast<long long>(dy) * d.X;     // same x in the neighbour row
+      if (CONN == 6) {
+        if (parent[jb] >= 0 && !(left && parent[jb - 1] >= 0)) uf_union(parent, static_cast<int>(i), static_cast<int>(jb));
+      } else {
+        const bool f2 = x > 1 && parent[jb - 2] >= 0;
+        const bool fm = x > 0 && parent[jb - 1] >= 0;
+        const bool f0 = parent[jb] >= 0;
+        const bool fp = x + 1 < d.X && parent[jb + 1] >= 0;
+        if (fm && !(left && f2)) uf_union(parent, static_cast<int>(i), static_cast<int>(jb - 1));
+        if (f0 && !fm && !(left && fm)) uf_union(parent, static_cast<int>(i), static_cast<int>(jb));
+        if (fp && !f0 && !(left && f0)) uf_union(parent, static_cast<int>(i), static_cast<int>(jb + 1));
       }
     }
   }
 }
 
+// Read-only walk to the root (the merge pass is over: the forest is final).  No path halving here: a late halving store of
+// another thread could overwrite parent[i] = root with a mere ancestor, and the numbering pass needs roots.
 __global__ void __launch_bounds__(256) label_compress_kernel(int* parent, long long n) {
+  const int* vp = parent;                   // the forest is final: parent[] only changes to roots here, which a walk also accepts
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
-    if (parent[i] >= 0) parent[i] = uf_find(parent, static_cast<int>(i));
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int x = vp[i];
+    if (x < 0) continue;
+    int q = vp[x];
+    while (q != x) { x = q; q = vp[x]; }
+    parent[i] = x;
+  }
 }
 
 // block b owns voxels [b * kScanItems, (b + 1) * kScanItems); thread t owns 16 consecutive ones
@@ -182,31 +221,66 @@ __global__ void __launch_bounds__(256) bbox_init_kernel(int* bbox, long long* si
     sizes[i] = 0;
   }
 }
-__device__ __forceinline__ void bbox_flush(int* bbox, long long* sizes, int lab, int z, int y, int x0, int x1) {
+__device__ __forceinline__ void bbox_flush(int* bbox, long long* sizes, int lab, int z0, int y0, int x0, int z1, int y1, int x1,
+                                           unsigned long long cnt) {
   int* b = bbox + 6LL * (lab - 1);
-  atomicMin(b + 0, z); atomicMin(b + 1, y); atomicMin(b + 2, x0);
-  atomicMax(b + 3, z + 1); atomicMax(b + 4, y + 1); atomicMax(b + 5, x1 + 1);
-  atomicAdd(reinterpret_cast<unsigned long long*>(sizes + (lab - 1)), static_cast<unsigned long long>(x1 - x0 + 1));
+  atomicMin(b + 0, z0); atomicMin(b + 1, y0); atomicMin(b + 2, x0);
+  atomicMax(b + 3, z1); atomicMax(b + 4, y1); atomicMax(b + 5, x1);
+  atomicAdd(reinterpret_cast<unsigned long long*>(sizes + (lab - 1)), cnt);
 }
+// A thread walks 32 consecutive x of one row and emits one record per run of equal labels.  Records first go to a
+// 256-entry hash table in shared memory (a block covers a few neighbouring rows, i.e. a handful of labels; shared-memory
+// atomics absorb the hot labels), the table is flushed with one set of global atomics per label and block; a full table
+// falls back to global atomics.
+constexpr int kTab = 256;
 __global__ void __launch_bounds__(256) bbox_kernel(const int* __restrict__ labels, Dim3 d, long long n_labels, int* bbox, long long* sizes) {
+  __shared__ int t_lab[kTab];
+  __shared__ int t_box[kTab][6];
+  __shared__ unsigned long long t_cnt[kTab];
   const int segs = (d.X + 31) / 32;
   const long long items = static_cast<long long>(d.Z) * d.Y * segs;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long it = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; it < items; it += stride) {
-    const int sg = static_cast<int>(it % segs);
-    const long long row = it / segs;
-    const int y = static_cast<int>(row % d.Y), z = static_cast<int>(row / d.Y);
-    const int xa = sg * 32, xb = min(d.X, xa + 32);
-    const int* r = labels + row * d.X;
-    int cur = 0, x0 = 0;
-    for (int x = xa; x < xb; ++x) {
-      const int l = r[x];
-      if (l != cur) {
-        if (cur > 0 && cur <= n_labels) bbox_flush(bbox, sizes, cur, z, y, x0, x - 1);
+  const long long per_block = 256LL * 8;
+  for (long long base = static_cast<long long>(blockIdx.x) * per_block; base < items; base += static_cast<long long>(gridDim.x) * per_block) {
+    for (int k = threadIdx.x; k < kTab; k += 256) {
+      t_lab[k] = 0; t_cnt[k] = 0;
+      t_box[k][0] = t_box[k][1] = t_box[k][2] = 0x7fffffff;
+      t_box[k][3] = t_box[k][4] = t_box[k][5] = 0;
+    }
+    __syncthreads();
+    for (int q = 0; q < 8; ++q) {
+      const long long it = base + q * 256 + threadIdx.x;
+      if (it >= items) break;
+      const int sg = static_cast<int>(it % segs);
+      const long long row = it / segs;
+      const int y = static_cast<int>(row % d.Y), z = static_cast<int>(row / d.Y);
+      const int xa = sg * 32, xb = min(d.X, xa + 32);
+      const int* r = labels + row * d.X;
+      int cur = 0, x0 = 0;
+      for (int x = xa; x <= xb; ++x) {
+        const int l = x < xb ? r[x] : 0;
+        if (l == cur) continue;
+        if (cur > 0 && cur <= n_labels) {
+          // insert the run [x0, x) of label cur
+          unsigned h = (static_cast<unsigned>(cur) * 2654435761u) >> 24;      // 8-bit hash
+          bool done = false;
+          for (int probe = 0; probe < 8 && !done; ++probe, h = (h + 1) & (kTab - 1)) {
+            const int old = atomicCAS(&t_lab[h], 0, cur);
+            if (old == 0 || old == cur) {
+              atomicMin(&t_box[h][0], z); atomicMin(&t_box[h][1], y); atomicMin(&t_box[h][2], x0);
+              atomicMax(&t_box[h][3], z + 1); atomicMax(&t_box[h][4], y + 1); atomicMax(&t_box[h][5], x);
+              atomicAdd(&t_cnt[h], static_cast<unsigned long long>(x - x0));
+              done = true;
+            }
+          }
+          if (!done) bbox_flush(bbox, sizes, cur, z, y, x0, z + 1, y + 1, x, static_cast<unsigned long long>(x - x0));
+        }
         cur = l; x0 = x;
       }
     }
-    if (cur > 0 && cur <= n_labels) bbox_flush(bbox, sizes, cur, z, y, x0, xb - 1);
+    __syncthreads();
+    for (int k = threadIdx.x; k < kTab; k += 256)
+      if (t_lab[k] > 0) bbox_flush(bbox, sizes, t_lab[k], t_box[k][0], t_box[k][1], t_box[k][2], t_box[k][3], t_box[k][4], t_box[k][5], t_cnt[k]);
+    __syncthreads();
   }
 }
 
@@ -250,36 +324,27 @@ __global__ void __launch_bounds__(256) paint_boxes_kernel(const uint8_t* __restr
   }
 }
 
-// ---- flags[tile] = 1 if any voxel of the wd^3 tile of the regular grid is non-zero (tiles z-major, like Grid.points)
-template <int ES>
-__global__ void __launch_bounds__(256) tile_any_kernel(const uint8_t* __restrict__ vol, Dim3 d, int wd, uint8_t* flags) {
+// ---- flags[tile] = 1 if any voxel of the wd^3 tile of the regular grid is non-zero (tiles z-major, like Grid.points).
+// item = the wd * ES contiguous bytes of one tile in one row, OR-reduced with the widest aligned loads; adjacent threads
+// take adjacent tiles of the same row (coalesced).
+__global__ void __launch_bounds__(256) tile_any_kernel(const uint8_t* __restrict__ vol, Dim3 d, int wd, int es, uint8_t* flags) {
   const int ty = d.Y / wd, tx = d.X / wd, tz = d.Z / wd;
-  const long long n = static_cast<long long>(d.Z) * d.Y * d.X;
-  const long long items = (n * ES + 15) / 16;
+  const long long items = static_cast<long long>(tz) * wd * ty * wd * tx;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  const bool vec = (reinterpret_cast<uintptr_t>(vol) & 15) == 0;
+  const int nb = wd * es;
   for (long long it = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; it < items; it += stride) {
-    const long long e0 = it * (16 / ES);
-    const int cnt = static_cast<int>(min(static_cast<long long>(16 / ES), n - e0));
-    bool any = false;
-    if (vec && cnt == 16 / ES) {
-      const uint4 w = *reinterpret_cast<const uint4*>(vol + it * 16);
-      any = (w.x | w.y | w.z | w.w) != 0;
-    } else {
-      for (int k = 0; k < cnt * ES; ++k) any |= vol[e0 * ES + k] != 0;
-    }
-    if (!any) continue;
-    for (int k = 0; k < cnt; ++k) {
-      bool nz = false;
-      for (int bb = 0; bb < ES; ++bb) nz |= vol[(e0 + k) * ES + bb] != 0;
-      if (!nz) continue;
-      const long long e = e0 + k;
-      const int x = static_cast<int>(e % d.X);
-      const long long t = e / d.X;
-      const int y = static_cast<int>(t % d.Y), z = static_cast<int>(t / d.Y);
-      const int a = z / wd, b = y / wd, c = x / wd;
-      if (a < tz && b < ty && c < tx) flags[(static_cast<long long>(a) * ty + b) * tx + c] = 1;
-    }
+    const int c = static_cast<int>(it % tx);
+    const long long row = it / tx;
+    const int y = static_cast<int>(row % (static_cast<long long>(ty) * wd)), z = static_cast<int>(row / (static_cast<long long>(ty) * wd));
+    const uint8_t* p = vol + ((static_cast<long long>(z) * d.Y + y) * d.X + static_cast<long long>(c) * wd) * es;
+    unsigned acc = 0;
+    int k = 0;
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0)
+      for (; k + 16 <= nb; k += 16) { const uint4 w = *reinterpret_cast<const uint4*>(p + k); acc |= w.x | w.y | w.z | w.w; }
+    else if ((reinterpret_cast<uintptr_t>(p) & 3) == 0)
+      for (; k + 4 <= nb; k += 4) acc |= *reinterpret_cast<const unsigned*>(p + k);
+    for (; k < nb; ++k) acc |= p[k];
+    if (acc) flags[(static_cast<long long>(z / wd) * ty + y / wd) * tx + c] = 1;
   }
 }
 
@@ -317,9 +382,10 @@ extern "C" int te_label(const void* vol, int vol_dtype, const int64_t vol_shape[
   const Dim3 d{static_cast<int>(vol_shape[0]), static_cast<int>(vol_shape[1]), static_cast<int>(vol_shape[2])};
   const int g = grid_for(n, 256);
   // non-zero test on the raw bits (-0.0 would count as foreground; masks and label images never hold it)
-  if (es == 1) label_init_kernel<uint8_t><<<g, 256, 0, st>>>(static_cast<const uint8_t*>(vol), parent, n);
-  else if (es == 2) label_init_kernel<uint16_t><<<g, 256, 0, st>>>(static_cast<const uint16_t*>(vol), parent, n);
-  else label_init_kernel<uint32_t><<<g, 256, 0, st>>>(static_cast<const uint32_t*>(vol), parent, n);
+  const int gi = grid_for(static_cast<long long>(d.Z) * d.Y * ((d.X + 31) / 32) * 32, 256);
+  if (es == 1) label_init_kernel<uint8_t><<<gi, 256, 0, st>>>(static_cast<const uint8_t*>(vol), parent, d);
+  else if (es == 2) label_init_kernel<uint16_t><<<gi, 256, 0, st>>>(static_cast<const uint16_t*>(vol), parent, d);
+  else label_init_kernel<uint32_t><<<gi, 256, 0, st>>>(static_cast<const uint32_t*>(vol), parent, d);
   TE_LAUNCH_CHECK();
   if (connectivity == 6) label_merge_kernel<6><<<g, 256, 0, st>>>(parent, d);
   else label_merge_kernel<26><<<g, 256, 0, st>>>(parent, d);
@@ -349,7 +415,7 @@ extern "C" int te_label_stats(const int32_t* labels, const int64_t vol_shape[3],
   TE_LAUNCH_CHECK();
   const long long items = static_cast<long long>(d.Z) * d.Y * ((d.X + 31) / 32);
   if (items > 0) {
-    bbox_kernel<<<grid_for(items, 256), 256, 0, st>>>(labels, d, n_labels, bbox6, reinterpret_cast<long long*>(sizes));
+    bbox_kernel<<<grid_for((items + 7) / 8, 256), 256, 0, st>>>(labels, d, n_labels, bbox6, reinterpret_cast<long long*>(sizes));
     TE_LAUNCH_CHECK();
   }
   return TE_OK;
@@ -398,11 +464,8 @@ extern "C" int te_tile_any(const void* vol, int elem_size, const int64_t vol_sha
   TE_CHECK_ARG(vol && flags, "te_tile_any: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TE_CUDA(cudaMemsetAsync(flags, 0, static_cast<size_t>(ntiles), st));
-  const long long items = (n * elem_size + 15) / 16;
-  const uint8_t* v = static_cast<const uint8_t*>(vol);
-  if (elem_size == 1) tile_any_kernel<1><<<grid_for(items, 256), 256, 0, st>>>(v, d, width, flags);
-  else if (elem_size == 2) tile_any_kernel<2><<<grid_for(items, 256), 256, 0, st>>>(v, d, width, flags);
-  else tile_any_kernel<4><<<grid_for(items, 256), 256, 0, st>>>(v, d, width, flags);
+  const long long items = static_cast<long long>(d.Z / width) * width * (d.Y / width) * width * (d.X / width);
+  tile_any_kernel<<<grid_for(items, 256), 256, 0, st>>>(static_cast<const uint8_t*>(vol), d, width, elem_size, flags);
   TE_LAUNCH_CHECK();
   return TE_OK;
 }
