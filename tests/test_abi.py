@@ -39,12 +39,15 @@ def test_sass_contains_blackwell_instructions(built_lib):
     sass = subprocess.run(["cuobjdump", "-sass", built_lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass, "no tcgen05.mma in the library"
     assert "UTMALDG" in sass, "no TMA tensor loads in the library"
-    # legacy mma.sync is tolerated in exactly one place: the weight-gradient kernel of the training
-    # step (wgrad_mma_kernel); every forward / data-gradient conv is tcgen05
+    # legacy mma.sync is tolerated in exactly one place: wgrad_mma_kernel, the 1-tap product of the transposed-conv
+    # backward and the fallback for odd channel counts; every forward / data-gradient conv and
+    # the 3x3x3 weight gradient (wgrad_umma_kernel) are tcgen05
     legacy = set()
     for block in sass.split("Function : ")[1:]:
         name = block.split("\n", 1)[0]
         if "HMMA." in block.replace("UTCHMMA", ""):
             legacy.add(name)
     assert all("wgrad_mma_kernel" in n for n in legacy), "legacy mma.sync found in %s" % sorted(legacy)
-    assert not any("conv_umma_kernel" in n for n in legacy)
+    assert not any("conv_umma_kernel" in n or "wgrad_umma_kernel" in n for n in legacy)
+    umma = [b.split("\n", 1)[0] for b in sass.split("Function : ")[1:] if "UTCHMMA" in b]
+    assert any("wgrad_umma_kernel" in n for n in umma), "the weight-gradient kernel must be tcgen05 code"
