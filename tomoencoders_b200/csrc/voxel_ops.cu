@@ -132,29 +132,31 @@ __global__ void minmax_nd_final_kernel(const float* partial, int nblocks, float*
 // bin is closed (numpy/lib/_histograms_impl.py: the uniform-bin estimate followed by the correction
 // against the edges -- the corrected index IS this definition, so the estimate's rounding is free).
 // Values outside [edges[0], edges[nbins]] and NaNs are dropped, like numpy's `keep` mask.
+// All comparisons run in fp32 and are still EXACT: every supported element is a float, and for a float a and a double
+// edge e,  a >= e  <=>  a >= ru(e)  (ru = e rounded UP to float), hence a < e <=> a < ru(e); the closed upper end
+// a <= eN <=> a <= rd(eN).  No fp64 instruction in the element loop.
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) histogram_nd_kernel(View4 v, const double* __restrict__ edges, int nbins,
                                                            unsigned long long* __restrict__ counts) {
   extern __shared__ double hsm[];
-  double* ed = hsm;                                                     // nbins + 1 edges
-  unsigned int* hist = reinterpret_cast<unsigned int*>(ed + nbins + 1);  // 8 warps x nbins
-  for (int i = threadIdx.x; i <= nbins; i += blockDim.x) ed[i] = edges[i];
+  float* ed = reinterpret_cast<float*>(hsm);                            // nbins + 1 edges, rounded up
+  unsigned int* hist = reinterpret_cast<unsigned int*>(ed + nbins + 2);  // 8 warps x nbins
+  for (int i = threadIdx.x; i <= nbins; i += blockDim.x) ed[i] = __double2float_ru(edges[i]);
   for (int i = threadIdx.x; i < 8 * nbins; i += blockDim.x) hist[i] = 0u;
   __syncthreads();
-  const double e0 = ed[0], eN = ed[nbins];
-  const float e0f = static_cast<float>(e0);
-  const float scale = eN > e0 ? static_cast<float>(nbins / (eN - e0)) : 0.f;
+  const double e0d = edges[0], eNd = edges[nbins];
+  const float e0 = ed[0], eN = __double2float_rd(eNd);
+  const float scale = eNd > e0d ? static_cast<float>(nbins / (eNd - e0d)) : 0.f;
   unsigned int* mine = hist + (threadIdx.x >> 5) * nbins;
   // neighbouring voxels of a tomogram mostly fall into the same bin: a thread keeps the bin of its previous
   // element and a run count, and touches shared memory only when the bin changes
   int cur = -1;
   unsigned int run = 0;
-  double clo = 0.0, chi = 0.0;
-  for_each_elem<T, VEC>(v, [&](float af) {
-    const double a = static_cast<double>(af);          // every supported element type is exact in fp32
+  float clo = 0.f, chi = 0.f;
+  for_each_elem<T, VEC>(v, [&](float a) {
     if (cur >= 0 && a >= clo && a < chi) { ++run; return; }
     if (!(a >= e0 && a <= eN)) return;
-    int i = static_cast<int>((af - e0f) * scale);      // estimate; the comparisons below decide
+    int i = static_cast<int>((a - e0) * scale);        // estimate; the comparisons below decide
     i = i < 0 ? 0 : (i > nbins - 1 ? nbins - 1 : i);
     while (i > 0 && a < ed[i]) --i;
     while (i < nbins - 1 && a >= ed[i + 1]) ++i;
@@ -170,6 +172,61 @@ __global__ void __launch_bounds__(256) histogram_nd_kernel(View4 v, const double
     for (int w = 0; w < 8; ++w) s += hist[w * nbins + i];
     if (s) atomicAdd(counts + i, s);
   }
+}
+
+// uint8 volumes have 256 possible values: count them directly (per-warp privatised 256-entry tables, one shared-memory
+// atomic per element, no bin search), then thread k maps value k to its bin with the same exact comparisons.
+template <bool VEC>
+__global__ void __launch_bounds__(256) histogram_u8_kernel(View4 v, const double* __restrict__ edges, int nbins,
+                                                           unsigned long long* __restrict__ counts) {
+  __shared__ unsigned int hist[8][256];
+  for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) (&hist[0][0])[i] = 0u;
+  __syncthreads();
+  unsigned int* mine = hist[threadIdx.x >> 5];
+  const long long rows = v.n[0] * v.n[1] * v.n[2];
+  const uint8_t* base = v.base;
+  if (VEC && v.n[3] >= kSeg) {
+    // raw 16-byte words: four bytes at a time, equal neighbours merged before the atomic
+    const long long segs = (v.n[3] + kSeg - 1) / kSeg;
+    const long long units = rows * segs;
+    for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+      const long long row = u / segs, seg = u - row * segs;
+      const long long i2 = row % v.n[2], t = row / v.n[2];
+      const long long i1 = t % v.n[1], i0 = t / v.n[1];
+      const long long x0 = seg * kSeg;
+      const int len = static_cast<int>(v.n[3] - x0 < kSeg ? v.n[3] - x0 : kSeg);
+      const uint8_t* rp = base + i0 * v.st[0] + i1 * v.st[1] + i2 * v.st[2] + x0;
+      const int nvec = len / 16;
+      for (int c = threadIdx.x; c < nvec; c += blockDim.x) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(rp) + c);
+        const unsigned w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const unsigned b0 = w[k] & 255u, b1 = (w[k] >> 8) & 255u, b2 = (w[k] >> 16) & 255u, b3 = w[k] >> 24;
+          if (b0 == b1 && b1 == b2 && b2 == b3) { atomicAdd(mine + b0, 4u); continue; }
+          atomicAdd(mine + b0, 1u); atomicAdd(mine + b1, 1u); atomicAdd(mine + b2, 1u); atomicAdd(mine + b3, 1u);
+        }
+      }
+      for (int x = nvec * 16 + threadIdx.x; x < len; x += blockDim.x) atomicAdd(mine + rp[x], 1u);
+    }
+  } else {
+    for_each_elem<uint8_t, VEC>(v, [&](float a) { atomicAdd(mine + static_cast<int>(a), 1u); });
+  }
+  __syncthreads();
+  // thread k owns value k
+  const int k = threadIdx.x;
+  unsigned long long s = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += hist[w][k];
+  if (s == 0) return;
+  const double a = static_cast<double>(k);
+  const double e0 = edges[0], eN = edges[nbins];
+  if (!(a >= e0 && a <= eN)) return;
+  int i = eN > e0 ? static_cast<int>((a - e0) * (nbins / (eN - e0))) : 0;
+  i = i < 0 ? 0 : (i > nbins - 1 ? nbins - 1 : i);
+  while (i > 0 && a < edges[i]) --i;
+  while (i < nbins - 1 && a >= edges[i + 1]) ++i;
+  atomicAdd(counts + i, s);
 }
 
 // out = (in - lo) / denom in fp32 (IEEE round-to-nearest subtract and divide: bit-exact against numpy
@@ -429,7 +486,13 @@ extern "C" int te_histogram_nd(const void* data, int dtype, const int64_t shape[
   TE_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * nbins, st));
   if (view_units(v) == 0) return TE_OK;
   const int blocks = blocks_for(view_units(v), 1, 4);
-  const size_t smem = sizeof(double) * (nbins + 1) + sizeof(unsigned int) * 8 * nbins;
+  const size_t smem = sizeof(float) * (nbins + 2) + sizeof(unsigned int) * 8 * nbins;
+  if (dtype == TE_U8) {
+    if (vec) histogram_u8_kernel<true><<<blocks, 256, 0, st>>>(v, edges, nbins, counts);
+    else histogram_u8_kernel<false><<<blocks, 256, 0, st>>>(v, edges, nbins, counts);
+    TE_LAUNCH_CHECK();
+    return TE_OK;
+  }
   TE_DISPATCH_DTYPE(dtype, {
     if (vec) histogram_nd_kernel<T, true><<<blocks, 256, smem, st>>>(v, edges, nbins, counts);
     else histogram_nd_kernel<T, false><<<blocks, 256, smem, st>>>(v, edges, nbins, counts);
