@@ -45,7 +45,7 @@ VOL = (512, 512, 512)
 PATCH = 64
 CHUNK = 32
 ENC_PATCHES = 4096          # 64^3 patches encoded per rank per step in the "encode" leg
-CPU_TILES = 48              # bounded CPU sample of the same workload (10-30 s on the box's host cores)
+CPU_TILES = 64              # bounded CPU sample of the same workload: two FULL chunks (a partial chunk is padded to 32 by the reference)
 ENC_CHUNK = 128             # patches per encoder launch (the encoder keeps only pooled tensors: 128 patches = 1.3 GB)
 METRIC = "voxels/sec segmented (3-D U-net M_a01, 64^3 tiles of a 512^3 fp16 volume per GPU)"
 
@@ -135,7 +135,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_patches = 2
+    # one full chunk per step: the reference pads a partial last chunk to chunk_size (surface_segmenter.py:277-281),
+    # so a smaller sample would charge the CPU arm for 32 patches' worth of work while crediting it with fewer
+    n_patches = CHUNK
     times = []
     for i in range(args.warmup + args.steps):
         v, dt, threads = cpu_reference_leg(n_patches)
