@@ -342,6 +342,44 @@ int te_paint_boxes(const uint8_t* masks, const int64_t* offsets, const int32_t* 
 /* flags[tile] = 1 iff any voxel of the width^3 tile of Grid(vol_shape, width) is non-zero (tiles in Grid.points order). */
 int te_tile_any(const void* vol, int elem_size, const int64_t vol_shape[3], int32_t width, uint8_t* flags, void* stream);
 
+/* ---- filtered back-projection: replaces the CuPy RawKernels and cuFFT calls of
+ * /root/reference/tomo_encoders/reconstruction/cuda_kernels.py:21-317, prep.py:21-77 and the device side of
+ * recon.py:135-381.  All pointers are device pointers; projections are float32 (ntheta, nz, n), C order.
+ *
+ * te_fbp_padding: prep.py:21-31 (calc_padding).  te_fbp_filter: prep.py:33-60 in place over `rows` = ntheta * nz
+ * detector rows of n samples: edge-pad to n_pad, rfft, multiply by rfftfreq(n_pad), irfft, crop (cuFFT, batched so
+ * that a batch stays in L2); workspace of te_fbp_workspace_bytes(rows, n) bytes (a smaller one only lowers the batch).
+ * te_preprocess: prep.py:63-77, data = -log(max((data - dark) / max(flat - dark, 1e-6), 1e-6)), dark / flat (nz, n).
+ * te_make_mask: recon.py:369-381, mask (float32, shape) = 1 inside the wd^3 boxes at points (n, 3) uint32, else 0. */
+void te_fbp_padding(int32_t n, int32_t* pad_left, int32_t* pad_right);
+int64_t te_fbp_workspace_bytes(int64_t rows, int32_t n);
+int te_fbp_filter(float* data, int64_t rows, int32_t n, void* workspace, int64_t workspace_bytes, void* stream);
+int te_fbp_release_plans(void);
+int te_preprocess(float* data, const float* dark, const float* flat, int32_t ntheta, int32_t nz, int32_t n, void* stream);
+int te_make_mask(float* mask, const int64_t shape[3], const uint32_t* points, int64_t n, int32_t wd, void* stream);
+/* Back-projection.  te_bp_prepare re-lays the (filtered) projections out for the kernels below and tabulates
+ * cos / sin(theta) (evaluated in fp64, rounded to fp32) into `workspace` (te_bp_workspace_bytes); the projections may
+ * be overwritten afterwards.  Per voxel (x, y, z): sum over k of g[k][z][s0] + (g[k][z][s0+1] - g[k][z][s0]) *
+ * (sp - s0) / n with sp = (x - n/2) cos - (y - n/2) sin + center, s0 = roundf(sp), 0 <= s0 < n - 1
+ * (cuda_kernels.py:73-147).  exact = 1: one IEEE rounding per reference operation (parity mode); 0: FMA-contracted.
+ *   te_bp_box      rec_patch / rec (cuda_kernels.py:73-98, 269-302): out (pz, py, px) = voxels [stz:stz+pz, sty:sty+py,
+ *                  stx:stx+px]; with stx = sty = stz = 0, px = py = n, pz = nz it is rec_all (:125-147); masked = 1 is
+ *                  rec_mask (:100-123): voxels with out > 0 are reconstructed, all others set to 0.
+ *   te_bp_patches  the fused recon_patches_3d + extract_segmented path (recon.py:199-203, 256-300): out (npatch, wd, wd,
+ *                  wd) float32 / float16 / bfloat16 = the wd^3 boxes at points (z, y, x) uint32; normalize = 1 applies
+ *                  clip(v, lo, hi) then (v - lo) / (hi - lo) (recon.py:283-285) before the store.
+ *   te_bp_points   rec_pts (:23-43; pts (npts, 3) int32 z, y, x; out (npts)) or, xy_mode = 1, rec_pts_xy (:47-68;
+ *                  pts (npts, 2) y, x; out (nz, npts)). */
+int64_t te_bp_workspace_bytes(int32_t ntheta, int32_t nz, int32_t n);
+int te_bp_prepare(const float* data, const float* theta, int32_t ntheta, int32_t nz, int32_t n, void* workspace, void* stream);
+int te_bp_box(const void* workspace, int32_t ntheta, int32_t nz, int32_t n, float center, int32_t stx, int32_t px, int32_t sty,
+              int32_t py, int32_t stz, int32_t pz, float* out, int32_t masked, int32_t exact, void* stream);
+int te_bp_patches(const void* workspace, int32_t ntheta, int32_t nz, int32_t n, float center, const uint32_t* points,
+                  int64_t npatch, int32_t wd, void* out, int32_t out_dtype, int32_t normalize, float clip_lo, float clip_hi,
+                  int32_t exact, void* stream);
+int te_bp_points(const void* workspace, int32_t ntheta, int32_t nz, int32_t n, float center, const int32_t* pts, int32_t npts,
+                 int32_t xy_mode, float* out, int32_t exact, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,7 +73,10 @@ def build_library(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
         list(ex.map(run, jobs))
     tmp = LIB_PATH + ".tmp.%d" % os.getpid()
-    run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp] + objs)
+    # cuFFT (the FBP ramp filter, csrc/recon_ops.cu) comes from the toolkit next to nvcc; same path on the GPU box
+    cuda_lib = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "lib64")
+    run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp] + objs +
+        ["-L" + cuda_lib, "-lcufft", "-Xlinker", "-rpath=" + cuda_lib])
     os.replace(tmp, LIB_PATH)
     return LIB_PATH
 
@@ -177,6 +180,18 @@ _SIGNATURES = {
     "te_label_crop_masks": (ctypes.c_int, [_P, ctypes.POINTER(_I64), _P, _P, _I64, _P, _I64, _P, _P]),
     "te_paint_boxes": (ctypes.c_int, [_P, _P, _P, _I64, _I64, _P, ctypes.POINTER(_I64), _P, _P]),
     "te_tile_any": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_I64), _I32, _P, _P]),
+    # reconstruction
+    "te_fbp_padding": (None, [_I32, ctypes.POINTER(_I32), ctypes.POINTER(_I32)]),
+    "te_fbp_workspace_bytes": (_I64, [_I64, _I32]),
+    "te_fbp_filter": (ctypes.c_int, [_P, _I64, _I32, _P, _I64, _P]),
+    "te_fbp_release_plans": (ctypes.c_int, []),
+    "te_preprocess": (ctypes.c_int, [_P, _P, _P, _I32, _I32, _I32, _P]),
+    "te_make_mask": (ctypes.c_int, [_P, ctypes.POINTER(_I64), _P, _I64, _I32, _P]),
+    "te_bp_workspace_bytes": (_I64, [_I32, _I32, _I32]),
+    "te_bp_prepare": (ctypes.c_int, [_P, _P, _I32, _I32, _I32, _P, _P]),
+    "te_bp_box": (ctypes.c_int, [_P, _I32, _I32, _I32, _F, _I32, _I32, _I32, _I32, _I32, _I32, _P, _I32, _I32, _P]),
+    "te_bp_patches": (ctypes.c_int, [_P, _I32, _I32, _I32, _F, _P, _I64, _I32, _P, _I32, _I32, _F, _F, _I32, _P]),
+    "te_bp_points": (ctypes.c_int, [_P, _I32, _I32, _I32, _F, _P, _I32, _I32, _P, _I32, _P]),
     "te_tr_adam": (ctypes.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I64, _F, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
