@@ -9,12 +9,14 @@
 //     if (0 <= s0 < n-1)  f += g[k][z][s0] + (g[k][z][s0+1] - g[k][z][s0]) * (sp - s0) / n
 // (the "/ n" and the round-instead-of-floor are the reference's; they are kept).  sp, s0 and the weight do not depend on
 // z, so the design here is column-wise:
-//   * te_bp_prepare re-lays the filtered projections out as gT[zb][k][s][16] (16 consecutive z innermost): the two
-//     detector samples a voxel column needs for one angle are 128 contiguous bytes = eight 128-bit loads instead of 32
-//     scalar ones, and the trigonometry is tabulated once per angle (cos / sin evaluated in fp64, rounded to fp32);
-//   * one thread owns CPT (x, y) columns x 16 z accumulators; a warp covers 8 x 4 columns so the detector samples it
-//     touches for one angle span <= ~10 rows of 64 bytes (L1-resident); per column and angle the address / weight
-//     arithmetic is amortised over 16 voxels;
+//   * te_bp_prepare re-lays the filtered projections out as gT[zb][k][q][s][4] (z = 16 zb + 4 q + j): a voxel column
+//     reads eight 128-bit words per angle (4 z quads x {s0, s0 + 1}) instead of 32 scalars, and the trigonometry is
+//     tabulated once per angle (cos / sin evaluated in fp64, rounded to fp32);
+//   * one thread owns CPT (x, y) columns x 16 z accumulators; a warp covers 8 x 4 columns, whose detector samples for
+//     one angle span <= ~10 consecutive s: with s next to the quad in memory one warp-wide load touches 1-2 cache
+//     lines.  (The first layout, [s][16 z], touched ~5 lines per load and ran at the L1 wavefront rate: 2 cycles per
+//     line and load, 5.6 updates / clk / SM measured; see profiles/r01_notes.md.)  Per column and angle the address /
+//     weight arithmetic is amortised over 16 voxels;
 //   * the same kernel body serves the whole volume, a mask (rec_mask), one box (rec), a list of patches (the fused
 //     recon -> clip -> rescale -> network-input path of recon_patches_3d + extract_segmented, which never materialises
 //     the tomogram) and point lists.
@@ -37,7 +39,7 @@ constexpr int kZT = 16;          // z values per column block
 constexpr int kTrigChunk = 1024;  // angles staged in shared memory at a time
 
 struct BpParams {
-  const float* gT;     // [nzb][ntheta][n][16]
+  const float* gT;     // [nzb][ntheta + 1][4][n][4]
   const float2* trig;  // [ntheta] (cos, sin)
   int ntheta, nz, n, nzb;
   float center;
@@ -57,37 +59,55 @@ struct BpParams {
   int npts;
 };
 
-template <bool EXACT>
-__device__ __forceinline__ void bp_column(const BpParams& p, const float2* __restrict__ trig_s, int k0, int kn,
-                                          const float* __restrict__ gz, float fx, float fy, float (&acc)[kZT]) {
+// One angle step of CPT columns: all 8 * CPT 128-bit loads are issued before the arithmetic (16 independent loads in
+// flight per thread at CPT = 2).  Layout: float4 index ((k * 4 + q) * n + s) inside the z block's slice, q = z quad; the
+// slice ends with one all-zero "angle" (k = ntheta) that out-of-range samples are redirected to, so the loop has no branch:
+// g0 = g1 = 0 contributes exactly 0.
+template <int CPT, bool EXACT>
+__device__ __forceinline__ void bp_columns(const BpParams& p, const float2* __restrict__ trig_s, int k0, int kn,
+                                           const float4* __restrict__ gz4, const float (&fx)[CPT], const float (&fy)[CPT],
+                                           const bool (&active)[CPT], float (&acc)[CPT][kZT]) {
   const float nf = static_cast<float>(p.n);
   const float inv_n = 1.0f / nf;
-#pragma unroll 2
-  for (int kk = 0; kk < kn; ++kk) {
+  const int n = p.n, zero_off = p.ntheta * 4 * n;
+  int kofs = k0 * 4 * n;
+#pragma unroll 1
+  for (int kk = 0; kk < kn; ++kk, kofs += 4 * n) {
     const float2 cs = trig_s[kk];
-    float sp;
-    if (EXACT) sp = __fadd_rn(__fsub_rn(__fmul_rn(fx, cs.x), __fmul_rn(fy, cs.y)), p.center);
-    else sp = fmaf(fx, cs.x, -(fy * cs.y)) + p.center;
-    const float s0f = roundf(sp);
-    const int s0 = static_cast<int>(s0f);
-    if (s0 >= 0 && s0 < p.n - 1) {
-      const float w = __fsub_rn(sp, s0f);
-      const float4* q = reinterpret_cast<const float4*>(gz + (static_cast<size_t>(k0 + kk) * p.n + s0) * kZT);
-      float4 a[4], b[4];
+    int off[CPT];
+    float w[CPT];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = __ldg(q + i);
+    for (int c = 0; c < CPT; ++c) {
+      float sp;
+      if (EXACT) sp = __fadd_rn(__fsub_rn(__fmul_rn(fx[c], cs.x), __fmul_rn(fy[c], cs.y)), p.center);
+      else sp = fmaf(fx[c], cs.x, -(fy[c] * cs.y)) + p.center;
+      const float s0f = roundf(sp);
+      const int s0 = static_cast<int>(s0f);
+      const bool ok = active[c] && s0 >= 0 && s0 < n - 1;
+      off[c] = ok ? kofs + s0 : zero_off;
+      w[c] = __fsub_rn(sp, s0f);
+      if (!EXACT) w[c] *= inv_n;
+    }
+    float4 a[CPT][4], b[CPT][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) b[i] = __ldg(q + 4 + i);
-      const float* g0 = reinterpret_cast<const float*>(a);
-      const float* g1 = reinterpret_cast<const float*>(b);
+    for (int c = 0; c < CPT; ++c) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        a[c][q] = __ldg(gz4 + off[c] + q * n);
+        b[c][q] = __ldg(gz4 + off[c] + q * n + 1);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      const float* g0 = reinterpret_cast<const float*>(a[c]);
+      const float* g1 = reinterpret_cast<const float*>(b[c]);
       if (EXACT) {
 #pragma unroll
         for (int i = 0; i < kZT; ++i)
-          acc[i] = __fadd_rn(acc[i], __fadd_rn(g0[i], __fdiv_rn(__fmul_rn(__fsub_rn(g1[i], g0[i]), w), nf)));
+          acc[c][i] = __fadd_rn(acc[c][i], __fadd_rn(g0[i], __fdiv_rn(__fmul_rn(__fsub_rn(g1[i], g0[i]), w[c]), nf)));
       } else {
-        const float wn = w * inv_n;
 #pragma unroll
-        for (int i = 0; i < kZT; ++i) acc[i] += fmaf(g1[i] - g0[i], wn, g0[i]);
+        for (int i = 0; i < kZT; ++i) acc[c][i] += fmaf(g1[i] - g0[i], w[c], g0[i]);
       }
     }
   }
@@ -97,7 +117,7 @@ enum { MODE_VOLUME = 0, MODE_PATCHES = 1, MODE_PTS_XY = 2 };
 
 // 256 threads: warp w covers an 8 x 4 block of columns, the CTA 32 x 8, CPT columns per thread stacked in y (32 x 8*CPT).
 template <int MODE, int CPT, bool EXACT>
-__global__ void __launch_bounds__(256) bp_kernel(const BpParams p) {
+__global__ void __launch_bounds__(256, 2) bp_kernel(const BpParams p) {
   __shared__ float2 trig_s[kTrigChunk];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lx = (warp & 3) * 8 + (lane & 7), ly = (warp >> 2) * 4 + (lane >> 3);
@@ -178,18 +198,25 @@ __global__ void __launch_bounds__(256) bp_kernel(const BpParams p) {
     }
   }
 
-  const float* gz = p.gT + static_cast<size_t>(zb) * p.ntheta * p.n * kZT;
+  const float4* gz4 = reinterpret_cast<const float4*>(p.gT) + static_cast<size_t>(zb) * (p.ntheta + 1) * 4 * p.n;
   const int half = p.n / 2;
+  float fx[CPT], fy[CPT];
+  bool active[CPT];
+  bool any_active = false;
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) {
+    fx[c] = static_cast<float>(x[c] - half);
+    fy[c] = static_cast<float>(y[c] - half);
+    active[c] = valid[c] && mbits[c] != 0u;
+    any_active |= active[c];
+  }
+  any_active = __any_sync(0xffffffffu, any_active);
   for (int k0 = 0; k0 < p.ntheta; k0 += kTrigChunk) {
     const int kn = min(kTrigChunk, p.ntheta - k0);
     __syncthreads();
     for (int i = threadIdx.x; i < kn; i += blockDim.x) trig_s[i] = p.trig[k0 + i];
     __syncthreads();
-#pragma unroll
-    for (int c = 0; c < CPT; ++c) {
-      if (!valid[c] || mbits[c] == 0u) continue;
-      bp_column<EXACT>(p, trig_s, k0, kn, gz, static_cast<float>(x[c] - half), static_cast<float>(y[c] - half), acc[c]);
-    }
+    if (any_active) bp_columns<CPT, EXACT>(p, trig_s, k0, kn, gz4, fx, fy, active, acc);
   }
 
 #pragma unroll
@@ -224,7 +251,7 @@ __global__ void __launch_bounds__(256) bp_pts_kernel(const BpParams p) {
   const int z = p.pts[3 * i], y = p.pts[3 * i + 1], x = p.pts[3 * i + 2];
   const float fx = static_cast<float>(x - p.n / 2), fy = static_cast<float>(y - p.n / 2);
   const float nf = static_cast<float>(p.n), inv_n = 1.0f / nf;
-  const float* gz = p.gT + static_cast<size_t>(z / kZT) * p.ntheta * p.n * kZT + (z % kZT);
+  const float* gz = p.gT + (static_cast<size_t>(z / kZT) * (p.ntheta + 1) * 4 + ((z % kZT) >> 2)) * p.n * 4 + (z & 3);
   float f = 0.f;
   for (int k = 0; k < p.ntheta; ++k) {
     const float2 cs = __ldg(p.trig + k);
@@ -235,8 +262,8 @@ __global__ void __launch_bounds__(256) bp_pts_kernel(const BpParams p) {
     const int s0 = static_cast<int>(s0f);
     if (s0 >= 0 && s0 < p.n - 1) {
       const float w = __fsub_rn(sp, s0f);
-      const float* q = gz + (static_cast<size_t>(k) * p.n + s0) * kZT;
-      const float g0 = __ldg(q), g1 = __ldg(q + kZT);
+      const float* q = gz + (static_cast<size_t>(k) * 4 * p.n + s0) * 4;
+      const float g0 = __ldg(q), g1 = __ldg(q + 4);
       if (EXACT) f = __fadd_rn(f, __fadd_rn(g0, __fdiv_rn(__fmul_rn(__fsub_rn(g1, g0), w), nf)));
       else f += fmaf(g1 - g0, w * inv_n, g0);
     }
@@ -244,7 +271,8 @@ __global__ void __launch_bounds__(256) bp_pts_kernel(const BpParams p) {
   p.out[i] = f;
 }
 
-// (ntheta, nz, n) -> gT[zb][k][s][16], z beyond nz zero-filled.  One CTA: one angle, one z block, 64 detector columns.
+// (ntheta, nz, n) -> gT[zb][k][q][s][4] (z = zb * 16 + q * 4 + j), z beyond nz zero-filled.  One CTA: one angle, one z
+// block, 64 detector columns; every z quad is written as 1 KB of contiguous memory.
 __global__ void __launch_bounds__(256) bp_relayout_kernel(const float* __restrict__ g, float* __restrict__ gT, int ntheta,
                                                           int nz, int n) {
   __shared__ float tile[kZT][65];
@@ -255,10 +283,10 @@ __global__ void __launch_bounds__(256) bp_relayout_kernel(const float* __restric
     tile[zl][s] = (z < nz && s_base + s < n) ? g[(static_cast<size_t>(k) * nz + z) * n + s_base + s] : 0.f;
   }
   __syncthreads();
-  float* dst = gT + ((static_cast<size_t>(zb) * ntheta + k) * n + s_base) * kZT;
+  float* dst = gT + (static_cast<size_t>(zb) * (ntheta + 1) + k) * 4 * n * 4;
   for (int i = threadIdx.x; i < kZT * 64; i += blockDim.x) {
-    const int s = i >> 4, zl = i & 15;
-    if (s_base + s < n) dst[i] = tile[zl][s];
+    const int q = i >> 8, s = (i >> 2) & 63, j = i & 3;
+    if (s_base + s < n) dst[(static_cast<size_t>(q) * n + s_base + s) * 4 + j] = tile[q * 4 + j][s];
   }
 }
 
@@ -271,7 +299,7 @@ __global__ void bp_trig_kernel(const float* __restrict__ theta, float2* __restri
 
 inline size_t gT_floats(int ntheta, int nz, int n) {
   const size_t nzb = (nz + kZT - 1) / kZT;
-  return nzb * ntheta * static_cast<size_t>(n) * kZT;
+  return nzb * (ntheta + 1) * static_cast<size_t>(n) * kZT;   // + one all-zero angle per z block
 }
 
 int fill_params(BpParams& p, const void* ws, int ntheta, int nz, int n, float center) {
@@ -510,6 +538,9 @@ extern "C" int te_bp_prepare(const float* data, const float* theta, int ntheta, 
   float2* trig = reinterpret_cast<float2*>(gT + gT_floats(ntheta, nz, n));
   const int nzb = (nz + kZT - 1) / kZT;
   TE_CHECK_ARG(nzb <= 65535, "te_bp_prepare: nz too large");
+  TE_CHECK_ARG(static_cast<long long>(ntheta + 1) * 4 * n < (1LL << 31), "te_bp_prepare: ntheta * n too large");
+  for (int zb = 0; zb < nzb; ++zb)   // the all-zero angle that out-of-range samples read
+    TE_CUDA(cudaMemsetAsync(gT + (static_cast<size_t>(zb) * (ntheta + 1) + ntheta) * 4 * n * 4, 0, sizeof(float) * 16 * n, st));
   bp_relayout_kernel<<<dim3((n + 63) / 64, ntheta, nzb), 256, 0, st>>>(data, gT, ntheta, nz, n);
   TE_LAUNCH_CHECK();
   bp_trig_kernel<<<(ntheta + 255) / 256, 256, 0, st>>>(theta, trig, ntheta);
