@@ -391,6 +391,39 @@ def run_ours(args):
                  "collectives": "all-reduce(flat fp32 gradient, 4.77 M values) + SyncBN all-reduces of per-channel sums" if world > 1 else "none (1 rank)"}
         del tr, tx, ty
 
+    # reconstruction leg, rank 0 only: one z chunk of a 2048-wide scan, 1500 angles -- ramp filter, then the
+    # fused back-projection of every 32^3 patch of the chunk straight into clipped / rescaled fp16 network input
+    recon = None
+    if rank == 0 and not args.no_recon:
+        from tomoencoders_b200 import reconstruction as RC
+        r_n, r_nz, r_nt = 2048, 32, 1500
+        rd = torch.randn((r_nt, r_nz, r_n), device=dev, generator=torch.Generator(device=dev).manual_seed(9))
+        rth = torch.linspace(0, float(np.pi), r_nt + 1, device=dev)[:-1].contiguous()
+        rpts = torch.from_numpy(Grid((r_nz, r_n, r_n), width=32).points.astype(np.int32)).to(dev)
+        rout = torch.empty((len(rpts), 32, 32, 32), dtype=torch.float16, device=dev)
+
+        def recon_step():
+            RC.fbp_filter(rd)
+            RC.BackProjector(rd, rth).patches(r_n / 2 + 0.5, rpts, 32, min_max=(-50.0, 50.0), out=rout)
+        recon_step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            recon_step()
+        e1.record()
+        torch.cuda.synchronize()
+        r_ms = e0.elapsed_time(e1) / 3
+        updates = r_nt * r_nz * r_n * r_n
+        sm_hz = clocks.summary()["sm_mhz"] * 1e6
+        recon = {"metric": "voxels/sec reconstructed (FBP: ramp filter + back-projection of all 32^3 patches of a 1500 x 32 x 2048 chunk into fp16 network input)",
+                 "value": r_nz * r_n * r_n / (r_ms / 1e3), "unit": "voxels/s", "ms_per_step": r_ms,
+                 "updates_per_s": updates / (r_ms / 1e3),
+                 "bound": "L1 data pipe: 8 bytes (two fp32 detector samples) per voxel-angle update through a 128 B/clk/SM load path",
+                 "frac_of_l1_bound": updates / (r_ms / 1e3) / (148 * 16 * sm_hz),
+                 "note": "ncu of the kernel: profiles/ncu_r01_recon.txt (l1tex data-pipe wavefronts 83 % of peak)"}
+        del rd, rout
+
     if rank == 0:
         cpu_v, cpu_dt, cpu_threads = cpu_reference_leg(CPU_TILES)
         flops_patch = net.flops_per_patch
@@ -427,6 +460,7 @@ def run_ours(args):
                        "tflops_effective": enc_value * enc_flops / 1e12,
                        "collectives": "allreduce(16513 f64 PCA moments) + allgather((n,2) projections)" if world > 1 else "none (1 rank)"},
             "train": train,
+            "recon": recon,
             "cpu_baseline": {"value": cpu_v, "unit": "voxels/s", "cores": cpu_threads, "kind": "port",
                              "sample": "%d x 64^3 tiles: oracle extract + torch-CPU fp32 U-net M_a01 + fill (%.1f s)" % (CPU_TILES, cpu_dt)},
         }
@@ -441,6 +475,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-recon", action="store_true", help="skip the reconstruction leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
