@@ -104,13 +104,93 @@ def extract_segmented(obj_mask, cpts, wd, segmenter, batch_size, rec_min_max):
     return _segment_normalized(segmenter, x, int(batch_size)).cpu().numpy()
 
 
+_COPY_THREADS = 8
+_pool = None
+
+
+def _copy_pool():
+    global _pool
+    if _pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _pool = ThreadPoolExecutor(max_workers=_COPY_THREADS, thread_name_prefix="tomoenc-stage")
+    return _pool
+
+
+class _ChunkFeeder:
+    """Projection chunks projs[:, z:z+nc, :] as float32 CUDA tensors, one chunk ahead of the consumer: the strided host
+    copy goes into one of two pinned staging buffers and the upload runs on a side stream while the previous chunk is
+    being filtered / back-projected (host arrays); device stacks are sliced on the device."""
+
+    def __init__(self, projs, z_list, nc):
+        self.projs, self.z_list, self.nc = projs, [int(z) for z in z_list], int(nc)
+        self.on_device = isinstance(projs, torch.Tensor) and projs.is_cuda
+        self.i = 0
+        if not self.on_device:
+            dev = _device.device()
+            shape = (int(projs.shape[0]), self.nc, int(projs.shape[2]))
+            self.pinned = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(2)]
+            self.dev = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(2)]
+            self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self.free = [torch.cuda.Event(), torch.cuda.Event()]       # the consumer is done with dev[b]
+            self.staged = [torch.cuda.Event(), torch.cuda.Event()]     # the upload out of pinned[b] has finished
+            self.stream = torch.cuda.Stream()
+            self.used = [False, False]
+            self._stage(0)
+
+    def _stage(self, j):
+        if j >= len(self.z_list):
+            return
+        b = j & 1
+        z = self.z_list[j]
+        if self.used[b]:
+            self.staged[b].synchronize()                               # pinned[b] may be overwritten
+        src = self.projs[:, z:z + self.nc, :]
+        if isinstance(src, torch.Tensor):
+            self.pinned[b].copy_(src)
+        else:
+            # strided host copy (one nc * n run per angle) split over a few threads: numpy releases the GIL in copyto
+            dst = self.pinned[b].numpy()
+            nth = dst.shape[0]
+            step = -(-nth // _COPY_THREADS)
+            list(_copy_pool().map(lambda a: np.copyto(dst[a:a + step], src[a:a + step], casting="unsafe"), range(0, nth, step)))
+        with torch.cuda.stream(self.stream):
+            if self.used[b]:
+                self.stream.wait_event(self.free[b])
+            self.dev[b].copy_(self.pinned[b], non_blocking=True)
+            self.staged[b].record(self.stream)
+            self.ready[b].record(self.stream)
+        self.used[b] = True
+
+    def next(self):
+        """Chunk i (valid until the call after next()); chunk i + 1 is staged before returning."""
+        j = self.i
+        self.i += 1
+        if self.on_device:
+            z = self.z_list[j]
+            out = torch.empty((self.projs.shape[0], self.nc, self.projs.shape[2]), dtype=torch.float32, device=self.projs.device)
+            out.copy_(self.projs[:, z:z + self.nc, :])
+            return out
+        b = j & 1
+        torch.cuda.current_stream().wait_event(self.ready[b])
+        return self.dev[b]
+
+    def release(self, j):
+        """The consumer has enqueued all its work on chunk j: stage chunk j + 1 (overlaps with that work)."""
+        if self.on_device:
+            return
+        self.free[j & 1].record(torch.cuda.current_stream())
+        self._stage(j + 1)
+
+
 def recon_patches_3d(projs, theta, center, p3d, apply_fbp=True, TIMEIT=False, segmenter=None, segmenter_batch_size=256,
                      dark_flat=None, rec_min_max=None, exact=False):
     """recon.py:135-233: reconstruct (and optionally segment) the patches of Grid `p3d` chunk by chunk along z.
 
     Returns (x, p3d_new[, times]): x (n, wd, wd, wd) float32 reconstructions, or uint8 labels with a segmenter; p3d_new
     lists the patches in the order of x (grouped by z like the reference).  times rows: [ntheta, nc, n, t_cpu2gpu,
-    t_filt, t_mask, t_rec(, t_gpu2cpu)] in milliseconds (t_mask is 0: no mask is built here)."""
+    t_filt, t_mask, t_rec(, t_gpu2cpu)] in milliseconds (t_mask is 0: no mask is built here; with TIMEIT the chunks are
+    timed one by one, which serialises the upload / compute overlap).  The upload of chunk i + 1 overlaps the filter,
+    back-projection and segmentation of chunk i; results stay on the device until the last chunk."""
     _device.require_cuda()
     if segmenter is not None and rec_min_max is None:
         raise ValueError("rec_min_max is required with a segmenter")
@@ -121,37 +201,42 @@ def recon_patches_3d(projs, theta, center, p3d, apply_fbp=True, TIMEIT=False, se
     act_dtype = torch.float32
     if segmenter is not None:
         act_dtype = segmenter.models["segmenter"].net_for((wd,) * 3, min(int(segmenter_batch_size), len(points))).act_dtype
+    z_pts = np.unique(points[:, 0])
+    feeder = _ChunkFeeder(projs, z_pts, nc)
     x, times, cpts_all = [], [], []
     ws = None
-    for z_pt in np.unique(points[:, 0]):
+    for j, z_pt in enumerate(z_pts):
         cpts = points[points[:, 0] == z_pt]
         cpts_all.append(cpts.copy())
         local = cpts.copy()
         local[:, 0] = 0
-        t = _Timer()
-        data = _chunk_to_device(projs, slice(int(z_pt), int(z_pt) + nc))
+        t = _Timer() if TIMEIT else None
+        data = feeder.next()
         if dark_flat is not None:
             _preprocess_dev(data, dark_flat[0][z_pt:z_pt + nc], dark_flat[1][z_pt:z_pt + nc])
-        t_cpu2gpu = t.stop()
-        t = _Timer()
+        t_cpu2gpu = t.stop() if TIMEIT else 0.0
+        t = _Timer() if TIMEIT else None
         _filter_dev(data)
-        t_filt = t.stop()
-        t = _Timer()
+        t_filt = t.stop() if TIMEIT else 0.0
+        t = _Timer() if TIMEIT else None
         bp = BackProjector(data, th, workspace=ws)
         ws = bp.ws
         if segmenter is not None:
             xn = bp.patches(center, local, wd, out_dtype=act_dtype, min_max=rec_min_max, exact=exact)
-            t_rec = t.stop()
-            x.append(_segment_normalized(segmenter, xn, int(segmenter_batch_size)).cpu().numpy())
+            t_rec = t.stop() if TIMEIT else 0.0
+            x.append(_segment_normalized(segmenter, xn, int(segmenter_batch_size)))
             times.append([ntheta, nc, n, t_cpu2gpu, t_filt, 0.0, t_rec])
         else:
-            xr = bp.patches(center, local, wd, exact=exact)
-            t_rec = t.stop()
-            t = _Timer()
-            x.append(xr.cpu().numpy())
-            times.append([ntheta, nc, n, t_cpu2gpu, t_filt, 0.0, t_rec, t.stop()])
+            x.append(bp.patches(center, local, wd, exact=exact))
+            t_rec = t.stop() if TIMEIT else 0.0
+            times.append([ntheta, nc, n, t_cpu2gpu, t_filt, 0.0, t_rec, 0.0])
+        feeder.release(j)                         # all device work of chunk j is enqueued: stage chunk j + 1 behind it
     cpts_all = np.concatenate(cpts_all, axis=0)
-    x = np.concatenate(x, axis=0)
+    t = _Timer()
+    x = torch.cat(x, dim=0).cpu().numpy()
+    t_gpu2cpu = t.stop()
+    if segmenter is None and times:
+        times[-1][-1] = t_gpu2cpu                 # one download at the end
     p3d = Grid(p3d.vol_shape, initialize_by="data", points=cpts_all, width=wd)
     if TIMEIT:
         return x, p3d, np.asarray(times)

@@ -65,6 +65,23 @@ def main():
     clock = 1.9e9
     out["fp32_lane_ops_peak_per_s"] = 148 * 128 * clock
     out["fast_frac_of_3op_bound"] = out["rec_all_fast"]["Gupdates_per_s"] * 1e9 * 3 / (148 * 128 * clock)
+    # end to end through the reference-facing call: HOST projections (4 z chunks), pinned double-buffered uploads
+    # overlapped with filter + back-projection (+ segmentation), labels back on the host
+    e_nz = 128
+    host = np.random.default_rng(1).standard_normal((ntheta, e_nz, n)).astype(np.float32)
+    th_h = np.linspace(0, np.pi, ntheta, endpoint=False).astype(np.float32)
+    grid = Grid((e_nz, n, n), width=32)
+    sel = grid.select_random_sample(len(grid) // 4)
+    from tomoencoders_b200.neural_nets import SurfaceSegmenter
+    fe = SurfaceSegmenter(model_initialization="define-new", descriptor_tag="bench", mode="fp16", n_filters=[16, 32, 64],
+                          n_blocks=3, activation="lrelu", batch_norm=True, isconcat=[True, True, True], pool_size=[2, 2, 2])
+    for name, kw in (("recon_patches_3d_r0.25_host", {}), ("recon_segment_patches_3d_r0.25_host", dict(segmenter=fe, segmenter_batch_size=256, rec_min_max=(-50.0, 50.0)))):
+        RC.recon_patches_3d(host[:, :32], th_h, center, Grid((32, n, n), width=32).select_random_sample(64), **kw)   # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        x, _ = RC.recon_patches_3d(host, th_h, center, sel, **kw)
+        dt = time.perf_counter() - t0
+        out[name] = {"patches": len(sel), "s": dt, "voxels_per_s": len(sel) * 32 ** 3 / dt, "h2d_bytes": host.nbytes, "d2h_bytes": x.nbytes}
     try:
         from oracle import build_ref as R
         if R.built():
