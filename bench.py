@@ -114,8 +114,8 @@ def cpu_reference_leg(n_patches, threads=None):
     threads) -> round -> fill, on `n_patches` 64^3 tiles of a float16 volume.  Returns voxels/s."""
     import torch
     from oracle import nets_torch as O, structures_np as S, weights as OW
-    if threads:
-        torch.set_num_threads(threads)
+    # all host cores, explicitly: torchrun exports OMP_NUM_THREADS=1, which would silently run this arm on one core
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     g = np.random.default_rng(5)
     nz = max(1, (n_patches + 3) // 4)
     vol = g.uniform(0, 1, (PATCH * nz, PATCH * 2, PATCH * 2)).astype(np.float16)
@@ -425,7 +425,11 @@ def run_ours(args):
         del rd, rout
 
     if rank == 0:
-        cpu_v, cpu_dt, cpu_threads = cpu_reference_leg(CPU_TILES)
+        cpu_baseline = None                  # timed on rank 0 at N = 1 only (the other ranks would idle on it)
+        if world == 1:
+            cpu_v, cpu_dt, cpu_threads = cpu_reference_leg(CPU_TILES)
+            cpu_baseline = {"value": cpu_v, "unit": "voxels/s", "cores": cpu_threads, "kind": "port",
+                            "sample": "%d x 64^3 tiles: oracle extract + torch-CPU fp32 U-net M_a01 + fill (%.1f s)" % (CPU_TILES, cpu_dt)}
         flops_patch = net.flops_per_patch
         line = {
             "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
@@ -461,8 +465,7 @@ def run_ours(args):
                        "collectives": "allreduce(16513 f64 PCA moments) + allgather((n,2) projections)" if world > 1 else "none (1 rank)"},
             "train": train,
             "recon": recon,
-            "cpu_baseline": {"value": cpu_v, "unit": "voxels/s", "cores": cpu_threads, "kind": "port",
-                             "sample": "%d x 64^3 tiles: oracle extract + torch-CPU fp32 U-net M_a01 + fill (%.1f s)" % (CPU_TILES, cpu_dt)},
+            "cpu_baseline": cpu_baseline,
         }
         emit(line)
     if world > 1:

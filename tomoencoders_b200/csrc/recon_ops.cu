@@ -318,59 +318,54 @@ int fill_params(BpParams& p, const void* ws, int ntheta, int nz, int n, float ce
 
 // ------------------------------------------------------------------------------------------- FBP filter / preprocess
 // padded[r][j] = data[r][clamp(j - pad_left, 0, n-1)] for j < n_pad (np.pad mode='edge'); row pitch n_pad + 2 floats
-// (in-place R2C layout)
-__global__ void __launch_bounds__(256) fbp_pad_kernel(const float* __restrict__ data, float* __restrict__ padded, long long rows,
-                                                      int n, int n_pad, int pad_left) {
+// (in-place R2C layout).  Grid: (column blocks, rows) -- no per-element division.
+__global__ void __launch_bounds__(256) fbp_pad_kernel(const float* __restrict__ data, float* __restrict__ padded, int n, int n_pad,
+                                                      int pad_left) {
   const int pitch = n_pad + 2;
-  const long long total = rows * pitch;
-  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
-    const long long r = i / pitch;
-    const int j = static_cast<int>(i - r * pitch);
-    float v = 0.f;
-    if (j < n_pad) {
-      int s = j - pad_left;
-      s = s < 0 ? 0 : (s > n - 1 ? n - 1 : s);
-      v = data[r * n + s];
-    }
-    padded[i] = v;
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= pitch) return;
+  const long long r = blockIdx.y;
+  float v = 0.f;
+  if (j < n_pad) {
+    int s = j - pad_left;
+    s = s < 0 ? 0 : (s > n - 1 ? n - 1 : s);
+    v = __ldg(data + r * n + s);
   }
+  padded[r * pitch + j] = v;
 }
 
 // spectrum *= rfftfreq(n_pad)[j] / n_pad (the 1/n_pad is numpy's irfft normalisation, which cuFFT leaves out)
-__global__ void __launch_bounds__(256) fbp_ramp_kernel(float2* __restrict__ spec, long long rows, int n_pad) {
+__global__ void __launch_bounds__(256) fbp_ramp_kernel(float2* __restrict__ spec, int n_pad) {
   const int nc = n_pad / 2 + 1;
-  const long long total = rows * nc;
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= nc) return;
   const float inv = 1.0f / static_cast<float>(n_pad);
-  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
-    const int j = static_cast<int>(i % nc);
-    const float w = (static_cast<float>(j) * inv) * inv;
-    float2 v = spec[i];
-    v.x *= w;
-    v.y *= w;
-    spec[i] = v;
-  }
+  const float w = (static_cast<float>(j) * inv) * inv;
+  float2* p = spec + static_cast<long long>(blockIdx.y) * nc + j;
+  float2 v = *p;
+  v.x *= w;
+  v.y *= w;
+  *p = v;
 }
 
-__global__ void __launch_bounds__(256) fbp_crop_kernel(const float* __restrict__ padded, float* __restrict__ data, long long rows,
-                                                       int n, int n_pad, int pad_left) {
+__global__ void __launch_bounds__(256) fbp_crop_kernel(const float* __restrict__ padded, float* __restrict__ data, int n, int n_pad,
+                                                       int pad_left) {
   const int pitch = n_pad + 2;
-  const long long total = rows * n;
-  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
-    const long long r = i / n;
-    const int s = static_cast<int>(i - r * n);
-    data[i] = padded[r * pitch + pad_left + s];
-  }
+  const int s = blockIdx.x * 256 + threadIdx.x;
+  if (s >= n) return;
+  const long long r = blockIdx.y;
+  data[r * n + s] = padded[r * pitch + pad_left + s];
 }
 
 // prep.py:63-77 with the identity median filter removed: data = -log(max((data - dark) / max(flat - dark, 1e-6), 1e-6)),
 // dark / flat (nz, n) broadcast over the angles
 __global__ void __launch_bounds__(256) preprocess_kernel(float* __restrict__ data, const float* __restrict__ dark,
-                                                         const float* __restrict__ flat, long long total, long long plane) {
-  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
-    const long long j = i % plane;
-    const float d = dark[j];
-    const float v = __fdiv_rn(__fsub_rn(data[i], d), fmaxf(__fsub_rn(flat[j], d), 1.0e-6f));
-    data[i] = -logf(fmaxf(v, 1.0e-6f));
+                                                         const float* __restrict__ flat, long long plane) {
+  float* row = data + static_cast<long long>(blockIdx.y) * plane;   // one angle per blockIdx.y
+  for (long long j = blockIdx.x * 256LL + threadIdx.x; j < plane; j += gridDim.x * 256LL) {
+    const float d = __ldg(dark + j);
+    const float v = __fdiv_rn(__fsub_rn(row[j], d), fmaxf(__fsub_rn(__ldg(flat + j), d), 1.0e-6f));
+    row[j] = -logf(fmaxf(v, 1.0e-6f));
   }
 }
 
@@ -450,6 +445,7 @@ extern "C" int64_t te_fbp_workspace_bytes(int64_t rows, int n) {
   // rows are filtered in batches that keep the padded block inside L2
   int64_t batch = (48LL << 20) / (pitch * 4);
   batch = batch < 1 ? 1 : (batch > rows ? rows : batch);
+  batch = batch > 65535 ? 65535 : batch;   // rows ride on gridDim.y
   return batch * pitch * 4;
 }
 
@@ -460,7 +456,8 @@ extern "C" int te_fbp_filter(float* data, int64_t rows, int n, void* workspace, 
   te_fbp_padding(n, &pl, &pr);
   const int n_pad = n + pl + pr;
   const int64_t pitch = n_pad + 2;
-  const int64_t batch = workspace_bytes / (pitch * 4) < rows ? workspace_bytes / (pitch * 4) : rows;
+  int64_t batch = workspace_bytes / (pitch * 4) < rows ? workspace_bytes / (pitch * 4) : rows;
+  batch = batch > 65535 ? 65535 : batch;
   TE_CHECK_ARG(batch >= 1, "te_fbp_filter: workspace too small (%lld bytes)", static_cast<long long>(workspace_bytes));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* pad = reinterpret_cast<float*>(workspace);
@@ -470,7 +467,7 @@ extern "C" int te_fbp_filter(float* data, int64_t rows, int n, void* workspace, 
     const int rc = get_plans(n_pad, nb, plans);
     if (rc != TE_OK) return rc;
     float* d = data + r0 * n;
-    fbp_pad_kernel<<<grid_for(nb * pitch), 256, 0, st>>>(d, pad, nb, n, n_pad, pl);
+    fbp_pad_kernel<<<dim3((pitch + 255) / 256, nb), 256, 0, st>>>(d, pad, n, n_pad, pl);
     TE_LAUNCH_CHECK();
     if (cufftSetStream(plans.fwd, st) != CUFFT_SUCCESS || cufftSetStream(plans.inv, st) != CUFFT_SUCCESS) {
       set_error("cufftSetStream failed");
@@ -480,13 +477,13 @@ extern "C" int te_fbp_filter(float* data, int64_t rows, int n, void* workspace, 
       set_error("cufftExecR2C failed");
       return TE_ERR_CUDA;
     }
-    fbp_ramp_kernel<<<grid_for(nb * (n_pad / 2 + 1)), 256, 0, st>>>(reinterpret_cast<float2*>(pad), nb, n_pad);
+    fbp_ramp_kernel<<<dim3((n_pad / 2 + 256) / 256, nb), 256, 0, st>>>(reinterpret_cast<float2*>(pad), n_pad);
     TE_LAUNCH_CHECK();
     if (cufftExecC2R(plans.inv, reinterpret_cast<cufftComplex*>(pad), pad) != CUFFT_SUCCESS) {
       set_error("cufftExecC2R failed");
       return TE_ERR_CUDA;
     }
-    fbp_crop_kernel<<<grid_for(nb * n), 256, 0, st>>>(pad, d, nb, n, n_pad, pl);
+    fbp_crop_kernel<<<dim3((n + 255) / 256, nb), 256, 0, st>>>(pad, d, n, n_pad, pl);
     TE_LAUNCH_CHECK();
   }
   return TE_OK;
@@ -505,8 +502,10 @@ extern "C" int te_fbp_release_plans(void) {
 extern "C" int te_preprocess(float* data, const float* dark, const float* flat, int ntheta, int nz, int n, void* stream) {
   TE_CHECK_ARG(data && dark && flat, "te_preprocess: null pointer");
   TE_CHECK_ARG(ntheta > 0 && nz > 0 && n > 0, "te_preprocess: bad shape");
-  const long long plane = static_cast<long long>(nz) * n, total = plane * ntheta;
-  preprocess_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(data, dark, flat, total, plane);
+  TE_CHECK_ARG(ntheta <= 65535, "te_preprocess: at most 65535 angles");
+  const long long plane = static_cast<long long>(nz) * n;
+  const int bx = static_cast<int>((plane + 255) / 256 > 64 ? 64 : (plane + 255) / 256);
+  preprocess_kernel<<<dim3(bx, ntheta), 256, 0, static_cast<cudaStream_t>(stream)>>>(data, dark, flat, plane);
   TE_LAUNCH_CHECK();
   return TE_OK;
 }
