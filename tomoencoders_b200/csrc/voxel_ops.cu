@@ -11,6 +11,9 @@
 // shared memory, grids sized as multiples of the SM count.  No tensor cores.
 #include "te_common.cuh"
 
+#include <type_traits>
+#include <utility>
+
 namespace te {
 namespace {
 
@@ -40,6 +43,12 @@ template <> __device__ __forceinline__ float elem_f32<float>(float v) { return v
 // takes kSeg / n[3] consecutive rows, one warp per row, so that every lane has work whatever the row
 // length (a 64^3 patch row is 64 elements).  VEC = true reads 16 bytes per lane (innermost stride 1,
 // 16-byte aligned rows).
+// A functor may also take a whole 16-byte word of packed integers (f.vec16(q)): the uint8 / uint16 min-max uses the
+// packed-SIMD integer instructions instead of converting every element to fp32.
+template <typename F, typename = void> struct has_vec16 : std::false_type {};
+template <typename F>
+struct has_vec16<F, std::void_t<decltype(std::declval<F&>().vec16(std::declval<const uint4&>()))>> : std::true_type {};
+
 template <typename T, bool VEC, typename F>
 __device__ __forceinline__ void for_each_in_row(const T* rp, long long sx, int len, int first, int step, F&& f) {
   constexpr int EPV = 16 / sizeof(T);
@@ -47,9 +56,13 @@ __device__ __forceinline__ void for_each_in_row(const T* rp, long long sx, int l
     const int nvec = len / EPV;
     for (int c = first; c < nvec; c += step) {
       const uint4 q = __ldg(reinterpret_cast<const uint4*>(rp) + c);
-      const T* e = reinterpret_cast<const T*>(&q);
+      if constexpr (has_vec16<std::decay_t<F>>::value) {
+        f.vec16(q);
+      } else {
+        const T* e = reinterpret_cast<const T*>(&q);
 #pragma unroll
-      for (int i = 0; i < EPV; ++i) f(elem_f32<T>(e[i]));
+        for (int i = 0; i < EPV; ++i) f(elem_f32<T>(e[i]));
+      }
     }
     for (int x = nvec * EPV + first; x < len; x += step) f(elem_f32<T>(rp[x]));
   } else {
@@ -95,10 +108,47 @@ __device__ __forceinline__ void for_each_elem(const View4& v, F&& f) {
   }
 }
 
+template <typename T> struct MinMaxAcc {
+  float lo = INFINITY, hi = -INFINITY;
+  __device__ __forceinline__ void operator()(float a) { lo = fminf(lo, a); hi = fmaxf(hi, a); }
+  __device__ __forceinline__ void finish() {}
+};
+template <> struct MinMaxAcc<uint8_t> {
+  float lo = INFINITY, hi = -INFINITY;
+  unsigned lo4 = 0xffffffffu, hi4 = 0u;
+  __device__ __forceinline__ void operator()(float a) { lo = fminf(lo, a); hi = fmaxf(hi, a); }
+  __device__ __forceinline__ void vec16(const uint4& q) {
+    lo4 = __vminu4(__vminu4(lo4, q.x), __vminu4(__vminu4(q.y, q.z), q.w));
+    hi4 = __vmaxu4(__vmaxu4(hi4, q.x), __vmaxu4(__vmaxu4(q.y, q.z), q.w));
+  }
+  __device__ __forceinline__ void finish() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      lo = fminf(lo, static_cast<float>((lo4 >> (8 * i)) & 255u));
+      hi = fmaxf(hi, static_cast<float>((hi4 >> (8 * i)) & 255u));
+    }
+  }
+};
+template <> struct MinMaxAcc<uint16_t> {
+  float lo = INFINITY, hi = -INFINITY;
+  unsigned lo2 = 0xffffffffu, hi2 = 0u;
+  __device__ __forceinline__ void operator()(float a) { lo = fminf(lo, a); hi = fmaxf(hi, a); }
+  __device__ __forceinline__ void vec16(const uint4& q) {
+    lo2 = __vminu2(__vminu2(lo2, q.x), __vminu2(__vminu2(q.y, q.z), q.w));
+    hi2 = __vmaxu2(__vmaxu2(hi2, q.x), __vmaxu2(__vmaxu2(q.y, q.z), q.w));
+  }
+  __device__ __forceinline__ void finish() {
+    lo = fminf(lo, fminf(static_cast<float>(lo2 & 0xffffu), static_cast<float>(lo2 >> 16)));
+    hi = fmaxf(hi, fmaxf(static_cast<float>(hi2 & 0xffffu), static_cast<float>(hi2 >> 16)));
+  }
+};
+
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) minmax_nd_kernel(View4 v, float* partial) {
-  float lo = INFINITY, hi = -INFINITY;
-  for_each_elem<T, VEC>(v, [&](float a) { lo = fminf(lo, a); hi = fmaxf(hi, a); });
+  MinMaxAcc<T> acc;
+  for_each_elem<T, VEC>(v, acc);
+  acc.finish();
+  float lo = acc.lo, hi = acc.hi;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
