@@ -168,3 +168,46 @@ def test_predict_patches_argument_checks():
     from tomoencoders_b200.neural_nets import Enhancer_fCNN
     with pytest.raises(NotImplementedError):
         Enhancer_fCNN(model_initialization="define-new", descriptor_tag="t", **SMALL).train(None, None)
+
+
+@pytest.mark.parametrize("slab_bytes", [16 << 20, 3 * 32768, 32768])
+def test_segment_volume_host_paths_stream_slabs_and_match_the_device_path(vol_f16, slab_bytes, monkeypatch):
+    """(slab sizes: the whole 128^3 volume / 3 planes / 1 plane per slab.)  Host volumes go up in z slabs on a side stream (chunks wait only for the slabs they read) and, with a pinned
+    `out`, finished slabs of the mask come back the same way: every variant equals the device-resident path."""
+    from tomoencoders_b200.misc.voxel_processing import _find_min_max
+    from tomoencoders_b200.neural_nets import keras_processor as KP
+    monkeypatch.setattr(KP, "_SLAB_BYTES", slab_bytes)
+    w = OW.draw(O.unet_spec(**oparams(SMALL)), 5)
+    fe = SurfaceSegmenter(model_initialization="define-new", descriptor_tag="small", mode="fp16", **SMALL)
+    fe.models["segmenter"].set_weights(w)
+    g = Grid(vol_f16.shape, width=32)
+    tv = torch.from_numpy(vol_f16).cuda()
+    mm_dev = fe.calc_voxel_min_max(tv, 4)
+    mm_host = fe.calc_voxel_min_max(vol_f16, 4)                       # uploads only every 4th plane
+    assert mm_host == mm_dev == _find_min_max(torch.from_numpy(vol_f16), 4)
+    assert mm_host == (float(vol_f16[::4, ::4, ::4].min()), float(vol_f16[::4, ::4, ::4].max()))
+    want = fe.segment_volume(tv, g, 8, min_max=mm_dev).cpu().numpy()
+    assert 0.02 < want.mean() < 0.98
+    # numpy in, freshly allocated numpy out
+    np.testing.assert_array_equal(fe.segment_volume(vol_f16, g, 8, min_max=mm_dev), want)
+    # pinned in, pinned out (uploads issued up front, downloads slab by slab)
+    hv = torch.from_numpy(vol_f16).pin_memory()
+    ho = torch.full(vol_f16.shape, 7, dtype=torch.uint8).pin_memory()
+    r = fe.segment_volume(hv, g, 5, min_max=mm_dev, out=ho)
+    assert r is ho
+    np.testing.assert_array_equal(ho.numpy(), want)
+    # pageable numpy out
+    no = np.full(vol_f16.shape, 7, np.uint8)
+    fe.segment_volume(vol_f16, g, 8, min_max=mm_dev, out=no)
+    np.testing.assert_array_equal(no, want)
+    # a tiling that does NOT cover the volume keeps the previous contents of `out` elsewhere, in any chunk order
+    sub = g.select_by_indices(np.random.default_rng(0).permutation(len(g))[: len(g) // 2])
+    ho.fill_(7)
+    fe.segment_volume(hv, sub, 3, min_max=mm_dev, out=ho)
+    expect = np.full(vol_f16.shape, 7, np.uint8)
+    for p in sub.points:
+        z, y, x = (int(v) for v in p)
+        expect[z:z + 32, y:y + 32, x:x + 32] = want[z:z + 32, y:y + 32, x:x + 32]
+    np.testing.assert_array_equal(ho.numpy(), expect)
+    with pytest.raises(TypeError):
+        fe.segment_volume(vol_f16, g, 8, min_max=mm_dev, out=np.zeros(vol_f16.shape, np.float32))

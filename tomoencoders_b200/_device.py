@@ -69,6 +69,26 @@ def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
+_SIDE_STREAMS = {}
+
+
+def side_stream():
+    """One extra stream per device for host<->device copies that overlap the kernels of the current stream."""
+    d = torch.cuda.current_device()
+    if d not in _SIDE_STREAMS:
+        _SIDE_STREAMS[d] = torch.cuda.Stream(device=d)
+    return _SIDE_STREAMS[d]
+
+
+def as_host_tensor(a):
+    """numpy array / torch CPU tensor -> torch CPU tensor sharing its memory (None if that is not possible)."""
+    if isinstance(a, torch.Tensor):
+        return a if (not a.is_cuda and a.is_contiguous()) else None
+    if isinstance(a, np.ndarray) and a.flags.c_contiguous and a.dtype in _NP_TO_TE and a.flags.writeable:
+        return torch.from_numpy(a)
+    return None
+
+
 _POINTS_CACHE = {}
 _POINTS_CACHE_MAX_ROWS = 65536
 _POINTS_CACHE_ENTRIES = 16

@@ -45,6 +45,18 @@ def _rescale_data(data, min_val, max_val):
 def _find_min_max(vol, sampling_factor, TIMEIT=False):
     """voxel_processing.py:91-104: (min, max) of vol[::s, ::s, ::s]; returns Python floats."""
     t0 = time.time()
+    s = int(sampling_factor)
+    h = None if _device.is_device_array(vol) else _device.as_host_tensor(vol)
+    if h is not None and h.dim() == 3 and s > 1 and h.shape[0] >= s:
+        # host volume: only every s-th z plane is needed -- upload those (1 / s of the bytes), then the strided view
+        dev = _device.device()
+        planes = torch.empty((-(-h.shape[0] // s),) + tuple(h.shape[1:]), dtype=h.dtype, device=dev)
+        for k in range(planes.shape[0]):
+            planes[k].copy_(h[k * s], non_blocking=True)
+        lo, hi = _minmax_view(planes[:, ::s, ::s])
+        if TIMEIT:
+            _msg_exec_time("find voxel min max", time.time() - t0)
+        return float(lo), float(hi)
     t = _device.to_device(vol)
     if t.dim() != 3:
         raise ValueError("expected a 3-D volume")

@@ -176,6 +176,9 @@ def gather_normalized(vol_dev, vol_shape, d_points, d_widths, n, patch, min_max,
     return out
 
 
+_SLAB_BYTES = 16 << 20        # z-slab size of the streamed host <-> device copies in process_volume
+
+
 class GenericKerasProcessor:
     """keras_processor.py:25-196."""
 
@@ -327,40 +330,102 @@ class Vox2VoxProcessor_fCNN(GenericKerasProcessor):
         n = len(patches)
         labels = self.output_type == "labels"
         host = not _device.is_device_array(vol)
-        t_vol = _device.to_device(vol)
-        dev = t_vol.device
+        w3 = tuple(int(v) for v in widths[0]) if n else None
+        # Host volumes are uploaded in z slabs on a side stream; a chunk only waits for the slabs it reads, so the
+        # upload overlaps the network (and, with a pinned `out`, finished slabs of the result go back the same way).
+        src = _device.as_host_tensor(vol) if host and n else None
         o_dtype = torch.uint8 if labels else torch.float32
+        if src is not None:
+            dev = _device.device()
+            t_vol = torch.empty(vs, dtype=src.dtype, device=dev)
+            plane_bytes = vs[1] * vs[2] * src.element_size()
+            zs = max(1, min(vs[0], -(-_SLAB_BYTES // max(1, plane_bytes))))
+            n_slabs = -(-vs[0] // zs)
+            side = _device.side_stream()
+            side.wait_stream(torch.cuda.current_stream())
+            ev_up = [torch.cuda.Event() for _ in range(n_slabs)]
+            issued = [0]
+            pinned_in = src.is_pinned()
+
+            def upload_to(s_last):
+                s_last = min(s_last, n_slabs - 1)
+                with torch.cuda.stream(side):
+                    while issued[0] <= s_last:
+                        k = issued[0]
+                        t_vol[k * zs:(k + 1) * zs].copy_(src[k * zs:(k + 1) * zs], non_blocking=True)
+                        ev_up[k].record(side)
+                        issued[0] += 1
+        else:
+            t_vol = _device.to_device(vol)
+        dev = t_vol.device
+        o_es = 1 if labels else 4
+        disjoint = n > 0 and _table._disjoint(patches.points, w3, vs) and (w3[2] * o_es) % 16 == 0
+        # disjoint patches that fill the volume overwrite every voxel: the previous contents of `out` are not needed
+        covers = disjoint and n * w3[0] * w3[1] * w3[2] == vs[0] * vs[1] * vs[2]
         if out is None:
             t_out = torch.zeros(vs, dtype=o_dtype, device=dev)
+        elif covers and not _device.is_device_array(out):
+            if tuple(out.shape) != vs or _device.as_host_tensor(out) is None or _device.as_host_tensor(out).dtype != o_dtype:
+                raise TypeError("out must be a contiguous %s array of shape %s" % (o_dtype, vs))
+            t_out = torch.empty(vs, dtype=o_dtype, device=dev)
         else:
             t_out = _device.to_device(out)
             if t_out.dtype != o_dtype:
                 raise TypeError("out must be %s" % o_dtype)
         if n == 0:
             return _device.to_host_like(t_out, vol) if out is None else out
-        w3 = tuple(int(v) for v in widths[0])
         model = self.models[model_key]
         net = model.net_for(w3, min(chunk_size, n))
         d_pts = _device.points_to_device(patches.points)
         d_wds = _device.points_to_device(widths)
-        disjoint = _table._disjoint(patches.points, w3, vs) and (w3[2] * t_out.element_size()) % 16 == 0
         if not disjoint:
             # overlapping patches: stitch once at the end through the ordered path
             all_out = torch.empty((n,) + w3, dtype=o_dtype, device=dev)
         L = _lib.lib()
         hint = _table._aligned_hint(np.asarray(patches.points), None, w3, t_out.element_size()) if disjoint else 0
-        for a in range(0, n, chunk_size):
+        pz = np.asarray(patches.points)[:, 0].astype(np.int64)
+        starts = list(range(0, n, chunk_size))
+        # pipelined download: slabs below every later chunk are final once the current chunk is done
+        out_host = _device.as_host_tensor(out) if (src is not None and out is not None and disjoint) else None
+        stream_out = out_host is not None and out_host.is_pinned() and out_host.dtype == o_dtype
+        if stream_out:
+            zmin_after = [vs[0]] * len(starts)
+            run = vs[0]
+            for ci in range(len(starts) - 1, -1, -1):
+                zmin_after[ci] = run
+                run = min(run, int(pz[starts[ci]:starts[ci] + chunk_size].min()))
+            down = 0                                     # slabs [0, down) have been sent back
+        for ci, a in enumerate(starts):
             b = min(a + chunk_size, n)
+            if src is not None:
+                need = min(n_slabs - 1, (int(pz[a:b].max()) + int(np.asarray(widths)[a:b, 0].max()) - 1) // zs)
+                upload_to(n_slabs - 1 if pinned_in else need + 1)
+                torch.cuda.current_stream().wait_event(ev_up[need])
             xa = gather_normalized(t_vol, vs, d_pts[a:b], d_wds[a:b], b - a, w3, min_max, self._clip_input, net)
             y = all_out[a:b] if not disjoint else torch.empty((b - a,) + w3, dtype=o_dtype, device=dev)
             net.unet_forward_into(xa, y)
             if disjoint:
                 _lib.check(L.te_scatter(y.data_ptr(), y.element_size(), d_pts[a:b].data_ptr(), b - a, _lib.i32x3(w3),
                                         t_out.data_ptr(), _lib.i64x3(vs), None, hint, _device.stream_ptr()), "te_scatter")
+            if stream_out:
+                final = min(n_slabs, zmin_after[ci] // zs) if zmin_after[ci] < vs[0] else n_slabs
+                if final > down:
+                    ev = torch.cuda.Event()
+                    ev.record(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
+                        side.wait_event(ev)
+                        out_host[down * zs:final * zs].copy_(t_out[down * zs:final * zs], non_blocking=True)
+                    down = final
+        if src is not None:
+            upload_to(n_slabs - 1)
+            torch.cuda.current_stream().wait_stream(side)
         if not disjoint:
             _table.scatter(all_out, t_out, vs, patches.points, widths)
         if out is None:
             return _device.to_host_like(t_out, vol) if host else t_out
+        if stream_out:
+            side.synchronize()                           # every slab has been written into the caller's array
+            return out
         if host:
             res = t_out.cpu()
             if isinstance(out, torch.Tensor):
