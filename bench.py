@@ -44,7 +44,7 @@ ENC = dict(n_filters=[16, 32, 64], n_blocks=3, activation="lrelu", batch_norm=Tr
 VOL = (512, 512, 512)
 PATCH = 64
 CHUNK = 32
-ENC_PATCHES = 4096          # 64^3 patches encoded per rank per step in the "encode" leg
+ENC_PATCHES = 16384         # 64^3 patches encoded per rank per step in the "encode" leg, ONE PCA fit per step (configs[2]: 125 000 patches per rank and fit)
 CPU_TILES = 64              # bounded CPU sample of the same workload: two FULL chunks (a partial chunk is padded to 32 by the reference)
 ENC_CHUNK = 128             # patches per encoder launch (the encoder keeps only pooled tensors: 128 patches = 1.3 GB)
 METRIC = "voxels/sec segmented (3-D U-net M_a01, 64^3 tiles of a 512^3 fp16 volume per GPU)"
