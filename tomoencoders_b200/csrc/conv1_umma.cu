@@ -48,7 +48,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 template <int NT>
-__global__ void __launch_bounds__(kThreadsC1, 1) conv1_umma_kernel(const C1Params p) {
+// NT = 16: two CTAs per SM (72 registers, 2 x 74 KB shared memory, 2 x 256 TMEM columns): builders, issuer and epilogue of
+// one CTA are each latency-bound, a second CTA fills the gaps.  NT = 32 needs all 512 TMEM columns: one CTA per SM.
+__global__ void __launch_bounds__(kThreadsC1, NT <= 16 ? 2 : 1) conv1_umma_kernel(const C1Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_stage = smem;                                   // kStagesA x 8 KB
@@ -270,7 +272,8 @@ bool conv1_umma_try(const TView& in, const TView& out, const float* w, const flo
   p.total_tiles = static_cast<long long>(in.N) * p.tiles_z * p.tiles_y * p.tiles_x;
   p.lrelu = lrelu; p.alpha = alpha; p.fp16 = act_type == ACT_F16;
   if (p.total_tiles <= 0) { *err = cudaSuccess; return true; }
-  const int grid = static_cast<int>(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs);
+  const int ctas = (out.C == 16 ? 2 : 1) * kNumSMs;
+  const int grid = static_cast<int>(p.total_tiles < ctas ? p.total_tiles : ctas);
   *err = out.C == 16 ? launch_nt<16>(p, grid, st) : launch_nt<32>(p, grid, st);
   return true;
 }
