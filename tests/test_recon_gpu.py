@@ -231,3 +231,19 @@ def test_full_size_properties():
     for i in (0, 17, 63):
         z0, y0, x0 = (int(v) for v in pts[i])
         assert torch.equal(x[i], va[z0:z0 + wd, y0:y0 + wd, x0:x0 + wd])
+
+
+def test_recon_patches_3d_uploads_raw_detector_types_natively():
+    """uint16 projections (raw counts) are staged / uploaded as uint16 and widened on the device: same result as the float32 stack."""
+    n, nz, ntheta, wd = 64, 64, 24, 16
+    projs, theta = _projections_of_phantom(n, nz, ntheta, 8)
+    raw = np.clip(40000.0 * np.exp(-projs / 60.0), 0, 65535).astype(np.uint16)
+    dark = np.zeros((nz, n), np.float32)
+    flat = np.full((nz, n), 40000.0, np.float32)
+    p3d = Grid((nz, n, n), width=wd).select_by_indices([0, 5, 21, 40, 63])
+    a, pa = RC.recon_patches_3d(raw, theta, n / 2, p3d, dark_flat=(dark, flat), exact=True)
+    b, pb = RC.recon_patches_3d(raw.astype(np.float32), theta, n / 2, p3d, dark_flat=(dark, flat), exact=True)
+    np.testing.assert_array_equal(pa.points, pb.points)
+    np.testing.assert_array_equal(a, b)
+    c, _ = RC.recon_patches_3d(torch.from_numpy(raw.astype(np.float32)).cuda(), theta, n / 2, p3d, dark_flat=(dark, flat), exact=True)
+    np.testing.assert_array_equal(a, c)

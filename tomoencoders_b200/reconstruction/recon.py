@@ -119,7 +119,9 @@ def _copy_pool():
 class _ChunkFeeder:
     """Projection chunks projs[:, z:z+nc, :] as float32 CUDA tensors, one chunk ahead of the consumer: the strided host
     copy goes into one of two pinned staging buffers and the upload runs on a side stream while the previous chunk is
-    being filtered / back-projected (host arrays); device stacks are sliced on the device."""
+    being filtered / back-projected (host arrays); device stacks are sliced on the device.  uint8 / uint16 / float16
+    stacks (raw detector counts are uint16) are staged and uploaded in their own type -- half the PCIe bytes of the
+    reference's host-side .astype(float32) -- and widened to float32 on the device."""
 
     def __init__(self, projs, z_list, nc):
         self.projs, self.z_list, self.nc = projs, [int(z) for z in z_list], int(nc)
@@ -128,8 +130,12 @@ class _ChunkFeeder:
         if not self.on_device:
             dev = _device.device()
             shape = (int(projs.shape[0]), self.nc, int(projs.shape[2]))
-            self.pinned = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(2)]
-            self.dev = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(2)]
+            native = {"uint8": torch.uint8, "uint16": torch.uint16, "float16": torch.float16}
+            name = str(projs.dtype).replace("torch.", "")
+            self.sd = native.get(name, torch.float32)                   # staging / upload element type
+            self.pinned = [torch.empty(shape, dtype=self.sd).pin_memory() for _ in range(2)]
+            self.dev = [torch.empty(shape, dtype=self.sd, device=dev) for _ in range(2)]
+            self.work = torch.empty(shape, dtype=torch.float32, device=dev) if self.sd != torch.float32 else None
             self.ready = [torch.cuda.Event(), torch.cuda.Event()]
             self.free = [torch.cuda.Event(), torch.cuda.Event()]       # the consumer is done with dev[b]
             self.staged = [torch.cuda.Event(), torch.cuda.Event()]     # the upload out of pinned[b] has finished
@@ -172,7 +178,12 @@ class _ChunkFeeder:
             return out
         b = j & 1
         torch.cuda.current_stream().wait_event(self.ready[b])
-        return self.dev[b]
+        if self.work is None:
+            return self.dev[b]
+        d = self.dev[b]                                                # exact widening: (x - 0) / 1 in fp32
+        _lib.check(_lib.lib().te_rescale(d.data_ptr(), _device.te_dtype(d), self.work.data_ptr(), _lib.TE_F32, d.numel(), 0.0, 1.0,
+                                         _device.stream_ptr()), "te_rescale")
+        return self.work
 
     def release(self, j):
         """The consumer has enqueued all its work on chunk j: stage chunk j + 1 (overlaps with that work)."""

@@ -75,13 +75,16 @@ def main():
     from tomoencoders_b200.neural_nets import SurfaceSegmenter
     fe = SurfaceSegmenter(model_initialization="define-new", descriptor_tag="bench", mode="fp16", n_filters=[16, 32, 64],
                           n_blocks=3, activation="lrelu", batch_norm=True, isconcat=[True, True, True], pool_size=[2, 2, 2])
-    for name, kw in (("recon_patches_3d_r0.25_host", {}), ("recon_segment_patches_3d_r0.25_host", dict(segmenter=fe, segmenter_batch_size=256, rec_min_max=(-50.0, 50.0)))):
-        RC.recon_patches_3d(host[:, :32], th_h, center, Grid((32, n, n), width=32).select_random_sample(64), **kw)   # warm-up
+    host16 = np.clip(host * 1000 + 30000, 0, 65535).astype(np.uint16)       # raw detector counts: uploaded as uint16
+    seg_kw = dict(segmenter=fe, segmenter_batch_size=256, rec_min_max=(-50.0, 50.0))
+    for name, src, kw in (("recon_patches_3d_r0.25_host", host, {}), ("recon_segment_patches_3d_r0.25_host", host, seg_kw),
+                          ("recon_segment_patches_3d_r0.25_host_uint16", host16, seg_kw)):
+        RC.recon_patches_3d(src[:, :32], th_h, center, Grid((32, n, n), width=32).select_random_sample(64), **kw)   # warm-up
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        x, _ = RC.recon_patches_3d(host, th_h, center, sel, **kw)
+        x, _ = RC.recon_patches_3d(src, th_h, center, sel, **kw)
         dt = time.perf_counter() - t0
-        out[name] = {"patches": len(sel), "s": dt, "voxels_per_s": len(sel) * 32 ** 3 / dt, "h2d_bytes": host.nbytes, "d2h_bytes": x.nbytes}
+        out[name] = {"patches": len(sel), "s": dt, "voxels_per_s": len(sel) * 32 ** 3 / dt, "h2d_bytes": src.nbytes, "d2h_bytes": x.nbytes}
     try:
         from oracle import build_ref as R
         if R.built():
