@@ -24,6 +24,7 @@ def timed(fn, flush, reps=10):
     tot = 0.0
     for _ in range(reps):
         flush.zero_()
+        flush.view(torch.int32)[: flush.numel() // 8].sum()   # read pass: the dirty lines of the write leave L2 before the timed call
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         fn()
