@@ -78,6 +78,15 @@ int te_gather_norm(const void* vol, int vol_dtype, const int64_t vol_shape[3], c
                    const uint32_t* widths, int64_t n, const int32_t patch[3], int rescale, int do_clip,
                    float lo, float hi, void* out, int out_dtype, void* stream);
 
+/* Gather fused with the in-graph input standardisation of the ICIP porosity encoder (build_CAE_3D(stdinput=True),
+ * /root/reference/scratchpad/IEEE_ICIP_paper/porosity_encoders.py:89-98, 298-302): after the optional global rescale
+ * (rescale = 1: (v - lo) / (hi - lo + 1e-12), no clip, as in predict_embeddings) every patch is mapped to
+ *     (v - min_patch) / (max_patch - min_patch + 1e-12)        (fp32, IEEE divisions)
+ * minmax_scratch: device float32 scratch of 2 * n values (receives the per-patch raw extrema). */
+int te_gather_standardize(const void* vol, int vol_dtype, const int64_t vol_shape[3], const uint32_t* points,
+                          const uint32_t* widths, int64_t n, const int32_t patch[3], int rescale, float lo, float hi,
+                          float* minmax_scratch, void* out, int out_dtype, void* stream);
+
 /* Patch scatter / stitch.  Replaces Patches.fill_patches_in_volume (structures/patches.py:811-821)
  * and Grid.fill_patches_in_volume (structures/grid.py:338-348): sequential
  *     vol_out[z:z+wz, y:y+wy, x:x+wx] = sub_vols[i]

@@ -318,11 +318,24 @@ def segmenter_predict_probs(x, chunk_size, weights, min_max=None, **model_params
     return _chunked(x, chunk_size, min_max, True, lambda xi: unet_forward(xi, weights, **model_params), out)
 
 
-def encoder_predict_embeddings(x, chunk_size, weights, min_max=None, **model_params):
+def standardize(x):
+    """``standardize`` / ``stdize_vol`` of the ICIP porosity encoder (scratchpad/IEEE_ICIP_paper/porosity_encoders.py:89-98,
+    the Lambda in front of build_CAE_3D when stdinput=True, :298-302): every volume of the batch is mapped to
+    (vol - min) / (max - min + 1e-12) in float32.  x: (N, D, H, W, 1)."""
+    x = np.asarray(x, dtype=np.float32)
+    ax = tuple(range(1, x.ndim))
+    mn = x.min(axis=ax, keepdims=True)
+    mx = x.max(axis=ax, keepdims=True)
+    return ((x - mn) / (mx - mn + np.float32(1e-12))).astype(np.float32)
+
+
+def encoder_predict_embeddings(x, chunk_size, weights, min_max=None, stdinput=False, **model_params):
     """SelfSupervisedCAE.predict_embeddings, autoencoders.py:729-777 (no clip).  The reference's
     NameError on ``_rescale_data`` when min_max is given (quirk Q4) is not reproduced."""
     assert x.ndim == 5
     W = _W(None)
     z, _, _ = encoder_graph(_T(1, x.shape[1:4]), W, **model_params)
     out = np.zeros((len(x), z.c), dtype=np.float32)
-    return _chunked(x, chunk_size, min_max, False, lambda xi: encoder_forward(xi, weights, **model_params), out)
+    fwd = (lambda xi: encoder_forward(standardize(xi), weights, **model_params)) if stdinput else \
+        (lambda xi: encoder_forward(xi, weights, **model_params))
+    return _chunked(x, chunk_size, min_max, False, fwd, out)

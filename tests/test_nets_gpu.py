@@ -211,3 +211,61 @@ def test_segment_volume_host_paths_stream_slabs_and_match_the_device_path(vol_f1
     np.testing.assert_array_equal(ho.numpy(), expect)
     with pytest.raises(TypeError):
         fe.segment_volume(vol_f16, g, 8, min_max=mm_dev, out=np.zeros(vol_f16.shape, np.float32))
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("fp16", 2e-3)])
+def test_icip_porosity_encoder_config1b_stdinput(mode, tol):
+    """BASELINE config 1, variant 1b: the ICIP build_CAE_3D encoder (n_filters [32, 64, 128], no extra pool,
+    hidden_units [128, 32], stdinput=True: every patch standardised to its own [0, 1] in front of the encoder)."""
+    ICIP = dict(n_filters=[32, 64, 128], n_blocks=3, activation="lrelu", batch_norm=True, pool_size=[2, 2, 2],
+                hidden_units=[128, 32], POOL_FLAG=False)
+    vol, _ = phantom.volume_u8((96, 96, 96))
+    pts = phantom.random_points(vol.shape, 32, 24, 4)
+    p = Patches(vol.shape, "data", points=pts, widths=np.full_like(pts, 32))
+    w = OW.draw(O.encoder_spec((32,) * 3, **oparams(ICIP))[0], 13)
+    fe = SelfSupervisedCAE(model_initialization="define-new", model_size=(32,) * 3, descriptor_tag="icip", mode=mode,
+                           stdinput=True, **ICIP)
+    fe.models["encoder"].set_weights(w)
+    x = p.extract(vol, (32,) * 3)[..., np.newaxis]
+    ref = O.encoder_predict_embeddings(x, 8, w, stdinput=True, **oparams(ICIP))       # raw uint8 patches, like latent_vis.py:49
+    z = fe.predict_embeddings(x, 7, min_max=None)
+    assert z.shape == (24, 32) and relerr(z, ref) < tol, relerr(z, ref)
+    np.testing.assert_array_equal(fe.embed_volume(vol, p, 7), z)
+    # a global rescale in front of the standardisation changes nothing but rounding
+    mm = (float(vol[::2, ::2, ::2].min()), float(vol[::2, ::2, ::2].max()))
+    z_mm = fe.predict_embeddings(x, 7, min_max=mm)
+    ref_mm = O.encoder_predict_embeddings(x, 8, w, min_max=mm, stdinput=True, **oparams(ICIP))
+    assert relerr(z_mm, ref_mm) < tol and relerr(z_mm, z) < 10 * tol
+    # without the flag the same weights see un-standardised input: different latents
+    fe0 = SelfSupervisedCAE(model_initialization="define-new", model_size=(32,) * 3, descriptor_tag="icip", mode=mode, **ICIP)
+    fe0.models["encoder"].set_weights(w)
+    assert relerr(fe0.predict_embeddings(x, 7, min_max=mm), z) > 10 * tol
+
+
+def test_gather_standardize_is_bit_exact_in_fp32():
+    """te_gather_standardize, float32 output: (v - min_patch) / (max_patch - min_patch + 1e-12) per patch with numpy's
+    float32 arithmetic, binned (strided) patches and a constant patch included."""
+    from tomoencoders_b200 import _device, _lib
+    g = np.random.default_rng(3)
+    vol = g.integers(0, 4000, (40, 48, 64)).astype(np.uint16)
+    vol[:8, :8, :8] = 77                                              # a constant patch: 0 / 1e-12 = 0
+    pts = np.array([[0, 0, 0], [3, 5, 9], [8, 16, 24], [0, 0, 0]], np.uint32)
+    wds = np.array([[8, 8, 8], [8, 8, 8], [8, 8, 8], [32, 32, 32]], np.uint32)      # last one: binning 4
+    tv = torch.from_numpy(vol).cuda()
+    out = torch.empty((4, 8, 8, 8), dtype=torch.float32, device="cuda")
+    mm = torch.empty((4, 2), dtype=torch.float32, device="cuda")
+    for rescale, lo, hi in ((0, 0.0, 1.0), (1, 10.0, 3500.0)):
+        _lib.check(_lib.lib().te_gather_standardize(tv.data_ptr(), _lib.TE_U16, _lib.i64x3(vol.shape),
+                                                    _device.points_to_device(pts).data_ptr(), _device.points_to_device(wds).data_ptr(),
+                                                    4, _lib.i32x3((8, 8, 8)), rescale, lo, hi, mm.data_ptr(), out.data_ptr(),
+                                                    _lib.TE_F32, _device.stream_ptr()), "te_gather_standardize")
+        got = out.cpu().numpy()
+        for i in range(4):
+            b = int(wds[i, 0]) // 8
+            z, y, x = (int(v) for v in pts[i])
+            raw = vol[z:z + 8 * b:b, y:y + 8 * b:b, x:x + 8 * b:b].astype(np.float32)
+            if rescale:
+                raw = (raw - np.float32(lo)) / (np.float32(hi) - np.float32(lo) + np.float32(1e-12))
+            want = (raw - raw.min()) / (raw.max() - raw.min() + np.float32(1e-12))
+            np.testing.assert_array_equal(got[i], want.astype(np.float32))
+        assert not got[0].any() and got[1].min() == 0.0 and got[1].max() == 1.0

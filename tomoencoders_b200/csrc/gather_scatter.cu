@@ -161,6 +161,7 @@ template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; 
 struct NormParams {
   int rescale, do_clip;
   float lo, hi, inv;   // inv = 1 / (hi - lo + 1e-12) evaluated in fp32 as a division below
+  const float* pp;     // per-patch (min, max) of the raw voxels: "stdinput" standardisation after the optional rescale
 };
 
 // 8 consecutive elements (8 * sizeof(TIn) contiguous bytes at an arbitrary alignment) as raw 32-bit words:
@@ -244,6 +245,57 @@ __device__ __forceinline__ void norm_store8(float (&f)[8], const struct NormPara
   }
 }
 
+// per-patch standardisation of the ICIP encoder (scratchpad/IEEE_ICIP_paper/porosity_encoders.py:89-98):
+// v = (v - min_patch) / (max_patch - min_patch + 1e-12), fp32 with IEEE divisions, applied after the optional global
+// rescale (a monotone map, so the patch extrema are the mapped raw extrema)
+template <typename TOut>
+__device__ __forceinline__ void std_store8(float (&f)[8], const NormParams& q, float gden, float plo, float pden, TOut* o) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    float v = f[e];
+    if (q.rescale) v = __fdiv_rn(__fsub_rn(v, q.lo), gden);
+    f[e] = __fdiv_rn(__fsub_rn(v, plo), pden);
+  }
+  NormParams none = q;
+  none.rescale = 0;
+  norm_store8<TOut>(f, none, 1.f, 1.f, o);
+}
+
+// (min, max) of the raw voxels of every patch (binning included): one block per patch
+template <typename TIn>
+__global__ void __launch_bounds__(256) patch_minmax_kernel(GatherParams p, float* __restrict__ mm) {
+  const long long i = blockIdx.x;
+  const uint32_t z0 = __ldg(p.points + 3 * i), y0 = __ldg(p.points + 3 * i + 1), x0 = __ldg(p.points + 3 * i + 2);
+  const uint32_t b = __ldg(p.widths + 3 * i) / static_cast<uint32_t>(p.pz);
+  const TIn* src0 = reinterpret_cast<const TIn*>(p.vol) + (static_cast<long long>(z0) * p.Y + y0) * p.X + x0;
+  const long long row_pitch = static_cast<long long>(b) * p.X, plane_pitch = static_cast<long long>(b) * p.Y * p.X;
+  float lo = INFINITY, hi = -INFINITY;
+  const int rows = p.pz * p.py;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = warp; r < rows; r += 8) {                    // one warp per row of the patch
+    const int iz = r / p.py, iy = r - iz * p.py;
+    const TIn* row = src0 + iz * plane_pitch + iy * row_pitch;
+    for (int ix = lane; ix < p.px; ix += 32) {
+      const float v = to_f32<TIn>(row[static_cast<long long>(ix) * b]);
+      lo = fminf(lo, v);
+      hi = fmaxf(hi, v);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  __shared__ float slo[8], shi[8];
+  if (lane == 0) { slo[warp] = lo; shi[warp] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { lo = fminf(lo, slo[w]); hi = fmaxf(hi, shi[w]); }
+    mm[2 * i] = lo;
+    mm[2 * i + 1] = hi;
+  }
+}
+
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256) gather_norm_kernel(GatherParams p, NormParams q) {
   // item = 8 consecutive output elements (px % 8 == 0 checked on the host); unit = ppu planes of a patch
@@ -265,6 +317,13 @@ __global__ void __launch_bounds__(256) gather_norm_kernel(GatherParams p, NormPa
                       ((static_cast<long long>(z0) + static_cast<long long>(iz0) * b) * p.Y + y0) * p.X + x0;
     const long long row_pitch = static_cast<long long>(b) * p.X, plane_pitch = static_cast<long long>(b) * p.Y * p.X;
     TOut* dst0 = reinterpret_cast<TOut*>(p.out) + u * static_cast<long long>(items_per_unit) * 8;
+    float plo = 0.f, pden = 1.f;
+    if (q.pp) {
+      float a = __ldg(q.pp + 2 * i), c = __ldg(q.pp + 2 * i + 1);
+      if (q.rescale) { a = __fdiv_rn(__fsub_rn(a, q.lo), denom); c = __fdiv_rn(__fsub_rn(c, q.lo), denom); }
+      plo = a;
+      pden = __fadd_rn(__fsub_rn(c, a), 1e-12f);
+    }
     if (b == 1) {
       for (int it0 = threadIdx.x; it0 < items_per_unit; it0 += U * 256) {
         Raw8<TIn> raw[U];
@@ -283,7 +342,8 @@ __global__ void __launch_bounds__(256) gather_norm_kernel(GatherParams p, NormPa
           if (it >= items_per_unit) continue;
           float f[8];
           convert8<TIn>(raw[k], f);
-          norm_store8<TOut>(f, q, denom, inv, dst0 + static_cast<long long>(it) * 8);
+          if (q.pp) std_store8<TOut>(f, q, denom, plo, pden, dst0 + static_cast<long long>(it) * 8);
+          else norm_store8<TOut>(f, q, denom, inv, dst0 + static_cast<long long>(it) * 8);
         }
       }
     } else {
@@ -292,7 +352,8 @@ __global__ void __launch_bounds__(256) gather_norm_kernel(GatherParams p, NormPa
         const int iy = r / groups_per_row, gx = r - iy * groups_per_row;
         float f[8];
         load8_binned<TIn>(src0 + pl * plane_pitch + iy * row_pitch + static_cast<long long>(gx) * 8 * b, b, f);
-        norm_store8<TOut>(f, q, denom, inv, dst0 + static_cast<long long>(it) * 8);
+        if (q.pp) std_store8<TOut>(f, q, denom, plo, pden, dst0 + static_cast<long long>(it) * 8);
+        else norm_store8<TOut>(f, q, denom, inv, dst0 + static_cast<long long>(it) * 8);
       }
     }
   }
@@ -539,7 +600,7 @@ extern "C" int te_gather_norm(const void* vol, int vol_dtype, const int64_t vol_
   p.pz = patch[0]; p.py = patch[1]; p.px = patch[2];
   p.chunks_per_row = 0;
   p.total_chunks = 0;
-  NormParams q{rescale, do_clip, lo, hi, 0.f};
+  NormParams q{rescale, do_clip, lo, hi, 0.f, nullptr};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (tma_enabled() && tma_forced()) {   // measured slower than the SIMT kernel: opt-in only
     cudaError_t e = cudaSuccess;
@@ -555,6 +616,46 @@ extern "C" int te_gather_norm(const void* vol, int vol_dtype, const int64_t vol_
     case TE_F16: return launch_gather_norm<__half>(p, q, out_dtype, st);
     case TE_F32: return launch_gather_norm<float>(p, q, out_dtype, st);
     default: set_error("te_gather_norm: unsupported vol_dtype %d", vol_dtype); return TE_ERR_ARG;
+  }
+}
+
+template <typename TIn>
+static int launch_gather_std(const GatherParams& p, const NormParams& q, float* mm, int out_dtype, cudaStream_t st) {
+  TE_CHECK_ARG(p.n < (1LL << 31), "te_gather_standardize: too many patches for one launch");
+  patch_minmax_kernel<TIn><<<static_cast<unsigned>(p.n), 256, 0, st>>>(p, mm);
+  TE_LAUNCH_CHECK();
+  return launch_gather_norm<TIn>(p, q, out_dtype, st);
+}
+
+extern "C" int te_gather_standardize(const void* vol, int vol_dtype, const int64_t vol_shape[3], const uint32_t* points,
+                                     const uint32_t* widths, int64_t n, const int32_t patch[3], int rescale, float lo,
+                                     float hi, float* minmax_scratch, void* out, int out_dtype, void* stream) {
+  TE_CHECK_ARG(n >= 0, "te_gather_standardize: n < 0");
+  if (n == 0) return TE_OK;
+  TE_CHECK_ARG(vol && points && widths && out && minmax_scratch, "te_gather_standardize: null pointer");
+  TE_CHECK_ARG(out_dtype == TE_BF16 || out_dtype == TE_F16 || out_dtype == TE_F32,
+               "te_gather_standardize: out_dtype must be bf16, f16 or f32");
+  TE_CHECK_ARG(patch[2] % 8 == 0, "te_gather_standardize: patch x extent must be a multiple of 8");
+  TE_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "te_gather_standardize: out must be 16-byte aligned");
+  GatherParams p;
+  p.vol = static_cast<const uint8_t*>(vol);
+  p.out = static_cast<uint8_t*>(out);
+  p.points = points;
+  p.widths = widths;
+  p.n = n;
+  p.Y = vol_shape[1];
+  p.X = vol_shape[2];
+  p.pz = patch[0]; p.py = patch[1]; p.px = patch[2];
+  p.chunks_per_row = 0;
+  p.total_chunks = 0;
+  NormParams q{rescale, 0, lo, hi, 0.f, minmax_scratch};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (vol_dtype) {
+    case TE_U8: return launch_gather_std<uint8_t>(p, q, minmax_scratch, out_dtype, st);
+    case TE_U16: return launch_gather_std<uint16_t>(p, q, minmax_scratch, out_dtype, st);
+    case TE_F16: return launch_gather_std<__half>(p, q, minmax_scratch, out_dtype, st);
+    case TE_F32: return launch_gather_std<float>(p, q, minmax_scratch, out_dtype, st);
+    default: set_error("te_gather_standardize: unsupported vol_dtype %d", vol_dtype); return TE_ERR_ARG;
   }
 }
 

@@ -38,9 +38,12 @@ class SelfSupervisedCAE(EmbeddingLearner):
         super().__init__(**kwargs)
 
     def _build_models(self, model_size=(64, 64, 64), descriptor_tag="misc", **model_params):
-        """autoencoders.py:551-577."""
+        """autoencoders.py:551-577.  ``stdinput=True`` (build_CAE_3D of the ICIP porosity encoder,
+        scratchpad/IEEE_ICIP_paper/porosity_encoders.py:246-302; its encoder is build_encoder_r with POOL_FLAG=False)
+        standardises every input patch to its own [0, 1] range in front of the encoder, fused into the gather."""
         if model_params is None:
             raise ValueError("Need model hyperparameters or instance of model. Neither were provided")
+        self.stdinput = bool(model_params.pop("stdinput", False))
         self.models = {}
         self.model_size = tuple(int(s) for s in model_size)
         self.model_tag = "%s" % descriptor_tag
@@ -142,7 +145,7 @@ class SelfSupervisedCAE(EmbeddingLearner):
             xc = x[a:b, ..., 0]
             xc = _device.to_device(xc if on_device else np.ascontiguousarray(xc))
             net = enc.net_for(patch, max(chunk_size, b - a))
-            net.encoder_forward(normalize_chunk(xc, min_max, False, net), out=out[a:b])
+            net.encoder_forward(normalize_chunk(xc, min_max, False, net, standardize=self.stdinput), out=out[a:b])
         res = out if on_device else out.cpu().numpy()
         t_unit = (time.time() - t0) * 1000.0 / max(nb, 1)
         if TIMEIT:
@@ -172,7 +175,8 @@ class SelfSupervisedCAE(EmbeddingLearner):
             d_wds = _device.points_to_device(widths)
             for a in range(0, n, chunk_size):
                 b = min(a + chunk_size, n)
-                xa = gather_normalized(t_vol, vs, d_pts[a:b], d_wds[a:b], b - a, self.model_size, min_max, False, net)
+                xa = gather_normalized(t_vol, vs, d_pts[a:b], d_wds[a:b], b - a, self.model_size, min_max, False, net,
+                                       standardize=self.stdinput)
                 net.encoder_forward(xa, out=z[a:b])
         if out is not None and not _device.is_device_array(out):
             out[...] = z.cpu().numpy()

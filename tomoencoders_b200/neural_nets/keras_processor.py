@@ -147,7 +147,20 @@ class Model:
         return out[..., np.newaxis] if self.kind == "unet" else out
 
 
-def normalize_chunk(x_dev, min_max, clip, net):
+def _standardized(vol_dev, vol_shape, d_points, d_widths, n, patch, min_max, net):
+    """Gather + optional rescale + per-patch min-max standardisation (build_CAE_3D(stdinput=True),
+    scratchpad/IEEE_ICIP_paper/porosity_encoders.py:89-98) into network-input layout."""
+    out = torch.empty((n,) + tuple(patch), dtype=net.act_dtype, device=vol_dev.device)
+    mm = torch.empty((max(n, 1), 2), dtype=torch.float32, device=vol_dev.device)
+    lo, hi = (0.0, 1.0) if min_max is None else (float(min_max[0]), float(min_max[1]))
+    _lib.check(_lib.lib().te_gather_standardize(vol_dev.data_ptr(), _device.te_dtype(vol_dev), _lib.i64x3(vol_shape),
+                                                d_points.data_ptr(), d_widths.data_ptr(), n, _lib.i32x3(patch),
+                                                0 if min_max is None else 1, lo, hi, mm.data_ptr(), out.data_ptr(), net.act_te,
+                                                _device.stream_ptr()), "te_gather_standardize")
+    return out
+
+
+def normalize_chunk(x_dev, min_max, clip, net, standardize=False):
     """(n,pz,py,px) device tensor of any supported dtype -> activation dtype of ``net``, with the
     clip / rescale of predict_patches fused (te_gather_norm on the chunk viewed as a volume)."""
     n, pz, py, px = x_dev.shape
@@ -155,6 +168,8 @@ def normalize_chunk(x_dev, min_max, clip, net):
     pts = torch.zeros((n, 3), dtype=torch.int32, device=x_dev.device)
     pts[:, 0] = torch.arange(n, device=x_dev.device, dtype=torch.int32) * pz
     wds = torch.tensor([pz, py, px], dtype=torch.int32, device=x_dev.device).repeat(n, 1).contiguous()
+    if standardize:
+        return _standardized(x_dev, (n * pz, py, px), pts, wds, n, (pz, py, px), min_max, net)
     lo, hi = (0.0, 1.0) if min_max is None else (float(min_max[0]), float(min_max[1]))
     L = _lib.lib()
     _lib.check(L.te_gather_norm(x_dev.data_ptr(), _device.te_dtype(x_dev), _lib.i64x3((n * pz, py, px)),
@@ -164,8 +179,10 @@ def normalize_chunk(x_dev, min_max, clip, net):
     return out
 
 
-def gather_normalized(vol_dev, vol_shape, d_points, d_widths, n, patch, min_max, clip, net):
+def gather_normalized(vol_dev, vol_shape, d_points, d_widths, n, patch, min_max, clip, net, standardize=False):
     """Fused gather + clip + rescale straight from the volume into network-input layout."""
+    if standardize:
+        return _standardized(vol_dev, vol_shape, d_points, d_widths, n, patch, min_max, net)
     out = torch.empty((n,) + tuple(patch), dtype=net.act_dtype, device=vol_dev.device)
     lo, hi = (0.0, 1.0) if min_max is None else (float(min_max[0]), float(min_max[1]))
     L = _lib.lib()
