@@ -230,7 +230,9 @@ def test_icip_porosity_encoder_config1b_stdinput(mode, tol):
     ref = O.encoder_predict_embeddings(x, 8, w, stdinput=True, **oparams(ICIP))       # raw uint8 patches, like latent_vis.py:49
     z = fe.predict_embeddings(x, 7, min_max=None)
     assert z.shape == (24, 32) and relerr(z, ref) < tol, relerr(z, ref)
-    np.testing.assert_array_equal(fe.embed_volume(vol, p, 7), z)
+    # same standardised input through the fused gather; the 16384-wide dense layer sums its split-K partials with float
+    # atomics, so the two runs agree to rounding only
+    assert relerr(fe.embed_volume(vol, p, 7), z) < 1e-5
     # a global rescale in front of the standardisation changes nothing but rounding
     mm = (float(vol[::2, ::2, ::2].min()), float(vol[::2, ::2, ::2].max()))
     z_mm = fe.predict_embeddings(x, 7, min_max=mm)

@@ -478,21 +478,6 @@ static bool make_view(View4& v, const void* data, int dtype, const int64_t shape
     v.st[i] = strides[i];
     total *= shape[i];
   }
-  // merge adjacent dimensions that are contiguous in memory (a C-contiguous volume becomes ONE long row): the traversal
-  // then works on kSeg-element segments instead of paying its per-row index arithmetic for every 1 KB uint8 row
-  for (int i = 2; i >= 0;) {
-    if (v.n[i] > 1 && v.n[i + 1] > 0 && v.st[i] == v.st[i + 1] * v.n[i + 1]) {
-      v.n[i + 1] *= v.n[i];
-      for (int j = i; j > 0; --j) { v.n[j] = v.n[j - 1]; v.st[j] = v.st[j - 1]; }
-      v.n[0] = 1;
-      v.st[0] = 0;                    // position i now holds the next outer dimension: test it against i + 1 again
-      bool any = false;
-      for (int j = 0; j <= i; ++j) any |= v.n[j] > 1;
-      if (!any) break;
-    } else {
-      --i;
-    }
-  }
   const int es = dtype_size(dtype);
   *vec = v.st[3] == 1 && (reinterpret_cast<uintptr_t>(data) & 15) == 0 && (v.st[0] * es) % 16 == 0 &&
          (v.st[1] * es) % 16 == 0 && (v.st[2] * es) % 16 == 0;
