@@ -164,6 +164,48 @@ __global__ void __launch_bounds__(256) minmax_nd_kernel(View4 v, float* partial)
   }
 }
 
+// C-contiguous, 16-byte aligned data: plain grid-stride loop over 16-byte words, four independent loads per thread and trip
+// (the per-row traversal above pays its index arithmetic for every 1 KB row of a uint8 volume: 2.5 TB/s)
+template <typename T>
+__global__ void __launch_bounds__(256) minmax_flat_kernel(const T* __restrict__ data, long long n, float* partial) {
+  constexpr int EPV = 16 / sizeof(T);
+  MinMaxAcc<T> acc;
+  const long long nvec = n / EPV;
+  const uint4* p = reinterpret_cast<const uint4*>(data);
+  const long long stride = static_cast<long long>(gridDim.x) * 256;
+  long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  auto take = [&](const uint4& q) {
+    if constexpr (has_vec16<MinMaxAcc<T>>::value) {
+      acc.vec16(q);
+    } else {
+      const T* e = reinterpret_cast<const T*>(&q);
+#pragma unroll
+      for (int k = 0; k < EPV; ++k) acc(elem_f32<T>(e[k]));
+    }
+  };
+  for (; i + 3 * stride < nvec; i += 4 * stride) {
+    const uint4 q0 = __ldg(p + i), q1 = __ldg(p + i + stride), q2 = __ldg(p + i + 2 * stride), q3 = __ldg(p + i + 3 * stride);
+    take(q0); take(q1); take(q2); take(q3);
+  }
+  for (; i < nvec; i += stride) take(__ldg(p + i));
+  if (blockIdx.x == 0) for (long long x = nvec * EPV + threadIdx.x; x < n; x += 256) acc(elem_f32<T>(data[x]));
+  acc.finish();
+  float lo = acc.lo, hi = acc.hi;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  __shared__ float slo[8], shi[8];
+  if ((threadIdx.x & 31) == 0) { slo[threadIdx.x >> 5] = lo; shi[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { lo = fminf(lo, slo[w]); hi = fmaxf(hi, shi[w]); }
+    partial[2 * blockIdx.x] = lo;
+    partial[2 * blockIdx.x + 1] = hi;
+  }
+}
+
 __global__ void minmax_nd_final_kernel(const float* partial, int nblocks, float* out2) {
   float lo = INFINITY, hi = -INFINITY;
   for (int i = threadIdx.x; i < nblocks; i += 32) {
@@ -513,12 +555,23 @@ extern "C" int te_minmax_nd(const void* data, int dtype, const int64_t shape[4],
   bool vec;
   TE_CHECK_ARG(make_view(v, data, dtype, shape, strides, &vec), "te_minmax_nd: bad shape / strides");
   TE_CHECK_ARG(view_units(v) > 0, "te_minmax_nd: empty view");
-  const int blocks = blocks_for(view_units(v), 1, 4);   // <= 592: scratch holds 2 floats per block
+  int blocks = blocks_for(view_units(v), 1, 4);   // <= 592: scratch holds 2 floats per block
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  TE_DISPATCH_DTYPE(dtype, {
-    if (vec) minmax_nd_kernel<T, true><<<blocks, 256, 0, st>>>(v, scratch);
-    else minmax_nd_kernel<T, false><<<blocks, 256, 0, st>>>(v, scratch);
-  });
+  bool flat = (reinterpret_cast<uintptr_t>(data) & 15) == 0;
+  long long total = 1;
+  for (int i = 3; i >= 0; --i) {
+    if (v.n[i] > 1 && v.st[i] != total) flat = false;
+    total *= v.n[i];
+  }
+  if (flat) {
+    blocks = kNumSMs * 4;
+    TE_DISPATCH_DTYPE(dtype, { minmax_flat_kernel<T><<<blocks, 256, 0, st>>>(reinterpret_cast<const T*>(data), total, scratch); });
+  } else {
+    TE_DISPATCH_DTYPE(dtype, {
+      if (vec) minmax_nd_kernel<T, true><<<blocks, 256, 0, st>>>(v, scratch);
+      else minmax_nd_kernel<T, false><<<blocks, 256, 0, st>>>(v, scratch);
+    });
+  }
   TE_LAUNCH_CHECK();
   minmax_nd_final_kernel<<<1, 32, 0, st>>>(scratch, blocks, out2);
   TE_LAUNCH_CHECK();
