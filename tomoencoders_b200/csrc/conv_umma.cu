@@ -157,7 +157,9 @@ struct Cfg {
   static constexpr int NUM_W = W_FIT >= 4 ? 4 : W_FIT;
   static_assert(NUM_W >= 2, "weight ring needs two stages");
   static constexpr int STG_BYTES = EPI_GROUPS * STG_NBUF * STG_BUF;
-  static constexpr int SMEM_BYTES = STG_BYTES + NUM_A * A_STAGE + NUM_W * W_STAGE + 1024 /*barriers*/ + 1024 /*align*/;
+  static constexpr int BIAS_BYTES = 512;    // fp32 bias of up to 128 output channels lives in the second half of the barrier KB
+  static constexpr int SMEM_BYTES = STG_BYTES + NUM_A * A_STAGE + NUM_W * W_STAGE + 1024 /*barriers + bias*/ + 1024 /*align*/;
+  static_assert((2 * NUM_A + 2 * NUM_W + 4) * 8 + 4 <= 512, "barriers overlap the bias staging area");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
 };
 
@@ -185,6 +187,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   uint64_t* acc_empty = acc_full + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   uint8_t* stg = reinterpret_cast<uint8_t*>(bars) + 1024;    // [EPI_GROUPS][STG_NBUF][STG_BUF], 1024-aligned
+  // bias of all output channels: the epilogues read it 16 channels at a time as 128-bit shared-memory loads (it was one
+  // global load per accumulator element: 30 % of the epilogue's stall samples in the thin layers)
+  float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
+  const bool bias_in_smem = p.n_ntiles * NT * 4 <= C::BIAS_BYTES;
+  if (bias_in_smem)
+    for (int i = threadIdx.x; i < p.n_ntiles * NT; i += blockDim.x) s_bias[i] = __ldg(p.bias + i);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -392,7 +400,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       tc_fence_after();
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ab * C::ACC_COLS;
       const int iy = tc.y0 + my, ix = tc.x0 + mx;
-      const float* bias = p.bias + tc.ntile * NT;
+      const float* bias = (bias_in_smem ? s_bias : p.bias) + tc.ntile * NT;
       static_assert(TZ % 2 == 0, "the epilogue walks the z planes of a tile in pairs");
       bool done_by_tma = false;
       {
@@ -425,7 +433,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
                 float v[16];
 #pragma unroll
                 for (int j2 = 0; j2 < 16; ++j2) {
-                  float x = __uint_as_float(r[j2]) + __ldg(bias + cg + c0 + j2);
+                  float x = __uint_as_float(r[j2]) + bias[cg + c0 + j2];
                   if (p.act_lrelu) x = x > 0.f ? x : p.alpha * x;
                   v[j2] = x;
                 }
@@ -477,7 +485,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
             float v[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              float x = __uint_as_float(r[j]) + __ldg(bias + c0 + j);
+              float x = __uint_as_float(r[j]) + bias[c0 + j];
               if (p.act_lrelu) x = x > 0.f ? x : p.alpha * x;
               v[j] = x;
             }
@@ -526,7 +534,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
               float mval = fmaxf(__uint_as_float(r0[j]), __uint_as_float(r1[j]));
               mval = fmaxf(mval, __shfl_xor_sync(0xffffffffu, mval, 1));
               mval = fmaxf(mval, __shfl_xor_sync(0xffffffffu, mval, 8));
-              mval += __ldg(bias + c0 + j);
+              mval += bias[c0 + j];
               if (p.act_lrelu) mval = mval > 0.f ? mval : p.alpha * mval;
               v[j] = mval;
             }
