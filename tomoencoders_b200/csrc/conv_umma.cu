@@ -106,6 +106,15 @@ __device__ __forceinline__ void named_barrier(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// element-wise max of two packed 16-bit pairs (fp16 or bf16)
+__device__ __forceinline__ uint32_t max2_16(uint32_t a, uint32_t b, int fp16) {
+  if (fp16) {
+    const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+  const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
 __device__ __forceinline__ uint32_t pack2(float a, float b, int fp16) {
   if (fp16) {
     __half2 h = __floats2half2_rn(a, b);
@@ -460,7 +469,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
           done_by_tma = true;
         }
       }
-      if (!done_by_tma) {
+      // pooled-only layers (encoder: the un-pooled tensor has no consumer) and no fused head: nothing to do at full resolution
+      if (!done_by_tma && (p.out != nullptr || p.head_w != nullptr)) {
         // one z plane at a time: a voxel's channels are written back to back (interleaving the
         // stores of two planes measured 10-50 % slower on the store-bound layers)
 #pragma unroll 1
@@ -527,24 +537,27 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
             tmem_ld16(tbase + pz * NT + c0, r0);
             tmem_ld16(tbase + (pz + 1) * NT + c0, r1);
             tmem_ld_wait();
-            float v[16];
+            // bias, LeakyReLU (alpha > 0) and the rounding to 16 bits are all monotonic, so they commute with max: take
+            // the z pair in fp32, activate and round, then pool x (lane ^ 1) and y (lane ^ 8) on PACKED pairs -- half the
+            // shuffles of the fp32 version, identical results
+            uint32_t w[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              // bias + LeakyReLU are monotonic: pool the raw accumulators, activate once
-              float mval = fmaxf(__uint_as_float(r0[j]), __uint_as_float(r1[j]));
-              mval = fmaxf(mval, __shfl_xor_sync(0xffffffffu, mval, 1));
-              mval = fmaxf(mval, __shfl_xor_sync(0xffffffffu, mval, 8));
-              mval += bias[c0 + j];
-              if (p.act_lrelu) mval = mval > 0.f ? mval : p.alpha * mval;
-              v[j] = mval;
+            for (int j = 0; j < 16; j += 2) {
+              float a = fmaxf(__uint_as_float(r0[j]), __uint_as_float(r1[j])) + bias[c0 + j];
+              float b = fmaxf(__uint_as_float(r0[j + 1]), __uint_as_float(r1[j + 1])) + bias[c0 + j + 1];
+              if (p.act_lrelu) { a = a > 0.f ? a : p.alpha * a; b = b > 0.f ? b : p.alpha * b; }
+              w[j >> 1] = pack2(a, b, p.fp16);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              w[j] = max2_16(w[j], __shfl_xor_sync(0xffffffffu, w[j], 1), p.fp16);
+              w[j] = max2_16(w[j], __shfl_xor_sync(0xffffffffu, w[j], 8), p.fp16);
             }
             if (valid) {
               uint4* dst = reinterpret_cast<uint4*>(p.pool_out +
                                                     (pvox * p.pool_ctot + p.pool_coff + tc.ntile * NT + c0) * 2);
-              dst[0] = make_uint4(pack2(v[0], v[1], p.fp16), pack2(v[2], v[3], p.fp16), pack2(v[4], v[5], p.fp16),
-                                  pack2(v[6], v[7], p.fp16));
-              dst[1] = make_uint4(pack2(v[8], v[9], p.fp16), pack2(v[10], v[11], p.fp16), pack2(v[12], v[13], p.fp16),
-                                  pack2(v[14], v[15], p.fp16));
+              dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+              dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
             }
           }
         }
