@@ -106,6 +106,17 @@ __device__ __forceinline__ void named_barrier(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// 16 consecutive floats from shared memory as four 128-bit loads (the pointer arithmetic on the aligned dynamic buffer hides
+// the address space from the compiler, which would otherwise emit 16 generic loads)
+__device__ __forceinline__ void lds_f16x(const float* p, float (&b)[16]) {
+  const uint32_t a = smem_u32(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(b[4 * i]), "=f"(b[4 * i + 1]), "=f"(b[4 * i + 2]), "=f"(b[4 * i + 3])
+                 : "r"(a + 16 * i));
+}
+
 // element-wise max of two packed 16-bit pairs (fp16 or bf16)
 __device__ __forceinline__ uint32_t max2_16(uint32_t a, uint32_t b, int fp16) {
   if (fp16) {
@@ -166,8 +177,8 @@ struct Cfg {
   static constexpr int NUM_W = W_FIT >= 4 ? 4 : W_FIT;
   static_assert(NUM_W >= 2, "weight ring needs two stages");
   static constexpr int STG_BYTES = EPI_GROUPS * STG_NBUF * STG_BUF;
-  static constexpr int BIAS_BYTES = 512;    // fp32 bias of up to 128 output channels lives in the second half of the barrier KB
-  static constexpr int SMEM_BYTES = STG_BYTES + NUM_A * A_STAGE + NUM_W * W_STAGE + 1024 /*barriers + bias*/ + 1024 /*align*/;
+  static constexpr int BIAS_BYTES = 1024;   // fp32 bias of up to 256 output channels behind the barriers, then 128 head weights
+  static constexpr int SMEM_BYTES = STG_BYTES + NUM_A * A_STAGE + NUM_W * W_STAGE + 2048 /*barriers + bias*/ + 1024 /*align*/;
   static_assert((2 * NUM_A + 2 * NUM_W + 4) * 8 + 4 <= 512, "barriers overlap the bias staging area");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
 };
@@ -195,13 +206,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   uint64_t* acc_full = w_empty + kNumWStages;    // [2]
   uint64_t* acc_empty = acc_full + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  uint8_t* stg = reinterpret_cast<uint8_t*>(bars) + 1024;    // [EPI_GROUPS][STG_NBUF][STG_BUF], 1024-aligned
+  uint8_t* stg = reinterpret_cast<uint8_t*>(bars) + 2048;    // [EPI_GROUPS][STG_NBUF][STG_BUF], 1024-aligned
   // bias of all output channels: the epilogues read it 16 channels at a time as 128-bit shared-memory loads (it was one
   // global load per accumulator element: 30 % of the epilogue's stall samples in the thin layers)
   float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
-  const bool bias_in_smem = p.n_ntiles * NT * 4 <= C::BIAS_BYTES;
-  if (bias_in_smem)
+  const bool bias_all = p.n_ntiles * NT * 4 <= C::BIAS_BYTES;    // else the epilogue stages one NT slice per tile
+  if (bias_all)
     for (int i = threadIdx.x; i < p.n_ntiles * NT; i += blockDim.x) s_bias[i] = __ldg(p.bias + i);
+  float* s_head = s_bias + 256;                                  // weights of the fused 1x1x1 head (one Cout tile)
+  if (p.head_w != nullptr)
+    for (int i = threadIdx.x; i < NT && i < 128; i += blockDim.x) s_head[i] = __ldg(p.head_w + i);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -409,7 +423,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       tc_fence_after();
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ab * C::ACC_COLS;
       const int iy = tc.y0 + my, ix = tc.x0 + mx;
-      const float* bias = (bias_in_smem ? s_bias : p.bias) + tc.ntile * NT;
+      const float* bias = s_bias + tc.ntile * NT;
+      if (!bias_all) {                            // rare (> 384 output channels): this tile's slice, all epilogue warps together
+        constexpr int NEPI = 128 * C::EPI_GROUPS;
+        named_barrier(3, NEPI);                   // everybody is done with the previous tile's slice
+        for (int i = eg * 128 + m; i < NT; i += NEPI) s_bias[i] = __ldg(p.bias + tc.ntile * NT + i);
+        named_barrier(3, NEPI);
+        bias = s_bias;
+      }
       static_assert(TZ % 2 == 0, "the epilogue walks the z planes of a tile in pairs");
       bool done_by_tma = false;
       {
@@ -439,10 +460,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
                 uint32_t r[16];
                 tmem_ld16(tbase + pz * NT + cg + c0, r);
                 tmem_ld_wait();
-                float v[16];
+                float v[16], bs[16];
+                lds_f16x(bias + cg + c0, bs);
 #pragma unroll
                 for (int j2 = 0; j2 < 16; ++j2) {
-                  float x = __uint_as_float(r[j2]) + bias[cg + c0 + j2];
+                  float x = __uint_as_float(r[j2]) + bs[j2];
                   if (p.act_lrelu) x = x > 0.f ? x : p.alpha * x;
                   v[j2] = x;
                 }
@@ -492,16 +514,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
             uint32_t r[16];
             tmem_ld16(tbase + pz * NT + c0, r);     // warp-collective: executed by all lanes, valid or not
             tmem_ld_wait();
-            float v[16];
+            float v[16], bs[16];
+            lds_f16x(bias + c0, bs);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              float x = __uint_as_float(r[j]) + bias[c0 + j];
+              float x = __uint_as_float(r[j]) + bs[j];
               if (p.act_lrelu) x = x > 0.f ? x : p.alpha * x;
               v[j] = x;
             }
             if (p.head_w != nullptr) {
+              float hw[16];
+              lds_f16x(s_head + c0, hw);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) head_acc = fmaf(v[j], __ldg(p.head_w + c0 + j), head_acc);
+              for (int j = 0; j < 16; ++j) head_acc = fmaf(v[j], hw[j], head_acc);
             }
             if (p.out != nullptr && valid) {
               uint4* dst = reinterpret_cast<uint4*>(p.out + (ovox * p.out_ctot + p.out_coff + tc.ntile * NT + c0) * 2);
@@ -541,10 +566,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
             // the z pair in fp32, activate and round, then pool x (lane ^ 1) and y (lane ^ 8) on PACKED pairs -- half the
             // shuffles of the fp32 version, identical results
             uint32_t w[8];
+            float bs[16];
+            lds_f16x(bias + c0, bs);
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
-              float a = fmaxf(__uint_as_float(r0[j]), __uint_as_float(r1[j])) + bias[c0 + j];
-              float b = fmaxf(__uint_as_float(r0[j + 1]), __uint_as_float(r1[j + 1])) + bias[c0 + j + 1];
+              float a = fmaxf(__uint_as_float(r0[j]), __uint_as_float(r1[j])) + bs[j];
+              float b = fmaxf(__uint_as_float(r0[j + 1]), __uint_as_float(r1[j + 1])) + bs[j + 1];
               if (p.act_lrelu) { a = a > 0.f ? a : p.alpha * a; b = b > 0.f ? b : p.alpha * b; }
               w[j >> 1] = pack2(a, b, p.fp16);
             }
