@@ -76,24 +76,28 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* s
 // `reuse` (un-haloed kernels whose channel chunks all fit the input ring): the outer index is the
 // spatial tile, the inner index j enumerates the (Cout tile, sub-position) pairs that share its
 // input boxes.  Otherwise j = 0 and t enumerates everything.
-__device__ __forceinline__ TileCoord decode_tile(const KParams& p, long long t, int TZ, bool reuse = false, int j = 0) {
+__device__ __forceinline__ TileCoord decode_tile(const KParams& p, long long tile, int TZ, bool reuse = false, int j = 0) {
   TileCoord c;
+  // 32-bit index arithmetic (the launch checks total_tiles < 2^31): the 64-bit divisions of the first version cost
+  // ~100 instructions each and sat on the critical path of every role at every tile
+  unsigned t = static_cast<unsigned>(tile);
+  const unsigned tx = p.tiles_x, ty = p.tiles_y, tz = p.tiles_z;
   if (reuse) {
-    c.x0 = static_cast<int>(t % p.tiles_x) * 8;  t /= p.tiles_x;
-    c.y0 = static_cast<int>(t % p.tiles_y) * 16; t /= p.tiles_y;
-    c.z0 = static_cast<int>(t % p.tiles_z) * TZ; t /= p.tiles_z;
+    c.x0 = static_cast<int>(t % tx) * 8;  t /= tx;
+    c.y0 = static_cast<int>(t % ty) * 16; t /= ty;
+    c.z0 = static_cast<int>(t % tz) * TZ; t /= tz;
     c.n = static_cast<int>(t);
     c.sub = j % p.nsub;
     c.ntile = j / p.nsub;
     return c;
   }
-  c.x0 = static_cast<int>(t % p.tiles_x) * 8;  t /= p.tiles_x;
-  c.y0 = static_cast<int>(t % p.tiles_y) * 16; t /= p.tiles_y;
-  c.z0 = static_cast<int>(t % p.tiles_z) * TZ; t /= p.tiles_z;
-  c.n = static_cast<int>(t % p.N);             t /= p.N;
+  c.x0 = static_cast<int>(t % tx) * 8;  t /= tx;
+  c.y0 = static_cast<int>(t % ty) * 16; t /= ty;
+  c.z0 = static_cast<int>(t % tz) * TZ; t /= tz;
+  c.n = static_cast<int>(t % static_cast<unsigned>(p.N)); t /= static_cast<unsigned>(p.N);
   // sub-positions of a transposed conv are the slowest index: measured faster on B200 than
   // interleaving the 8 sub-position CTAs of one output block (623 vs 706 us for dec0.upconv)
-  c.sub = static_cast<int>(t % p.nsub);        t /= p.nsub;
+  c.sub = static_cast<int>(t % static_cast<unsigned>(p.nsub)); t /= static_cast<unsigned>(p.nsub);
   c.ntile = static_cast<int>(t);
   return c;
 }
@@ -772,6 +776,7 @@ int conv_umma_grid(const ConvUmmaLaunch& L) {
 cudaError_t conv_umma_launch(const ConvUmmaLaunch& L, cudaStream_t stream) {
   const KParams p = make_params(L);
   if (p.total_tiles <= 0) return cudaSuccess;
+  if (p.total_tiles >= (1LL << 31)) return cudaErrorInvalidValue;   // decode_tile works on 32-bit indices
   // un-haloed kernels may iterate the (Cout tile, sub-position) pairs inside a spatial tile (input reuse)
   const int grid = static_cast<int>(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs);
 #define TE_CONV_CASE(cb, nt, tz)                                                          \
