@@ -122,10 +122,11 @@ __global__ void __launch_bounds__(kThreadsC1, NT <= 16 ? 2 : 1) conv1_umma_kerne
     constexpr int kPre = (kInTile + 255) / 256;       // input elements per builder thread
     uint16_t pre[kPre];
     auto fetch = [&](long long tile) {
-      long long t = tile;
-      const int x0 = static_cast<int>(t % p.tiles_x) * 8; t /= p.tiles_x;
-      const int y0 = static_cast<int>(t % p.tiles_y) * 16; t /= p.tiles_y;
-      const int z0 = static_cast<int>(t % p.tiles_z) * kTZ; t /= p.tiles_z;
+      unsigned t = static_cast<unsigned>(tile);           // 32-bit divisions (the launch checks total_tiles < 2^31)
+      const unsigned ntx = p.tiles_x, nty = p.tiles_y, ntz = p.tiles_z;
+      const int x0 = static_cast<int>(t % ntx) * 8; t /= ntx;
+      const int y0 = static_cast<int>(t % nty) * 16; t /= nty;
+      const int z0 = static_cast<int>(t % ntz) * kTZ; t /= ntz;
       const long long n = t;
 #pragma unroll
       for (int j = 0; j < kPre; ++j) {
@@ -190,10 +191,11 @@ __global__ void __launch_bounds__(kThreadsC1, NT <= 16 ? 2 : 1) conv1_umma_kerne
     const int m = q * 32 + lane, my = m >> 3, mx = m & 7;
     uint32_t ab = 0, abph = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      long long t = tile;
-      const int x0 = static_cast<int>(t % p.tiles_x) * 8; t /= p.tiles_x;
-      const int y0 = static_cast<int>(t % p.tiles_y) * 16; t /= p.tiles_y;
-      const int z0 = static_cast<int>(t % p.tiles_z) * kTZ; t /= p.tiles_z;
+      unsigned t = static_cast<unsigned>(tile);           // 32-bit divisions (the launch checks total_tiles < 2^31)
+      const unsigned ntx = p.tiles_x, nty = p.tiles_y, ntz = p.tiles_z;
+      const int x0 = static_cast<int>(t % ntx) * 8; t /= ntx;
+      const int y0 = static_cast<int>(t % nty) * 16; t /= nty;
+      const int z0 = static_cast<int>(t % ntz) * kTZ; t /= ntz;
       const long long n = t;
       mbar_wait(acc_full + ab, abph);
       tc_fence_after();
@@ -272,6 +274,7 @@ bool conv1_umma_try(const TView& in, const TView& out, const float* w, const flo
   p.total_tiles = static_cast<long long>(in.N) * p.tiles_z * p.tiles_y * p.tiles_x;
   p.lrelu = lrelu; p.alpha = alpha; p.fp16 = act_type == ACT_F16;
   if (p.total_tiles <= 0) { *err = cudaSuccess; return true; }
+  if (p.total_tiles >= (1LL << 31)) return false;       // 32-bit tile indices in the kernel: let the caller fall back
   const int ctas = (out.C == 16 ? 2 : 1) * kNumSMs;
   const int grid = static_cast<int>(p.total_tiles < ctas ? p.total_tiles : ctas);
   *err = out.C == 16 ? launch_nt<16>(p, grid, st) : launch_nt<32>(p, grid, st);

@@ -99,10 +99,11 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     if (elect_one()) {
       uint32_t xc = 0, yc = 0;
       for (long long u = first; u < p.units && group < p.ngroups; u += step) {
-        long long t = u;
-        const int x0 = static_cast<int>(t % p.tiles_x) * 8; t /= p.tiles_x;
-        const int y0 = static_cast<int>(t % p.tiles_y) * 16; t /= p.tiles_y;
-        const int z0 = static_cast<int>(t % p.zsegs) * p.zs; t /= p.zsegs;
+        unsigned t = static_cast<unsigned>(u);             // 32-bit divisions (unit counts are far below 2^31)
+        const unsigned ntx = p.tiles_x, nty = p.tiles_y, nzs = p.zsegs;
+        const int x0 = static_cast<int>(t % ntx) * 8; t /= ntx;
+        const int y0 = static_cast<int>(t % nty) * 16; t /= nty;
+        const int z0 = static_cast<int>(t % nzs) * p.zs; t /= nzs;
         const int n = static_cast<int>(t);
         for (int pi = 0; pi < p.zs + 2; ++pi) {
           const uint32_t s = xc % kNXS;
