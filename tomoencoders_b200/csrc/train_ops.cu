@@ -22,6 +22,19 @@ namespace te {
 bool wgrad_umma_ok(const te_tensor& x, const te_tensor& dy);                                                    // wgrad_umma.cu
 int wgrad_umma(const te_tensor& x, const te_tensor& dy, float* dw, int dw_cin, int ci_off, cudaStream_t st);
 namespace {
+// t / b with the remainder, through a 32-bit division whenever the dividend fits (it practically always does): the element
+// and tile decodes below chain 3-5 of these per item, and a 64-bit division is ~5x the instructions of a 32-bit one
+__device__ __forceinline__ long long divmod32(long long a, int b, int& rem) {
+  if (static_cast<unsigned long long>(a) <= 0xffffffffull) {
+    const unsigned q = static_cast<unsigned>(a) / static_cast<unsigned>(b);
+    rem = static_cast<int>(static_cast<unsigned>(a) - q * static_cast<unsigned>(b));
+    return q;
+  }
+  const long long q = a / b;
+  rem = static_cast<int>(a - q * b);
+  return q;
+}
+
 
 template <typename T> __device__ __forceinline__ float ldv(const T* p);
 template <> __device__ __forceinline__ float ldv<float>(const float* p) { return *p; }
@@ -394,8 +407,8 @@ __global__ void __launch_bounds__(256) lrelu_bwd_s2d_v8_kernel(TView a, TView da
     long long t = item;
     const int sub = static_cast<int>(t & 7); t >>= 3;
     const long long lv = t;
-    const int x = static_cast<int>(t % Wl); t /= Wl;
-    const int y = static_cast<int>(t % Hl); t /= Hl;
+    int x_r; t = divmod32(t, Wl, x_r); const int x = x_r;
+    int y_r; t = divmod32(t, Hl, y_r); const int y = y_r;
     const int z = static_cast<int>(t % Dl);
     const long long n = t / Dl;
     const long long hv = ((n * a.D + 2 * z + (sub >> 2)) * a.H + 2 * y + ((sub >> 1) & 1)) * a.W + 2 * x + (sub & 1);
@@ -424,8 +437,8 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_v8_kernel(TView x, TView dpo
   for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
     const int c0 = static_cast<int>(e % G) * 8;
     long long t = e / G;
-    const int ox = static_cast<int>(t % Wo); t /= Wo;
-    const int oy = static_cast<int>(t % Ho); t /= Ho;
+    int ox_r; t = divmod32(t, Wo, ox_r); const int ox = ox_r;
+    int oy_r; t = divmod32(t, Ho, oy_r); const int oy = oy_r;
     const int oz = static_cast<int>(t % Do);
     const long long n = t / Do;
     float v[8][8];
@@ -474,8 +487,8 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(TView x, TView dpool, 
   for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
     const int c = static_cast<int>(e % C);
     long long t = e / C;
-    const int ox = static_cast<int>(t % Wo); t /= Wo;
-    const int oy = static_cast<int>(t % Ho); t /= Ho;
+    int ox_r; t = divmod32(t, Wo, ox_r); const int ox = ox_r;
+    int oy_r; t = divmod32(t, Ho, oy_r); const int oy = oy_r;
     const int oz = static_cast<int>(t % Do);
     const long long n = t / Do;
     float best = -INFINITY;
@@ -519,8 +532,8 @@ __global__ void __launch_bounds__(256) lrelu_bwd_s2d_kernel(TView a, TView da, T
   for (long long e = start; e < total; e += stride) {
     long long t = e / C;
     const int sub = static_cast<int>(t & 7); t >>= 3;
-    const int x = static_cast<int>(t % Wl); t /= Wl;
-    const int y = static_cast<int>(t % Hl); t /= Hl;
+    int x_r; t = divmod32(t, Wl, x_r); const int x = x_r;
+    int y_r; t = divmod32(t, Hl, y_r); const int y = y_r;
     const int z = static_cast<int>(t % Dl);
     const long long n = t / Dl;
     const long long hv = ((n * a.D + 2 * z + (sub >> 2)) * a.H + 2 * y + ((sub >> 1) & 1)) * a.W + 2 * x + (sub & 1);
@@ -560,8 +573,8 @@ __global__ void __launch_bounds__(256) upconv_dgrad_kernel(TView dz, TView dx, c
   for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
     const int ci = static_cast<int>(e % Ci);
     long long t = e / Ci;
-    const int x = static_cast<int>(t % dx.W); t /= dx.W;
-    const int y = static_cast<int>(t % dx.H); t /= dx.H;
+    int x_r; t = divmod32(t, dx.W, x_r); const int x = x_r;
+    int y_r; t = divmod32(t, dx.H, y_r); const int y = y_r;
     const int z = static_cast<int>(t % dx.D);
     const long long n = t / dx.D;
     float acc = 0.f;
@@ -595,8 +608,8 @@ __global__ void __launch_bounds__(256) upconv_wgrad_kernel(TView x, TView dz, fl
   float acc = 0.f;
   for (long long v = v0; v < v1; ++v) {
     long long t = v;
-    const int xx = static_cast<int>(t % x.W); t /= x.W;
-    const int yy = static_cast<int>(t % x.H); t /= x.H;
+    int xx_r; t = divmod32(t, x.W, xx_r); const int xx = xx_r;
+    int yy_r; t = divmod32(t, x.H, yy_r); const int yy = yy_r;
     const int zz = static_cast<int>(t % x.D);
     const long long n = t / x.D;
     const long long hv = ((n * dz.D + zz * s + a) * dz.H + yy * s + b) * dz.W + xx * s + c;
@@ -625,8 +638,8 @@ __global__ void __launch_bounds__(256) conv3_wgrad_simt_kernel(TView x, TView dy
   float acc = 0.f;
   for (long long v = v0; v < v1; ++v) {
     long long t = v;
-    const int xx = static_cast<int>(t % dy.W) + dxx; t /= dy.W;
-    const int yy = static_cast<int>(t % dy.H) + dyy; t /= dy.H;
+    int xx_r; t = divmod32(t, dy.W, xx_r); const int xx = xx_r + dxx;
+    int yy_r; t = divmod32(t, dy.H, yy_r); const int yy = yy_r + dyy;
     const int zz = static_cast<int>(t % dy.D) + dz;
     const long long n = t / dy.D;
     if (xx < 0 || xx >= x.W || yy < 0 || yy >= x.H || zz < 0 || zz >= x.D) continue;
@@ -656,9 +669,9 @@ __global__ void __launch_bounds__(1024) conv3_wgrad_c1_kernel(TView x, TView dy,
   float acc = 0.f;
   for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
     long long t = tile;
-    const int x0 = static_cast<int>(t % tiles_x) * 8; t /= tiles_x;
-    const int y0 = static_cast<int>(t % tiles_y) * 16; t /= tiles_y;
-    const int z0 = static_cast<int>(t % tiles_z) * TZ; t /= tiles_z;
+    int x0_r; t = divmod32(t, tiles_x, x0_r); const int x0 = x0_r * 8;
+    int y0_r; t = divmod32(t, tiles_y, y0_r); const int y0 = y0_r * 16;
+    int z0_r; t = divmod32(t, tiles_z, z0_r); const int z0 = z0_r * TZ;
     const long long n = t;
     __syncthreads();
     for (int i = tid; i < (TZ + 2) * 180; i += blockDim.x) {
@@ -715,9 +728,9 @@ __global__ void __launch_bounds__(384, 2) conv3_wgrad_c1_tiled_kernel(TView x, T
     for (int b = 0; b < 3; ++b) acc[a][b][0] = acc[a][b][1] = acc[a][b][2] = acc[a][b][3] = 0.f;
   for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
     long long t = tile;
-    const int x0 = static_cast<int>(t % tiles_x) * 8; t /= tiles_x;
-    const int y0 = static_cast<int>(t % tiles_y) * 16; t /= tiles_y;
-    const int z0 = static_cast<int>(t % tiles_z) * TZ; t /= tiles_z;
+    int x0_r; t = divmod32(t, tiles_x, x0_r); const int x0 = x0_r * 8;
+    int y0_r; t = divmod32(t, tiles_y, y0_r); const int y0 = y0_r * 16;
+    int z0_r; t = divmod32(t, tiles_z, z0_r); const int z0 = z0_r * TZ;
     const long long n = t;
     __syncthreads();
     for (int i = tid; i < (TZ + 2) * 180; i += blockDim.x) {
@@ -871,9 +884,9 @@ wgrad_mma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
   auto issue = [&](long long tile, int stage) {          // warp 0, warp-uniform; one elected lane issues
     long long t = tile;
-    const int x0 = static_cast<int>(t % p.tiles_x) * 8; t /= p.tiles_x;
-    const int y0 = static_cast<int>(t % p.tiles_y) * 16; t /= p.tiles_y;
-    const int z0 = static_cast<int>(t % p.tiles_z) * kWgTZ; t /= p.tiles_z;
+    int x0_r; t = divmod32(t, p.tiles_x, x0_r); const int x0 = x0_r * 8;
+    int y0_r; t = divmod32(t, p.tiles_y, y0_r); const int y0 = y0_r * 16;
+    int z0_r; t = divmod32(t, p.tiles_z, z0_r); const int z0 = z0_r * kWgTZ;
     const int n = static_cast<int>(t);
     if (elect_one()) {
       mbar_expect_tx(full + stage, X_BYTES + D_BYTES);
