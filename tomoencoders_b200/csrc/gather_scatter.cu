@@ -307,6 +307,8 @@ __global__ void __launch_bounds__(256) gather_norm_kernel(GatherParams p, NormPa
   const float denom = q.hi - q.lo + 1e-12f;
   const float inv = 1.0f / denom;
   constexpr int U = sizeof(TIn) == 4 ? 4 : 8;   // independent items (raw loads) in flight per thread
+  const int d_gx = 256 % groups_per_row, d_rows = 256 / groups_per_row;      // what +256 items means in (group, row, plane)
+  const int d_iy = d_rows % p.py, d_pl = d_rows / p.py;
   for (long long u = blockIdx.x; u < units; u += gridDim.x) {
     const long long i = u / upp;
     const int iz0 = static_cast<int>(u - i * upp) * p.ppu;
@@ -327,14 +329,18 @@ __global__ void __launch_bounds__(256) gather_norm_kernel(GatherParams p, NormPa
     if (b == 1) {
       for (int it0 = threadIdx.x; it0 < items_per_unit; it0 += U * 256) {
         Raw8<TIn> raw[U];
+        // (plane, row, group) of the first item by division, the following ones (+256 items each) by carries
+        int pl = it0 / items_per_plane, r0 = it0 - pl * items_per_plane;
+        int iy = r0 / groups_per_row, gx = r0 - iy * groups_per_row;
 #pragma unroll
         for (int k = 0; k < U; ++k) {
           const int it = it0 + k * 256;
-          if (it < items_per_unit) {
-            const int pl = it / items_per_plane, r = it - pl * items_per_plane;
-            const int iy = r / groups_per_row, gx = r - iy * groups_per_row;
-            load8_raw<TIn>(src0 + pl * plane_pitch + iy * row_pitch + gx * 8, raw[k]);
-          }
+          if (it < items_per_unit) load8_raw<TIn>(src0 + pl * plane_pitch + iy * row_pitch + gx * 8, raw[k]);
+          gx += d_gx;
+          if (gx >= groups_per_row) { gx -= groups_per_row; ++iy; }
+          iy += d_iy;
+          if (iy >= p.py) { iy -= p.py; ++pl; }
+          pl += d_pl;
         }
 #pragma unroll
         for (int k = 0; k < U; ++k) {
