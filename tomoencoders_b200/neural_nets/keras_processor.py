@@ -381,9 +381,9 @@ class Vox2VoxProcessor_fCNN(GenericKerasProcessor):
         covers = disjoint and n * w3[0] * w3[1] * w3[2] == vs[0] * vs[1] * vs[2]
         if out is None:
             t_out = torch.zeros(vs, dtype=o_dtype, device=dev)
-        elif covers and not _device.is_device_array(out):
-            if tuple(out.shape) != vs or _device.as_host_tensor(out) is None or _device.as_host_tensor(out).dtype != o_dtype:
-                raise TypeError("out must be a contiguous %s array of shape %s" % (o_dtype, vs))
+        elif covers and not _device.is_device_array(out) and _device.as_host_tensor(out) is not None:
+            if tuple(out.shape) != vs or _device.as_host_tensor(out).dtype != o_dtype:
+                raise TypeError("out must be a %s array of shape %s" % (o_dtype, vs))
             t_out = torch.empty(vs, dtype=o_dtype, device=dev)
         else:
             t_out = _device.to_device(out)
