@@ -271,3 +271,16 @@ def test_gather_standardize_is_bit_exact_in_fp32():
             want = (raw - raw.min()) / (raw.max() - raw.min() + np.float32(1e-12))
             np.testing.assert_array_equal(got[i], want.astype(np.float32))
         assert not got[0].any() and got[1].min() == 0.0 and got[1].max() == 1.0
+
+
+def test_wide_unet_512_bottleneck_channels():
+    """M_a03-like filters [32, 64, 128]: the bottleneck has 512 output channels, more than the conv kernel keeps in its
+    shared-memory bias table, so the epilogue stages one 128-channel slice per tile."""
+    P = dict(n_filters=[32, 64, 128], n_blocks=3, activation="lrelu", batch_norm=True, isconcat=[True] * 3, pool_size=[2, 2, 2])
+    w = OW.draw(O.unet_spec(**oparams(P)), 31)
+    fe = SurfaceSegmenter(model_initialization="define-new", descriptor_tag="M_a03", mode="fp16", **P)
+    fe.models["segmenter"].set_weights(w)
+    x = np.random.default_rng(0).uniform(0, 1, (3, 32, 32, 32, 1)).astype(np.float32)
+    y = fe.predict_patches("segmenter", x, 2, None, min_max=(0.0, 1.0))
+    ref = O.segmenter_predict_patches(x, 2, w, min_max=(0.0, 1.0), **oparams(P))
+    assert 0.02 < ref.mean() < 0.98 and (y == ref).mean() >= 0.995
