@@ -237,7 +237,8 @@ int te_pca_accumulate(const float* h, int64_t n, int32_t d, double* moments, voi
 /* Solves the d x d symmetric eigenproblem of the covariance (cyclic Jacobi, float64, one CTA) and
  * writes mean (d), the top-k components (k,d) with sklearn's sign convention (largest-|v| entry of
  * each component positive) and their explained variances (k), all float64 device arrays.
- * work: device float64 scratch of 2*d*d values. */
+ * work: device float64 scratch of 2*d*d values (d > 128: the matrices; d <= 128: everything lives in shared memory and
+ * work[0] receives the number of Jacobi sweeps of the solve). */
 int te_pca_solve(const double* moments, int32_t d, int32_t k, double* mean, double* components,
                  double* explained_variance, double* work, void* stream);
 /* z[i] = (h[i] - mean) @ components^T ; z (n,k) fp32. */
