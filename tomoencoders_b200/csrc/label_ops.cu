@@ -114,6 +114,7 @@ template <typename T, int CONN>
 __global__ void __launch_bounds__(256) label_tile_kernel(const T* __restrict__ vol, int* __restrict__ parent, Dim3 d, int tiles_x,
                                                          int tiles_y) {
   __shared__ int lab[kTileVox];
+  __shared__ unsigned rowmask[kTY * kTZ];     // foreground bits of every 32-voxel row: the merge predicates are bit tests
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int t = blockIdx.x;
   const int x0 = (t % tiles_x) * kTX; t /= tiles_x;
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(256) label_tile_kernel(const T* __restrict__ v
     const unsigned below = ~m & ((1u << lane) - 1u);
     const int start = below ? 32 - __clz(below) : 0;
     lab[r * kTX + lane] = fg ? r * kTX + start : -1;
+    if (lane == 0) rowmask[r] = m;
   }
   __syncthreads();
   // merge inside the tile (voxel l = (lz * kTY + ly) * kTX + lx; neighbour rows r - kTY - 1, r - kTY, r - kTY + 1, r - 1).
@@ -138,24 +140,30 @@ __global__ void __launch_bounds__(256) label_tile_kernel(const T* __restrict__ v
   // the duplicate shared-memory unions it saves: 12.8 vs 7.3 ms at 512^3.)
   for (int r = warp; r < kTY * kTZ; r += 8) {
     const int l = r * kTX + lane;
-    const int me = lab[l];
-    const bool fg = me >= 0;
+    const unsigned mrow = rowmask[r];
+    if (mrow == 0u) continue;                                              // warp-uniform: empty row
+    const bool fg = (mrow >> lane) & 1u;
+    const int me = fg ? lab[l] : -1;
     const int ly = r % kTY, lz = r / kTY;
-    const bool left = lane > 0 && lab[l - 1] >= 0;
+    const bool left = lane > 0 && ((mrow >> (lane - 1)) & 1u);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int dz = q < 3 ? -1 : 0, dy = q < 3 ? q - 1 : -1;
       if (CONN == 6 && !((dz == -1 && dy == 0) || (dz == 0 && dy == -1))) continue;
       if (lz + dz < 0 || ly + dy < 0 || ly + dy >= kTY) continue;          // warp-uniform
+      const unsigned mj = rowmask[r + dz * kTY + dy];                       // neighbour row's foreground bits
+      if (mj == 0u) continue;
       const int jb = l + (dz * kTY + dy) * kTX;
-      const int vm = lane > 0 ? lab[jb - 1] : -1, v0 = lab[jb];
+      const bool f0 = (mj >> lane) & 1u;
+      const bool fm = lane > 0 && ((mj >> (lane - 1)) & 1u);
       if (CONN == 6) {
-        if (fg && v0 >= 0 && !(left && vm >= 0)) sunion(lab, me, v0);
+        if (fg && f0 && !(left && fm)) sunion(lab, me, lab[jb]);
       } else {
-        const int vm2 = lane > 1 ? lab[jb - 2] : -1, vp = lane + 1 < kTX ? lab[jb + 1] : -1;
-        if (fg && vm >= 0 && !(left && vm2 >= 0)) sunion(lab, me, vm);
-        if (fg && v0 >= 0 && vm < 0) sunion(lab, me, v0);
-        if (fg && vp >= 0 && v0 < 0) sunion(lab, me, vp);
+        const bool f2 = lane > 1 && ((mj >> (lane - 2)) & 1u);
+        const bool fp = lane + 1 < kTX && ((mj >> (lane + 1)) & 1u);
+        if (fg && fm && !(left && f2)) sunion(lab, me, lab[jb - 1]);
+        if (fg && f0 && !fm) sunion(lab, me, lab[jb]);
+        if (fg && fp && !f0) sunion(lab, me, lab[jb + 1]);
       }
     }
   }
