@@ -296,7 +296,9 @@ __global__ void __launch_bounds__(256) patch_minmax_kernel(GatherParams p, float
   }
 }
 
-template <typename TIn, typename TOut>
+// PP = true: per-patch standardisation (te_gather_standardize).  A separate instantiation: its IEEE divisions (16 per item,
+// 8 items unrolled) would otherwise sit in the hot kernel's instruction stream and register budget.
+template <typename TIn, typename TOut, bool PP>
 __global__ void __launch_bounds__(256) gather_norm_kernel(GatherParams p, NormParams q) {
   // item = 8 consecutive output elements (px % 8 == 0 checked on the host); unit = ppu planes of a patch
   const int upp = p.pz / p.ppu;
@@ -320,7 +322,7 @@ __global__ void __launch_bounds__(256) gather_norm_kernel(GatherParams p, NormPa
     const long long row_pitch = static_cast<long long>(b) * p.X, plane_pitch = static_cast<long long>(b) * p.Y * p.X;
     TOut* dst0 = reinterpret_cast<TOut*>(p.out) + u * static_cast<long long>(items_per_unit) * 8;
     float plo = 0.f, pden = 1.f;
-    if (q.pp) {
+    if (PP) {
       float a = __ldg(q.pp + 2 * i), c = __ldg(q.pp + 2 * i + 1);
       if (q.rescale) { a = __fdiv_rn(__fsub_rn(a, q.lo), denom); c = __fdiv_rn(__fsub_rn(c, q.lo), denom); }
       plo = a;
@@ -348,7 +350,7 @@ __global__ void __launch_bounds__(256) gather_norm_kernel(GatherParams p, NormPa
           if (it >= items_per_unit) continue;
           float f[8];
           convert8<TIn>(raw[k], f);
-          if (q.pp) std_store8<TOut>(f, q, denom, plo, pden, dst0 + static_cast<long long>(it) * 8);
+          if constexpr (PP) std_store8<TOut>(f, q, denom, plo, pden, dst0 + static_cast<long long>(it) * 8);
           else norm_store8<TOut>(f, q, denom, inv, dst0 + static_cast<long long>(it) * 8);
         }
       }
@@ -358,7 +360,7 @@ __global__ void __launch_bounds__(256) gather_norm_kernel(GatherParams p, NormPa
         const int iy = r / groups_per_row, gx = r - iy * groups_per_row;
         float f[8];
         load8_binned<TIn>(src0 + pl * plane_pitch + iy * row_pitch + static_cast<long long>(gx) * 8 * b, b, f);
-        if (q.pp) std_store8<TOut>(f, q, denom, plo, pden, dst0 + static_cast<long long>(it) * 8);
+        if constexpr (PP) std_store8<TOut>(f, q, denom, plo, pden, dst0 + static_cast<long long>(it) * 8);
         else norm_store8<TOut>(f, q, denom, inv, dst0 + static_cast<long long>(it) * 8);
       }
     }
@@ -578,9 +580,15 @@ static int launch_gather_norm(const GatherParams& p, const NormParams& q, int ou
   GatherParams pp = p;
   pp.ppu = planes_per_unit(p.pz, p.py * (p.px / 8), sizeof(TIn) == 4 ? 1024 : 2048);
   const int grid = grid_for(p.n * (p.pz / pp.ppu), 1, 8);
-  if (out_dtype == TE_BF16) gather_norm_kernel<TIn, __nv_bfloat16><<<grid, 256, 0, st>>>(pp, q);
-  else if (out_dtype == TE_F16) gather_norm_kernel<TIn, __half><<<grid, 256, 0, st>>>(pp, q);
-  else gather_norm_kernel<TIn, float><<<grid, 256, 0, st>>>(pp, q);
+  if (q.pp != nullptr) {
+    if (out_dtype == TE_BF16) gather_norm_kernel<TIn, __nv_bfloat16, true><<<grid, 256, 0, st>>>(pp, q);
+    else if (out_dtype == TE_F16) gather_norm_kernel<TIn, __half, true><<<grid, 256, 0, st>>>(pp, q);
+    else gather_norm_kernel<TIn, float, true><<<grid, 256, 0, st>>>(pp, q);
+  } else {
+    if (out_dtype == TE_BF16) gather_norm_kernel<TIn, __nv_bfloat16, false><<<grid, 256, 0, st>>>(pp, q);
+    else if (out_dtype == TE_F16) gather_norm_kernel<TIn, __half, false><<<grid, 256, 0, st>>>(pp, q);
+    else gather_norm_kernel<TIn, float, false><<<grid, 256, 0, st>>>(pp, q);
+  }
   TE_LAUNCH_CHECK();
   return TE_OK;
 }
