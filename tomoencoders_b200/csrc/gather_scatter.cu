@@ -77,6 +77,8 @@ __global__ void __launch_bounds__(256) gather_chunks_kernel(GatherParams p) {
   const long long units = p.n * upp;
   const int chunks_per_plane = p.py * p.chunks_per_row;
   const int chunks_per_unit = p.ppu * chunks_per_plane;
+  const int d_cx = 256 % p.chunks_per_row, d_rows = 256 / p.chunks_per_row;     // +256 chunks in (chunk, row, plane)
+  const int d_iy = d_rows % p.py, d_pl = d_rows / p.py;
   for (long long u = blockIdx.x; u < units; u += gridDim.x) {
     const long long i = u / upp;
     const int iz0 = static_cast<int>(u - i * upp) * p.ppu;
@@ -91,14 +93,18 @@ __global__ void __launch_bounds__(256) gather_chunks_kernel(GatherParams p) {
       // four independent 16-byte loads in flight per thread before the first store
       for (int c0 = threadIdx.x; c0 < chunks_per_unit; c0 += 4 * 256) {
         uint4 v[4];
+        // (plane, row, chunk) of the first chunk by division, the next ones (+256 chunks each) by carries
+        int pl = c0 / chunks_per_plane, r0 = c0 - pl * chunks_per_plane;
+        int iy = r0 / p.chunks_per_row, cx = r0 - iy * p.chunks_per_row;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int cc = c0 + k * 256;
-          if (cc < chunks_per_unit) {
-            const int pl = cc / chunks_per_plane, r = cc - pl * chunks_per_plane;
-            const int iy = r / p.chunks_per_row, cx = r - iy * p.chunks_per_row;
-            v[k] = load16_unaligned(src0 + pl * plane_pitch + iy * row_pitch + cx * 16);
-          }
+          if (cc < chunks_per_unit) v[k] = load16_unaligned(src0 + pl * plane_pitch + iy * row_pitch + cx * 16);
+          cx += d_cx;
+          if (cx >= p.chunks_per_row) { cx -= p.chunks_per_row; ++iy; }
+          iy += d_iy;
+          if (iy >= p.py) { iy -= p.py; ++pl; }
+          pl += d_pl;
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -408,6 +414,8 @@ __global__ void __launch_bounds__(256) scatter_chunks_kernel(ScatterParams p) {
   const long long units = p.n * upp;
   const int chunks_per_plane = p.wy * p.chunks_per_row;
   const int chunks_per_unit = p.ppu * chunks_per_plane;
+  const int d_cx = 256 % p.chunks_per_row, d_rows = 256 / p.chunks_per_row;     // +256 chunks in (chunk, row, plane)
+  const int d_iy = d_rows % p.wy, d_pl = d_rows / p.wy;
   const long long row_pitch = p.X * ES, plane_pitch = p.Y * p.X * ES;
   for (long long u = blockIdx.x; u < units; u += gridDim.x) {
     const long long i = u / upp;
@@ -422,14 +430,17 @@ __global__ void __launch_bounds__(256) scatter_chunks_kernel(ScatterParams p) {
         const int cc = c0 + k * 256;
         if (cc < chunks_per_unit) v[k] = ldg_nc_u4(src0 + static_cast<long long>(cc) * 16);
       }
+      int pl = c0 / chunks_per_plane, r0 = c0 - pl * chunks_per_plane;
+      int iy = r0 / p.chunks_per_row, cx = r0 - iy * p.chunks_per_row;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int cc = c0 + k * 256;
-        if (cc < chunks_per_unit) {
-          const int pl = cc / chunks_per_plane, r = cc - pl * chunks_per_plane;
-          const int iy = r / p.chunks_per_row, cx = r - iy * p.chunks_per_row;
-          store16_unaligned<ES>(dst0 + pl * plane_pitch + iy * row_pitch + cx * 16, v[k]);
-        }
+        if (cc < chunks_per_unit) store16_unaligned<ES>(dst0 + pl * plane_pitch + iy * row_pitch + cx * 16, v[k]);
+        cx += d_cx;
+        if (cx >= p.chunks_per_row) { cx -= p.chunks_per_row; ++iy; }
+        iy += d_iy;
+        if (iy >= p.wy) { iy -= p.wy; ++pl; }
+        pl += d_pl;
       }
     }
   }
