@@ -72,10 +72,13 @@ __global__ void __launch_bounds__(kThreadsC1, NT <= 16 ? 2 : 1) conv1_umma_kerne
     fence_barrier_init();
   }
   if (warp == 0) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
-  // weights: B[n][k] = w[k][n] for k < 27, zero for the 5 padding taps; 64-byte rows, SW64 swizzle
+  // weights: K slot k = 10 * dz + (3 * dy + dx) holds tap (dz, dy, dx); slots 9, 19, 29, 30, 31 are zero padding (each input
+  // plane owns 10 slots = 5 packed 32-bit words, so the builders keep a plane's taps packed while the window rolls);
+  // 64-byte rows, SW64 swizzle
   for (int i = threadIdx.x; i < NT * 32; i += kThreadsC1) {
     const int n = i >> 5, k = i & 31;
-    const float v = k < 27 ? __ldg(p.w + k * NT + n) : 0.f;
+    const int kz = k / 10, kr = k - kz * 10;
+    const float v = (k < 30 && kr < 9) ? __ldg(p.w + (kz * 9 + kr) * NT + n) : 0.f;
     const uint32_t lo = static_cast<uint32_t>(n * 64 + k * 2);
     *reinterpret_cast<uint16_t*>(b_tile + (lo ^ (((lo >> 7) & 3u) << 4))) = to_bits(v, p.fp16);
   }
@@ -153,36 +156,36 @@ __global__ void __launch_bounds__(kThreadsC1, NT <= 16 ? 2 : 1) conv1_umma_kerne
       // instead of 27
       constexpr int PPG = kTZ / 2;
       const int pz0 = grp * PPG;
-      uint16_t nb[3][9];
+      // pk[q][0..4] = the 3 x 3 in-plane neighbourhood of input plane q as five packed words (taps 0..8 + one zero)
+      uint32_t pk[3][5];
+      auto load_plane = [&](int pzi, uint32_t (&w)[5]) {
+        const uint16_t* base = in_tile + (pzi * 18 + my) * 10 + mx;
+        uint16_t t9[9];
 #pragma unroll
-      for (int q = 0; q < 2; ++q)
+        for (int t = 0; t < 9; ++t) t9[t] = base[(t / 3) * 10 + t % 3];
 #pragma unroll
-        for (int t9 = 0; t9 < 9; ++t9) nb[q][t9] = in_tile[((pz0 + q) * 18 + my + t9 / 3) * 10 + mx + t9 % 3];
+        for (int j = 0; j < 4; ++j) w[j] = static_cast<uint32_t>(t9[2 * j]) | (static_cast<uint32_t>(t9[2 * j + 1]) << 16);
+        w[4] = static_cast<uint32_t>(t9[8]);
+      };
+      load_plane(pz0, pk[0]);
+      load_plane(pz0 + 1, pk[1]);
 #pragma unroll
       for (int pp = 0; pp < PPG; ++pp) {
         const int pz = pz0 + pp;
-#pragma unroll
-        for (int t9 = 0; t9 < 9; ++t9) nb[2][t9] = in_tile[((pz + 2) * 18 + my + t9 / 3) * 10 + mx + t9 % 3];
-        // row = 27 taps (dz, dy, dx) of voxel (pz, my, mx), 5 zeros: 16 packed 32-bit words
-        uint16_t v[32];
-#pragma unroll
-        for (int tp = 0; tp < 27; ++tp) v[tp] = nb[tp / 9][tp % 9];
-#pragma unroll
-        for (int tp = 27; tp < 32; ++tp) v[tp] = 0;
-        uint32_t wv[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) wv[j] = static_cast<uint32_t>(v[2 * j]) | (static_cast<uint32_t>(v[2 * j + 1]) << 16);
+        load_plane(pz + 2, pk[2]);
         const uint32_t as = pz, aph = k & 1u;
         mbar_wait(a_empty + as, aph ^ 1);
         uint8_t* dst = a_stage + as * 8192 + row * 64;
         const int sw = (row >> 1) & 3;
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          *reinterpret_cast<uint4*>(dst + ((c ^ sw) << 4)) = make_uint4(wv[4 * c], wv[4 * c + 1], wv[4 * c + 2], wv[4 * c + 3]);
+        // 16 words: plane 0 (5), plane 1 (5), plane 2 (5), one zero word
+        *reinterpret_cast<uint4*>(dst + ((0 ^ sw) << 4)) = make_uint4(pk[0][0], pk[0][1], pk[0][2], pk[0][3]);
+        *reinterpret_cast<uint4*>(dst + ((1 ^ sw) << 4)) = make_uint4(pk[0][4], pk[1][0], pk[1][1], pk[1][2]);
+        *reinterpret_cast<uint4*>(dst + ((2 ^ sw) << 4)) = make_uint4(pk[1][3], pk[1][4], pk[2][0], pk[2][1]);
+        *reinterpret_cast<uint4*>(dst + ((3 ^ sw) << 4)) = make_uint4(pk[2][2], pk[2][3], pk[2][4], 0u);
         fence_proxy_async_smem();                       // generic-proxy writes -> visible to the UMMA (async proxy)
         mbar_arrive(a_full + as);
 #pragma unroll
-        for (int t9 = 0; t9 < 9; ++t9) { nb[0][t9] = nb[1][t9]; nb[1][t9] = nb[2][t9]; }
+        for (int j = 0; j < 5; ++j) { pk[0][j] = pk[1][j]; pk[1][j] = pk[2][j]; }
       }
     }
   } else if (warp >= 2) {
