@@ -47,6 +47,10 @@ int te_version(void);
 const char* te_last_error(void);
 /* Number of kernel launches this library has enqueued since load (process-wide, monotonic). */
 int64_t te_launch_count(void);
+/* A host layer that replays kernels of this library through a captured CUDA graph (the launches then bypass the entry
+ * points that count) reports the number of kernel nodes it replayed here, so the counter stays "kernels of this library
+ * enqueued".  Returns the new total. */
+int64_t te_launch_count_add(int64_t n);
 
 /* ------------------------------------------------------------------------------------------------
  * Patch gather.  Replaces Patches.extract (structures/patches.py:748-781, with _calc_binning
@@ -217,6 +221,14 @@ int te_net_num_layers(const te_net* net);
 double te_net_flops_per_patch(const te_net* net);
 /* Name, algorithmic FLOPs and kernel class of layer i (host strings owned by the handle). */
 int te_net_layer_info(const te_net* net, int layer_index, const char** name, double* flops, int* uses_tensor_cores);
+
+/* fp16 activations (TE_MODE_FP16) have a finite range of +-65504.  Random-init and BN-folded shipped weights keep
+ * activations O(1), but a trained net with large gamma / sigma ratios can exceed it; Keras computes in float32
+ * (Unet3D.py:44-81) and has no such limit.  Every conv epilogue therefore tracks the largest |activation| it produced
+ * (fp32, before rounding) and raises a sticky per-handle flag when one leaves the finite fp16 range.  *flag = 1 if any
+ * forward call since the last reset overflowed (always 0 for bf16 / fp32 handles); the call synchronises `stream`.
+ * The host mirror re-runs such a call in bf16 (neural_nets/keras_processor.py). */
+int te_net_overflow(te_net* net, int reset, int* flag, void* stream);
 
 /* Per-layer device timing (bench.py's roofline leg): when enabled, every layer launch of a forward
  * call is bracketed by CUDA events on the launching stream.  te_net_layer_time synchronises on the

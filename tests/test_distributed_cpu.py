@@ -92,3 +92,59 @@ def test_slabs_partition_a_tiling_without_overlap():
             allp = np.concatenate(seen)
             assert len(allp) == len(table)
             np.testing.assert_array_equal(np.unique(allp, axis=0), np.unique(np.asarray(table.points), axis=0))
+
+
+def test_local_slab_rebases_tiles_and_z_sorted_shard_covers_the_list():
+    g = Grid((256, 128, 192), width=64)
+    p = Patches((256, 128, 192), "regular-grid", patch_size=(64,) * 3)
+    for table in (g, p):
+        for ws in (1, 2, 4):
+            total = 0
+            for r in range(ws):
+                loc, (z0, z1) = sharding.local_slab(table, r, ws)
+                assert type(loc) is type(table) and loc.vol_shape == (z1 - z0, 128, 192)
+                sub, _ = sharding.slab_of(table, r, ws)
+                back = np.asarray(loc.points).astype(np.int64)
+                back[:, 0] += z0
+                np.testing.assert_array_equal(back, np.asarray(sub.points).astype(np.int64))
+                total += len(loc)
+            assert total == len(table)
+    # more ranks than tile rows: the surplus ranks own nothing
+    loc, (z0, z1) = sharding.local_slab(Grid((64, 64, 64), width=64), 1, 2)
+    assert loc is None and z0 == z1
+    # arbitrary patch list: equal runs in z order, each touching only [z_lo, z_hi)
+    rng = np.random.default_rng(3)
+    vs = (300, 100, 100)
+    pts = np.stack([rng.integers(0, vs[a] - 32, 1001) for a in range(3)], axis=1).astype(np.uint32)
+    wds = np.full_like(pts, 32)
+    order = sharding.z_sorted_order(pts)
+    for ws in (1, 3, 8):
+        got = []
+        for r in range(ws):
+            idx, loc, (z_lo, z_hi) = sharding.z_sorted_shard(pts, wds, vs, r, ws)
+            assert abs(len(idx) - 1001 / ws) < 1
+            assert loc[:, 0].min() == 0 and int(loc[:, 0].max()) + 32 == z_hi - z_lo
+            np.testing.assert_array_equal(loc[:, 1:], pts[idx, 1:])
+            np.testing.assert_array_equal(loc[:, 0].astype(np.int64) + z_lo, pts[idx, 0].astype(np.int64))
+            got.append(idx)
+        np.testing.assert_array_equal(np.concatenate(got), order)
+    rows = rng.standard_normal((1001, 2)).astype(np.float32)
+    np.testing.assert_array_equal(sharding.unpermute(rows[order], order), rows)
+
+
+def _worker_ragged(rank, world_size, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        a, b = sharding.shard_range(7, rank, world_size)              # 4 + 3 rows
+        z = torch.arange(a, b, dtype=torch.float32)[:, None].repeat(1, 2)
+        allz = sharding.allgather_rows(z)
+        assert allz.shape == (7, 2) and torch.equal(allz[:, 0], torch.arange(7, dtype=torch.float32))
+        lo, hi = sharding.allreduce_minmax(-1.0 - rank, 5.0 + rank)
+        assert (lo, hi) == (-1.0 - (world_size - 1), 5.0 + world_size - 1)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ragged_allgather_and_minmax_allreduce_world2(tmp_path):
+    mp.spawn(_worker_ragged, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)

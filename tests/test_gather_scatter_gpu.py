@@ -178,3 +178,71 @@ def test_find_min_max_matches_oracle():
             lo, hi = voxel_processing._find_min_max(vol, s)
             elo, ehi = V.find_min_max(vol, s)
             assert lo == float(elo) and hi == float(ehi)
+
+
+# ------------------------------------------------------------------ round-2 additions (ADVICE.md findings)
+@pytest.mark.parametrize("dt", [np.uint8, np.float32])
+def test_2d_binned_extract_matches_numpy_slicing(dt):
+    """2-D tables are single-slice volumes: the binning of the image axes must survive the z padding
+    (reference: patches.py:748-781 works on any ndim through slices)."""
+    img = seeded_volume((1, 96, 128), dt, 300)[0]
+    pts = np.array([[0, 0], [3, 5], [32, 64], [17, 33]], dtype=np.uint32)
+    wds = np.array([[64, 64], [32, 32], [64, 64], [32, 32]], dtype=np.uint32)
+    p = Patches(img.shape, "data", points=pts, widths=wds)
+    out = p.extract(img, (32, 32))
+    assert out.shape == (4, 32, 32) and out.dtype == img.dtype
+    for i in range(4):
+        b = int(wds[i, 0]) // 32
+        y, x = int(pts[i, 0]), int(pts[i, 1])
+        np.testing.assert_array_equal(out[i], img[y:y + wds[i, 0]:b, x:x + wds[i, 1]:b])
+    # 2-D scatter of unbinned patches (fill is assignment of full-width patches)
+    p1 = Patches(img.shape, "data", points=pts[[1, 3]], widths=wds[[1, 3]])
+    sub = p1.extract(img, (32, 32))
+    tgt = np.zeros_like(img)
+    p1.fill_patches_in_volume(sub, tgt)
+    exp = np.zeros_like(img)
+    for i in (1, 3):
+        y, x = int(pts[i, 0]), int(pts[i, 1])
+        exp[y:y + 32, x:x + 32] = img[y:y + 32, x:x + 32]
+    np.testing.assert_array_equal(tgt, exp)
+
+
+def test_variable_width_device_round_trip():
+    """extract(vol_cuda, None) returns a list of CUDA tensors (device in -> device out); feeding that list back into
+    fill_patches_in_volume must work (patches.py:774-781, 811-821)."""
+    vol = seeded_volume(SVS, np.uint16, 301)
+    pts = np.array([[0, 0, 0], [8, 8, 16], [20, 4, 0], [1, 20, 30]], dtype=np.uint32)
+    wds = np.array([[16, 16, 16], [16, 16, 16], [8, 8, 8], [8, 8, 8]], dtype=np.uint32)
+    p = Patches(SVS, "data", points=pts, widths=wds)
+    subs = p.extract(torch.from_numpy(vol.astype(np.int32)).to(torch.uint16).cuda(), None)
+    assert isinstance(subs, list) and all(t.is_cuda for t in subs)
+    out = torch.zeros(SVS, dtype=torch.uint16, device="cuda")
+    p.fill_patches_in_volume(subs, out)
+    exp = np.zeros_like(vol)
+    S.fill_patches_in_volume([vol[z:z + w, y:y + w, x:x + w] for (z, y, x), w in zip(pts.astype(int), wds[:, 0].astype(int))],
+                             pts, wds, exp)
+    np.testing.assert_array_equal(out.cpu().numpy().view(np.uint16), exp)
+    # host lists of arrays still work
+    out_h = np.zeros_like(vol)
+    p.fill_patches_in_volume([t.cpu().numpy().view(np.uint16) for t in subs], out_h)
+    np.testing.assert_array_equal(out_h, exp)
+
+
+def test_float64_volume_unbinned_gather_scatter_and_refusal():
+    """numpy's default dtype: unbinned extract / fill move 64-bit elements as pairs of 32-bit words; a decimating extract
+    is refused with one clear message up front."""
+    g = np.random.default_rng(302)
+    vol = g.normal(size=SVS)
+    p = Patches(SVS, "data", points=np.array([[1, 3, 5], [24, 28, 31], [0, 0, 0]], dtype=np.uint32),
+                widths=np.full((3, 3), 16, dtype=np.uint32))
+    x = p.extract(vol, (16,) * 3)
+    assert x.dtype == np.float64
+    np.testing.assert_array_equal(x, S.extract(vol, p.points, p.widths, (16,) * 3))
+    out = np.zeros_like(vol)
+    p.fill_patches_in_volume(x, out)
+    exp = np.zeros_like(vol)
+    S.fill_patches_in_volume(x, p.points, p.widths, exp)
+    np.testing.assert_array_equal(out, exp)
+    pb = Patches(SVS, "data", points=np.zeros((1, 3), dtype=np.uint32), widths=np.full((1, 3), 32, dtype=np.uint32))
+    with pytest.raises(TypeError, match="binned extract"):
+        pb.extract(vol, (16,) * 3)

@@ -284,3 +284,165 @@ def test_wide_unet_512_bottleneck_channels():
     y = fe.predict_patches("segmenter", x, 2, None, min_max=(0.0, 1.0))
     ref = O.segmenter_predict_patches(x, 2, w, min_max=(0.0, 1.0), **oparams(P))
     assert 0.02 < ref.mean() < 0.98 and (y == ref).mean() >= 0.995
+
+
+# ------------------------------------------------------------------ round-2 additions (ADVICE)
+# Largest |oracle logit| at which a 16-bit run may flip a label.  Measured on B200 (tools/margin_hist.py ->
+# profiles/r02_margin_hist.txt): the flipped voxels of M_a01 all sit below these margins; everything with a clearer
+# decision agrees 100 %.
+MARGIN = {"fp16": 0.02, "bf16": 0.25}
+
+
+def _gpu_and_oracle_logits(params, w, x, mode, min_max=(0.0, 1.0)):
+    fe = SurfaceSegmenter(model_initialization="define-new", descriptor_tag="m", mode=mode, **params)
+    fe.models["segmenter"].set_weights(w)
+    from tomoencoders_b200 import _device
+    from tomoencoders_b200.neural_nets.keras_processor import normalize_chunk
+    net = fe.models["segmenter"].net_for(x.shape[1:4], len(x))
+    xa = normalize_chunk(_device.to_device(np.ascontiguousarray(x[..., 0])), min_max, True, net)
+    labels, logits = net.unet_forward(xa, want_logits=True)
+    xr = O._rescale_reference(x.astype(np.float32), min_max, True).astype(np.float32)
+    ref = O.unet_forward(xr, w, return_logits=True, **oparams(params))[..., 0]
+    return labels.cpu().numpy(), logits.cpu().numpy(), ref
+
+
+@pytest.mark.parametrize("mode", ["fp16", "bf16"])
+def test_mask_disagreements_are_near_tie_logits_only(vol_f16, mode):
+    """The claim behind the bf16 mask tolerance, tested: a 16-bit run flips a label only where the oracle's own decision
+    is a near tie (|logit| < MARGIN); every voxel with a clearer decision agrees, 100 %."""
+    w = OW.draw(O.unet_spec(**oparams(M_A01)), 11)
+    x = Grid(vol_f16.shape, width=64).extract(vol_f16)[..., np.newaxis]
+    mm = (float(vol_f16[::4, ::4, ::4].min()), float(vol_f16[::4, ::4, ::4].max()))
+    labels, logits, ref = _gpu_and_oracle_logits(M_A01, w, x, mode, mm)
+    assert np.array_equal(labels, (logits > 0).astype(np.uint8))
+    flipped = (logits > 0) != (ref > 0)
+    delta = MARGIN[mode]
+    clear = np.abs(ref) >= delta
+    assert clear.mean() > 0.5, "margin too wide to mean anything: %.3f of the voxels are 'clear'" % clear.mean()
+    worst = float(np.abs(ref[flipped]).max()) if flipped.any() else 0.0
+    assert not (flipped & clear).any(), "flipped a voxel with |oracle logit| = %.4f >= %.3f" % (worst, delta)
+    # and the logits themselves track the oracle (max-abs error relative to the logit scale)
+    err = np.abs(logits - ref).max() / np.abs(ref).std()
+    assert err < (0.02 if mode == "fp16" else 0.25), err
+
+
+def test_bf16_decoder_round_trip_matches_oracle():
+    """bf16 counterpart of test_autoencoder_round_trip_matches_oracle (probabilities after 2 dense + 6 conv layers)."""
+    params = dict(n_filters=[16, 32], n_blocks=2, activation="lrelu", batch_norm=True, pool_size=[2, 2],
+                  hidden_units=[64, 16], POOL_FLAG=True)
+    size = (32, 32, 32)
+    we = OW.draw(O.encoder_spec(size, **oparams(params))[0], 20)
+    wd = OW.draw(O.decoder_spec(size, **oparams(params)), 21)
+    x = np.random.default_rng(2).uniform(0, 1, (5,) + size + (1,)).astype(np.float32)
+    yr = O.decoder_forward(O.encoder_forward(x, we, **oparams(params)), wd, size, **oparams(params))
+    fe = SelfSupervisedCAE(model_initialization="define-new", model_size=size, descriptor_tag="t", mode="bf16", **params)
+    fe.models["encoder"].set_weights(we)
+    fe.models["decoder"].set_weights(wd)
+    y = fe.predict_patches("autoencoder", x, 2, None)
+    assert y.shape == x.shape and np.abs(y - yr).max() < 8e-2, np.abs(y - yr).max()
+    assert relerr(y, yr) < 1e-2, relerr(y, yr)
+
+
+def test_fp16_overflow_is_detected_and_falls_back_to_bf16():
+    """A net whose BN scales push activations past 65504 (gamma x 3000 on two layers): fp16 stores +-inf, Keras (float32)
+    does not care.  The conv epilogues flag the overflow, the call is repeated in bf16 and matches the oracle."""
+    spec = O.unet_spec(**oparams(SMALL))
+    w = OW.draw(spec, 7)
+    gammas = [i for i, (k, _) in enumerate(spec) if k == "bn_gamma"]
+    for i in gammas[:2]:
+        w[i] = w[i] * 3000.0
+    # keep the logits O(1): undo the scale in the very last BN (the test is about the range in between)
+    w[gammas[-1]] = w[gammas[-1]] / 9.0e6
+    x = np.random.default_rng(1).uniform(0, 1, (3, 32, 32, 32, 1)).astype(np.float32)
+    ref = O.segmenter_predict_patches(x, 4, w, min_max=(0.0, 1.0), **oparams(SMALL))
+    ref_act = O.unet_forward(x, w, return_logits=True, **oparams(SMALL))
+    assert np.isfinite(ref_act).all()
+    fe = SurfaceSegmenter(model_initialization="define-new", descriptor_tag="ovf", mode="fp16", **SMALL)
+    fe.models["segmenter"].set_weights(w)
+    # the raw plan: the flag goes up, and clears on read
+    from tomoencoders_b200 import _device
+    net = fe.models["segmenter"].net_for((32, 32, 32), 3)
+    net.unet_forward(_device.to_device(x[..., 0]).to(torch.float16).contiguous())
+    assert net.overflowed() and not net.overflowed()
+    with pytest.warns(RuntimeWarning, match="fp16 activations overflowed"):
+        y = fe.predict_patches("segmenter", x, 4, None, min_max=(0.0, 1.0))
+    assert fe.models["segmenter"].mode == "bf16"
+    assert 0.02 < ref.mean() < 0.98 and (y == ref).mean() >= 0.99, (y == ref).mean()
+    # a well-scaled net never trips the guard
+    fe2 = SurfaceSegmenter(model_initialization="define-new", descriptor_tag="ok", mode="fp16", **SMALL)
+    fe2.models["segmenter"].set_weights(OW.draw(spec, 7))
+    import warnings as _w
+    with _w.catch_warnings():
+        _w.simplefilter("error")
+        fe2.predict_patches("segmenter", x, 4, None, min_max=(0.0, 1.0))
+    assert fe2.models["segmenter"].mode == "fp16"
+
+
+def test_float64_patches_and_patch_extents_that_are_not_multiples_of_8():
+    """numpy's default dtype (the reference's own random_data_generator yields float64) and a patch x extent of 36: the
+    fused gather + rescale falls back to its element-wise kernel, the conv tiles clip at the patch border."""
+    w = OW.draw(O.unet_spec(**oparams(SMALL)), 9)
+    fe = SurfaceSegmenter(model_initialization="define-new", descriptor_tag="odd", mode="fp32", **SMALL)
+    fe.models["segmenter"].set_weights(w)
+    x = np.random.default_rng(4).uniform(0, 1, (3, 16, 20, 36, 1))                   # float64
+    y = fe.predict_patches("segmenter", x, 2, None, min_max=(0.1, 0.9))
+    ref = O.segmenter_predict_patches(x.astype(np.float32), 2, w, min_max=(0.1, 0.9), **oparams(SMALL))
+    assert y.dtype == np.uint8 and y.shape == x.shape
+    assert 0.02 < ref.mean() < 0.98 and (y == ref).mean() >= 0.9999, (y == ref).mean()
+    fe16 = SurfaceSegmenter(model_initialization="define-new", descriptor_tag="odd", mode="fp16", **SMALL)
+    fe16.models["segmenter"].set_weights(w)
+    y16 = fe16.predict_patches("segmenter", x, 2, None, min_max=(0.1, 0.9))
+    assert (y16 == ref).mean() >= 0.995, (y16 == ref).mean()
+    # volume path: a float64 host volume is cast once on the device
+    vol = np.random.default_rng(5).uniform(0, 1, (32, 32, 64))
+    g = Grid(vol.shape, width=32)
+    seg = fe16.segment_volume(vol, g, 1, min_max=(0.0, 1.0))
+    xs = g.extract(vol.astype(np.float32))[..., np.newaxis]
+    np.testing.assert_array_equal(g.extract(seg)[..., np.newaxis], fe16.predict_patches("segmenter", xs, 1, None, min_max=(0.0, 1.0)))
+    assert fe16.calc_voxel_min_max(vol, 2) == (float(vol[::2, ::2, ::2].astype(np.float32).min()),
+                                               float(vol[::2, ::2, ::2].astype(np.float32).max()))
+
+
+def test_decoder_with_stride_1_transposed_conv_is_refused():
+    """Conv3DTranspose(k=2, strides=1) overlaps its taps; the kernels assume k <= stride: refuse instead of mis-computing."""
+    params = dict(n_filters=[8, 8], n_blocks=2, activation="lrelu", batch_norm=True, pool_size=[2, 1],
+                  hidden_units=[16, 4], POOL_FLAG=False)
+    with pytest.raises(NotImplementedError):
+        SelfSupervisedCAE(model_initialization="define-new", model_size=(16, 16, 16), descriptor_tag="t", **params)
+    from tomoencoders_b200.neural_nets._net import Net
+    from tomoencoders_b200 import _lib
+    with pytest.raises(_lib.TomoEncError):
+        Net("decoder", (16, 16, 16), 2, mode="fp32", **params)
+
+
+def test_chunk_graph_replay_equals_eager(vol_f16):
+    """process_volume replays one captured CUDA graph per chunk length; the eager path (TOMOENC_NO_GRAPH) must give the
+    same mask, chunk boundaries and ragged tail included, on repeated calls and after the volume changes in place."""
+    w = OW.draw(O.unet_spec(**oparams(SMALL)), 5)
+    fe = SurfaceSegmenter(model_initialization="define-new", descriptor_tag="g", mode="fp16", **SMALL)
+    fe.models["segmenter"].set_weights(w)
+    g = Grid(vol_f16.shape, width=32)
+    tv = torch.from_numpy(vol_f16).cuda()
+    out = torch.zeros(vol_f16.shape, dtype=torch.uint8, device="cuda")
+    fe.use_graphs = False
+    want = fe.segment_volume(tv, g, 7, min_max=(0.0, 1.0)).clone()
+    fe.use_graphs = True
+    from tomoencoders_b200 import _lib
+    for rep in range(3):
+        out.zero_()
+        c0 = _lib.lib().te_launch_count()
+        fe.segment_volume(tv, g, 7, min_max=(0.0, 1.0), out=out)
+        launched = _lib.lib().te_launch_count() - c0
+        assert torch.equal(out, want), rep
+    eager = None
+    fe.use_graphs = False
+    c0 = _lib.lib().te_launch_count()
+    fe.segment_volume(tv, g, 7, min_max=(0.0, 1.0), out=out)
+    eager = _lib.lib().te_launch_count() - c0
+    assert launched == eager, "graph replays must report the kernels they replay (%d vs %d)" % (launched, eager)
+    # new contents at the same address: the graph reads the volume, not a snapshot
+    fe.use_graphs = True
+    tv.copy_(torch.flip(tv, dims=(0,)))
+    got = fe.segment_volume(tv, g, 7, min_max=(0.0, 1.0), out=out).clone()
+    fe.use_graphs = False
+    assert torch.equal(got, fe.segment_volume(tv, g, 7, min_max=(0.0, 1.0)))

@@ -65,6 +65,19 @@ def to_host_like(t, like):
     return out.numpy()
 
 
+def to_supported(t):
+    """Device tensor of any numeric dtype -> a dtype the kernels read (uint8 / uint16 / float16 / float32).
+
+    The reference accepts whatever numpy holds: float64 is numpy's default (its own random_data_generator yields it,
+    keras_processor.py:234-243) and Keras casts the network input to float32 anyway, so float64 / bfloat16 go to
+    float32; signed and wide integers go to float32 as well (exact up to 2**24, far beyond any detector's range)."""
+    if t.dtype in _TORCH_TO_TE and t.dtype != torch.bfloat16:
+        return t
+    if t.dtype == torch.bool:
+        return t.to(torch.uint8)
+    return t.to(torch.float32)
+
+
 def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
@@ -83,7 +96,8 @@ def side_stream():
 def as_host_tensor(a):
     """numpy array / torch CPU tensor -> torch CPU tensor sharing its memory (None if that is not possible)."""
     if isinstance(a, torch.Tensor):
-        return a if (not a.is_cuda and a.is_contiguous()) else None
+        ok = not a.is_cuda and a.is_contiguous() and a.dtype in _TORCH_TO_TE and a.dtype != torch.bfloat16
+        return a if ok else None
     if isinstance(a, np.ndarray) and a.flags.c_contiguous and a.dtype in _NP_TO_TE and a.flags.writeable:
         return torch.from_numpy(a)
     return None

@@ -121,6 +121,7 @@ _SIGNATURES = {
     "te_version": (ctypes.c_int, []),
     "te_last_error": (ctypes.c_char_p, []),
     "te_launch_count": (_I64, []),
+    "te_launch_count_add": (_I64, [_I64]),
     "te_gather": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_I64), _P, _P, _I64,
                                  ctypes.POINTER(_I32), _P, ctypes.c_int, _P]),
     "te_gather_norm": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_I64), _P, _P, _I64,
@@ -152,6 +153,7 @@ _SIGNATURES = {
     "te_net_layer_info": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p),
                                          ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)]),
     "te_net_set_profiling": (ctypes.c_int, [_P, ctypes.c_int]),
+    "te_net_overflow": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(ctypes.c_int), _P]),
     "te_net_layer_time": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_I64)]),
     "te_net_layer_kernel": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_char_p, ctypes.c_int]),
     "te_pca_accumulate": (ctypes.c_int, [_P, _I64, _I32, _P, _P]),

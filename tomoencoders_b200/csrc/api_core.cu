@@ -16,3 +16,7 @@ void set_error(const char* fmt, ...) {
 extern "C" int te_version(void) { return 100; }
 extern "C" const char* te_last_error(void) { return te::g_err; }
 extern "C" int64_t te_launch_count(void) { return te::g_launches.load(); }
+extern "C" int64_t te_launch_count_add(int64_t n) {
+  te::count_launch(static_cast<int>(n));                  // n < 0: a capture pass went through the counting entry points
+  return te::g_launches.load();
+}

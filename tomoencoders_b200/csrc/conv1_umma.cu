@@ -31,6 +31,7 @@ struct C1Params {
   long long total_tiles;
   int lrelu, fp16;
   float alpha;
+  int* overflow;            // fp16: OR-ed with 1 when an output leaves the finite fp16 range (nullptr = not tracked)
 };
 
 __device__ __forceinline__ uint16_t to_bits(float v, int fp16) {
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(kThreadsC1, NT <= 16 ? 2 : 1) conv1_umma_kerne
     const int q = warp & 3;
     const int m = q * 32 + lane, my = m >> 3, mx = m & 7;
     uint32_t ab = 0, abph = 0;
+    float amax = 0.f;                                     // see conv_umma.cu: one FMNMX per element detects fp16 overflow
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       unsigned t = static_cast<unsigned>(tile);           // 32-bit divisions (the launch checks total_tiles < 2^31)
       const unsigned ntx = p.tiles_x, nty = p.tiles_y, ntz = p.tiles_z;
@@ -220,6 +222,7 @@ __global__ void __launch_bounds__(kThreadsC1, NT <= 16 ? 2 : 1) conv1_umma_kerne
             for (int j = 0; j < 16; ++j) {
               float x = __uint_as_float(h ? r1[j] : r0[j]) + s_bias[c0 + j];
               if (p.lrelu) x = x > 0.f ? x : p.alpha * x;
+              amax = fmaxf(amax, fabsf(x));
               v[j] = x;
             }
             if (iz < p.D && iy < p.H && ix < p.W) {
@@ -238,6 +241,7 @@ __global__ void __launch_bounds__(kThreadsC1, NT <= 16 ? 2 : 1) conv1_umma_kerne
       if (lane == 0) mbar_arrive(acc_empty + ab);
       if (++ab == 2) { ab = 0; abph ^= 1; }
     }
+    if (p.fp16 && p.overflow != nullptr && amax > 65504.f) atomicOr(p.overflow, 1);
   }
   tc_fence_before();
   __syncthreads();
@@ -248,12 +252,9 @@ constexpr int kSmemC1 = kStagesA * 8192 + 4096 + 4096 + 512 + 512 + 1024;
 
 template <int NT>
 cudaError_t launch_nt(const C1Params& p, int grid, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv1_umma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemC1);
-    if (e != cudaSuccess) return e;
-    attr = true;
-  }
+  static unsigned long long attr = 0;
+  cudaError_t e = smem_attr_once(conv1_umma_kernel<NT>, kSmemC1, &attr);
+  if (e != cudaSuccess) return e;
   conv1_umma_kernel<NT><<<grid, kThreadsC1, kSmemC1, st>>>(p);
   return cudaGetLastError();
 }
@@ -262,7 +263,7 @@ cudaError_t launch_nt(const C1Params& p, int grid, cudaStream_t st) {
 
 // Returns true when the layer was taken (Cin = 1, 16-bit activations, Cout in {16, 32}); *err = launch status.
 bool conv1_umma_try(const TView& in, const TView& out, const float* w, const float* bias, int lrelu, float alpha, int act_type,
-                    cudaStream_t st, cudaError_t* err) {
+                    cudaStream_t st, cudaError_t* err, int* overflow) {
   static const bool off = getenv("TOMOENC_NO_C1_UMMA") != nullptr;
   if (off || in.C != 1 || in.ctot != 1 || act_type == ACT_F32) return false;
   if (out.C != 16 && out.C != 32) return false;             // TMEM: 2 x kTZ x Cout <= 512 columns
@@ -276,6 +277,7 @@ bool conv1_umma_try(const TView& in, const TView& out, const float* w, const flo
   p.tiles_x = (in.W + 7) / 8; p.tiles_y = (in.H + 15) / 16; p.tiles_z = (in.D + kTZ - 1) / kTZ;
   p.total_tiles = static_cast<long long>(in.N) * p.tiles_z * p.tiles_y * p.tiles_x;
   p.lrelu = lrelu; p.alpha = alpha; p.fp16 = act_type == ACT_F16;
+  p.overflow = overflow;
   if (p.total_tiles <= 0) { *err = cudaSuccess; return true; }
   if (p.total_tiles >= (1LL << 31)) return false;       // 32-bit tile indices in the kernel: let the caller fall back
   const int ctas = (out.C == 16 ? 2 : 1) * kNumSMs;

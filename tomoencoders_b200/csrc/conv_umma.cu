@@ -59,6 +59,7 @@ struct KParams {
   float* head_logits;
   uint8_t* pool_out;    // fused MaxPool3D(2) output (nullptr = none)
   int pool_ctot, pool_coff;
+  int* overflow;        // fp16 only: set to 1 when an activation leaves the finite fp16 range (nullptr = not tracked)
   int tma_out;          // un-haloed kernels: epilogue writes through the output tensor maps
   int reuse_ok;         // host: enough spatial tiles to fill the GPU when the (Cout tile, sub) pairs are looped inside a CTA
 };
@@ -420,6 +421,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     const int m = q * 32 + lane;                  // accumulator row = voxel (y = m / 8, x = m % 8)
     const int my = m >> 3, mx = m & 7;
     uint32_t ab = 0, abph = 0;
+    // largest |activation| this thread produced (fp32, before the rounding to 16 bits): the FIRST value of a forward pass
+    // that leaves the finite fp16 range is always a finite-or-infinite fp32 number here (NaNs only descend from it), so one
+    // FMNMX per element is a complete overflow detector
+    float amax = 0.f;
     for (long long tile = blockIdx.x; tile < outer_tiles; tile += gridDim.x) {
      for (int j = 0; j < J; ++j) {
       const TileCoord tc = decode_tile(p, tile, TZ, reuse, j);
@@ -470,6 +475,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
                 for (int j2 = 0; j2 < 16; ++j2) {
                   float x = __uint_as_float(r[j2]) + bs[j2];
                   if (p.act_lrelu) x = x > 0.f ? x : p.alpha * x;
+                  amax = fmaxf(amax, fabsf(x));
                   v[j2] = x;
                 }
                 // row m of the box, 16-byte chunks (c0 / 8) and (c0 / 8 + 1), swizzled like the TMA expects
@@ -524,6 +530,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
             for (int j = 0; j < 16; ++j) {
               float x = __uint_as_float(r[j]) + bs[j];
               if (p.act_lrelu) x = x > 0.f ? x : p.alpha * x;
+              amax = fmaxf(amax, fabsf(x));
               v[j] = x;
             }
             if (p.head_w != nullptr) {
@@ -577,6 +584,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
               float a = fmaxf(__uint_as_float(r0[j]), __uint_as_float(r1[j])) + bs[j];
               float b = fmaxf(__uint_as_float(r0[j + 1]), __uint_as_float(r1[j + 1])) + bs[j + 1];
               if (p.act_lrelu) { a = a > 0.f ? a : p.alpha * a; b = b > 0.f ? b : p.alpha * b; }
+              amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(b)));
               w[j >> 1] = pack2(a, b, p.fp16);
             }
 #pragma unroll
@@ -599,6 +607,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       if (++ab == 2) { ab = 0; abph ^= 1; }
      }
     }
+    if (p.fp16 && p.overflow != nullptr && amax > 65504.f) atomicOr(p.overflow, 1);
   }
 
   if (p.tma_out && (warp == 2 || (C::EPI_GROUPS == 2 && warp == 7))) {
@@ -613,13 +622,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
 template <int CB, int NT, int TZ, int HALO>
 cudaError_t launch_cfg(const ConvUmmaLaunch& L, const KParams& p, int grid, cudaStream_t stream) {
   using C = Cfg<CB, NT, TZ, HALO>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<CB, NT, TZ, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static unsigned long long attr_set = 0;
+  cudaError_t e = smem_attr_once(conv_umma_kernel<CB, NT, TZ, HALO>, C::SMEM_BYTES, &attr_set);
+  if (e != cudaSuccess) return e;
   OutMaps om;
   for (int i = 0; i < 8; ++i) om.m[i] = L.tmap_out[i];
   conv_umma_kernel<CB, NT, TZ, HALO><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(L.tmap_in, L.tmap_in2, om, p);
@@ -657,6 +662,7 @@ KParams make_params(const ConvUmmaLaunch& L) {
   p.pool_out = static_cast<uint8_t*>(L.pool_out);
   p.pool_ctot = L.pool_ctot;
   p.pool_coff = L.pool_coff;
+  p.overflow = L.overflow;
   p.tma_out = (L.use_tma_out && L.out != nullptr) ? 1 : 0;
   p.reuse_ok = !p.halo && p.total_tiles / (static_cast<long long>(p.n_ntiles) * p.nsub) >= kNumSMs ? 1 : 0;
   return p;

@@ -33,6 +33,9 @@ struct ConvUmmaLaunch {
   // fused MaxPool3D(2) of the activated output (conv only; D, H, W even): written next to `out`
   void* pool_out;           // nullptr = no fused pool
   int pool_ctot, pool_coff;
+  // fp16 launches: *overflow is OR-ed with 1 when an activation (fp32, before rounding) exceeds the largest finite fp16
+  // value, i.e. the stored tensor holds +-inf; nullptr = not tracked
+  int* overflow;
   // kernel configuration chosen by conv_umma_config()
   int CB, NT, TZ;
   // un-haloed kernels (transposed / pointwise convs): output through TMA box stores.  tmap_out[sub] is a

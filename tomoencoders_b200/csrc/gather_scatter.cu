@@ -386,6 +386,47 @@ __global__ void __launch_bounds__(256) gather_norm_kernel(GatherParams p, NormPa
   }
 }
 
+// Any patch x extent (px % 8 != 0: no 8-element items): one output element per thread, same arithmetic as the item kernel.
+template <typename TIn, typename TOut, bool PP>
+__global__ void __launch_bounds__(256) gather_norm_elems_kernel(GatherParams p, NormParams q) {
+  const long long per_patch = static_cast<long long>(p.pz) * p.py * p.px;
+  const long long total = p.n * per_patch;
+  const float denom = q.hi - q.lo + 1e-12f;
+  const float inv = 1.0f / denom;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+    long long r_;
+    long long t = divmod32(e, p.px, r_);
+    const int ix = static_cast<int>(r_);
+    t = divmod32(t, p.py, r_);
+    const int iy = static_cast<int>(r_);
+    const long long i = divmod32(t, p.pz, r_);
+    const int iz = static_cast<int>(r_);
+    const uint32_t b = __ldg(p.widths + 3 * i) / static_cast<uint32_t>(p.pz);
+    const long long src = ((static_cast<long long>(__ldg(p.points + 3 * i)) + static_cast<long long>(iz) * b) * p.Y +
+                           (static_cast<long long>(__ldg(p.points + 3 * i + 1)) + static_cast<long long>(iy) * b)) * p.X +
+                          __ldg(p.points + 3 * i + 2) + static_cast<long long>(ix) * b;
+    float v = to_f32<TIn>(reinterpret_cast<const TIn*>(p.vol)[src]);
+    if constexpr (PP) {
+      float a = __ldg(q.pp + 2 * i), c = __ldg(q.pp + 2 * i + 1);
+      if (q.rescale) {
+        a = __fdiv_rn(__fsub_rn(a, q.lo), denom);
+        c = __fdiv_rn(__fsub_rn(c, q.lo), denom);
+        v = __fdiv_rn(__fsub_rn(v, q.lo), denom);
+      }
+      v = __fdiv_rn(__fsub_rn(v, a), __fadd_rn(__fsub_rn(c, a), 1e-12f));
+    } else if (q.rescale) {
+      if (q.do_clip) v = fminf(fmaxf(v, q.lo), q.hi);
+      if constexpr (sizeof(TOut) == 4) v = (v - q.lo) / denom;
+      else v = (v - q.lo) * inv;
+    }
+    TOut* o = reinterpret_cast<TOut*>(p.out) + e;
+    if constexpr (std::is_same<TOut, __nv_bfloat16>::value) *o = __float2bfloat16_rn(v);
+    else if constexpr (std::is_same<TOut, __half>::value) *o = __float2half_rn(v);
+    else *o = v;
+  }
+}
+
 // ----------------------------------------------------------------------------------- scatter
 struct ScatterParams {
   const uint8_t* sub;
@@ -605,6 +646,21 @@ extern "C" int te_gather(const void* vol, int elem_size, const int64_t vol_shape
 template <typename TIn>
 static int launch_gather_norm(const GatherParams& p, const NormParams& q, int out_dtype, cudaStream_t st) {
   GatherParams pp = p;
+  if (p.px % 8 != 0) {
+    // no 8-element items in a row: element-wise kernel (any extent)
+    const int grid = grid_for(p.n * p.pz * p.py * p.px, 256, 16);
+#define TE_GN_ELEMS(TO)                                                                          \
+    do {                                                                                           \
+      if (q.pp != nullptr) gather_norm_elems_kernel<TIn, TO, true><<<grid, 256, 0, st>>>(pp, q);   \
+      else gather_norm_elems_kernel<TIn, TO, false><<<grid, 256, 0, st>>>(pp, q);                  \
+    } while (0)
+    if (out_dtype == TE_BF16) TE_GN_ELEMS(__nv_bfloat16);
+    else if (out_dtype == TE_F16) TE_GN_ELEMS(__half);
+    else TE_GN_ELEMS(float);
+#undef TE_GN_ELEMS
+    TE_LAUNCH_CHECK();
+    return TE_OK;
+  }
   pp.ppu = planes_per_unit(p.pz, p.py * (p.px / 8), sizeof(TIn) == 4 ? 1024 : 2048);
   const int grid = grid_for(p.n * (p.pz / pp.ppu), 1, 8);
   if (q.pp != nullptr) {
@@ -628,8 +684,7 @@ extern "C" int te_gather_norm(const void* vol, int vol_dtype, const int64_t vol_
   TE_CHECK_ARG(vol && points && widths && out, "te_gather_norm: null pointer");
   TE_CHECK_ARG(out_dtype == TE_BF16 || out_dtype == TE_F16 || out_dtype == TE_F32,
                "te_gather_norm: out_dtype must be bf16, f16 or f32");
-  TE_CHECK_ARG(patch[2] % 8 == 0, "te_gather_norm: patch x extent must be a multiple of 8");
-  TE_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "te_gather_norm: out must be 16-byte aligned");
+  TE_CHECK_ARG(patch[2] % 8 != 0 || (reinterpret_cast<uintptr_t>(out) & 15) == 0, "te_gather_norm: out must be 16-byte aligned");
   GatherParams p;
   p.vol = static_cast<const uint8_t*>(vol);
   p.out = static_cast<uint8_t*>(out);
@@ -676,8 +731,8 @@ extern "C" int te_gather_standardize(const void* vol, int vol_dtype, const int64
   TE_CHECK_ARG(vol && points && widths && out && minmax_scratch, "te_gather_standardize: null pointer");
   TE_CHECK_ARG(out_dtype == TE_BF16 || out_dtype == TE_F16 || out_dtype == TE_F32,
                "te_gather_standardize: out_dtype must be bf16, f16 or f32");
-  TE_CHECK_ARG(patch[2] % 8 == 0, "te_gather_standardize: patch x extent must be a multiple of 8");
-  TE_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "te_gather_standardize: out must be 16-byte aligned");
+  TE_CHECK_ARG(patch[2] % 8 != 0 || (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+               "te_gather_standardize: out must be 16-byte aligned");
   GatherParams p;
   p.vol = static_cast<const uint8_t*>(vol);
   p.out = static_cast<uint8_t*>(out);

@@ -423,16 +423,13 @@ int grid_for_units(long long units) {
 }
 
 template <typename K>
-cudaError_t launch_with_smem(K kernel, bool* attr_set) {
-  if (*attr_set) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-  if (e == cudaSuccess) *attr_set = true;
-  return e;
+cudaError_t launch_with_smem(K kernel, unsigned long long* attr_set) {
+  return smem_attr_once(kernel, kSmemBytes, attr_set);
 }
 
 template <typename T>
 cudaError_t launch_raw(const CUtensorMap& td, const CUtensorMap& tp, const TmaGatherParams& p, int grid, cudaStream_t st) {
-  static bool attr = false;
+  static unsigned long long attr = 0;
   cudaError_t e = launch_with_smem(gather_tma_kernel<T, T, true>, &attr);
   if (e != cudaSuccess) return e;
   gather_tma_kernel<T, T, true><<<grid, kThreadsG, kSmemBytes, st>>>(td, tp, p);
@@ -440,7 +437,7 @@ cudaError_t launch_raw(const CUtensorMap& td, const CUtensorMap& tp, const TmaGa
 }
 template <typename TIn, typename TOut>
 cudaError_t launch_norm(const CUtensorMap& tp, const TmaGatherParams& p, int grid, cudaStream_t st) {
-  static bool attr = false;
+  static unsigned long long attr = 0;
   cudaError_t e = launch_with_smem(gather_tma_kernel<TIn, TOut, false>, &attr);
   if (e != cudaSuccess) return e;
   gather_tma_kernel<TIn, TOut, false><<<grid, kThreadsG, kSmemBytes, st>>>(tp, tp, p);
@@ -454,7 +451,7 @@ cudaError_t launch_norm_in(const CUtensorMap& tp, const TmaGatherParams& p, int 
 }
 template <int ES>
 cudaError_t launch_scatter(const CUtensorMap& td, const TmaGatherParams& p, int grid, cudaStream_t st) {
-  static bool attr = false;
+  static unsigned long long attr = 0;
   cudaError_t e = launch_with_smem(scatter_tma_kernel<ES>, &attr);
   if (e != cudaSuccess) return e;
   scatter_tma_kernel<ES><<<grid, kThreadsG, kSmemBytes, st>>>(td, p);

@@ -388,10 +388,10 @@ __global__ void __launch_bounds__(256) from_f32_kernel(const float* in, T* out, 
   }
 
 cudaError_t simt_conv3(const TView& in, const TView& out, const float* w, const float* bias, int lrelu, float alpha,
-                       int act_type, cudaStream_t st) {
+                       int act_type, cudaStream_t st, int* overflow) {
   {
     cudaError_t e = cudaSuccess;
-    if (conv1_umma_try(in, out, w, bias, lrelu, alpha, act_type, st, &e)) { count_launch(); return e; }
+    if (conv1_umma_try(in, out, w, bias, lrelu, alpha, act_type, st, &e, overflow)) { count_launch(); return e; }
   }
   if (in.C == 1 && act_type != ACT_F32 && out.C % 16 == 0 && out.ctot % 8 == 0 && out.coff % 8 == 0 && out.C <= 256) {
     const size_t smem = static_cast<size_t>(28) * out.C * sizeof(float);

@@ -17,11 +17,13 @@ struct TView {
 enum ActType { ACT_F32 = 0, ACT_BF16 = 1, ACT_F16 = 2 };
 
 // 3x3x3 'same' conv, w = [27][Cin][Cout] fp32 (Keras layout, BN folded), fp32 accumulation.
+// overflow (optional, fp16 activations): OR-ed with 1 when the tensor-core first layer produces a value outside the finite
+// fp16 range (see ConvUmmaLaunch::overflow).
 cudaError_t simt_conv3(const TView& in, const TView& out, const float* w, const float* bias, int lrelu, float alpha,
-                       int act_type, cudaStream_t st);
+                       int act_type, cudaStream_t st, int* overflow = nullptr);
 // Tensor-core version of the Cin = 1 first layer (conv1_umma.cu); returns false when it does not apply.
 bool conv1_umma_try(const TView& in, const TView& out, const float* w, const float* bias, int lrelu, float alpha, int act_type,
-                    cudaStream_t st, cudaError_t* err);
+                    cudaStream_t st, cudaError_t* err, int* overflow = nullptr);
 // transposed conv k=2, stride s ('same': output = s x input; gaps get bias only), w = [8][Cout][Cin].
 cudaError_t simt_upconv(const TView& in, const TView& out, const float* w, const float* bias, int stride, int lrelu,
                         float alpha, int act_type, cudaStream_t st);

@@ -81,6 +81,7 @@ struct te_net {
   bool profiling = false;
   float* d_dense_tmp[2] = {nullptr, nullptr};
   float* d_dense_acc = nullptr;     // split-K accumulation scratch of the dense layers
+  int* d_overflow = nullptr;        // fp16 mode: sticky flag set by the conv epilogues when an activation overflows fp16
   te::TView input{};                // network input view (C = 1)
 };
 
@@ -327,6 +328,13 @@ int plan(te_net* net, bool count_only, long long* weight_count) {
   } else {
     // ------------------------------------------------------------------ decoder
     TE_CHECK_ARG(d.n_hidden >= 1 && d.n_hidden <= 8, "te_net: n_hidden must be in [1, 8]");
+    // Conv3DTranspose(k = 2, strides = 1, 'same') is a real overlapping 2x2x2 convolution (autoencoders.py:213); the
+    // transposed-conv kernels here assume non-overlapping taps (k <= stride), so a stride of 1 is refused, not mis-computed
+    for (int i = 0; i < d.n_blocks; ++i)
+      if (d.pool_size[i] < 2) {
+        set_error("te_net: decoder blocks need pool_size >= 2 (a stride-1 transposed conv with kernel 2 is not implemented)");
+        return TE_ERR_UNSUPPORTED;
+      }
     // pre-flatten shape of the matching encoder
     int pd = D, ph = H, pw = W;
     for (int i = 0; i < d.n_blocks; ++i) {
@@ -387,6 +395,7 @@ void free_net(te_net* net) {
   }
   for (int i = 0; i < 2; ++i) if (net->d_dense_tmp[i]) cudaFree(net->d_dense_tmp[i]);
   if (net->d_dense_acc) cudaFree(net->d_dense_acc);
+  if (net->d_overflow) cudaFree(net->d_overflow);
   delete net;
 }
 
@@ -477,6 +486,13 @@ extern "C" int te_net_create(const te_net_desc* desc, te_net** out) {
         Cv.store_out = desc->kind == 0;      // U-net: the skip connection still needs the full tensor
         Pl.skip = true;
       }
+    }
+  }
+  if (net->act_type == ACT_F16) {
+    if (cudaMalloc(&net->d_overflow, sizeof(int)) != cudaSuccess || cudaMemset(net->d_overflow, 0, sizeof(int)) != cudaSuccess) {
+      set_error("te_net_create: out of device memory");
+      free_net(net);
+      return TE_ERR_CUDA;
     }
   }
   if (desc->kind != 0) {
@@ -631,6 +647,7 @@ int run_layers(te_net* net, int n, const HeadOut& ho, cudaStream_t st) {
           C.alpha = alpha;
           C.fp16 = net->act_type == ACT_F16;
           C.CB = L.cfg.CB; C.NT = L.cfg.NT; C.TZ = L.cfg.TZ;
+          C.overflow = net->d_overflow;
           if (L.fused_head) {
             const Layer& H = net->layers[i + 1];
             C.head_w = H.d_w;
@@ -667,7 +684,7 @@ int run_layers(te_net* net, int n, const HeadOut& ho, cudaStream_t st) {
           e = conv_umma_launch(C, st);
           count_launch();
         } else if (L.op == OP_CONV3) {
-          e = simt_conv3(with_n(L.in, n), with_n(L.out, n), L.d_w, L.d_bias, L.lrelu, alpha, net->act_type, st);
+          e = simt_conv3(with_n(L.in, n), with_n(L.out, n), L.d_w, L.d_bias, L.lrelu, alpha, net->act_type, st, net->d_overflow);
         } else {
           e = simt_upconv(with_n(L.in, n), with_n(L.out, n), L.d_w, L.d_bias, L.stride, L.lrelu, alpha, net->act_type, st);
         }
@@ -774,6 +791,17 @@ extern "C" int64_t te_net_layer_output(te_net* net, int i, float* out, int64_t c
   cudaError_t e = simt_to_f32(v, out, net->act_type, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) { set_error("te_net_layer_output: %s", cudaGetErrorString(e)); return TE_ERR_CUDA; }
   return count;
+}
+
+extern "C" int te_net_overflow(te_net* net, int reset, int* flag, void* stream) {
+  TE_CHECK_ARG(net && flag, "te_net_overflow: null pointer");
+  *flag = 0;
+  if (!net->d_overflow) return TE_OK;                     // bf16 / fp32: the activation range is fp32's
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TE_CUDA(cudaMemcpyAsync(flag, net->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+  TE_CUDA(cudaStreamSynchronize(st));
+  if (reset && *flag) TE_CUDA(cudaMemsetAsync(net->d_overflow, 0, sizeof(int), st));
+  return TE_OK;
 }
 
 extern "C" int te_net_set_profiling(te_net* net, int enable) {

@@ -409,12 +409,8 @@ extern "C" int te_pca_solve(const double* moments, int32_t d, int32_t k, double*
     const int m = (d + 1) / 2 * 2;
     const size_t smem = (static_cast<size_t>(m) * (m + 1) / 2 + static_cast<size_t>(d) * d) * sizeof(double) +
                         static_cast<size_t>(m / 2) * (m / 2 + 1) / 2 * sizeof(unsigned short) + 16;
-    static bool attr_set = false;
-    if (!attr_set) {
-      TE_CUDA(cudaFuncSetAttribute(pca_solve_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (128 * 129 / 2 + 128 * 128) * 8 + 64 * 65 / 2 * 2 + 16));
-      attr_set = true;
-    }
+    static unsigned long long attr_set = 0;
+    TE_CUDA(smem_attr_once(pca_solve_smem_kernel, (128 * 129 / 2 + 128 * 128) * 8 + 64 * 65 / 2 * 2 + 16, &attr_set));
     pca_solve_smem_kernel<<<1, 1024, smem, static_cast<cudaStream_t>(stream)>>>(moments, d, k, mean, components,
                                                                                  explained_variance, work);
   } else {

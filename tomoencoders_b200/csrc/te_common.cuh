@@ -56,4 +56,19 @@ inline int dtype_size(int dt) {
   }
 }
 
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: the "already set" cache is a bit
+// mask over device ordinals (a process that touches a second GPU must opt in there too), not one process-wide flag.
+template <typename K>
+inline cudaError_t smem_attr_once(K kernel, int bytes, unsigned long long* device_mask) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (dev < 64 && (*device_mask & bit)) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev < 64) *device_mask |= bit;
+  return e;
+}
+
 }  // namespace te

@@ -1490,12 +1490,9 @@ constexpr int kWgSmem = 2 * (((kWgTZ + 2) * 18 * 10 * 64 + 1023) / 1024 * 1024 +
 
 template <bool FP16, int NTAPS>
 cudaError_t launch_wgrad_mma_t(const CUtensorMap& tx, const CUtensorMap& td, const WgParams& p, dim3 g, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_mma_kernel<FP16, NTAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem);
-    if (e != cudaSuccess) return e;
-    attr = true;
-  }
+  static unsigned long long attr = 0;
+  cudaError_t e = smem_attr_once(wgrad_mma_kernel<FP16, NTAPS>, kWgSmem, &attr);
+  if (e != cudaSuccess) return e;
   wgrad_mma_kernel<FP16, NTAPS><<<g, kWgThreads, kWgSmem, st>>>(tx, td, p);
   return cudaGetLastError();
 }

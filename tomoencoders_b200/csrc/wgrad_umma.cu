@@ -215,12 +215,9 @@ template <int CB>
 cudaError_t launch(const CUtensorMap& tx, const CUtensorMap& td, const WuParams& p, int grid, cudaStream_t st) {
   constexpr int XSLOT = (18 * 8 * CB * 2 + 1023) / 1024 * 1024;
   constexpr int smem = 1024 + kNXS * XSLOT + kNYS * kYBytes + 256;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_umma_kernel<CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    attr = true;
-  }
+  static unsigned long long attr = 0;
+  cudaError_t e = smem_attr_once(wgrad_umma_kernel<CB>, smem, &attr);
+  if (e != cudaSuccess) return e;
   wgrad_umma_kernel<CB><<<grid, kThreads, smem, st>>>(tx, td, p);
   return cudaGetLastError();
 }

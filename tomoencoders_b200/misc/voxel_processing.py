@@ -57,7 +57,7 @@ def _find_min_max(vol, sampling_factor, TIMEIT=False):
         if TIMEIT:
             _msg_exec_time("find voxel min max", time.time() - t0)
         return float(lo), float(hi)
-    t = _device.to_device(vol)
+    t = _device.to_supported(_device.to_device(vol))
     if t.dim() != 3:
         raise ValueError("expected a 3-D volume")
     out = torch.empty(2, dtype=torch.float32, device=t.device)

@@ -68,6 +68,7 @@ class Net:
         self.latent = hidden_units[-1] if hidden_units else 0
         self.act_dtype = {0: torch.bfloat16, 1: torch.float16, 2: torch.float32}[d.mode]
         self.act_te = {0: _lib.TE_BF16, 1: _lib.TE_F16, 2: _lib.TE_F32}[d.mode]
+        self.profiling = False
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -104,8 +105,19 @@ class Net:
             out.append((name.value.decode(), fl.value, bool(tc.value)))
         return out
 
+    def overflowed(self, reset=True):
+        """True when a forward call since the last reset produced an activation outside the finite fp16 range
+        (te_net_overflow; always False for bf16 / fp32 handles).  Synchronises the current stream."""
+        if self.act_dtype != torch.float16:
+            return False
+        flag = ctypes.c_int(0)
+        _lib.check(self._L.te_net_overflow(self._h, 1 if reset else 0, ctypes.byref(flag), _device.stream_ptr()),
+                   "te_net_overflow")
+        return bool(flag.value)
+
     def set_profiling(self, enable):
         _lib.check(self._L.te_net_set_profiling(self._h, 1 if enable else 0), "te_net_set_profiling")
+        self.profiling = bool(enable)
 
     def layer_times(self):
         """[(name, kernel, flops_per_patch, total_ms, launches)] accumulated since set_profiling(True)."""

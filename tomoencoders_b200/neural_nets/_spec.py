@@ -103,6 +103,10 @@ def encoder_spec(model_size, n_filters=(32, 64), n_blocks=2, activation="lrelu",
 
 def decoder_spec(model_size, n_filters=(32, 64), n_blocks=2, activation="lrelu", batch_norm=True, kern_size=3,
                  kern_size_upconv=2, hidden_units=(128, 32, 2), pool_size=2, POOL_FLAG=True):
+    pools = [pool_size] * n_blocks if isinstance(pool_size, (int, np.integer)) else list(pool_size)
+    if any(int(p) < 2 for p in pools[:n_blocks]):
+        # Conv3DTranspose(kern_size_upconv = 2, strides = 1) overlaps its taps (autoencoders.py:213); not implemented
+        raise NotImplementedError("decoder blocks need pool_size >= 2")
     flat, preflatten = encoder_shapes(model_size, n_filters, n_blocks, pool_size, POOL_FLAG)
     spec = []
     nin = hidden_units[-1]

@@ -7,9 +7,9 @@ import time
 import numpy as np
 import torch
 
-from .. import _device
+from .. import _device, _lib
 from ..structures.patches import Patches
-from .keras_processor import EmbeddingLearner, Model, gather_normalized, normalize_chunk
+from .keras_processor import _ChunkGraph, EmbeddingLearner, Model, gather_normalized, normalize_chunk
 
 
 def build_encoder_r(input_shape, **model_params):
@@ -158,6 +158,9 @@ class SelfSupervisedCAE(EmbeddingLearner):
         """Fused patches.extract(vol, model_size) -> predict_embeddings: the (n,P,P,P) patch array is
         never materialised; each chunk is gathered (with binning) and rescaled straight into the
         encoder's input layout.  Returns (n, latent) float32 where vol lives (host / device)."""
+        return self._guard_fp16("encoder", lambda: self._embed_volume(vol, patches, chunk_size, min_max, out))
+
+    def _embed_volume(self, vol, patches, chunk_size, min_max, out):
         vs = tuple(int(v) for v in patches.vol_shape)
         assert tuple(vol.shape) == vs, "Shape of big volume does not match vol_shape attribute of patches data"
         widths = patches.widths if hasattr(patches, "widths") else patches._widths()
@@ -165,7 +168,7 @@ class SelfSupervisedCAE(EmbeddingLearner):
             patches._calc_binning(self.model_size)
         n = len(patches)
         host = not _device.is_device_array(vol)
-        t_vol = _device.to_device(vol)
+        t_vol = _device.to_supported(_device.to_device(vol))
         enc = self.models["encoder"]
         z = out if (out is not None and _device.is_device_array(out)) else \
             torch.empty((n, enc.latent), dtype=torch.float32, device=t_vol.device)
@@ -173,11 +176,35 @@ class SelfSupervisedCAE(EmbeddingLearner):
             net = enc.net_for(self.model_size, min(chunk_size, n))
             d_pts = _device.points_to_device(patches.points)
             d_wds = _device.points_to_device(widths)
-            for a in range(0, n, chunk_size):
+            L = _lib.lib()
+            lo, hi = (0.0, 1.0) if min_max is None else (float(min_max[0]), float(min_max[1]))
+            vs64, p32 = _lib.i64x3(vs), _lib.i32x3(self.model_size)
+            msize = tuple(int(v) for v in self.model_size)
+
+            def chunk_body(pts_t, wds_t, nn, xa, zc):
+                if self.stdinput:
+                    xa = gather_normalized(t_vol, vs, pts_t, wds_t, nn, msize, min_max, False, net, standardize=True)
+                else:
+                    _lib.check(L.te_gather_norm(t_vol.data_ptr(), _device.te_dtype(t_vol), vs64, pts_t.data_ptr(), wds_t.data_ptr(),
+                                                nn, p32, 0 if min_max is None else 1, 0, lo, hi, xa.data_ptr(), net.act_te,
+                                                _device.stream_ptr()), "te_gather_norm")
+                net.encoder_forward(xa, out=zc)
+
+            starts = list(range(0, n, chunk_size))
+            # one captured graph per chunk length (gather + rescale -> encoder), replayed with the chunk's corner table
+            graphs = self.use_graphs and not self.stdinput and not net.profiling and len(starts) > 1
+            for a in starts:
                 b = min(a + chunk_size, n)
-                xa = gather_normalized(t_vol, vs, d_pts[a:b], d_wds[a:b], b - a, self.model_size, min_max, False, net,
-                                       standardize=self.stdinput)
-                net.encoder_forward(xa, out=z[a:b])
+                if graphs:
+                    key = ("enc", b - a, t_vol.data_ptr(), str(t_vol.dtype), vs, msize, min_max is None, lo, hi)
+                    g = self._chunk_graph(net, key, lambda: _ChunkGraph(b - a, msize, net.act_dtype, torch.float32, t_vol.device,
+                                                                       out_shape=(b - a, enc.latent)))
+                    g.varying_widths = True
+                    g.run(d_pts[a:b], d_wds[a:b], chunk_body)
+                    z[a:b].copy_(g.y)
+                else:
+                    xa = torch.empty((b - a,) + msize, dtype=net.act_dtype, device=t_vol.device)
+                    chunk_body(d_pts[a:b], d_wds[a:b], b - a, xa, z[a:b])
         if out is not None and not _device.is_device_array(out):
             out[...] = z.cpu().numpy()
             return out

@@ -16,6 +16,7 @@ embeddings) are not reproduced.
 """
 import os
 import time
+import warnings
 
 import numpy as np
 import torch
@@ -97,6 +98,21 @@ class Model:
         with np.load(filepath) as f:
             self.set_weights([f["w%04d" % i] for i in range(len(f.files))])
 
+    # ---- fp16 range guard
+    def fp16_overflowed(self):
+        """True (and the flags are cleared) when any fp16 plan of this model saw an activation leave the finite fp16 range
+        since the last check."""
+        hit = False
+        for net in self._nets.values():
+            hit = net.overflowed(reset=True) or hit
+        return hit
+
+    def set_mode(self, mode):
+        """Switches the arithmetic mode ("fp16" / "bf16" / "fp32"); execution plans are rebuilt on next use."""
+        if mode != self.mode:
+            self.mode = mode
+            self._nets = {}
+
     # ---- execution
     def net(self, patch, max_batch):
         patch = tuple(int(p) for p in patch)
@@ -163,6 +179,7 @@ def _standardized(vol_dev, vol_shape, d_points, d_widths, n, patch, min_max, net
 def normalize_chunk(x_dev, min_max, clip, net, standardize=False):
     """(n,pz,py,px) device tensor of any supported dtype -> activation dtype of ``net``, with the
     clip / rescale of predict_patches fused (te_gather_norm on the chunk viewed as a volume)."""
+    x_dev = _device.to_supported(x_dev)
     n, pz, py, px = x_dev.shape
     out = torch.empty((n, pz, py, px), dtype=net.act_dtype, device=x_dev.device)
     pts = torch.zeros((n, 3), dtype=torch.int32, device=x_dev.device)
@@ -210,6 +227,54 @@ class GenericKerasProcessor:
         else:
             raise NotImplementedError("method is not implemented")
 
+    # ---- fp16 range guard: Keras computes in float32 and cannot overflow where fp16 activations can (|x| > 65504).  The conv
+    #      epilogues flag it (te_net_overflow); the call is then repeated with bf16 activations (same exponent range as
+    #      float32) and the model stays in bf16 from there on.
+    def _model_keys(self, model_key):
+        return ["encoder", "decoder"] if model_key == "autoencoder" else [model_key]
+
+    def _guard_fp16(self, model_key, run):
+        """run() executes the forward work; if an fp16 plan overflowed, switches the models to bf16 and runs again."""
+        out = run()
+        models = [self.models.get(k) for k in self._model_keys(model_key)]
+        models = [m for m in models if isinstance(m, Model) and m.mode == "fp16"]
+        if any([m.fp16_overflowed() for m in models]):
+            warnings.warn("fp16 activations overflowed (|x| > 65504) in model %r: re-running with bf16 activations; the model "
+                          "stays in bf16 mode (construct the processor with mode='bf16' to avoid the repeated pass)" % model_key,
+                          RuntimeWarning, stacklevel=3)
+            for m in models:
+                m.set_mode("bf16")
+            out = run()
+        return out
+
+    # ---- CUDA-graph replay of the per-chunk kernel sequence (process_volume, embed_volume)
+    use_graphs = os.environ.get("TOMOENC_NO_GRAPH", "0") != "1"
+    _GRAPH_CACHE_MAX = 8
+    _STAGING_MAX_BYTES = 48 << 30
+
+    def _staging(self, tag, shape, dtype, dev):
+        """Device staging buffer for a HOST volume / result, kept between calls (one per tag): the same host-to-host call
+        repeated on volumes of one shape then runs on stable device addresses, so its captured chunk graphs are reused."""
+        cache = self.__dict__.setdefault("_staging_bufs", {})
+        t = cache.get(tag)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != dev:
+            cache.pop(tag, None)
+            t = torch.empty(shape, dtype=dtype, device=dev)
+            if t.numel() * t.element_size() <= self._STAGING_MAX_BYTES:
+                cache[tag] = t
+        return t
+
+    def _chunk_graph(self, net, key, build):
+        """Captured chunk graphs live on the plan (``Net``) whose workspace they address, so they die with it."""
+        cache = net.__dict__.setdefault("_chunk_graphs", {})
+        g = cache.pop(key, None)
+        if g is None:
+            g = build()
+            while len(cache) >= self._GRAPH_CACHE_MAX:
+                cache.pop(next(iter(cache)))
+        cache[key] = g                                   # most recently used last
+        return g
+
     # ---- helpers shared by the subclasses
     _clip_input = False      # SurfaceSegmenter clips to min_max before rescaling (surface_segmenter.py:272-275)
 
@@ -235,11 +300,14 @@ class GenericKerasProcessor:
         dev = _device.device()
         out_t_dtype = torch.uint8 if labels else torch.float32
         res = torch.empty((nb,) + patch, dtype=out_t_dtype, device=dev)
-        for a in range(0, nb, chunk_size):
-            b = min(a + chunk_size, nb)
-            xc = x[a:b, ..., 0]
-            xc = _device.to_device(xc if on_device else np.ascontiguousarray(xc))
-            self._predict_chunk(model_key, xc, res[a:b], min_max, chunk_size)
+
+        def run():
+            for a in range(0, nb, chunk_size):
+                b = min(a + chunk_size, nb)
+                xc = x[a:b, ..., 0]
+                xc = _device.to_device(xc if on_device else np.ascontiguousarray(xc))
+                self._predict_chunk(model_key, xc, res[a:b], min_max, chunk_size)
+        self._guard_fp16(model_key, run)
         if on_device:
             out = res.unsqueeze(-1)
             if out_arr is not None:
@@ -300,9 +368,10 @@ class GenericKerasProcessor:
             model.save(os.path.join(model_path, "%s_%s.npz" % (model_key, self.model_tag)))
 
     def train(self, *args, **kwargs):
-        raise NotImplementedError(
-            "training (SURVEY.md section 8 row a11) is not implemented in this round; load weights with "
-            "models[key].set_weights(...) or model_initialization='load-model'")
+        """Training lives in the subclasses that the reference trains (SurfaceSegmenter.train,
+        SelfSupervisedCAE.train); the generic base has no data generator (keras_processor.py:25-196)."""
+        raise NotImplementedError("%s does not define train(); use SurfaceSegmenter.train or SelfSupervisedCAE.train"
+                                  % type(self).__name__)
 
 
 class Vox2VoxProcessor_fCNN(GenericKerasProcessor):
@@ -337,7 +406,14 @@ class Vox2VoxProcessor_fCNN(GenericKerasProcessor):
             patches.fill_patches_in_volume(y[...,0], out)
         (/root/reference/scratchpad/void_metrology_v2/bin/vis_voids.py:64-73) for fixed-width
         patches, executed chunk by chunk on the device.  vol: numpy / torch (host or CUDA).  Returns
-        ``out`` (allocated as zeros of vol's shape if None): uint8 for labels, float32 otherwise."""
+        ``out`` (allocated as zeros of vol's shape if None): uint8 for labels, float32 otherwise.
+
+        Launch structure: gather+clip+rescale -> 17 fused layers -> stitch of ONE chunk is captured once as a CUDA graph
+        (per plan, chunk length, volume / result address) and replayed for every chunk; only the chunk's corner table
+        (a 12 n byte device copy) changes between replays."""
+        return self._guard_fp16(model_key, lambda: self._process_volume(vol, patches, chunk_size, min_max, model_key, out))
+
+    def _process_volume(self, vol, patches, chunk_size, min_max, model_key, out):
         from ..structures import _table
         vs = tuple(int(v) for v in patches.vol_shape)
         assert tuple(vol.shape) == vs, "Shape of big volume does not match vol_shape attribute of patches data"
@@ -354,7 +430,7 @@ class Vox2VoxProcessor_fCNN(GenericKerasProcessor):
         o_dtype = torch.uint8 if labels else torch.float32
         if src is not None:
             dev = _device.device()
-            t_vol = torch.empty(vs, dtype=src.dtype, device=dev)
+            t_vol = self._staging("vol", vs, src.dtype, dev)
             plane_bytes = vs[1] * vs[2] * src.element_size()
             zs = max(1, min(vs[0], -(-_SLAB_BYTES // max(1, plane_bytes))))
             n_slabs = -(-vs[0] // zs)
@@ -373,7 +449,8 @@ class Vox2VoxProcessor_fCNN(GenericKerasProcessor):
                         ev_up[k].record(side)
                         issued[0] += 1
         else:
-            t_vol = _device.to_device(vol)
+            # float64 / signed integer volumes (numpy defaults): one-shot upload, cast to float32 on the device
+            t_vol = _device.to_supported(_device.to_device(vol))
         dev = t_vol.device
         o_es = 1 if labels else 4
         disjoint = n > 0 and _table._disjoint(patches.points, w3, vs) and (w3[2] * o_es) % 16 == 0
@@ -384,7 +461,7 @@ class Vox2VoxProcessor_fCNN(GenericKerasProcessor):
         elif covers and not _device.is_device_array(out) and _device.as_host_tensor(out) is not None:
             if tuple(out.shape) != vs or _device.as_host_tensor(out).dtype != o_dtype:
                 raise TypeError("out must be a %s array of shape %s" % (o_dtype, vs))
-            t_out = torch.empty(vs, dtype=o_dtype, device=dev)
+            t_out = self._staging("out", vs, o_dtype, dev)
         else:
             t_out = _device.to_device(out)
             if t_out.dtype != o_dtype:
@@ -412,18 +489,35 @@ class Vox2VoxProcessor_fCNN(GenericKerasProcessor):
                 zmin_after[ci] = run
                 run = min(run, int(pz[starts[ci]:starts[ci] + chunk_size].min()))
             down = 0                                     # slabs [0, down) have been sent back
+        lo, hi = (0.0, 1.0) if min_max is None else (float(min_max[0]), float(min_max[1]))
+        vs64, w32 = _lib.i64x3(vs), _lib.i32x3(w3)
+
+        def chunk_body(pts_t, wds_t, nn, xa, y):
+            """gather + clip + rescale -> network -> stitch of one chunk, all on the current stream."""
+            _lib.check(L.te_gather_norm(t_vol.data_ptr(), _device.te_dtype(t_vol), vs64, pts_t.data_ptr(), wds_t.data_ptr(), nn,
+                                        w32, 0 if min_max is None else 1, 1 if self._clip_input else 0, lo, hi,
+                                        xa.data_ptr(), net.act_te, _device.stream_ptr()), "te_gather_norm")
+            net.unet_forward_into(xa, y)
+            if disjoint:
+                _lib.check(L.te_scatter(y.data_ptr(), y.element_size(), pts_t.data_ptr(), nn, w32, t_out.data_ptr(), vs64,
+                                        None, hint, _device.stream_ptr()), "te_scatter")
+
+        graphs = self.use_graphs and disjoint and not net.profiling and len(starts) > 1
         for ci, a in enumerate(starts):
             b = min(a + chunk_size, n)
             if src is not None:
                 need = min(n_slabs - 1, (int(pz[a:b].max()) + int(np.asarray(widths)[a:b, 0].max()) - 1) // zs)
                 upload_to(n_slabs - 1 if pinned_in else need + 1)
                 torch.cuda.current_stream().wait_event(ev_up[need])
-            xa = gather_normalized(t_vol, vs, d_pts[a:b], d_wds[a:b], b - a, w3, min_max, self._clip_input, net)
-            y = all_out[a:b] if not disjoint else torch.empty((b - a,) + w3, dtype=o_dtype, device=dev)
-            net.unet_forward_into(xa, y)
-            if disjoint:
-                _lib.check(L.te_scatter(y.data_ptr(), y.element_size(), d_pts[a:b].data_ptr(), b - a, _lib.i32x3(w3),
-                                        t_out.data_ptr(), _lib.i64x3(vs), None, hint, _device.stream_ptr()), "te_scatter")
+            if graphs:
+                key = (b - a, t_vol.data_ptr(), t_out.data_ptr(), str(t_vol.dtype), vs, w3, min_max is None, lo, hi,
+                       self._clip_input, hint)
+                g = self._chunk_graph(net, key, lambda: _ChunkGraph(b - a, w3, net.act_dtype, o_dtype, dev))
+                g.run(d_pts[a:b], d_wds[a:b], chunk_body)
+            else:
+                xa = torch.empty((b - a,) + w3, dtype=net.act_dtype, device=dev)
+                y = all_out[a:b] if not disjoint else torch.empty((b - a,) + w3, dtype=o_dtype, device=dev)
+                chunk_body(d_pts[a:b], d_wds[a:b], b - a, xa, y)
             if stream_out:
                 final = min(n_slabs, zmin_after[ci] // zs) if zmin_after[ci] < vs[0] else n_slabs
                 if final > down:
@@ -452,6 +546,43 @@ class Vox2VoxProcessor_fCNN(GenericKerasProcessor):
         elif t_out.data_ptr() != out.data_ptr():
             out.copy_(t_out)
         return out
+
+
+class _ChunkGraph:
+    """One chunk of the fused volume path (gather+clip+rescale -> network -> stitch) as a CUDA graph.
+
+    The kernels read the chunk's corner table from a static device buffer; ``run`` copies the current chunk's corners
+    there and replays.  The first ``run`` executes the body eagerly (it is that chunk's real work and doubles as the
+    warm-up: shared-memory attributes, TMA descriptors), counts its kernel launches and then captures."""
+
+    def __init__(self, n, w3, act_dtype, o_dtype, dev, out_shape=None):
+        self.n = n
+        self.pts = torch.empty((n, 3), dtype=torch.int32, device=dev)
+        self.wds = torch.empty((n, 3), dtype=torch.int32, device=dev)
+        self.xa = torch.empty((n,) + tuple(w3), dtype=act_dtype, device=dev)
+        self.y = torch.empty((n,) + tuple(w3) if out_shape is None else tuple(out_shape), dtype=o_dtype, device=dev)
+        self.graph = None
+        self.kernels = 0
+        self.varying_widths = False       # multi-scale patch lists (binned gathers): the width table changes per chunk too
+
+    def run(self, pts_chunk, wds_chunk, body):
+        self.pts.copy_(pts_chunk)
+        if self.graph is not None and self.varying_widths:
+            self.wds.copy_(wds_chunk)
+        if self.graph is not None:
+            self.graph.replay()
+            _lib.lib().te_launch_count_add(self.kernels)
+            return
+        self.wds.copy_(wds_chunk)
+        L = _lib.lib()
+        c0 = L.te_launch_count()
+        body(self.pts, self.wds, self.n, self.xa, self.y)
+        self.kernels = int(L.te_launch_count() - c0)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            body(self.pts, self.wds, self.n, self.xa, self.y)
+        L.te_launch_count_add(-self.kernels)             # the capture pass went through the counting entry points but enqueued nothing
+        self.graph = g
 
 
 class EmbeddingLearner(GenericKerasProcessor):

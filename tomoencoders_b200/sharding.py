@@ -47,6 +47,70 @@ def slab_of(patches, rank, world_size):
     return patches.select_by_indices(idx), (z0, z1)
 
 
+def local_slab(patches, rank, world_size):
+    """The tiles of this rank's z-slab re-based to the slab: returns (sub-table whose vol_shape is the slab's and whose
+    z corners start at 0, (z0, z1)).  The rank then only ever holds / uploads vol[z0:z1] (BASELINE configs[3]: "slab-
+    partitioned ... with no halo, because patches are independent"); stitching the per-rank masks back is the
+    concatenation of the slabs in rank order."""
+    sub, (z0, z1) = slab_of(patches, rank, world_size)
+    vs = tuple(int(v) for v in patches.vol_shape)
+    pts = np.asarray(sub.points).astype(np.int64).copy()
+    pts[:, 0] -= z0
+    from .structures.grid import Grid
+    from .structures.patches import Patches
+    shape = (z1 - z0,) + vs[1:]
+    if len(pts) == 0:
+        return None, (z0, z1)
+    if isinstance(patches, Grid):
+        return Grid(shape, initialize_by="data", points=pts.astype(np.uint32), width=patches.wd), (z0, z1)
+    return Patches(shape, "data", points=pts.astype(np.uint32), widths=np.asarray(sub.widths)), (z0, z1)
+
+
+def z_sorted_shard(points, widths, vol_shape, rank, world_size):
+    """Shard of an arbitrary patch list for latent extraction (BASELINE configs[2]): the list is ordered by corner z and
+    cut into `world_size` equal runs, so rank r needs only the planes [z_lo, z_hi) its run touches (its slab plus a
+    halo of width - 1 planes) instead of the whole volume.
+
+    Returns (idx, local_points, (z_lo, z_hi)): idx = indices of this rank's patches in the ORIGINAL list (ascending z,
+    stable), local_points = their corners with z re-based to z_lo.  Concatenating the per-rank results in rank order
+    gives the rows in ``np.concatenate(idx_of_every_rank)`` order; ``unpermute`` undoes it."""
+    points = np.asarray(points)
+    widths = np.asarray(widths)
+    order = np.argsort(points[:, 0].astype(np.int64), kind="stable")
+    a, b = shard_range(len(order), rank, world_size)
+    idx = order[a:b]
+    if len(idx) == 0:
+        return idx, points[:0].copy(), (0, 0)
+    z = points[idx, 0].astype(np.int64)
+    z_lo = int(z.min())
+    z_hi = int((z + widths[idx, 0].astype(np.int64)).max())
+    assert z_hi <= int(vol_shape[0])
+    loc = points[idx].astype(np.int64)
+    loc[:, 0] -= z_lo
+    return idx, loc.astype(points.dtype), (z_lo, z_hi)
+
+
+def z_sorted_order(points):
+    """The row order in which ``z_sorted_shard`` results concatenate over the ranks (independent of world_size)."""
+    return np.argsort(np.asarray(points)[:, 0].astype(np.int64), kind="stable")
+
+
+def unpermute(rows_sorted, order):
+    """rows_sorted[k] belongs to original row order[k] -> array in the original row order."""
+    out = np.empty_like(rows_sorted)
+    out[order] = rows_sorted
+    return out
+
+
+def allreduce_minmax(lo, hi, device=None, group=None):
+    """(min over ranks of lo, max over ranks of hi): the global ``calc_voxel_min_max`` of a slab-partitioned volume."""
+    if world(group)[1] == 1:
+        return float(lo), float(hi)
+    t = torch.tensor([-float(lo), float(hi)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return -float(t[0].item()), float(t[1].item())
+
+
 def allreduce_sum_(t, group=None):
     """In-place SUM all-reduce of a tensor (moments of LatentPCA); no-op for a single process."""
     if world(group)[1] > 1:
@@ -55,13 +119,23 @@ def allreduce_sum_(t, group=None):
 
 
 def allgather_rows(t, group=None):
-    """Concatenates equally sized per-rank row blocks (n_local, k) in rank order."""
+    """Concatenates per-rank row blocks (n_local, k) in rank order.  Row counts may differ between ranks (a balanced
+    shard of n rows differs by at most one row): the counts are gathered first and short blocks are padded for the
+    collective, then trimmed."""
     ws = world(group)[1]
     if ws == 1:
         return t
+    t = t.contiguous()
+    counts = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    all_counts = [torch.empty_like(counts) for _ in range(ws)]
+    dist.all_gather(all_counts, counts, group=group)
+    all_counts = [int(c.item()) for c in all_counts]
+    m = max(all_counts)
+    if t.shape[0] < m:
+        t = torch.cat([t, t.new_zeros((m - t.shape[0],) + tuple(t.shape[1:]))], dim=0)
     outs = [torch.empty_like(t) for _ in range(ws)]
-    dist.all_gather(outs, t.contiguous(), group=group)
-    return torch.cat(outs, dim=0)
+    dist.all_gather(outs, t, group=group)
+    return torch.cat([o[:c] for o, c in zip(outs, all_counts)], dim=0)
 
 
 def max_over_ranks(value, device=None, group=None):

@@ -39,15 +39,35 @@ def gather(vol, vol_shape, points, widths, patch_size):
     if tuple(t_vol.shape) != tuple(vol_shape):
         raise AssertionError("Shape of big volume does not match vol_shape attribute of patches data")
     es = t_vol.element_size()
+    if es == 8:
+        # float64 / int64 (numpy's defaults): data movement only, so an unbinned gather is the same gather over pairs of
+        # 32-bit words (x coordinates, widths and patch extent doubled); a decimating gather would need a 64-bit element
+        # path and is refused up front
+        if n and np.any(np.asarray(widths, dtype=np.int64) != np.asarray(patch_size, dtype=np.int64)[None, :]):
+            raise TypeError("binned extract of a %s volume is not supported: cast the volume to float32" % (t_vol.dtype,))
+        dbl = np.ones(ndim, dtype=np.int64)
+        dbl[-1] = 2
+        out32 = gather(t_vol.view(torch.int32), tuple(int(v) * int(d) for v, d in zip(vol_shape, dbl)),
+                       np.asarray(points, dtype=np.int64) * dbl[None, :], np.asarray(widths, dtype=np.int64) * dbl[None, :],
+                       tuple(int(p) * int(d) for p, d in zip(patch_size, dbl)))
+        return _device.to_host_like(out32.view(t_vol.dtype), vol)
     if es not in (1, 2, 4):
         raise TypeError("unsupported volume dtype %s" % (t_vol.dtype,))
     patch3 = (1,) * (3 - ndim) + tuple(int(p) for p in patch_size)
     out = torch.empty((n,) + patch3, dtype=t_vol.dtype, device=t_vol.device)
     if n > 0:
-        d_pts = _device.points_to_device(pad_cols(points, 0))
-        d_wds = _device.points_to_device(pad_cols(widths, 1))
+        pts3 = pad_cols(points, 0)
+        wds3 = np.asarray(widths)
+        if wds3.shape[1] == 2:
+            # the kernels derive the (isotropic) binning from the z column, widths[i][0] // patch[0]: a 2-D table is a
+            # single-slice volume whose padded z width must carry the binning of the image axes (a z extent of b
+            # sampled with step b is still exactly one slice)
+            binning = (wds3[:, -1].astype(np.int64) // int(patch_size[-1])).astype(wds3.dtype)
+            wds3 = np.concatenate([binning[:, None], wds3], axis=1)
+        d_pts = _device.points_to_device(pts3)
+        d_wds = _device.points_to_device(wds3)
         L = _lib.lib()
-        hint = _aligned_hint(pad_cols(points, 0), pad_cols(widths, 1), patch3, es)
+        hint = _aligned_hint(pts3, wds3, patch3, es)
         _lib.check(L.te_gather(t_vol.data_ptr(), es, _lib.i64x3(vs3), d_pts.data_ptr(), d_wds.data_ptr(), n,
                                _lib.i32x3(patch3), out.data_ptr(), hint, _device.stream_ptr()), "te_gather")
     out = out.reshape((n,) + tuple(int(p) for p in patch_size))
@@ -136,13 +156,34 @@ def scatter(sub_vols, vol_out, vol_shape, points, widths):
     host_out = not _device.is_device_array(vol_out)
     t_out = _device.to_device(vol_out)
     es = t_out.element_size()
+    if es == 8:
+        # 64-bit volumes: the same scatter over pairs of 32-bit words (see gather)
+        dbl = np.ones(ndim, dtype=np.int64)
+        dbl[-1] = 2
+        if isinstance(sub_vols, (list, tuple)):
+            subs32 = [_numpy_cast(_device.to_device(e), t_out.dtype).contiguous().view(torch.int32) for e in sub_vols]
+        else:
+            subs32 = _numpy_cast(_device.to_device(sub_vols), t_out.dtype).contiguous().view(torch.int32)
+        scatter(subs32, t_out.view(torch.int32), tuple(int(v) * int(d) for v, d in zip(vol_shape, dbl)),
+                np.asarray(points, dtype=np.int64) * dbl[None, :], widths.astype(np.int64) * dbl[None, :])
+        _copy_back(t_out, vol_out, host_out)
+        return
     if es not in (1, 2, 4):
         raise TypeError("unsupported volume dtype %s" % (t_out.dtype,))
     L = _lib.lib()
     owner = None
     for (a, b) in runs:
         w3 = (1,) * (3 - ndim) + tuple(int(v) for v in widths[a])
-        sv = sub_vols[a:b] if not isinstance(sub_vols, list) else np.asarray(sub_vols[a:b])
+        sv = sub_vols[a:b]
+        if isinstance(sv, (list, tuple)):
+            # a list of per-patch arrays (what extract(vol, patch_size=None) returns): torch tensors stay where they
+            # are (a list of CUDA tensors cannot go through numpy), anything else is stacked on the host
+            if any(isinstance(e, torch.Tensor) for e in sv):
+                dev_of = next((e.device for e in sv if isinstance(e, torch.Tensor) and e.is_cuda), None)
+                sv = torch.stack([(e if isinstance(e, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(e))).to(
+                    dev_of if dev_of is not None else "cpu") for e in sv])
+            else:
+                sv = np.asarray(sv)
         t_sub = _device.to_device(sv)
         if tuple(t_sub.shape[1:]) != tuple(int(v) for v in widths[a]):
             raise AssertionError("width mismatch between sub_vol and patch")
@@ -160,6 +201,10 @@ def scatter(sub_vols, vol_out, vol_shape, points, widths):
         hint = 0 if owner_ptr is not None else _aligned_hint(pts, None, w3, es)
         _lib.check(L.te_scatter(t_sub.data_ptr(), es, d_pts.data_ptr(), b - a, _lib.i32x3(w3), t_out.data_ptr(),
                                 _lib.i64x3(vs3), owner_ptr, hint, _device.stream_ptr()), "te_scatter")
+    _copy_back(t_out, vol_out, host_out)
+
+
+def _copy_back(t_out, vol_out, host_out):
     if host_out:
         res = t_out.cpu()
         if isinstance(vol_out, torch.Tensor):
