@@ -7,9 +7,14 @@ Workload at N=1 = BASELINE.json configs[1]: 3-D U-net segmenter (M_a01: n_filter
 [2,2,2], skip concatenation on) over a synthetic 512^3 float16 volume tiled into 512 patches of 64^3,
 chunked 32 patches at a time: fused gather+clip+rescale -> U-net (tcgen05) -> labels -> stitch.
 One "step" = one full pass over the volume.  With N ranks (torchrun) every rank segments its own
-512^3 slab (patches are independent: no data-path collective; weak scaling) and additionally encodes
-random 64^3 patches to latents whose PCA moments are all-reduced over NCCL (the only exchange step
-of the path).  Rank 0 prints ONE JSON line.
+512^3 slab (patches are independent: no data-path collective; weak scaling) -- that is `value`.
+The same JSON line carries, at every N, the two multi-GPU workloads BASELINE.json names at their stated sizes:
+  "cfg4": ONE 2048^3 fp16 volume, z-slab partitioned over the N ranks (sharding.local_slab), host -> host through
+          calc_voxel_min_max (+ a MIN/MAX all-reduce of two scalars) and SurfaceSegmenter.segment_volume: STRONG scaling;
+  "cfg3": 1 M random 64^3 patches of that volume encoded to 128-d latents (rank r takes the r-th run of the z-sorted list
+          and uploads only the planes it touches = slab + 63-plane halo), all-reduce of the 16 513 float64 PCA moments,
+          redundant eigensolve, projection, all-gather of the (n, 2) rows, host coordinates in -> host rows out.
+Rank 0 prints ONE JSON line.
 """
 import argparse
 import json
@@ -45,6 +50,9 @@ VOL = (512, 512, 512)
 PATCH = 64
 CHUNK = 32
 ENC_PATCHES = 16384         # 64^3 patches encoded per rank per step in the "encode" leg, ONE PCA fit per step (configs[2]: 125 000 patches per rank and fit)
+BIG = (2048, 2048, 2048)    # configs[2] / configs[3] volume
+BIG_PATCHES = 1_000_000     # configs[2]
+BIG_BLOCK = 128             # z planes per generated block of the synthetic 2048^3 volume (block b is seeded by b: any rank regenerates any plane)
 CPU_TILES = 64              # bounded CPU sample of the same workload: two FULL chunks (a partial chunk is padded to 32 by the reference)
 ENC_CHUNK = 128             # patches per encoder launch (the encoder keeps only pooled tensors: 128 patches = 1.3 GB)
 METRIC = "voxels/sec segmented (3-D U-net M_a01, 64^3 tiles of a 512^3 fp16 volume per GPU)"
@@ -159,6 +167,143 @@ def run_reference(args):
     emit(line)
 
 
+def fill_big_slab(host, z_lo, z_hi, dev):
+    """Planes [z_lo, z_hi) of the synthetic 2048^3 float16 volume (blobs + noise in [0, 1]) into the pinned host tensor
+    `host`; generated on the device in 128-plane blocks seeded by the block index, so every rank produces identical
+    planes whatever its slab is."""
+    import torch
+    b0, b1 = z_lo // BIG_BLOCK, -(-z_hi // BIG_BLOCK)
+    for b in range(b0, b1):
+        g = torch.Generator(device=dev).manual_seed(9000 + b)
+        coarse = torch.randn((1, 1, BIG_BLOCK // 16 + 1, BIG[1] // 16 + 1, BIG[2] // 16 + 1), generator=g, device=dev)
+        x = torch.nn.functional.interpolate(coarse, size=(BIG_BLOCK, BIG[1], BIG[2]), mode="trilinear", align_corners=True)[0, 0]
+        x = (x > 0).to(torch.float16)
+        x.add_(torch.randn(x.shape, generator=g, device=dev, dtype=torch.float16), alpha=0.1)
+        x.clamp_(-0.5, 1.5).add_(0.5).mul_(0.5)
+        a, c = max(z_lo, b * BIG_BLOCK), min(z_hi, (b + 1) * BIG_BLOCK)
+        host[a - z_lo:c - z_lo].copy_(x[a - b * BIG_BLOCK:c - b * BIG_BLOCK])
+        del x, coarse
+    torch.cuda.synchronize()
+
+
+def leg_cfg4(fe, rank, world, dev, barrier, max_over_ranks, host_slab, z0, z1, reps):
+    """BASELINE configs[3]: the rank's z-slab of ONE 2048^3 volume, host -> host."""
+    import torch
+    from tomoencoders_b200 import Grid, sharding
+    grid = Grid(BIG, width=PATCH)
+    loc, (a, b) = sharding.local_slab(grid, rank, world)
+    assert (a, b) == (z0, z1)
+    host_mask = torch.empty((z1 - z0,) + BIG[1:], dtype=torch.uint8, pin_memory=True)
+    mm_box = [None]
+
+    def step():
+        lo, hi = fe.calc_voxel_min_max(host_slab, 4)             # uploads every 4th plane of the slab
+        mm_box[0] = sharding.allreduce_minmax(lo, hi, device=dev)   # two scalars: the only exchange of this workload
+        fe.segment_volume(host_slab, loc, CHUNK, min_max=mm_box[0], out=host_mask)
+        torch.cuda.synchronize()
+
+    step()                                                       # plans, staging buffers, chunk graphs
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        step()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / reps
+    # checksum of the stitched mask (all ranks): identical at every N if the slabs reproduce the single-GPU result
+    csum = torch.tensor([int(fe._staging_bufs["out"].sum(dtype=torch.int64).item())], dtype=torch.int64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(csum)
+    nvox = BIG[0] * BIG[1] * BIG[2]
+    res = {"metric": "voxels/sec segmented: ONE 2048^3 float16 volume, z-slab per rank, host volume in -> host uint8 mask out",
+           "value": nvox / (ms / 1e3), "unit": "voxels/s", "ms_per_step": ms, "steps": reps, "scaling": "strong",
+           "tiles_total": len(grid), "tiles_this_rank": len(loc), "slab_rank0": [z0, z1], "min_max": list(mm_box[0]),
+           "h2d_bytes_per_step": int(nvox * 2 + nvox * 2 // 4), "d2h_bytes_per_step": int(nvox),
+           "mask_checksum": int(csum.item()), "mask_fraction_ones": float(csum.item()) / nvox,
+           "exchange": "all-reduce(MAX) of (-min, max): 2 float64" if world > 1 else "none (1 rank)"}
+    del host_mask
+    return res
+
+
+def leg_cfg3(ae, rank, world, dev, barrier, max_over_ranks, host_planes, z_base, reps=1):
+    """BASELINE configs[2]: 1 M random 64^3 patches of the 2048^3 volume -> latents -> PCA -> (n, 2), host -> host.
+    host_planes holds the volume planes from z_base upwards that this rank needs."""
+    import torch
+    import torch.distributed as dist
+    from tomoencoders_b200 import Patches, sharding
+    from tomoencoders_b200.neural_nets import LatentPCA
+    rng = np.random.default_rng(77)                               # the same list on every rank
+    pts = np.stack([rng.integers(0, BIG[a] - PATCH, BIG_PATCHES) for a in range(3)], axis=1).astype(np.uint32)
+    wds = np.full_like(pts, PATCH)
+    idx, loc_pts, (z_lo, z_hi) = sharding.z_sorted_shard(pts, wds, BIG, rank, world)
+    order = sharding.z_sorted_order(pts)
+    assert z_lo >= z_base and z_hi - z_base <= host_planes.shape[0]
+    src = host_planes[z_lo - z_base:z_hi - z_base]
+    timings = {}
+
+    def step(n_use=None):
+        lp = loc_pts if n_use is None else loc_pts[:n_use]
+        t = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        t[0].record()
+        dvol = src.to(dev, non_blocking=True)                     # slab + halo of the host volume
+        p = Patches(tuple(dvol.shape), "data", points=lp, widths=np.full_like(lp, PATCH))
+        t[1].record()
+        lat = ae.embed_volume(dvol, p, ENC_CHUNK, min_max=(0.0, 1.0))
+        t[2].record()
+        pca = LatentPCA(2)
+        pca.partial_fit(lat)
+        pca.finalize()                                            # all-reduce of 16 513 float64 moments + eigensolve
+        t[3].record()
+        z = pca.transform_all_gather(lat)                         # projection + all-gather of the (n_local, 2) rows
+        z_host = z.cpu().numpy()
+        t[4].record()
+        torch.cuda.synchronize()
+        out = sharding.unpermute(z_host, order) if n_use is None else z_host
+        timings.update(upload_ms=t[0].elapsed_time(t[1]), encode_ms=t[1].elapsed_time(t[2]),
+                       fit_ms=t[2].elapsed_time(t[3]), project_gather_ms=t[3].elapsed_time(t[4]))
+        return out, pca
+
+    step(n_use=min(len(loc_pts), 8 * ENC_CHUNK))                  # warm-up: plans, graphs (a short list)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        z_all, pca = step()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / reps
+    assert z_all.shape == (BIG_PATCHES, 2)
+    # the collectives on their own (device-timed, 10 repetitions each)
+    coll = {"allreduce_moments_us": 0.0, "allgather_rows_us": 0.0}
+    if world > 1:
+        m = torch.zeros(1 + 128 + 128 * 128, dtype=torch.float64, device=dev)
+        rows = torch.zeros((len(loc_pts), 2), dtype=torch.float32, device=dev)
+        for name, fn in (("allreduce_moments_us", lambda: dist.all_reduce(m)),
+                         ("allgather_rows_us", lambda: sharding.allgather_rows(rows))):
+            fn()
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(10):
+                fn()
+            c1.record()
+            torch.cuda.synchronize()
+            coll[name] = 1e3 * c0.elapsed_time(c1) / 10
+    return {"metric": "64^3 patches/sec encoded + PCA-projected: 1 M random patches of ONE 2048^3 float16 volume, host volume + host coordinates in -> host (n, 2) rows out",
+            "value": BIG_PATCHES / (ms / 1e3), "unit": "patches/s", "ms_per_step": ms, "steps": reps, "scaling": "strong",
+            "patches_total": BIG_PATCHES, "patches_this_rank": int(len(loc_pts)), "planes_this_rank": [int(z_lo), int(z_hi)],
+            "volume_placement": "slab + halo per rank: the z-sorted patch list is cut into N equal runs, rank r uploads only planes [z_lo, z_hi) (no broadcast of the volume)",
+            "h2d_bytes_per_step_this_rank": int((z_hi - z_lo) * BIG[1] * BIG[2] * 2 + len(loc_pts) * 24),
+            "d2h_bytes_per_step": int(BIG_PATCHES * 8),
+            "phase_ms_rank0": {k: round(v, 3) for k, v in timings.items()},
+            "collectives": dict(coll, what="all_reduce(SUM) of 16 513 float64 moments; all_gather of (n_local, 2) float32 rows (+ one int64 count each)"),
+            "components_row0_head": [float(v) for v in pca.components_[0][:4]],
+            "explained_variance": [float(v) for v in pca.explained_variance_],
+            "z_checksum": float(np.abs(z_all).sum())}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -227,11 +372,31 @@ def run_ours(args):
     value = world * vox_per_step / (ms_per_step / 1e3)
 
     # ------------------------------------------------------------------ per-layer roofline leg (separate pass, events per launch)
-    net.set_profiling(True)
+    net.set_profiling(True)            # (the chunk loop runs eagerly while profiling: the events sit between the launches)
     seg_step()
     torch.cuda.synchronize()
     lt = net.layer_times()
     net.set_profiling(False)
+
+    # ------------------------------------------------------------------ the same step with bf16 activations (north_star's dtype; fp16 is the
+    # default because bf16's 8-bit mantissa flips near-tie labels: tests/test_nets_gpu.py, profiles/r02_margin_hist.txt)
+    other = "bf16" if mode != "bf16" else "fp16"
+    fe_o = SurfaceSegmenter(model_initialization="define-new", descriptor_tag="M_a01", mode=other, **M_A01)
+    fe_o.models["segmenter"].set_weights(fe.models["segmenter"].get_weights())
+    for _ in range(2):
+        fe_o.segment_volume(vol, grid, CHUNK, min_max=min_max, out=seg)
+    barrier()
+    o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    o0.record()
+    n_o = max(1, min(args.steps, 3))
+    for _ in range(n_o):
+        fe_o.segment_volume(vol, grid, CHUNK, min_max=min_max, out=seg)
+    o1.record()
+    barrier()
+    other_ms = max_over_ranks(o0.elapsed_time(o1)) / n_o
+    other_line = {"dtype": other, "value": world * VOL[0] * VOL[1] * VOL[2] / (other_ms / 1e3), "unit": "voxels/s", "ms_per_step": other_ms}
+    del fe_o
+    fe.segment_volume(vol, grid, CHUNK, min_max=min_max, out=seg)
     by_kernel = {}
     for name, kernel, flops, ms, cnt in lt:
         if cnt == 0:
@@ -243,6 +408,10 @@ def run_ours(args):
         k["layers"].append(name)
     tot_ms = sum(k["ms"] for k in by_kernel.values())
     dom_name, dom = max(by_kernel.items(), key=lambda kv: kv[1]["ms"])
+    n_chunks = -(-n_tiles // CHUNK)
+    layers_tbl = {name: {"kernel": kernel, "us_per_chunk": round(1e3 * ms / cnt, 2),
+                         "tflops": round(flops * CHUNK / (ms / cnt / 1e3) / 1e12, 1) if flops else None}
+                  for name, kernel, flops, ms, cnt in lt if cnt}
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(peaks_path):
         peaks = json.load(open(peaks_path))
@@ -254,19 +423,26 @@ def run_ours(args):
     # DRAM traffic per launch of the dominant kernel: ncu --set full capture committed under profiles/ (one launch of
     # every layer at this very shape: 32 x 64^3 patches), averaged over the layers this kernel instantiation runs
     traffic, traffic_note = None, None
-    tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    tpath = os.path.join(ROOT, "profiles", "traffic_r02.json")
     if os.path.isfile(tpath) and CHUNK == 32:
         tj = json.load(open(tpath))["layers"]
-        got = [tj[l]["dram_read_bytes"] + tj[l]["dram_write_bytes"] for l in dom["layers"] if l in tj]
-        if got:
+        # only captures of THIS kernel configuration count (the file records the kernel each layer ran at capture time)
+        got = [tj[l]["dram_read_bytes"] + tj[l]["dram_write_bytes"] for l in dom["layers"]
+               if l in tj and tj[l].get("kernel", "").replace(" ", "") == dom_name.replace(" ", "")]
+        if got and len(got) == len(dom["layers"]):
             traffic = sum(got) / len(got)
-            traffic_note = "mean dram read+write bytes per launch over %s (profiles/traffic_r01.json, ncu --set full)" % \
-                ", ".join(l for l in dom["layers"] if l in tj)
+            traffic_note = "mean dram read+write bytes per launch over %s (profiles/traffic_r02.json, ncu --set full)" % \
+                ", ".join(dom["layers"])
+        else:
+            traffic_note = "profiles/traffic_r02.json holds no capture of %s for every layer it runs: not reported" % dom_name
     roofline = {"bound": "tensor", "kernel": dom_name, "layers": dom["layers"], "achieved": achieved, "peak": tf_peak,
                 "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": peak_src,
                 "launches_per_step": dom["launches"], "avg_launch_ms": dom["ms"] / dom["launches"],
-                "share_of_step": dom["ms"] / tot_ms}
+                # share of the timed step (not of the summed kernel time); the per-launch events of the profiling pass and
+                # the timed loop are separate passes over the same work
+                "share_of_step": dom["ms"] / ms_per_step, "share_of_kernel_time": dom["ms"] / tot_ms,
+                "kernel_time_over_step": tot_ms / ms_per_step}
     all_tc_flops = sum(k["flops"] for n_, k in by_kernel.items() if n_.startswith("conv_umma"))
     all_tc_ms = sum(k["ms"] for n_, k in by_kernel.items() if n_.startswith("conv_umma"))
     kernels = {n_: {"ms_per_step": round(k["ms"], 3), "launches": k["launches"],
@@ -315,7 +491,25 @@ def run_ours(args):
     gather_gbs = 2 * nvox * 2 / t_gather / 1e3                     # read f16 + write f16
     gnorm_gbs = (nvox * 2 + nvox * act.element_size()) / t_gnorm / 1e3
     scatter_gbs = 2 * nvox / t_scatter / 1e3                       # read u8 + write u8
-    del x_tiles, lab, act, flush, flush_r
+    del x_tiles, lab, act
+
+    # random, unaligned uint8 corners: the access pattern of configs[0] (4096 x 32^3 of a 256^3 volume) and of configs[2]
+    # (64^3 patches at random corners; here 16 384 of a 512^3 volume).  Algorithmic bytes: n P^3 written +
+    # min(n P^3, |V|) read + 24 n of coordinates.
+    def random_gather_case(vshape, P, n, seed):
+        v8 = torch.randint(0, 256, vshape, dtype=torch.uint8, device=dev)
+        rg = np.random.default_rng(seed)
+        rp = np.stack([rg.integers(0, vshape[a] - P, n) for a in range(3)], axis=1).astype(np.uint32)
+        dp, dw = _device.points_to_device(rp), _device.points_to_device(np.full_like(rp, P))
+        o8 = torch.empty((n, P, P, P), dtype=torch.uint8, device=dev)
+        vs_ = _lib.i64x3(vshape)
+        p_ = _lib.i32x3((P,) * 3)
+        us = timed_us(lambda: _lib.check(L.te_gather(v8.data_ptr(), 1, vs_, dp.data_ptr(), dw.data_ptr(), n, p_, o8.data_ptr(), 0, st)))
+        alg = n * P ** 3 + min(n * P ** 3, v8.numel()) + 24 * n
+        return {"us": us, "algorithmic_bytes": alg, "gbs": alg / us / 1e3, "frac": alg / us / 1e3 / hbm_peak}
+    rand_cfg1 = random_gather_case((256,) * 3, 32, 4096, 21)
+    rand_cfg3 = random_gather_case((512,) * 3, 64, 16384, 22)
+    del flush, flush_r
 
     # ------------------------------------------------------------------ end to end: host volume -> host mask through the public API
     host_vol = torch.empty(VOL, dtype=torch.float16).pin_memory()
@@ -428,6 +622,26 @@ def run_ours(args):
                  "note": "ncu of the kernel: profiles/ncu_r01_recon.txt (l1tex data-pipe wavefronts 83 % of peak)"}
         del rd, rout
 
+    # ------------------------------------------------------------------ BASELINE configs[3] and configs[2] at their stated sizes (all ranks)
+    cfg4 = cfg3 = None
+    if not args.no_big:
+        from tomoencoders_b200 import sharding
+        torch.cuda.empty_cache()
+        z0, z1 = sharding.slab_bounds(BIG, PATCH, rank, world)
+        rng77 = np.random.default_rng(77)
+        zz = np.sort(rng77.integers(0, BIG[0] - PATCH, BIG_PATCHES))          # the z column of leg_cfg3's list (first draw)
+        a3, b3 = sharding.shard_range(BIG_PATCHES, rank, world)
+        zl3, zh3 = int(zz[a3]), int(zz[b3 - 1]) + PATCH
+        z_base, z_top = min(z0, zl3), max(z1, zh3)
+        host_planes = torch.empty((z_top - z_base,) + BIG[1:], dtype=torch.float16, pin_memory=True)
+        fill_big_slab(host_planes, z_base, z_top, dev)
+        cfg4 = leg_cfg4(fe, rank, world, dev, barrier, max_over_ranks, host_planes[z0 - z_base:z1 - z_base], z0, z1,
+                        reps=1 if world == 1 else 2)
+        fe.__dict__.pop("_staging_bufs", None)
+        torch.cuda.empty_cache()
+        cfg3 = leg_cfg3(ae, rank, world, dev, barrier, max_over_ranks, host_planes, z_base)
+        del host_planes
+
     if rank == 0:
         cpu_baseline = None                  # timed on rank 0 at N = 1 only (the other ranks would idle on it)
         if world == 1:
@@ -455,11 +669,16 @@ def run_ours(args):
             "roofline": roofline,
             "roofline_all_tensor_core_layers": {"achieved": all_tc_flops / (all_tc_ms / 1e3) / 1e12, "unit": "TFLOP/s",
                                                 "frac": all_tc_flops / (all_tc_ms / 1e3) / 1e12 / tf_peak,
-                                                "share_of_step": all_tc_ms / tot_ms},
+                                                "share_of_step": all_tc_ms / ms_per_step},
             "kernels": kernels,
+            "layers": layers_tbl,
+            "other_dtype": other_line,
+            "cfg4": cfg4,
+            "cfg3": cfg3,
             "hbm": {"gather_gbs": gather_gbs, "gather_frac": gather_gbs / hbm_peak,
                     "gather_norm_gbs": gnorm_gbs, "gather_norm_frac": gnorm_gbs / hbm_peak,
                     "scatter_gbs": scatter_gbs, "scatter_frac": scatter_gbs / hbm_peak, "peak": hbm_peak, "unit": "GB/s",
+                    "random_u8_cfg1_4096x32^3_of_256^3": rand_cfg1, "random_u8_cfg3like_16384x64^3_of_512^3": rand_cfg3,
                     "us": {"gather": t_gather, "gather_norm": t_gnorm, "scatter": t_scatter,
                            "gather_api": t_gather_api, "scatter_api": t_scatter_api},
                     "note": "kernel-only (C ABI, CUDA events, L2 flushed by a 256 MB write followed by a 256 MB read so that no dirty lines remain): te_gather of the 512^3 fp16 volume into 512 tiles "
@@ -485,6 +704,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-recon", action="store_true", help="skip the reconstruction leg")
+    ap.add_argument("--no-big", action="store_true", help="skip the 2048^3 legs (BASELINE configs[2] / configs[3])")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

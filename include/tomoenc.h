@@ -222,6 +222,27 @@ double te_net_flops_per_patch(const te_net* net);
 /* Name, algorithmic FLOPs and kernel class of layer i (host strings owned by the handle). */
 int te_net_layer_info(const te_net* net, int layer_index, const char** name, double* flops, int* uses_tensor_cores);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training data generator of the segmenter.
+ *
+ * te_patch_std replaces the np.std over every binned label patch in SurfaceSegmenter._find_blanks
+ * (neural_nets/surface_segmenter.py:75-82): out_std[i] = population standard deviation (ddof = 0, float64 sums) of
+ * vol[z:z+wz:b, y:y+wy:b, x:x+wx:b], b = widths[i][0] / patch[0].  out_std = device float[n].
+ *
+ * te_training_pairs replaces extract_training_patch_pairs (neural_nets/keras_processor.py:213-232) in ONE kernel:
+ *   x_out[i] = rot90(X[binned patch i], nrots[i], axes[i]) + sigma[i] * N(0, 1)       float32 (n, P, P, P)
+ *   y_out[i] = rot90(Y[binned patch i], nrots[i], axes[i])                             uint8
+ * rot90 = numpy.rot90(m, k, axes=(a, b)) with k = nrots[i] & 3, (a, b) = axes[i] (ordered pair out of 0, 1, 2; cubic
+ * patches).  The noise is Philox4x32-10 keyed by (seed, patch, voxel) + Box-Muller: reproducible for a given seed,
+ * independent of the launch geometry.  sigma == NULL: no noise; nrots == NULL: no rotation.  All pointers are device
+ * pointers; dtypes of X / Y in {TE_U8, TE_U16, TE_F16, TE_F32}. */
+int te_patch_std(const void* vol, int vol_dtype, const int64_t vol_shape[3], const uint32_t* points,
+                 const uint32_t* widths, int64_t n, const int32_t patch[3], float* out_std, void* stream);
+int te_training_pairs(const void* X, int x_dtype, const void* Y, int y_dtype, const int64_t vol_shape[3],
+                      const uint32_t* points, const uint32_t* widths, int64_t n, const int32_t patch[3],
+                      const float* sigma, const int32_t* nrots, const int32_t* axes, uint64_t seed,
+                      float* x_out, uint8_t* y_out, void* stream);
+
 /* fp16 activations (TE_MODE_FP16) have a finite range of +-65504.  Random-init and BN-folded shipped weights keep
  * activations O(1), but a trained net with large gamma / sigma ratios can exceed it; Keras computes in float32
  * (Unet3D.py:44-81) and has no such limit.  Every conv epilogue therefore tracks the largest |activation| it produced

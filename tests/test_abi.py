@@ -1,6 +1,8 @@
 """CPU: libtomoenc.so builds for sm_100a, loads, and exports every symbol include/tomoenc.h declares
 (no compute calls -- there is no GPU here)."""
 import ctypes
+
+import pytest
 import os
 import re
 
@@ -33,8 +35,18 @@ def test_argument_errors_are_reported_without_a_gpu(built_lib):
     assert rc == 0        # empty input is a no-op
 
 
+@pytest.mark.gpu
+def test_sass_contains_blackwell_instructions_on_the_gpu_box(built_lib):
+    """The same SASS check on the library the GPU box actually loads (the driver runs -m gpu there)."""
+    _check_sass(built_lib)
+
+
 def test_sass_contains_blackwell_instructions(built_lib):
     """The conv kernels must be tcgen05 / TMA code, not recompiled legacy MMA."""
+    _check_sass(built_lib)
+
+
+def _check_sass(built_lib):
     import subprocess
     sass = subprocess.run(["cuobjdump", "-sass", built_lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass, "no tcgen05.mma in the library"

@@ -46,7 +46,7 @@ def test_unet_fp32_check_mode_matches_oracle(vol_f16):
     assert np.abs(probs - ref).max() < 1e-4
 
 
-@pytest.mark.parametrize("mode,min_agree", [("fp16", 0.999), ("bf16", 0.99)])
+@pytest.mark.parametrize("mode,min_agree", [("fp16", 0.999), ("bf16", 0.995)])
 def test_segmenter_config2_masks_agree_with_oracle(vol_f16, mode, min_agree):
     """BASELINE config 2 model (M_a01, 64^3 tiles, fp16 volume), 8 tiles of a 128^3 phantom."""
     w = OW.draw(O.unet_spec(**oparams(M_A01)), 11)
@@ -283,14 +283,17 @@ def test_wide_unet_512_bottleneck_channels():
     x = np.random.default_rng(0).uniform(0, 1, (3, 32, 32, 32, 1)).astype(np.float32)
     y = fe.predict_patches("segmenter", x, 2, None, min_max=(0.0, 1.0))
     ref = O.segmenter_predict_patches(x, 2, w, min_max=(0.0, 1.0), **oparams(P))
-    assert 0.02 < ref.mean() < 0.98 and (y == ref).mean() >= 0.995
+    # measured 99.97 % (profiles/r02_margin_hist.txt); north_star's bar is 99.9 %
+    assert 0.02 < ref.mean() < 0.98 and (y == ref).mean() >= 0.999, (y == ref).mean()
 
 
 # ------------------------------------------------------------------ round-2 additions (ADVICE)
 # Largest |oracle logit| at which a 16-bit run may flip a label.  Measured on B200 (tools/margin_hist.py ->
 # profiles/r02_margin_hist.txt): the flipped voxels of M_a01 all sit below these margins; everything with a clearer
-# decision agrees 100 %.
-MARGIN = {"fp16": 0.02, "bf16": 0.25}
+# decision agrees 100 %.  Measured maxima: fp16 0.0077, bf16 0.081 (logit std 1.46); agreement fp16 99.96 %, bf16 99.68 %:
+# the bf16 shortfall against north_star's 99.9 % is the 8-bit mantissa of the ACTIVATIONS between 17 layers, not a kernel
+# error -- hence fp16 is the default mode and bf16 the fallback for nets that leave fp16's range.
+MARGIN = {"fp16": 0.015, "bf16": 0.12}
 
 
 def _gpu_and_oracle_logits(params, w, x, mode, min_max=(0.0, 1.0)):
@@ -323,7 +326,7 @@ def test_mask_disagreements_are_near_tie_logits_only(vol_f16, mode):
     assert not (flipped & clear).any(), "flipped a voxel with |oracle logit| = %.4f >= %.3f" % (worst, delta)
     # and the logits themselves track the oracle (max-abs error relative to the logit scale)
     err = np.abs(logits - ref).max() / np.abs(ref).std()
-    assert err < (0.02 if mode == "fp16" else 0.25), err
+    assert err < (0.02 if mode == "fp16" else 0.12), err
 
 
 def test_bf16_decoder_round_trip_matches_oracle():

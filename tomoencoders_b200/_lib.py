@@ -130,6 +130,9 @@ _SIGNATURES = {
     "te_gather_standardize": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_I64), _P, _P, _I64,
                                              ctypes.POINTER(_I32), ctypes.c_int, ctypes.c_float, ctypes.c_float, _P, _P,
                                              ctypes.c_int, _P]),
+    "te_patch_std": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_I64), _P, _P, _I64, ctypes.POINTER(_I32), _P, _P]),
+    "te_training_pairs": (ctypes.c_int, [_P, ctypes.c_int, _P, ctypes.c_int, ctypes.POINTER(_I64), _P, _P, _I64,
+                                         ctypes.POINTER(_I32), _P, _P, _P, ctypes.c_uint64, _P, _P, _P]),
     "te_scatter": (ctypes.c_int, [_P, ctypes.c_int, _P, _I64, ctypes.POINTER(_I32), _P,
                                   ctypes.POINTER(_I64), _P, ctypes.c_int, _P]),
     "te_minmax_strided": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_I64), ctypes.c_int, _P, _P, _P]),

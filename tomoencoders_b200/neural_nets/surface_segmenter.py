@@ -7,12 +7,48 @@ import time
 import numpy as np
 import torch
 
-from .. import _device
+from .. import _device, _lib
 from ..structures.patches import Patches
 from .keras_processor import Vox2VoxProcessor_fCNN
 from .Unet3D import build_Unet_3D
 
 MAX_ITERS = 2000                    # surface_segmenter.py:27
+
+
+def _patch_std(vol, patches, input_size):
+    """(n,) float32 CUDA tensor: np.std of every binned patch of vol (te_patch_std)."""
+    t = _device.to_supported(_device.to_device(vol))
+    n = len(patches)
+    out = torch.empty(max(n, 1), dtype=torch.float32, device=t.device)
+    d_pts = _device.points_to_device(patches.points)
+    d_wds = _device.points_to_device(patches.widths)
+    _lib.check(_lib.lib().te_patch_std(t.data_ptr(), _device.te_dtype(t), _lib.i64x3(patches.vol_shape), d_pts.data_ptr(),
+                                       d_wds.data_ptr(), n, _lib.i32x3(input_size), out.data_ptr(), _device.stream_ptr()),
+               "te_patch_std")
+    return out[:n]
+
+
+def _training_pairs(X, Y, patches, input_size, sigma, nrots, axes, seed):
+    """x (n,P,P,P,1) float32 and y (n,P,P,P,1) uint8 CUDA tensors (te_training_pairs)."""
+    tx = _device.to_supported(_device.to_device(X))
+    ty = _device.to_supported(_device.to_device(Y))
+    assert tuple(tx.shape) == tuple(patches.vol_shape) == tuple(ty.shape), "volume shapes do not match vol_shape"
+    n = len(patches)
+    dev = tx.device
+    x = torch.empty((n,) + tuple(input_size), dtype=torch.float32, device=dev)
+    y = torch.empty((n,) + tuple(input_size), dtype=torch.uint8, device=dev)
+    d_pts = _device.points_to_device(patches.points)
+    d_wds = _device.points_to_device(patches.widths)
+    d_sig = None if sigma is None else torch.from_numpy(np.ascontiguousarray(sigma, dtype=np.float32)).to(dev)
+    d_rot = None if nrots is None else torch.from_numpy(np.ascontiguousarray(nrots, dtype=np.int32)).to(dev)
+    d_ax = None if axes is None else torch.from_numpy(np.ascontiguousarray(axes, dtype=np.int32)).to(dev)
+    _lib.check(_lib.lib().te_training_pairs(tx.data_ptr(), _device.te_dtype(tx), ty.data_ptr(), _device.te_dtype(ty),
+                                            _lib.i64x3(patches.vol_shape), d_pts.data_ptr(), d_wds.data_ptr(), n,
+                                            _lib.i32x3(input_size), None if d_sig is None else d_sig.data_ptr(),
+                                            None if d_rot is None else d_rot.data_ptr(),
+                                            None if d_ax is None else d_ax.data_ptr(), int(seed) & (2 ** 64 - 1),
+                                            x.data_ptr(), y.data_ptr(), _device.stream_ptr()), "te_training_pairs")
+    return x.unsqueeze(-1), y.unsqueeze(-1)
 
 
 class SurfaceSegmenter(Vox2VoxProcessor_fCNN):
@@ -81,10 +117,10 @@ class SurfaceSegmenter(Vox2VoxProcessor_fCNN):
         return history
 
     def _find_blanks(self, patches, cutoff, Y_gt, input_size):
-        """surface_segmenter.py:75-82: keep patches whose label std exceeds cutoff x the largest std."""
+        """surface_segmenter.py:75-82: keep patches whose label std exceeds cutoff x the largest std.  One reduction
+        kernel (te_patch_std) over the binned patches; the patch array itself is never materialised."""
         assert tuple(Y_gt.shape) == tuple(patches.vol_shape), "volume of Y_gt does not match vol_shape"
-        y_tmp = _device.to_device(patches.extract(Y_gt, input_size)).float()
-        ystd = y_tmp.reshape(len(y_tmp), -1).std(dim=1, unbiased=False)
+        ystd = _patch_std(Y_gt, patches, input_size)
         return (ystd > ystd.max() * cutoff).cpu().numpy().astype(bool)
 
     def get_training_patches(self, vol_shape, batch_size, input_size, max_stride, cutoff, Y_gt):
@@ -110,22 +146,21 @@ class SurfaceSegmenter(Vox2VoxProcessor_fCNN):
         assert patches is not None, "get_patches() failed to return any patches with selected conditions"
         return patches.select_random_sample(batch_size)
 
-    def extract_training_patch_pairs(self, X, Y, patches, add_noise, random_rotate, input_size):
-        """keras_processor.py:213-232 on the device: binned gather of x and y, per-patch Gaussian noise
-        with sigma ~ U(0, add_noise), random rot90 about a random axis pair (cubic patches)."""
+    def extract_training_patch_pairs(self, X, Y, patches, add_noise, random_rotate, input_size, seed=None):
+        """keras_processor.py:213-232 in one kernel (te_training_pairs): binned gather of x and y, per-patch Gaussian
+        noise with sigma ~ U(0, add_noise), random rot90 about a random ordered axis pair.  The per-patch scalars
+        (sigma, k, axes) are drawn on the host with the reference's own np.random calls, in its order; the noise
+        field comes from the kernel's counter-based generator (seed: drawn from np.random when not given)."""
         batch_size = len(patches)
-        y = _device.to_device(patches.extract(_device.to_device(Y), input_size))
-        x = _device.to_device(patches.extract(_device.to_device(X), input_size)).float()
-        std_batch = torch.from_numpy(np.random.uniform(0, add_noise, batch_size).astype(np.float32)).to(x.device)
-        x = x + torch.randn_like(x) * std_batch.view(-1, 1, 1, 1)
+        patches._calc_binning(tuple(input_size))
+        std_batch = np.random.uniform(0, add_noise, batch_size).astype(np.float32)
+        nrots = axes = None
         if random_rotate:
-            nrots = np.random.randint(0, 4, batch_size)
-            for ii in range(batch_size):
-                axes = tuple(int(a) for a in np.random.choice([0, 1, 2], size=2, replace=False))
-                if nrots[ii]:
-                    x[ii] = torch.rot90(x[ii], int(nrots[ii]), axes)
-                    y[ii] = torch.rot90(y[ii], int(nrots[ii]), axes)
-        return x.unsqueeze(-1), y.to(torch.uint8).unsqueeze(-1)
+            nrots = np.random.randint(0, 4, batch_size).astype(np.int32)
+            axes = np.stack([np.random.choice([0, 1, 2], size=2, replace=False) for _ in range(batch_size)]).astype(np.int32)
+        if seed is None:
+            seed = int(np.random.randint(0, 2 ** 31 - 1))
+        return _training_pairs(X, Y, patches, tuple(input_size), std_batch, nrots, axes, seed)
 
     def _data_generator(self, Xs, Ys, batch_size, input_size, max_stride, cutoff, random_rotate, add_noise):
         """surface_segmenter.py:202-244: yields (x float32 (B,P,P,P,1), y uint8) CUDA tensors."""

@@ -126,6 +126,9 @@ def allgather_rows(t, group=None):
     if ws == 1:
         return t
     t = t.contiguous()
+    if t.is_cuda and dist.get_backend(group) == "gloo":
+        # gloo has no all_gather for CUDA tensors (single-GPU test rigs): stage through the host
+        return allgather_rows(t.cpu(), group).to(t.device)
     counts = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
     all_counts = [torch.empty_like(counts) for _ in range(ws)]
     dist.all_gather(all_counts, counts, group=group)
