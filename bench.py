@@ -504,9 +504,16 @@ def run_ours(args):
         o8 = torch.empty((n, P, P, P), dtype=torch.uint8, device=dev)
         vs_ = _lib.i64x3(vshape)
         p_ = _lib.i32x3((P,) * 3)
-        us = timed_us(lambda: _lib.check(L.te_gather(v8.data_ptr(), 1, vs_, dp.data_ptr(), dw.data_ptr(), n, p_, o8.data_ptr(), 0, st)))
+        us_plain = timed_us(lambda: _lib.check(L.te_gather(v8.data_ptr(), 1, vs_, dp.data_ptr(), dw.data_ptr(), n, p_, o8.data_ptr(),
+                                                          _lib.TE_HINT_UNBINNED, st)))
+        # the product path (structures/_table.py) hands the kernel a (z, y)-sorted processing order: output order unchanged
+        perm = torch.argsort(dp[:, 0].to(torch.int64) * vshape[1] + dp[:, 1].to(torch.int64)).to(torch.int32)
+        us = timed_us(lambda: _lib.check(L.te_gather_perm(v8.data_ptr(), 1, vs_, dp.data_ptr(), dw.data_ptr(), n, p_, o8.data_ptr(),
+                                                          _lib.TE_HINT_UNBINNED, perm.data_ptr(), st)))
+        us_api = timed_us(lambda: Patches(vshape, "data", points=rp, widths=np.full_like(rp, P)).extract(v8, (P,) * 3))
         alg = n * P ** 3 + min(n * P ** 3, v8.numel()) + 24 * n
-        return {"us": us, "algorithmic_bytes": alg, "gbs": alg / us / 1e3, "frac": alg / us / 1e3 / hbm_peak}
+        return {"us": us, "us_index_order": us_plain, "us_api": us_api, "algorithmic_bytes": alg, "gbs": alg / us / 1e3,
+                "frac": alg / us / 1e3 / hbm_peak}
     rand_cfg1 = random_gather_case((256,) * 3, 32, 4096, 21)
     rand_cfg3 = random_gather_case((512,) * 3, 64, 16384, 22)
     del flush, flush_r

@@ -67,8 +67,20 @@ int64_t te_launch_count_add(int64_t n);
  * The hint only selects the kernel: a violated promise costs speed, never correctness.
  */
 #define TE_HINT_ALIGNED 1
+/* TE_HINT_UNBINNED: the caller promises widths[i] == patch for every i (no decimation).  Lets te_gather pick the row-group
+ * kernel for short rows at arbitrary corners (random patches of BASELINE configs[0] / configs[2]).  Like every hint: a
+ * violated promise is a caller error here (the widths are not re-read), so only set it from a checked table. */
+#define TE_HINT_UNBINNED 2
 int te_gather(const void* vol, int elem_size, const int64_t vol_shape[3], const uint32_t* points,
               const uint32_t* widths, int64_t n, const int32_t patch[3], void* out, int flags, void* stream);
+
+/* te_gather with a processing order: work slot s handles patch perm[s] (perm = a permutation of 0..n-1, device uint32);
+ * out is still written in patch-index order, so the result is identical to te_gather.  A list of heavily overlapping
+ * random patches (BASELINE configs[0] / configs[2]: n P^3 is many times the volume) gathered in (z, y)-sorted order keeps
+ * the slab the running blocks read resident in the 126 MB L2 instead of re-fetching it from HBM for every patch. */
+int te_gather_perm(const void* vol, int elem_size, const int64_t vol_shape[3], const uint32_t* points,
+                   const uint32_t* widths, int64_t n, const int32_t patch[3], void* out, int flags,
+                   const uint32_t* perm, void* stream);
 
 /* Gather fused with the pre-network clip / rescale.  Replaces extract followed by the per-chunk
  * np.clip + _rescale_data of SurfaceSegmenter.predict_patches (neural_nets/surface_segmenter.py:
@@ -81,6 +93,10 @@ int te_gather(const void* vol, int elem_size, const int64_t vol_shape[3], const 
 int te_gather_norm(const void* vol, int vol_dtype, const int64_t vol_shape[3], const uint32_t* points,
                    const uint32_t* widths, int64_t n, const int32_t patch[3], int rescale, int do_clip,
                    float lo, float hi, void* out, int out_dtype, void* stream);
+/* te_gather_norm with a processing order (see te_gather_perm). */
+int te_gather_norm_perm(const void* vol, int vol_dtype, const int64_t vol_shape[3], const uint32_t* points,
+                        const uint32_t* widths, int64_t n, const int32_t patch[3], int rescale, int do_clip,
+                        float lo, float hi, void* out, int out_dtype, const uint32_t* perm, void* stream);
 
 /* Gather fused with the in-graph input standardisation of the ICIP porosity encoder (build_CAE_3D(stdinput=True),
  * /root/reference/scratchpad/IEEE_ICIP_paper/porosity_encoders.py:89-98, 298-302): after the optional global rescale

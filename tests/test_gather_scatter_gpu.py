@@ -13,7 +13,7 @@ SVS = (40, 44, 48)
 DTYPES = (("u8", np.uint8), ("u16", np.uint16), ("f16", np.float16), ("f32", np.float32))
 
 
-@pytest.fixture(autouse=True, params=["default", "tma", "simt"])
+@pytest.fixture(autouse=True, params=["default", "tma", "simt", "chunks"])
 def gather_path(request, monkeypatch):
     """Every test runs three times: default kernel selection (TMA-staged kernels for 16-byte-aligned
     2- and 4-byte tilings, SIMT otherwise), TMA kernels forced wherever the row pitch allows (covers
@@ -21,6 +21,8 @@ def gather_path(request, monkeypatch):
     every call."""
     monkeypatch.setenv("TOMOENC_NO_TMA_GATHER", "1" if request.param == "simt" else "0")
     monkeypatch.setenv("TOMOENC_FORCE_TMA_GATHER", "1" if request.param == "tma" else "0")
+    # "chunks": the row-group kernel for short unaligned rows switched off (the 16-byte chunk kernel takes them)
+    monkeypatch.setenv("TOMOENC_NO_ROW_GATHER", "1" if request.param == "chunks" else "0")
     return request.param
 
 
@@ -246,3 +248,19 @@ def test_float64_volume_unbinned_gather_scatter_and_refusal():
     pb = Patches(SVS, "data", points=np.zeros((1, 3), dtype=np.uint32), widths=np.full((1, 3), 32, dtype=np.uint32))
     with pytest.raises(TypeError, match="binned extract"):
         pb.extract(vol, (16,) * 3)
+
+
+@pytest.mark.parametrize("dt", [np.uint8, np.float16])
+def test_many_overlapping_random_patches_take_the_sorted_processing_order(dt):
+    """n P^3 >> volume: the host mirror hands te_gather_perm a (z, y)-sorted processing order (L2 reuse); the output is
+    still in patch-index order, bit-exact."""
+    vs = (64, 72, 80)
+    vol = seeded_volume(vs, dt, 310)
+    g = np.random.default_rng(311)
+    pts = np.stack([g.integers(0, vs[a] - 16, 3001) for a in range(3)], axis=1).astype(np.uint32)
+    p = Patches(vs, "data", points=pts, widths=np.full_like(pts, 16))
+    out = p.extract(vol, (16,) * 3)
+    np.testing.assert_array_equal(_bits(out), _bits(S.extract(vol, p.points, p.widths, (16,) * 3)))
+    tv = torch.from_numpy(vol.view(np.uint8 if dt == np.uint8 else np.int16)).cuda()
+    out_d = p.extract(tv, (16,) * 3)
+    assert out_d.is_cuda and np.array_equal(out_d.cpu().numpy().view(out.dtype), out)

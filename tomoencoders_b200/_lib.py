@@ -23,6 +23,7 @@ NVCC_FLAGS = [
 TE_U8, TE_U16, TE_F16, TE_F32, TE_BF16 = 0, 1, 2, 3, 4
 TE_MODE_BF16, TE_MODE_FP16, TE_MODE_FP32_CHECK = 0, 1, 2
 TE_HINT_ALIGNED = 1
+TE_HINT_UNBINNED = 2
 MODES = {"bf16": TE_MODE_BF16, "fp16": TE_MODE_FP16, "fp32": TE_MODE_FP32_CHECK,
          "fp32check": TE_MODE_FP32_CHECK}
 
@@ -124,6 +125,11 @@ _SIGNATURES = {
     "te_launch_count_add": (_I64, [_I64]),
     "te_gather": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_I64), _P, _P, _I64,
                                  ctypes.POINTER(_I32), _P, ctypes.c_int, _P]),
+    "te_gather_perm": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_I64), _P, _P, _I64,
+                                      ctypes.POINTER(_I32), _P, ctypes.c_int, _P, _P]),
+    "te_gather_norm_perm": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_I64), _P, _P, _I64,
+                                           ctypes.POINTER(_I32), ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                           ctypes.c_float, _P, ctypes.c_int, _P, _P]),
     "te_gather_norm": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_I64), _P, _P, _I64,
                                       ctypes.POINTER(_I32), ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                       ctypes.c_float, _P, ctypes.c_int, _P]),

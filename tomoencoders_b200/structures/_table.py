@@ -68,8 +68,18 @@ def gather(vol, vol_shape, points, widths, patch_size):
         d_wds = _device.points_to_device(wds3)
         L = _lib.lib()
         hint = _aligned_hint(pts3, wds3, patch3, es)
-        _lib.check(L.te_gather(t_vol.data_ptr(), es, _lib.i64x3(vs3), d_pts.data_ptr(), d_wds.data_ptr(), n,
-                               _lib.i32x3(patch3), out.data_ptr(), hint, _device.stream_ptr()), "te_gather")
+        gathered = n * int(np.prod(patch3))
+        if n >= 1024 and gathered >= 4 * int(np.prod(vs3)) and not (hint & _lib.TE_HINT_ALIGNED):
+            # many overlapping patches at scattered corners: process them in (z, y) order so that the slab the running
+            # blocks read stays in L2 (the output order does not change)
+            key = d_pts[:, 0].to(torch.int64) * int(vs3[1]) + d_pts[:, 1].to(torch.int64)
+            perm = torch.argsort(key).to(torch.int32)
+            _lib.check(L.te_gather_perm(t_vol.data_ptr(), es, _lib.i64x3(vs3), d_pts.data_ptr(), d_wds.data_ptr(), n,
+                                        _lib.i32x3(patch3), out.data_ptr(), hint, perm.data_ptr(), _device.stream_ptr()),
+                       "te_gather_perm")
+        else:
+            _lib.check(L.te_gather(t_vol.data_ptr(), es, _lib.i64x3(vs3), d_pts.data_ptr(), d_wds.data_ptr(), n,
+                                   _lib.i32x3(patch3), out.data_ptr(), hint, _device.stream_ptr()), "te_gather")
     out = out.reshape((n,) + tuple(int(p) for p in patch_size))
     return _device.to_host_like(out, vol)
 
@@ -99,8 +109,8 @@ def _aligned_hint_uncached(pts, wds, patch3, es):
     if wds is not None and np.any(np.asarray(wds, dtype=np.int64) != np.asarray(patch3, dtype=np.int64)[None, :]):
         return 0
     if np.any((pts[:, 2].astype(np.int64) * es) % 16):
-        return 0
-    return _lib.TE_HINT_ALIGNED
+        return _lib.TE_HINT_UNBINNED
+    return _lib.TE_HINT_ALIGNED | _lib.TE_HINT_UNBINNED
 
 
 def _disjoint(points, width, vs3):
