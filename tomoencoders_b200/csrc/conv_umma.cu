@@ -140,17 +140,35 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int fp16) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int CB, int NT, int TZ, int HALO>
+// Per-CTA weight image of one (dy, dx) slab in CTA-pair mode (cta_group::2: each CTA supplies HALF of the B rows of every
+// instruction, at the same shared-memory offset in both CTAs).  The dz-fused schedule issues five different row ranges
+// of the 3 * NT-row slab [t = 0 (dz = +1) | t = 1 | t = 2], plus the three single-tap ranges of a tile's first slab; the
+// image holds this CTA's half of each range (rows of CB * 2 bytes, offsets in rows):
+//   V96  rows [0, 3 NT)        -> 3 NT / 2 rows at 0            (interior input planes)
+//   V64H rows [NT, 3 NT)       -> NT rows at 3 NT / 2           (input plane 0 of a tile)
+//   V64L rows [0, 2 NT)        -> NT rows at 5 NT / 2           (input plane TZ - 1)
+//   V32L / V32M / V32H rows [0, NT) / [NT, 2 NT) / [2 NT, 3 NT) -> NT / 2 rows each at 7 NT / 2, 4 NT, 9 NT / 2
+struct PairImage {
+  template <int NT> __host__ __device__ static constexpr int v96() { return 0; }
+  template <int NT> __host__ __device__ static constexpr int v64h() { return 3 * NT / 2; }
+  template <int NT> __host__ __device__ static constexpr int v64l() { return 5 * NT / 2; }
+  template <int NT> __host__ __device__ static constexpr int v32(int t) { return 7 * NT / 2 + t * (NT / 2); }
+  template <int NT> __host__ __device__ static constexpr int rows() { return 5 * NT; }
+};
+
+template <int CB, int NT, int TZ, int HALO, bool PAIR = false>
 struct Cfg {
   static constexpr int ROWB = CB * 2;                                   // bytes of one voxel row of a chunk
   static constexpr uint32_t LAYOUT = CB == 16 ? kLayoutSW32 : (CB == 32 ? kLayoutSW64 : kLayoutSW128);
   static constexpr int KSTEPS = CB / 16;                                // UMMA K = 16 for 16-bit operands
   static constexpr int A_STAGE = (((TZ + 2 * HALO) * (16 + 2 * HALO) * (8 + 2 * HALO) * ROWB) + 1023) / 1024 * 1024;
-  static constexpr int SLAB = (HALO ? 3 : 1) * NT * ROWB;              // bytes of one weight slab (3 taps of a conv)
+  static_assert(!PAIR || (HALO && 3 * NT <= 256 && NT % 32 == 0), "CTA pairs: dz-fused 3x3x3 convs with NT a multiple of 32");
+  // bytes of one weight slab (3 taps of a conv; in pair mode this CTA's image of the slab, see PairImage)
+  static constexpr int SLAB = PAIR ? PairImage::rows<NT>() * ROWB : (HALO ? 3 : 1) * NT * ROWB;
   // Weight slabs per pipeline stage.  Every stage boundary costs a barrier wait plus a drain of the
   // UMMA issue queue (ncu: the uniform registers of queued UTCHMMAs are recycled there), so the
   // thin-channel layers, whose slabs are small, take 3 or 9 slabs per stage -> bursts of 36 / 108 UMMAs.
-  static constexpr int G = !HALO ? 1 : (NT >= 128 ? 1 : (SLAB * 9 <= 28 * 1024 ? 9 : 3));
+  static constexpr int G = !HALO ? 1 : (NT >= 128 ? 1 : (PAIR ? 9 : (SLAB * 9 <= 28 * 1024 ? 9 : 3)));
   static constexpr int NGROUPS = HALO ? 9 / G : 1;                      // stages per channel chunk
   static constexpr int W_STAGE = ((G * SLAB) + 1023) / 1024 * 1024;
   // input-box ring: the haloed boxes of the 3x3x3 conv are large (2 stages); the un-haloed boxes of
@@ -177,22 +195,30 @@ struct Cfg {
   static constexpr int ROOM0 = 227 * 1024 - 2048 - NUM_A * A_STAGE;
   static constexpr int W_FIT2 = (ROOM0 - EPI_GROUPS * 2 * STG_BUF) / W_STAGE;   // with double-buffered staging
   static constexpr int W_FIT1 = (ROOM0 - EPI_GROUPS * STG_BUF) / W_STAGE;       // with single-buffered staging
-  static constexpr int STG_NBUF = W_FIT2 >= 2 ? 2 : 1;
+  static constexpr int STG_NBUF = (W_FIT2 >= 2 && !PAIR) ? 2 : 1;
   static constexpr int W_FIT = STG_NBUF == 2 ? W_FIT2 : W_FIT1;
   static constexpr int NUM_W = W_FIT >= 4 ? 4 : W_FIT;
   static_assert(NUM_W >= 2, "weight ring needs two stages");
   static constexpr int STG_BYTES = EPI_GROUPS * STG_NBUF * STG_BUF;
   static constexpr int BIAS_BYTES = 1024;   // fp32 bias of up to 256 output channels behind the barriers, then 128 head weights
   static constexpr int SMEM_BYTES = STG_BYTES + NUM_A * A_STAGE + NUM_W * W_STAGE + 2048 /*barriers + bias*/ + 1024 /*align*/;
-  static_assert((2 * NUM_A + 2 * NUM_W + 4) * 8 + 4 <= 512, "barriers overlap the bias staging area");
+  static_assert((2 * NUM_A + 3 * NUM_W + 4) * 8 + 4 <= 512, "barriers overlap the bias staging area");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
 };
 
-template <int CB, int NT, int TZ, int HALO>
-__global__ void __launch_bounds__((Cfg<CB, NT, TZ, HALO>::THREADS), 1)
+template <int CB, int NT, int TZ, int HALO, bool PAIR = false>
+__global__ void __launch_bounds__((Cfg<CB, NT, TZ, HALO, PAIR>::THREADS), 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_in2,
                  const __grid_constant__ OutMaps omaps, const KParams p) {
-  using C = Cfg<CB, NT, TZ, HALO>;
+  using C = Cfg<CB, NT, TZ, HALO, PAIR>;
+  // CTA-pair mode (launched as clusters of 2): the two CTAs of a pair work on two different spatial tiles with the SAME
+  // weights; the leader (cluster rank 0) issues tcgen05.mma.cta_group::2 instructions of M = 256 whose B rows are read half
+  // from each CTA's shared memory (per-CTA smem operand traffic 32 + N/8 instead of 32 + N/4 cycles per instruction: the
+  // N = 96 dz-fused instruction becomes math-bound, tools/umma2_probe.cu).  Every CTA keeps its own producers and epilogue.
+  const uint32_t pair_rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = pair_rank == 0;
+  const long long tile0 = PAIR ? (2LL * (blockIdx.x >> 1) + pair_rank) : static_cast<long long>(blockIdx.x);
+  const long long tile_step = PAIR ? static_cast<long long>(gridDim.x & ~1u) : static_cast<long long>(gridDim.x);
   constexpr int kNumAStages = C::NUM_A;
   constexpr int BX = 8 + 2 * HALO, BY = 16 + 2 * HALO, BZ = TZ + 2 * HALO;   // input box (voxels)
   constexpr int kNumWStages = C::NUM_W;
@@ -210,7 +236,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   uint64_t* w_empty = w_full + kNumWStages;      // [kNumWStages]
   uint64_t* acc_full = w_empty + kNumWStages;    // [2]
   uint64_t* acc_empty = acc_full + 2;            // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* w_land = acc_empty + 2;              // [kNumWStages] pair mode, rank 1: its own weight copies land here first
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_land + kNumWStages);
   uint8_t* stg = reinterpret_cast<uint8_t*>(bars) + 2048;    // [EPI_GROUPS][STG_NBUF][STG_BUF], 1024-aligned
   // bias of all output channels: the epilogues read it 16 channels at a time as 128-bit shared-memory loads (it was one
   // global load per accumulator element: 30 % of the epilogue's stall samples in the thin layers)
@@ -225,15 +252,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kNumAStages; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
-    for (int i = 0; i < kNumWStages; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4 * C::EPI_GROUPS); }
+    // pair mode: the "full" barriers the issuer waits on live in the leader and collect one arrival per CTA; the
+    // accumulator-empty barriers collect the epilogue warps of both CTAs
+    constexpr uint32_t kFullCount = PAIR ? 2 : 1;
+    for (int i = 0; i < kNumAStages; ++i) { mbar_init(a_full + i, kFullCount); mbar_init(a_empty + i, 1); }
+    for (int i = 0; i < kNumWStages; ++i) { mbar_init(w_full + i, kFullCount); mbar_init(w_empty + i, 1); mbar_init(w_land + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, kFullCount * 4 * C::EPI_GROUPS); }
     fence_barrier_init();
     prefetch_tmap(&tmap_in);
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, C::TMEM_COLS); tmem_relinquish(); }
+  if (warp == 1) {
+    if constexpr (PAIR) { tmem_alloc2(tmem_slot, C::TMEM_COLS); tmem_relinquish2(); }
+    else { tmem_alloc(tmem_slot, C::TMEM_COLS); tmem_relinquish(); }
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();        // the peer's barriers exist before anybody signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -253,18 +287,25 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     // The whole warp runs the (warp-uniform) control flow; one elected lane issues the copies and
     // runs ahead of the MMAs by the depth of the ring.
     uint32_t as = 0, aph = 0;
-    for (long long tile = blockIdx.x; tile < outer_tiles; tile += gridDim.x) {
+    for (long long tile = tile0; tile < outer_tiles; tile += tile_step) {
       const TileCoord tc = decode_tile(p, tile, TZ, reuse, 0);
 #pragma unroll 1
       for (int kc = 0; kc < p.kchunks; ++kc) {
         mbar_wait(a_empty + as, aph ^ 1);
         if (elect_one()) {
-          mbar_expect_tx(a_full + as, a_bytes);
           // channel chunks [0, k1) come from the first input tensor, the rest from the second
           // (planar skip concatenation: the two halves are separate dense tensors)
           const bool second = kc >= p.k1_chunks;
-          tma_load_5d(a_stage + as * C::A_STAGE, second ? &tmap_in2 : &tmap_in, a_full + as,
-                      (second ? kc - p.k1_chunks : kc) * CB, tc.x0 - HALO, tc.y0 - HALO, tc.z0 - HALO, tc.n);
+          if constexpr (PAIR) {
+            // this CTA's box into its own shared memory, its bytes credited to the LEADER's barrier
+            mbar_expect_tx_leader(a_full + as, a_bytes);
+            tma_load_5d_pair(a_stage + as * C::A_STAGE, second ? &tmap_in2 : &tmap_in, a_full + as,
+                             (second ? kc - p.k1_chunks : kc) * CB, tc.x0 - HALO, tc.y0 - HALO, tc.z0 - HALO, tc.n);
+          } else {
+            mbar_expect_tx(a_full + as, a_bytes);
+            tma_load_5d(a_stage + as * C::A_STAGE, second ? &tmap_in2 : &tmap_in, a_full + as,
+                        (second ? kc - p.k1_chunks : kc) * CB, tc.x0 - HALO, tc.y0 - HALO, tc.z0 - HALO, tc.n);
+          }
         }
         __syncwarp();
         if (++as == kNumAStages) { as = 0; aph ^= 1; }
@@ -273,23 +314,42 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   } else if (warp == 6) {
     // ============================== weight-slab producer ==============================
     uint32_t ws = 0, wph = 0;
-    for (long long tile = blockIdx.x; tile < outer_tiles; tile += gridDim.x) {
+    for (long long tile = tile0; tile < outer_tiles; tile += tile_step) {
 #pragma unroll 1
       for (int j = 0; j < J; ++j) {
         const TileCoord tc = decode_tile(p, tile, TZ, reuse, j);
-        const uint8_t* wsrc = p.w_packed + (static_cast<size_t>(tc.ntile) * p.nsub + tc.sub) * p.kchunks * NGROUPS *
-                                               static_cast<size_t>(w_bytes);
+        // pair mode: one image per CTA rank (this CTA's half of every B row range)
+        const uint8_t* wsrc = p.w_packed + ((static_cast<size_t>(tc.ntile) * p.nsub + tc.sub) * (PAIR ? 2 : 1) + pair_rank) *
+                                               p.kchunks * NGROUPS * static_cast<size_t>(w_bytes);
         const int nstages = p.kchunks * NGROUPS;
 #pragma unroll 1
         for (int g = 0; g < nstages; ++g) {
           mbar_wait(w_empty + ws, wph ^ 1);
           if (elect_one()) {
-            mbar_expect_tx(w_full + ws, w_bytes);
-            bulk_load(w_stage + ws * C::W_STAGE, wsrc + static_cast<size_t>(g) * w_bytes, w_bytes, w_full + ws);
+            // (a plain bulk copy signals a barrier of its own CTA: the peer's copies land on w_land and its otherwise idle
+            // issuer warp forwards the arrival to the leader's w_full)
+            uint64_t* land = (PAIR && !leader) ? w_land + ws : w_full + ws;
+            mbar_expect_tx(land, w_bytes);
+            bulk_load(w_stage + ws * C::W_STAGE, wsrc + static_cast<size_t>(g) * w_bytes, w_bytes, land);
           }
           __syncwarp();
           if (++ws == kNumWStages) { ws = 0; wph ^= 1; }
         }
+      }
+      if (w_resident) break;
+    }
+  } else if (warp == 1 && PAIR && !leader) {
+    // ============================== peer of a CTA pair: weight-arrival forwarder ==============================
+    // (the leader issues the MMAs for both CTAs; this warp tells it when this CTA's weight stages have landed)
+    uint32_t ws = 0, wph = 0;
+    for (long long tile = tile0; tile < outer_tiles; tile += tile_step) {
+      const int nstages = p.kchunks * NGROUPS;
+#pragma unroll 1
+      for (int g = 0; g < nstages; ++g) {
+        mbar_wait(w_land + ws, wph);
+        if (elect_one()) mbar_arrive_leader(w_full + ws);
+        __syncwarp();
+        if (++ws == kNumWStages) { ws = 0; wph ^= 1; }
       }
       if (w_resident) break;
     }
@@ -298,12 +358,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     // Warp-uniform loop; the elected lane issues a fully unrolled burst of G x TAPS_G x TZ x KSTEPS
     // UMMAs per weight stage.  Descriptors differ from a per-stage base only by compile-time
     // constants (start-address field, 16-byte units).
-    const uint32_t idesc = make_idesc_f16(128, NT, p.fp16 ? 0u : 1u);
+    constexpr uint32_t MM = PAIR ? 256u : 128u;      // M of the instruction: both CTAs' tiles in pair mode
+    const uint32_t idesc = make_idesc_f16(MM, NT, p.fp16 ? 0u : 1u);
+    // one MMA (cta_group::1, or cta_group::2 over the pair) / one commit (to this CTA, or multicast to both)
+    auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
+      if constexpr (PAIR) umma_ss2(d, a, b, id, acc); else umma_ss(d, a, b, id, acc);
+    };
+    auto commit = [](uint64_t* bar) {
+      if constexpr (PAIR) umma_commit2(bar, 3); else umma_commit(bar);
+    };
     constexpr uint32_t sbo_a = BX * C::ROWB;
     constexpr uint32_t sbo_w = 8u * C::ROWB;
     uint32_t as = 0, aph = 0, ws = 0, wph = 0, ab = 0, abph = 0;
     bool w_ready = false;                       // resident weights: every stage has been waited for once
-    for (long long tile = blockIdx.x; tile < outer_tiles; tile += gridDim.x) {
+    for (long long tile = tile0; tile < outer_tiles; tile += tile_step) {
      const uint32_t as0 = as, aph0 = aph;       // ring position of this spatial tile's first input box
 #pragma unroll 1
      for (int j = 0; j < J; ++j) {
@@ -349,7 +417,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
                     for (int ks = 0; ks < C::KSTEPS; ++ks) {
                       const uint64_t ad = adesc_g + static_cast<uint64_t>(((pz * BY * BX + t) * C::ROWB + ks * 32) >> 4);
                       const uint64_t wd = wdesc_g + static_cast<uint64_t>((t * NT * C::ROWB + ks * 32) >> 4);
-                      umma_ss(acc_col + pz * NT, ad, wd, idesc, (t | ks) == 0 ? (first_slab ? 0u : 1u) : 1u);
+                      mma(acc_col + pz * NT, ad, wd, idesc, (t | ks) == 0 ? (first_slab ? 0u : 1u) : 1u);
                     }
                   }
                 }
@@ -363,8 +431,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
 #pragma unroll
                     for (int ks = 0; ks < C::KSTEPS; ++ks) {
                       const uint64_t ad = adesc_g + static_cast<uint64_t>((((pz + 2 - t) * BY * BX) * C::ROWB + ks * 32) >> 4);
-                      const uint64_t wd = wdesc_g + static_cast<uint64_t>((t * NT * C::ROWB + ks * 32) >> 4);
-                      umma_ss(acc_col + pz * NT, ad, wd, idesc, (t | ks) == 0 ? 0u : 1u);
+                      // B rows [t NT, (t + 1) NT) of the slab; pair mode: this CTA's half of them (PairImage V32 t)
+                      const int wrow = PAIR ? PairImage::v32<NT>(t) : t * NT;
+                      const uint64_t wd = wdesc_g + static_cast<uint64_t>((wrow * C::ROWB + ks * 32) >> 4);
+                      mma(acc_col + pz * NT, ad, wd, idesc, (t | ks) == 0 ? 0u : 1u);
                     }
                   }
                 }
@@ -377,27 +447,32 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
                 for (int i = -1; i <= TZ; ++i) {
                   const int lo = i - 1 < 0 ? 0 : i - 1, hi = i + 1 > TZ - 1 ? TZ - 1 : i + 1;
                   const int nblk = hi - lo + 1, toff = lo - (i - 1);
-                  const uint32_t idesc_n = make_idesc_f16(128, NT * nblk, p.fp16 ? 0u : 1u);
+                  const uint32_t idesc_n = make_idesc_f16(MM, NT * nblk, p.fp16 ? 0u : 1u);
+                  // B rows [toff NT, (toff + nblk) NT) of the slab; pair mode: this CTA's half of that range
+                  const int wrow = !PAIR ? toff * NT
+                                   : (nblk == 3 ? PairImage::v96<NT>()
+                                      : (nblk == 2 ? (toff == 1 ? PairImage::v64h<NT>() : PairImage::v64l<NT>())
+                                                   : PairImage::v32<NT>(toff)));
 #pragma unroll
                   for (int ks = 0; ks < C::KSTEPS; ++ks) {
                     const uint64_t ad = adesc_g + static_cast<uint64_t>((((i + 1) * BY * BX) * C::ROWB + ks * 32) >> 4);
-                    const uint64_t wd = wdesc_g + static_cast<uint64_t>((toff * NT * C::ROWB + ks * 32) >> 4);
-                    umma_ss(acc_col + lo * NT, ad, wd, idesc_n, 1u);
+                    const uint64_t wd = wdesc_g + static_cast<uint64_t>((wrow * C::ROWB + ks * 32) >> 4);
+                    mma(acc_col + lo * NT, ad, wd, idesc_n, 1u);
                   }
                 }
               }
             }
-            if (!w_resident) umma_commit(w_empty + ws);   // stage free once these MMAs retire
+            if (!w_resident) commit(w_empty + ws);   // stage free once these MMAs retire
             if (gs == NGROUPS - 1) {
-              if (!reuse) umma_commit(a_empty + as);
+              if (!reuse) commit(a_empty + as);
               if (kc == p.kchunks - 1) {
-                umma_commit(acc_full + ab);
+                commit(acc_full + ab);
                 if (reuse && j == J - 1) {
                   // every pair of this spatial tile has been issued: its input boxes are free once
                   // these MMAs retire (one commit per ring stage it occupied)
                   uint32_t s2 = as0;
                   for (int k2 = 0; k2 < p.kchunks; ++k2) {
-                    umma_commit(a_empty + s2);
+                    commit(a_empty + s2);
                     if (++s2 == kNumAStages) s2 = 0;
                   }
                 }
@@ -425,7 +500,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     // that leaves the finite fp16 range is always a finite-or-infinite fp32 number here (NaNs only descend from it), so one
     // FMNMX per element is a complete overflow detector
     float amax = 0.f;
-    for (long long tile = blockIdx.x; tile < outer_tiles; tile += gridDim.x) {
+    for (long long tile = tile0; tile < outer_tiles; tile += tile_step) {
      for (int j = 0; j < J; ++j) {
       const TileCoord tc = decode_tile(p, tile, TZ, reuse, j);
       mbar_wait(acc_full + ab, abph);
@@ -603,7 +678,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty + ab);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_leader(acc_empty + ab);   // the leader's issuer waits for both CTAs' epilogues
+        else mbar_arrive(acc_empty + ab);
+      }
       if (++ab == 2) { ab = 0; abph ^= 1; }
      }
     }
@@ -616,7 +694,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+  if constexpr (PAIR) {
+    cluster_sync_all();                          // both CTAs are done with the pair's TMEM and with each other's barriers
+    if (warp == 1) tmem_dealloc2(tmem_base, C::TMEM_COLS);
+  } else {
+    if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
 }
 
 template <int CB, int NT, int TZ, int HALO>
@@ -629,6 +712,33 @@ cudaError_t launch_cfg(const ConvUmmaLaunch& L, const KParams& p, int grid, cuda
   for (int i = 0; i < 8; ++i) om.m[i] = L.tmap_out[i];
   conv_umma_kernel<CB, NT, TZ, HALO><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(L.tmap_in, L.tmap_in2, om, p);
   return cudaGetLastError();
+}
+
+// CTA-pair variant: clusters of 2 (the two SMs of a TPC), one pair per two tiles.
+template <int CB, int NT, int TZ>
+cudaError_t launch_pair(const ConvUmmaLaunch& L, KParams p, cudaStream_t stream) {
+  using C = Cfg<CB, NT, TZ, 1, true>;
+  static unsigned long long attr_set = 0;
+  cudaError_t e = smem_attr_once(conv_umma_kernel<CB, NT, TZ, 1, true>, C::SMEM_BYTES, &attr_set);
+  if (e != cudaSuccess) return e;
+  OutMaps om;
+  for (int i = 0; i < 8; ++i) om.m[i] = L.tmap_out[i];
+  p.w_packed = static_cast<const uint8_t*>(L.w_packed_pair);
+  long long g = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+  g &= ~1LL;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(g));
+  cfg.blockDim = dim3(C::THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, conv_umma_kernel<CB, NT, TZ, 1, true>, L.tmap_in, L.tmap_in2, om, p);
 }
 
 KParams make_params(const ConvUmmaLaunch& L) {
@@ -686,7 +796,58 @@ bool conv_umma_config(int Cin, int Cout, ConvUmmaConfig* cfg) {
   // (ceiling 75 % of the tensor peak instead of 67 %); the haloed box then only fits with 16-channel chunks.
   static const bool tz8 = getenv("TOMOENC_NO_TZ8") == nullptr;
   if (tz8 && NT == 32) { cfg->TZ = 8; cfg->CB = 16; }
+  // ... and with the B rows of every instruction split over a CTA pair (cta_group::2) the N = 96 instruction is
+  // math-bound: 49 instead of 56 cycles (tools/umma2_probe.cu), ceiling 75 -> 83 % for a TZ = 8 tile
+  static const bool pair = getenv("TOMOENC_NO_PAIR") == nullptr;
+  cfg->pair = (pair && NT == 32 && cfg->TZ == 8 && cfg->CB == 16 && Cout == 32) ? 1 : 0;
   return true;
+}
+
+size_t conv_umma_pair_packed_bytes(int Cin, int Cout, const ConvUmmaConfig& cfg) {
+  if (!cfg.pair) return 0;
+  return static_cast<size_t>(2) * (Cin / cfg.CB) * 9 * PairImage::rows<32>() * (Cout / 32) * cfg.CB * 2;
+}
+
+// Pair-mode image of a 3x3x3 conv (Cout = NT = 32): [rank][channel chunk][slab g = (dy, dx)][PairImage rows][CB], rows
+// swizzled like the single-CTA slabs (the slab base is a multiple of 256 bytes).  w = [tap][cout][cin], BN folded.
+void conv_umma_pack_pair(const float* w, int Cin, int Cout, const ConvUmmaConfig& cfg, int fp16, void* dst_host) {
+  const int CB = cfg.CB, NT = cfg.NT;
+  const int rowb = CB * 2;
+  const uint32_t mask = CB == 16 ? 1u : (CB == 32 ? 3u : 7u);
+  const int kchunks = Cin / CB;
+  const int rows = 5 * NT;
+  const size_t slab = static_cast<size_t>(rows) * rowb;
+  // image row -> row of the full [t][cout] slab (t <-> dz = 1 - t), per rank
+  auto full_row = [&](int rank, int ir) -> int {
+    const int h = NT / 2;
+    if (ir < 3 * h) return 3 * h * rank + ir;                       // V96: rows [0, 3 NT) halved
+    ir -= 3 * h;
+    if (ir < NT) return NT + NT * rank + ir;                        // V64H: rows [NT, 3 NT) halved
+    ir -= NT;
+    if (ir < NT) return NT * rank + ir;                             // V64L: rows [0, 2 NT) halved
+    ir -= NT;
+    const int t = ir / h;                                           // V32 t: rows [t NT, (t + 1) NT) halved
+    return t * NT + h * rank + (ir - t * h);
+  };
+  for (int rank = 0; rank < 2; ++rank)
+    for (int kc = 0; kc < kchunks; ++kc)
+      for (int g = 0; g < 9; ++g) {
+        uint8_t* base = static_cast<uint8_t*>(dst_host) + ((static_cast<size_t>(rank) * kchunks + kc) * 9 + g) * slab;
+        for (int ir = 0; ir < rows; ++ir) {
+          const int fr = full_row(rank, ir);
+          const int t = fr / NT, r = fr % NT;
+          const int tap = (2 - t) * 9 + g;                          // slab g = (dy, dx), t <-> dz = 1 - t
+          for (int kk = 0; kk < CB; ++kk) {
+            const float val = w[(static_cast<size_t>(tap) * Cout + r) * Cin + kc * CB + kk];
+            uint16_t bits;
+            if (fp16) { __half h = __float2half_rn(val); bits = *reinterpret_cast<uint16_t*>(&h); }
+            else { __nv_bfloat16 h = __float2bfloat16_rn(val); bits = *reinterpret_cast<uint16_t*>(&h); }
+            const uint32_t Lo = static_cast<uint32_t>(ir * rowb + kk * 2);
+            const uint32_t P = Lo ^ (((Lo >> 7) & mask) << 4);
+            *reinterpret_cast<uint16_t*>(base + P) = bits;
+          }
+        }
+      }
 }
 
 size_t conv_umma_packed_bytes(int Cin, int Cout, int ntaps, int nsub, const ConvUmmaConfig& cfg) {
@@ -785,6 +946,10 @@ cudaError_t conv_umma_launch(const ConvUmmaLaunch& L, cudaStream_t stream) {
   if (p.total_tiles >= (1LL << 31)) return cudaErrorInvalidValue;   // decode_tile works on 32-bit indices
   // un-haloed kernels may iterate the (Cout tile, sub-position) pairs inside a spatial tile (input reuse)
   const int grid = static_cast<int>(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs);
+  // CTA pairs: both CTAs of a pair must see the same number of tiles
+  if (L.w_packed_pair != nullptr && p.halo && L.CB == 16 && L.NT == 32 && L.TZ == 8 && p.n_ntiles == 1 &&
+      p.total_tiles % 2 == 0 && p.total_tiles >= 2)
+    return launch_pair<16, 32, 8>(L, p, stream);
 #define TE_CONV_CASE(cb, nt, tz)                                                          \
   if (L.CB == cb && L.NT == nt && L.TZ == tz)                                             \
     return p.halo ? launch_cfg<cb, nt, tz, 1>(L, p, grid, stream) : launch_cfg<cb, nt, tz, 0>(L, p, grid, stream);

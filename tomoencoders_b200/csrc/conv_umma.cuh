@@ -14,6 +14,7 @@ struct ConvUmmaLaunch {
   CUtensorMap tmap_in2;     // second input tensor holding the last Cin2 channels (planar concat); unused if Cin2 == 0
   int Cin2;                 // channels taken from tmap_in2 (multiple of CB; Cin - Cin2 from tmap_in)
   const void* w_packed;     // pre-swizzled weights, see pack_conv_weights() in net.cu
+  const void* w_packed_pair;  // CTA-pair image of the same weights (conv_umma_pack_pair) or nullptr: single-CTA kernel
   const float* bias;        // Cout fp32 (conv bias with BN folded in)
   void* out;                // output activations (16-bit) or nullptr when the head is fused
   int out_ctot, out_coff;   // channel pitch / offset of the output buffer
@@ -49,7 +50,7 @@ struct ConvUmmaLaunch {
 // L.fp16 (un-haloed launches only; leaves use_tma_out = 0 when the layout does not qualify).
 void conv_umma_make_out_maps(ConvUmmaLaunch* L);
 
-struct ConvUmmaConfig { int CB, NT, TZ; };
+struct ConvUmmaConfig { int CB, NT, TZ; int pair; };   // pair: the layer may run on CTA pairs (cta_group::2) when its tile count is even
 // Picks (channel chunk, Cout tile, z planes per tile) for a layer; returns false if unsupported.
 bool conv_umma_config(int Cin, int Cout, ConvUmmaConfig* cfg);
 // Bytes of one packed weight tensor for the given layer shape.
@@ -57,6 +58,9 @@ size_t conv_umma_packed_bytes(int Cin, int Cout, int ntaps, int nsub, const Conv
 // Packs fp32 weights w[sub][tap][cout][cin] (already BN-folded) into the kernel's layout.
 void conv_umma_pack(const float* w, int Cin, int Cout, int ntaps, int nsub, const ConvUmmaConfig& cfg, int fp16,
                     void* dst_host);
+// CTA-pair image (cfg.pair only): bytes and packing of w[tap][cout][cin] (3x3x3 conv, BN folded).
+size_t conv_umma_pair_packed_bytes(int Cin, int Cout, const ConvUmmaConfig& cfg);
+void conv_umma_pack_pair(const float* w, int Cin, int Cout, const ConvUmmaConfig& cfg, int fp16, void* dst_host);
 // Enqueues the layer.  Returns cudaSuccess or the launch error.
 cudaError_t conv_umma_launch(const ConvUmmaLaunch& L, cudaStream_t stream);
 // Number of CTAs the launch uses (for accounting / tests).

@@ -45,6 +45,7 @@ struct Layer {
   float* d_w = nullptr;      // CUDA-core layout
   float* d_bias = nullptr;
   void* d_wpacked = nullptr; // tensor-core layout
+  void* d_wpair = nullptr;   // CTA-pair image of the same weights (cfg.pair)
   bool use_umma = false;
   bool fused_head = false;   // this conv also evaluates the following 1x1x1 head
   bool fused_pool = false;   // this conv also writes the MaxPool3D(2) of its output
@@ -392,6 +393,7 @@ void free_net(te_net* net) {
     if (L.d_w) cudaFree(L.d_w);
     if (L.d_bias) cudaFree(L.d_bias);
     if (L.d_wpacked) cudaFree(L.d_wpacked);
+    if (L.d_wpair) cudaFree(L.d_wpair);
   }
   for (int i = 0; i < 2; ++i) if (net->d_dense_tmp[i]) cudaFree(net->d_dense_tmp[i]);
   if (net->d_dense_acc) cudaFree(net->d_dense_acc);
@@ -549,6 +551,7 @@ extern "C" int te_net_set_weights(te_net* net, const float* w, int64_t count) {
     if (L.d_w) { cudaFree(L.d_w); L.d_w = nullptr; }
     if (L.d_bias) { cudaFree(L.d_bias); L.d_bias = nullptr; }
     if (L.d_wpacked) { cudaFree(L.d_wpacked); L.d_wpacked = nullptr; }
+    if (L.d_wpair) { cudaFree(L.d_wpair); L.d_wpair = nullptr; }
     std::vector<double> scale, shift;
     if (L.op == OP_CONV3) {
       const int Ci = L.Cin, Co = L.Cout;
@@ -568,6 +571,11 @@ extern "C" int te_net_set_weights(te_net* net, const float* w, int64_t count) {
         std::vector<uint8_t> packed(conv_umma_packed_bytes(Ci, Co, 27, 1, L.cfg));
         conv_umma_pack(canon.data(), Ci, Co, 27, 1, L.cfg, fp16, packed.data());
         rc = upload(packed.data(), packed.size(), &L.d_wpacked);
+        if (rc == TE_OK && L.cfg.pair) {
+          std::vector<uint8_t> pp(conv_umma_pair_packed_bytes(Ci, Co, L.cfg));
+          conv_umma_pack_pair(canon.data(), Ci, Co, L.cfg, fp16, pp.data());
+          rc = upload(pp.data(), pp.size(), &L.d_wpair);
+        }
       } else {
         rc = upload(wd.data(), wd.size() * 4, reinterpret_cast<void**>(&L.d_w));
       }
@@ -635,6 +643,7 @@ int run_layers(te_net* net, int n, const HeadOut& ho, cudaStream_t st) {
           C.tmap_in2 = L.has_in2 ? L.tmap2 : L.tmap;
           C.Cin2 = L.has_in2 ? L.in2.C : 0;
           C.w_packed = L.d_wpacked;
+          C.w_packed_pair = L.op == OP_CONV3 ? L.d_wpair : nullptr;
           C.bias = L.d_bias;
           C.out = L.out.ptr;
           C.out_ctot = L.out.ctot;
