@@ -13,16 +13,19 @@ SVS = (40, 44, 48)
 DTYPES = (("u8", np.uint8), ("u16", np.uint16), ("f16", np.float16), ("f32", np.float32))
 
 
-@pytest.fixture(autouse=True, params=["default", "tma", "simt", "chunks"])
+@pytest.fixture(autouse=True, params=["default", "tma", "simt", "chunks", "simt-rows"])
 def gather_path(request, monkeypatch):
-    """Every test runs three times: default kernel selection (TMA-staged kernels for 16-byte-aligned
-    2- and 4-byte tilings, SIMT otherwise), TMA kernels forced wherever the row pitch allows (covers
-    their per-unit unaligned / binned paths), and SIMT kernels forced.  The variables are read on
+    """Every test runs five times: default kernel selection (TMA-staged kernels for 16-byte-aligned
+    2- and 4-byte tilings and for short rows at random corners of a volume whose row pitch is a multiple of
+    16 bytes, SIMT otherwise), TMA kernels forced wherever the row pitch allows (covers
+    their per-unit unaligned / binned paths), SIMT kernels forced, the row kernels switched off, and the
+    TMA row kernel switched off (the SIMT row-group kernel takes its cases).  The variables are read on
     every call."""
     monkeypatch.setenv("TOMOENC_NO_TMA_GATHER", "1" if request.param == "simt" else "0")
     monkeypatch.setenv("TOMOENC_FORCE_TMA_GATHER", "1" if request.param == "tma" else "0")
     # "chunks": the row-group kernel for short unaligned rows switched off (the 16-byte chunk kernel takes them)
     monkeypatch.setenv("TOMOENC_NO_ROW_GATHER", "1" if request.param == "chunks" else "0")
+    monkeypatch.setenv("TOMOENC_NO_TMA_ROW_GATHER", "1" if request.param == "simt-rows" else "0")
     return request.param
 
 
@@ -83,6 +86,35 @@ def test_aligned_pitch_random_corners_and_mixed_binning(dt):
     g.fill_patches_in_volume(sub, out)
     S.fill_patches_in_volume(sub, g.points, np.full((len(g), 3), 32), exp)
     np.testing.assert_array_equal(_bits(out), _bits(exp))
+
+
+@pytest.mark.parametrize("dt", [np.uint8, np.uint16, np.float32])
+def test_row_gather_edges_and_odd_row_lengths(dt):
+    """Random-corner row kernels (TMA-staged box 16 bytes wider than the row, start rounded down): patches that touch
+    the far faces of the volume (the padded box hangs over the edge: out-of-bounds fill), every byte phase of the
+    corner, rows of 3 / 7 / 14 chunks (the generic chunks-per-row path), several units per patch and one unit for
+    several patches' worth of planes."""
+    vs = (70, 66, 160)
+    vol = seeded_volume(vs, dt, 31)
+    es = np.dtype(dt).itemsize
+    for patch in ((8, 8, 48 // es), (5, 9, 112 // es), (64, 64, 32), (3, 2, 16)):
+        pz, py, px = patch
+        if px * es % 16 or px * es > 240:
+            continue
+        g = np.random.default_rng(pz)
+        pts = np.stack([g.integers(0, vs[a] - patch[a] + 1, 200) for a in range(3)], axis=1)
+        pts[:40, 2] = vs[2] - px                # right face
+        pts[40:60, 0] = vs[0] - pz              # last planes
+        pts[60:80, 1] = vs[1] - py
+        pts[80:96, 2] = np.arange(16)           # every byte phase
+        pts[96] = (vs[0] - pz, vs[1] - py, vs[2] - px)
+        pts[97] = 0
+        p = Patches(vs, "data", points=pts, widths=np.tile(np.array(patch), (len(pts), 1)))
+        np.testing.assert_array_equal(_bits(p.extract(vol, patch)), _bits(S.extract(vol, p.points, p.widths, patch)))
+        tv = torch.from_numpy(_bits(vol).astype({1: np.uint8, 2: np.int16, 4: np.int32}[es], copy=False)).cuda()
+        out = p.extract(tv, patch)             # device in, device out
+        assert out.is_cuda
+        np.testing.assert_array_equal(_bits(out.cpu().numpy()), _bits(S.extract(vol, p.points, p.widths, patch)))
 
 
 @pytest.mark.parametrize("dt", [np.uint8, np.float16, np.float32])

@@ -111,7 +111,9 @@ def test_surface_segmenter_train_api_learns_a_synthetic_volume():
     np.random.seed(0)
     fe = SurfaceSegmenter(model_initialization="define-new", descriptor_tag="t", mode="bf16", **SMALL)
     w0 = fe.models["segmenter"].get_weights()
-    hist = fe.train([X], [Y], (32, 32, 32), 3, 8, 0.1, True, 0.05, 3, steps_per_epoch=10, verbose=0)
+    # 60 fit steps: with 30 the accuracy below depends on the draw of the initial weights (0.85 .. 0.99 observed); with 60 every
+    # seed tried reaches > 0.999 (tools/scratch/train_flaky.py)
+    hist = fe.train([X], [Y], (32, 32, 32), 3, 8, 0.1, True, 0.05, 6, steps_per_epoch=10, verbose=0)
     assert hist[-1] < hist[0] and hist[-1] < 0.5, hist
     w1 = fe.models["segmenter"].get_weights()
     assert any(np.abs(a - b).max() > 1e-4 for a, b in zip(w0, w1))

@@ -292,6 +292,172 @@ gather_tma_kernel(const __grid_constant__ CUtensorMap tmap_dense, const __grid_c
   }
 }
 
+// ------------------------------------------------------------------------------------------ random-corner row gather
+// Short patch rows (16..240 bytes) at arbitrary byte corners -- the access pattern of BASELINE configs[0] / configs[2].
+// The SIMT row-group kernel (gather_scatter.cu) spends ~45 warp instructions per 256 bytes on addresses, shuffles and
+// predicates and is issue-bound at ~3 TB/s (ncu: 53 % of the issue slots at 32 % occupancy).  Here the TMA unit does the
+// address generation: a unit (pzc planes of one patch) is ONE box load whose x start is rounded DOWN to 16 bytes and
+// whose rows are 16 bytes wider than the patch row (a box must start on a 16-byte boundary, see above), so a stage holds
+// rows of (row_bytes + 16) bytes with the wanted bytes at offset sh = x0 * es % 16.  Eight consumer warps re-align on
+// the way out: two aligned 128-bit shared-memory loads, four funnel shifts and one 128-bit coalesced store per 16
+// output bytes (the unit's output is contiguous: item i lands at dst + 16 i).  One producer warp runs ahead by the depth
+// of the ring (~200 KB of loads in flight per SM); corners are prefetched one unit, the processing order two units ahead.
+constexpr int kRowsConsumers = 256;
+constexpr int kRowsThreads = 32 + kRowsConsumers;
+constexpr int kRowsStageMax = 50 * 1024;
+constexpr int kRowsMaxStages = 8;
+constexpr int kRowsSmemData = 200 * 1024;
+
+struct RowsParams {
+  const uint32_t* points;
+  const uint32_t* perm;       // optional processing order (work slot -> patch index)
+  uint8_t* out;
+  long long n;
+  int es, pzc, upp;           // element size, planes per unit, units per patch
+  int rows_unit;              // py * pzc
+  int cpr;                    // 16-byte chunks per patch row
+  uint32_t pitch;             // bytes per staged row = row_bytes + 16
+  uint32_t box_bytes;         // pitch * rows_unit
+  uint32_t stage_bytes;       // box_bytes rounded up to 128
+  int nstages;
+  uint32_t unit_out_bytes;    // rows_unit * row_bytes
+};
+
+struct RowsMeta { uint8_t* dst; uint32_t sh; uint32_t pad; };
+
+__device__ __forceinline__ void tma_load_3d_hint(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void stg_cs128(void* p, uint4 v) {
+  asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// low 128 bits of (hi:lo) >> (32 Q + r) bits; Q words are a compile-time selection, r < 32 bits a funnel shift
+template <int Q>
+__device__ __forceinline__ uint4 realign(const uint4& lo, const uint4& hi, uint32_t r) {
+  const uint32_t w0 = Q == 0 ? lo.x : Q == 1 ? lo.y : Q == 2 ? lo.z : lo.w;
+  const uint32_t w1 = Q == 0 ? lo.y : Q == 1 ? lo.z : Q == 2 ? lo.w : hi.x;
+  const uint32_t w2 = Q == 0 ? lo.z : Q == 1 ? lo.w : Q == 2 ? hi.x : hi.y;
+  const uint32_t w3 = Q == 0 ? lo.w : Q == 1 ? hi.x : Q == 2 ? hi.y : hi.z;
+  const uint32_t w4 = Q == 0 ? hi.x : Q == 1 ? hi.y : Q == 2 ? hi.z : hi.w;
+  return make_uint4(__funnelshift_r(w0, w1, r), __funnelshift_r(w1, w2, r), __funnelshift_r(w2, w3, r), __funnelshift_r(w3, w4, r));
+}
+
+// items [ctid, items) of one staged unit, 256 consumer threads, four independent items per thread in flight
+template <int CPR, int Q>
+__device__ __forceinline__ void rows_copy_unit(uint32_t stage, uint8_t* __restrict__ dst, int items, uint32_t pitch, int cpr_rt,
+                                               uint32_t r, int ctid) {
+  constexpr int U = 4;
+  for (int it0 = ctid; it0 < items; it0 += U * kRowsConsumers) {
+    uint4 lo[U], hi[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int it = it0 + k * kRowsConsumers;
+      if (it < items) {
+        const uint32_t row = CPR > 0 ? static_cast<uint32_t>(it) / CPR : static_cast<uint32_t>(it) / static_cast<uint32_t>(cpr_rt);
+        const uint32_t c = static_cast<uint32_t>(it) - row * (CPR > 0 ? CPR : cpr_rt);
+        const uint32_t a = stage + row * pitch + 16u * c;
+        lo[k] = lds128(a);
+        hi[k] = lds128(a + 16u);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int it = it0 + k * kRowsConsumers;
+      if (it < items) stg_cs128(dst + 16ll * it, realign<Q>(lo[k], hi[k], r));
+    }
+  }
+}
+
+template <int CPR>
+__global__ void __launch_bounds__(kRowsThreads, 1)
+gather_rows_tma_kernel(const __grid_constant__ CUtensorMap tmap, const RowsParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kRowsSmemData);
+  uint64_t* empty = full + kRowsMaxStages;
+  RowsMeta* meta = reinterpret_cast<RowsMeta*>(empty + kRowsMaxStages);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NS = p.nstages;
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, kRowsConsumers / 32); }
+    fence_barrier_init();
+    prefetch_tmap(&tmap);
+  }
+  __syncthreads();
+  const long long units = p.n * p.upp;
+  const long long first = blockIdx.x, step = gridDim.x;
+  const long long mine = first < units ? (units - first + step - 1) / step : 0;
+  if (warp == 0) {
+    // ============================== producer ==============================
+    auto patch_of = [&](long long u) -> long long {
+      const long long slot = p.upp == 1 ? u : u / p.upp;
+      return p.perm ? static_cast<long long>(__ldg(p.perm + slot)) : slot;
+    };
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    if (mine > 0) {
+      long long i_cur = patch_of(first);
+      long long i_nxt = mine > 1 ? patch_of(first + step) : 0;
+      uint32_t z0 = __ldg(p.points + 3 * i_cur), y0 = __ldg(p.points + 3 * i_cur + 1), x0 = __ldg(p.points + 3 * i_cur + 2);
+      int s = 0;
+      uint32_t ph = 0;
+      for (long long k = 0; k < mine; ++k) {
+        const long long u = first + k * step;
+        const long long i = i_cur;
+        const uint32_t cz = z0, cy = y0, cx = x0;
+        if (k + 1 < mine) {
+          i_cur = i_nxt;
+          z0 = __ldg(p.points + 3 * i_cur); y0 = __ldg(p.points + 3 * i_cur + 1); x0 = __ldg(p.points + 3 * i_cur + 2);
+          if (k + 2 < mine) i_nxt = patch_of(u + 2 * step);
+        }
+        const int sub = p.upp == 1 ? 0 : static_cast<int>(u % p.upp);
+        mbar_wait(empty + s, ph ^ 1);
+        if (lane == 0) {
+          const uint32_t xb = cx * static_cast<uint32_t>(p.es), sh = xb & 15u;
+          meta[s].dst = p.out + (i * p.upp + sub) * static_cast<long long>(p.unit_out_bytes);
+          meta[s].sh = sh;
+          mbar_expect_tx(full + s, p.box_bytes);
+          tma_load_3d_hint(smem + static_cast<size_t>(s) * p.stage_bytes, &tmap, full + s, static_cast<int>(xb - sh), static_cast<int>(cy),
+                           static_cast<int>(cz) + sub * p.pzc, pol);
+        }
+        __syncwarp();
+        if (++s == NS) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ============================== consumers ==============================
+    const int ctid = tid - 32;
+    const int items = p.rows_unit * p.cpr;
+    int s = 0;
+    uint32_t ph = 0;
+    for (long long k = 0; k < mine; ++k) {
+      mbar_wait(full + s, ph);
+      uint8_t* dst = meta[s].dst;
+      const uint32_t sh = meta[s].sh;
+      const uint32_t stage = smem_u32(smem + static_cast<size_t>(s) * p.stage_bytes);
+      const uint32_t r = (sh & 3u) * 8u;
+      switch (sh >> 2) {                     // unit-uniform
+        case 0: rows_copy_unit<CPR, 0>(stage, dst, items, p.pitch, p.cpr, r, ctid); break;
+        case 1: rows_copy_unit<CPR, 1>(stage, dst, items, p.pitch, p.cpr, r, ctid); break;
+        case 2: rows_copy_unit<CPR, 2>(stage, dst, items, p.pitch, p.cpr, r, ctid); break;
+        default: rows_copy_unit<CPR, 3>(stage, dst, items, p.pitch, p.cpr, r, ctid); break;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + s);     // this warp has read everything it needs from the stage
+      if (++s == NS) { s = 0; ph ^= 1; }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ scatter (disjoint patches)
 // Mirror image: contiguous bulk load of a unit, TMA box store into the volume when the corner is
 // 16-byte aligned, otherwise the threads write the rows with the widest aligned stores available.
@@ -469,6 +635,61 @@ bool gather_tma(const void* vol, int es, const int64_t vs[3], const uint32_t* po
   const int grid = grid_for_units(n * p.units_per_patch);
   *err = es == 1 ? launch_raw<uint8_t>(td, tp, p, grid, st)
                  : (es == 2 ? launch_raw<uint16_t>(td, tp, p, grid, st) : launch_raw<uint32_t>(td, tp, p, grid, st));
+  return true;
+}
+
+template <int CPR>
+static cudaError_t launch_rows(const CUtensorMap& tm, const RowsParams& p, int grid, cudaStream_t st) {
+  constexpr int smem_bytes = kRowsSmemData + 1024 /*align*/ + 512 /*barriers + unit descriptors*/;
+  static unsigned long long attr = 0;
+  cudaError_t e = smem_attr_once(gather_rows_tma_kernel<CPR>, smem_bytes, &attr);
+  if (e != cudaSuccess) return e;
+  gather_rows_tma_kernel<CPR><<<grid, kRowsThreads, smem_bytes, st>>>(tm, p);
+  return cudaGetLastError();
+}
+
+bool gather_rows_tma(const void* vol, int es, const int64_t vs[3], const uint32_t* points, const uint32_t* perm, int64_t n,
+                     const int32_t patch[3], void* out, cudaStream_t st, cudaError_t* err) {
+  if (es != 1 && es != 2 && es != 4) return false;
+  const long long Z = vs[0], Y = vs[1], X = vs[2];
+  const long long xb = X * es;
+  if ((reinterpret_cast<uintptr_t>(vol) & 15) != 0 || (reinterpret_cast<uintptr_t>(out) & 15) != 0 || xb % 16 != 0) return false;
+  if (xb >= (1ll << 31) || Y >= (1ll << 31) || Z >= (1ll << 31)) return false;
+  const int pz = patch[0], py = patch[1], px = patch[2];
+  const long long row_bytes = static_cast<long long>(px) * es;
+  if (row_bytes % 16 != 0 || row_bytes + 16 > 256 || py > 256 || pz < 1 || py < 1) return false;
+  const long long plane = (row_bytes + 16) * py;
+  if (plane > kRowsStageMax) return false;
+  int pzc = static_cast<int>(kRowsStageMax / plane);
+  if (pzc > pz) pzc = pz;
+  if (pzc > 256) pzc = 256;
+  while (pz % pzc) --pzc;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  // byte-typed map: coordinates and extents of the innermost dimension are bytes, whatever the element size
+  CUtensorMap tm;
+  cuuint64_t gdim[3] = {(cuuint64_t)xb, (cuuint64_t)Y, (cuuint64_t)Z};
+  cuuint64_t gstr[2] = {(cuuint64_t)xb, (cuuint64_t)xb * Y};
+  cuuint32_t estr[3] = {1, 1, 1};
+  cuuint32_t box[3] = {(cuuint32_t)(row_bytes + 16), (cuuint32_t)py, (cuuint32_t)pzc};
+  if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(vol), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  RowsParams p{};
+  p.points = points; p.perm = perm; p.out = static_cast<uint8_t*>(out); p.n = n;
+  p.es = es; p.pzc = pzc; p.upp = pz / pzc;
+  p.rows_unit = py * pzc;
+  p.cpr = static_cast<int>(row_bytes / 16);
+  p.pitch = static_cast<uint32_t>(row_bytes + 16);
+  p.box_bytes = static_cast<uint32_t>(plane * pzc);
+  p.stage_bytes = (p.box_bytes + 127u) & ~127u;
+  p.nstages = static_cast<int>(kRowsSmemData / p.stage_bytes);
+  if (p.nstages > kRowsMaxStages) p.nstages = kRowsMaxStages;
+  if (p.nstages < 2) return false;
+  p.unit_out_bytes = static_cast<uint32_t>(row_bytes * p.rows_unit);
+  const int grid = grid_for_units(n * p.upp);
+  *err = p.cpr == 2 ? launch_rows<2>(tm, p, grid, st)
+                    : (p.cpr == 4 ? launch_rows<4>(tm, p, grid, st) : (p.cpr == 8 ? launch_rows<8>(tm, p, grid, st) : launch_rows<0>(tm, p, grid, st)));
   return true;
 }
 

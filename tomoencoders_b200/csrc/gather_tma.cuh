@@ -9,6 +9,9 @@ namespace te {
 
 bool gather_tma(const void* vol, int es, const int64_t vol_shape[3], const uint32_t* points, const uint32_t* widths,
                 int64_t n, const int32_t patch[3], void* out, cudaStream_t st, cudaError_t* err);
+// unbinned patches with short rows at arbitrary corners (row-group pattern); perm = optional processing order
+bool gather_rows_tma(const void* vol, int es, const int64_t vol_shape[3], const uint32_t* points, const uint32_t* perm,
+                     int64_t n, const int32_t patch[3], void* out, cudaStream_t st, cudaError_t* err);
 bool gather_norm_tma(const void* vol, int vol_dtype, const int64_t vol_shape[3], const uint32_t* points,
                      const uint32_t* widths, int64_t n, const int32_t patch[3], int rescale, int do_clip, float lo,
                      float hi, void* out, int out_dtype, cudaStream_t st, cudaError_t* err);
