@@ -26,6 +26,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 namespace te {
@@ -500,6 +501,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     // that leaves the finite fp16 range is always a finite-or-infinite fp32 number here (NaNs only descend from it), so one
     // FMNMX per element is a complete overflow detector
     float amax = 0.f;
+    uint32_t stg_it = 0;                          // staging-buffer round of this warp (TMA-store epilogue)
     for (long long tile = tile0; tile < outer_tiles; tile += tile_step) {
      for (int j = 0; j < J; ++j) {
       const TileCoord tc = decode_tile(p, tile, TZ, reuse, j);
@@ -519,60 +521,66 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       bool done_by_tma = false;
       {
         if (p.tma_out) {
-          // TMEM -> registers -> bias / LeakyReLU -> swizzled staging buffer -> ONE TMA box store per plane and
-          // 64-channel group.  (Per-thread 16-byte stores touch 32 different 128-byte lines per instruction;
-          // the L1 store path, shared by all warps of the SM, was the bound of these kernels.)
-          constexpr int OB = C::OUT_BOX, ROWB_O = OB * 2;      // channels and bytes per staged voxel row
-          constexpr uint32_t SWM = ROWB_O == 128 ? 7u : (ROWB_O == 64 ? 3u : 1u);
-          uint8_t* my_stg = stg + eg * C::STG_NBUF * C::STG_BUF;
-          const bool issuer = (warp == (eg ? 7 : 2));
-          uint32_t it = 0;
+          // TMEM -> registers -> bias / LeakyReLU -> swizzled staging buffer -> TMA box store.  (Per-thread 16-byte stores
+          // touch 32 different 128-byte lines per instruction; the L1 store path, shared by all warps of the SM, was the
+          // bound of these kernels.)  Every WARP owns the 32 voxels of its TMEM lane quarter (4 y rows x 8 x), its own
+          // staging buffers and its own bulk-store groups: no barrier couples the epilogue warps (the two named barriers per
+          // plane of the 128-voxel version were 25 % of the stall samples of enc0.conv2), and a warp only waits for its
+          // previous store's shared-memory read right before it overwrites the buffer, after the TMEM loads and the math.
+          auto run = [&](auto fp_tag) {
+            constexpr bool FP16 = decltype(fp_tag)::value;
+            constexpr int OB = C::OUT_BOX, ROWB_O = OB * 2, WBUF = 32 * ROWB_O;   // channels / bytes per staged voxel row, bytes per warp buffer
+            constexpr uint32_t SWM = ROWB_O == 128 ? 7u : (ROWB_O == 64 ? 3u : 1u);
+            constexpr int HC = OB < 32 ? OB : 32;                                 // channels per TMEM round trip
+            uint8_t* wbuf0 = stg + static_cast<size_t>((eg * 4 + q) * C::STG_NBUF) * WBUF;
+            const uint32_t rowoff = static_cast<uint32_t>(lane) * ROWB_O;
+            const uint32_t sw = (rowoff >> 7) & SWM;
+            const float al = p.act_lrelu ? p.alpha : 1.f;                         // 0 <= alpha <= 1 (checked at launch): lrelu(x) = max(x, alpha x)
+            const bool rows_inside = tc.y0 + 4 * q < p.H;
 #pragma unroll 1
-          for (int pz = eg * PZ_PER_GROUP; pz < (eg + 1) * PZ_PER_GROUP; ++pz) {
+            for (int pz = eg * PZ_PER_GROUP; pz < (eg + 1) * PZ_PER_GROUP; ++pz) {
 #pragma unroll 1
-            for (int cg = 0; cg < NT; cg += OB, ++it) {
-              uint8_t* buf = my_stg + (C::STG_NBUF == 2 ? (it & 1) : 0) * C::STG_BUF;
-              // the store issued from this buffer (two rounds ago, or the previous one with a single buffer) must have
-              // finished reading it
-              if (issuer) {
-                if (elect_one()) { if (C::STG_NBUF == 2) bulk_wait_read_le1(); else bulk_wait_read_0(); }
-                __syncwarp();
-              }
-              named_barrier(1 + eg, 128);
+              for (int cg = 0; cg < NT; cg += OB, ++stg_it) {
+                uint8_t* buf = wbuf0 + (C::STG_NBUF == 2 ? (stg_it & 1u) : 0u) * WBUF;
+                uint32_t pk[OB / 2];
 #pragma unroll
-              for (int c0 = 0; c0 < OB; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld16(tbase + pz * NT + cg + c0, r);
-                tmem_ld_wait();
-                float v[16], bs[16];
-                lds_f16x(bias + cg + c0, bs);
+                for (int h = 0; h < OB; h += HC) {
+                  uint32_t r[HC];
 #pragma unroll
-                for (int j2 = 0; j2 < 16; ++j2) {
-                  float x = __uint_as_float(r[j2]) + bs[j2];
-                  if (p.act_lrelu) x = x > 0.f ? x : p.alpha * x;
-                  amax = fmaxf(amax, fabsf(x));
-                  v[j2] = x;
+                  for (int c0 = 0; c0 < HC; c0 += 16) tmem_ld16(tbase + pz * NT + cg + h + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[c0]));
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int c0 = 0; c0 < HC; c0 += 16) {
+                    float bs[16];
+                    lds_f16x(bias + cg + h + c0, bs);
+#pragma unroll
+                    for (int j2 = 0; j2 < 16; j2 += 2) {
+                      float x0 = __uint_as_float(r[c0 + j2]) + bs[j2], x1 = __uint_as_float(r[c0 + j2 + 1]) + bs[j2 + 1];
+                      x0 = fmaxf(x0, al * x0);
+                      x1 = fmaxf(x1, al * x1);
+                      if (FP16) amax = fmaxf(amax, fmaxf(fabsf(x0), fabsf(x1)));
+                      pk[(h + c0 + j2) >> 1] = pack2(x0, x1, FP16 ? 1 : 0);
+                    }
+                  }
                 }
-                // row m of the box, 16-byte chunks (c0 / 8) and (c0 / 8 + 1), swizzled like the TMA expects
-                const uint32_t rowoff = static_cast<uint32_t>(m) * ROWB_O;
-                const uint32_t ch0 = static_cast<uint32_t>(c0 >> 3);
-                const uint32_t sw = (rowoff >> 7) & SWM;
-                *reinterpret_cast<uint4*>(buf + rowoff + (((ch0) ^ sw) << 4)) =
-                    make_uint4(pack2(v[0], v[1], p.fp16), pack2(v[2], v[3], p.fp16), pack2(v[4], v[5], p.fp16), pack2(v[6], v[7], p.fp16));
-                *reinterpret_cast<uint4*>(buf + rowoff + (((ch0 + 1) ^ sw) << 4)) =
-                    make_uint4(pack2(v[8], v[9], p.fp16), pack2(v[10], v[11], p.fp16), pack2(v[12], v[13], p.fp16), pack2(v[14], v[15], p.fp16));
-              }
-              fence_proxy_async_smem();
-              named_barrier(1 + eg, 128);
-              if (issuer) {
-                if (elect_one()) {
-                  tma_store_5d(&omaps.m[tc.sub], buf, tc.ntile * NT + cg, tc.x0, tc.y0, tc.z0 + pz, tc.n);
+                // the store issued from this buffer (two rounds ago, or the previous one with a single buffer) must have
+                // finished reading it (bulk groups belong to the issuing thread: always lane 0)
+                if (lane == 0) { if (C::STG_NBUF == 2) bulk_wait_read_le1(); else bulk_wait_read_0(); }
+                __syncwarp();
+#pragma unroll
+                for (int ch = 0; ch < OB / 8; ++ch)     // row `lane` of the warp's box, 16-byte chunk ch, swizzled like the TMA expects
+                  *reinterpret_cast<uint4*>(buf + rowoff + ((static_cast<uint32_t>(ch) ^ sw) << 4)) =
+                      make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0 && rows_inside) {
+                  tma_store_5d(&omaps.m[tc.sub], buf, tc.ntile * NT + cg, tc.x0, tc.y0 + 4 * q, tc.z0 + pz, tc.n);
                   bulk_commit_group();
                 }
-                __syncwarp();
               }
             }
-          }
+          };
+          if (p.fp16) run(std::true_type{}); else run(std::false_type{});
           done_by_tma = true;
         }
       }
@@ -688,8 +696,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     if (p.fp16 && p.overflow != nullptr && amax > 65504.f) atomicOr(p.overflow, 1);
   }
 
-  if (p.tma_out && (warp == 2 || (C::EPI_GROUPS == 2 && warp == 7))) {
-    if (elect_one()) bulk_wait_all_groups();
+  if (p.tma_out && warp >= 2 && warp != 6) {    // every epilogue warp drains its own bulk-store groups
+    if (lane == 0) bulk_wait_all_groups();
     __syncwarp();
   }
   tc_fence_before();
@@ -925,7 +933,7 @@ void conv_umma_make_out_maps(ConvUmmaLaunch* L) {
     cuuint64_t gdim[5] = {(cuuint64_t)L->Cout, (cuuint64_t)L->W, (cuuint64_t)L->H, (cuuint64_t)L->D, (cuuint64_t)L->N};
     cuuint64_t gstr[4] = {(cuuint64_t)(s * ct * 2), (cuuint64_t)(s * W2 * ct * 2), (cuuint64_t)(s * H2 * W2 * ct * 2),
                           (cuuint64_t)(D2 * H2 * W2 * ct * 2)};
-    cuuint32_t box[5] = {(cuuint32_t)ob, 8, 16, 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)ob, 8, 4, 1, 1};      // one epilogue warp: the 4 y rows x 8 x of its TMEM lane quarter
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     if (enc(&L->tmap_out[sub], L->fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, gdim, gstr, box,
             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -944,6 +952,7 @@ cudaError_t conv_umma_launch(const ConvUmmaLaunch& L, cudaStream_t stream) {
   const KParams p = make_params(L);
   if (p.total_tiles <= 0) return cudaSuccess;
   if (p.total_tiles >= (1LL << 31)) return cudaErrorInvalidValue;   // decode_tile works on 32-bit indices
+  if (p.act_lrelu && !(p.alpha >= 0.f && p.alpha <= 1.f)) return cudaErrorInvalidValue;   // epilogue: lrelu(x) = max(x, alpha x)
   // un-haloed kernels may iterate the (Cout tile, sub-position) pairs inside a spatial tile (input reuse)
   const int grid = static_cast<int>(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs);
   // CTA pairs: both CTAs of a pair must see the same number of tiles
