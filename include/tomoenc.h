@@ -316,6 +316,10 @@ typedef struct te_tensor {
 int64_t te_tr_conv3_wpack_bytes(int32_t Cin, int32_t Cout);
 int te_tr_conv3(const te_tensor* x, const te_tensor* x2, const float* w, const float* bias, const te_tensor* y,
                 void* wpack, void* stream);
+/* Which kernel te_tr_conv3 / the first layer of a network takes for a ONE-channel input x and output y (first Conv3D of
+ * every graph, Unet3D.py:117-122): 2 = Toeplitz tcgen05 kernel (conv1_tz.cu), 1 = im2col tcgen05 kernel (conv1_umma.cu),
+ * 0 = CUDA cores.  Host-only query (tests and the per-layer roofline table name the kernel with it). */
+int te_conv1_kernel_kind(const te_tensor* x, const te_tensor* y);
 /* wf[27][Cout][ci_n]: spatially flipped, channel-transposed slice [ci_lo, ci_lo + ci_n) of w[27][Cin][Cout];
  * te_tr_conv3(dy, NULL, wf, zero_bias, dx, ...) is then the data gradient of the convolution. */
 int te_tr_flip_weights(const float* w, int32_t Cin, int32_t Cout, int32_t ci_lo, int32_t ci_n, float* wf, void* stream);

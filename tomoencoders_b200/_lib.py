@@ -171,6 +171,7 @@ _SIGNATURES = {
     # training operators
     "te_tr_conv3_wpack_bytes": (_I64, [_I32, _I32]),
     "te_tr_conv3": (ctypes.c_int, [_TP, _TP, _P, _P, _TP, _P, _P]),
+    "te_conv1_kernel_kind": (ctypes.c_int, [_TP, _TP]),
     "te_tr_flip_weights": (ctypes.c_int, [_P, _I32, _I32, _I32, _I32, _P, _P]),
     "te_tr_conv3_wgrad": (ctypes.c_int, [_TP, _TP, _P, _I32, _I32, _P, _P]),
     "te_tr_bn_stats": (ctypes.c_int, [_TP, _P, _P]),

@@ -391,6 +391,7 @@ cudaError_t simt_conv3(const TView& in, const TView& out, const float* w, const 
                        int act_type, cudaStream_t st, int* overflow) {
   {
     cudaError_t e = cudaSuccess;
+    if (conv1_tz_try(in, out, w, bias, lrelu, alpha, act_type, st, &e, overflow)) { count_launch(); return e; }
     if (conv1_umma_try(in, out, w, bias, lrelu, alpha, act_type, st, &e, overflow)) { count_launch(); return e; }
   }
   if (in.C == 1 && act_type != ACT_F32 && out.C % 16 == 0 && out.ctot % 8 == 0 && out.coff % 8 == 0 && out.C <= 256) {

@@ -24,6 +24,10 @@ cudaError_t simt_conv3(const TView& in, const TView& out, const float* w, const 
 // Tensor-core version of the Cin = 1 first layer (conv1_umma.cu); returns false when it does not apply.
 bool conv1_umma_try(const TView& in, const TView& out, const float* w, const float* bias, int lrelu, float alpha, int act_type,
                     cudaStream_t st, cudaError_t* err, int* overflow = nullptr);
+// Toeplitz formulation of the same layer (conv1_tz.cu: raw input rows as the A operand, no im2col builder), tried first.
+bool conv1_tz_applies(const TView& in, const TView& out, int act_type);
+bool conv1_tz_try(const TView& in, const TView& out, const float* w, const float* bias, int lrelu, float alpha, int act_type,
+                  cudaStream_t st, cudaError_t* err, int* overflow = nullptr);
 // transposed conv k=2, stride s ('same': output = s x input; gaps get bias only), w = [8][Cout][Cin].
 cudaError_t simt_upconv(const TView& in, const TView& out, const float* w, const float* bias, int stride, int lrelu,
                         float alpha, int act_type, cudaStream_t st);

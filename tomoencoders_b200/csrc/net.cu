@@ -848,6 +848,8 @@ extern "C" int te_net_layer_kernel(const te_net* net, int i, char* buf, int bufl
   const Layer& L = net->layers[i];
   if (L.skip) snprintf(buf, buflen, "fused into previous layer");
   else if (L.use_umma) snprintf(buf, buflen, "conv_umma_kernel<%d,%d,%d>%s", L.cfg.CB, L.cfg.NT, L.cfg.TZ, L.fused_head ? "+head" : "");
+  else if (L.op == OP_CONV3 && L.Cin == 1 && conv1_tz_applies(L.in, L.out, net->act_type))
+    snprintf(buf, buflen, "conv1_tz_kernel<%d>", L.Cout);
   else if (L.op == OP_CONV3 && L.Cin == 1 && net->act_type != ACT_F32 && (L.Cout == 16 || L.Cout == 32))
     snprintf(buf, buflen, "conv1_umma_kernel<%d>", L.Cout);
   else {

@@ -1344,6 +1344,13 @@ extern "C" int te_tr_conv3(const te_tensor* x, const te_tensor* x2, const float*
   return TE_OK;
 }
 
+extern "C" int te_conv1_kernel_kind(const te_tensor* x, const te_tensor* y) {
+  if (!x || !y || x->C != 1 || x->ctot != 1 || x->dtype == TE_F32 || x->dtype != y->dtype) return 0;
+  if (conv1_tz_applies(view_of(*x), view_of(*y), act_of(x->dtype))) return 2;
+  static const bool off = getenv("TOMOENC_NO_C1_UMMA") != nullptr;
+  return (!off && (y->C == 16 || y->C == 32) && y->ctot % 8 == 0 && y->coff % 8 == 0) ? 1 : 0;
+}
+
 // wf[27][Cout][ci_n] = flipped / transposed slice of w[27][Cin][Cout] (dgrad weights)
 extern "C" int te_tr_flip_weights(const float* w, int32_t Cin, int32_t Cout, int32_t ci_lo, int32_t ci_n, float* wf, void* stream) {
   TE_CHECK_ARG(w && wf && ci_lo >= 0 && ci_n > 0 && ci_lo + ci_n <= Cin, "te_tr_flip_weights: bad argument");
