@@ -197,7 +197,7 @@ def leg_cfg4(fe, rank, world, dev, barrier, max_over_ranks, host_slab, z0, z1, r
     mm_box = [None]
 
     def step():
-        lo, hi = fe.calc_voxel_min_max(host_slab, 4)             # uploads every 4th plane of the slab
+        lo, hi = fe.calc_voxel_min_max(host_slab, 4)             # uploads every 4th row of every 4th plane of the slab
         mm_box[0] = sharding.allreduce_minmax(lo, hi, device=dev)   # two scalars: the only exchange of this workload
         fe.segment_volume(host_slab, loc, CHUNK, min_max=mm_box[0], out=host_mask)
         torch.cuda.synchronize()
@@ -220,7 +220,7 @@ def leg_cfg4(fe, rank, world, dev, barrier, max_over_ranks, host_slab, z0, z1, r
     res = {"metric": "voxels/sec segmented: ONE 2048^3 float16 volume, z-slab per rank, host volume in -> host uint8 mask out",
            "value": nvox / (ms / 1e3), "unit": "voxels/s", "ms_per_step": ms, "steps": reps, "scaling": "strong",
            "tiles_total": len(grid), "tiles_this_rank": len(loc), "slab_rank0": [z0, z1], "min_max": list(mm_box[0]),
-           "h2d_bytes_per_step": int(nvox * 2 + nvox * 2 // 4), "d2h_bytes_per_step": int(nvox),
+           "h2d_bytes_per_step": int(nvox * 2 + nvox * 2 // 16), "d2h_bytes_per_step": int(nvox),
            "mask_checksum": int(csum.item()), "mask_fraction_ones": float(csum.item()) / nvox,
            "exchange": "all-reduce(MAX) of (-min, max): 2 float64" if world > 1 else "none (1 rank)"}
     del host_mask
@@ -668,8 +668,9 @@ def run_ours(args):
             "tflops_effective": world * n_tiles * flops_patch / (ms_per_step / 1e3) / 1e12,
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": "voxels/s", "ms_per_step": e2e_ms,
-                    # the volume once + every 4th plane once more for the min/max that has to precede the first chunk
-                    "h2d_bytes_per_step": int(host_vol.numel() * 2 + (-(-VOL[0] // 4)) * VOL[1] * VOL[2] * 2),
+                    # the volume once + every 4th row of every 4th plane once more (one strided DMA) for the min/max that has
+                    # to precede the first chunk
+                    "h2d_bytes_per_step": int(host_vol.numel() * 2 + (-(-VOL[0] // 4)) * (-(-VOL[1] // 4)) * VOL[2] * 2),
                     "d2h_bytes_per_step": int(host_seg.numel()),
                     "api": "calc_voxel_min_max(host volume, 4) + SurfaceSegmenter.segment_volume(host volume, grid, chunk, min_max, out=host mask): pinned host tensors, slab-wise H2D / D2H overlapped with the network"},
             "gpu_launches": launches,

@@ -126,6 +126,12 @@ int te_scatter(const void* sub_vols, int elem_size, const uint32_t* points, int6
 int te_minmax_strided(const void* vol, int vol_dtype, const int64_t vol_shape[3], int stride,
                       float* out2, float* scratch, void* stream);
 
+/* Host volume -> device copy of vol[::s, ::s, :] (dense (ceil(Z/s), ceil(Y/s), X) on the device) as one strided 3-D DMA:
+ * the min / max pre-pass of a HOST volume (_find_min_max) moves 1 / s^2 of the bytes; the x stride is applied on the device
+ * (te_minmax_nd).  host_vol should be pinned (the copy is asynchronous on `stream` then). */
+int te_upload_sampled(const void* host_vol, int32_t elem_bytes, const int64_t vol_shape[3], int32_t s, void* dev_out,
+                      void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Volume normalisation / contrast / masking -- the calls every user of the path makes right before
  * (and after) it (misc/voxel_processing.py).  Views are described by up to

@@ -142,6 +142,7 @@ _SIGNATURES = {
     "te_scatter": (ctypes.c_int, [_P, ctypes.c_int, _P, _I64, ctypes.POINTER(_I32), _P,
                                   ctypes.POINTER(_I64), _P, ctypes.c_int, _P]),
     "te_minmax_strided": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_I64), ctypes.c_int, _P, _P, _P]),
+    "te_upload_sampled": (ctypes.c_int, [_P, _I32, ctypes.POINTER(_I64), _I32, _P, _P]),
     "te_minmax_nd": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_I64), ctypes.POINTER(_I64), _P, _P, _P]),
     "te_histogram_nd": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_I64), ctypes.POINTER(_I64), _P, _I32, _P, _P]),
     "te_rescale": (ctypes.c_int, [_P, ctypes.c_int, _P, ctypes.c_int, _I64, _F, _F, _P]),
