@@ -449,6 +449,21 @@ int te_bp_patches(const void* workspace, int32_t ntheta, int32_t nz, int32_t n, 
 int te_bp_points(const void* workspace, int32_t ntheta, int32_t nz, int32_t n, float center, const int32_t* pts, int32_t npts,
                  int32_t xy_mode, float* out, int32_t exact, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * One-shot all-reduce of small fp64 vectors over NVLink peer memory (csrc/peer_comm.cu): the SyncBN reductions of the
+ * data-parallel training step (per-channel sums of every BatchNormalization layer, forward and
+ * backward).  One process per GPU on one box; every rank: te_peer_create, te_peer_export -> exchange the 64-byte handles
+ * (all-gather of bytes, e.g. torch.distributed) -> te_peer_import, then the SAME sequence of te_peer_allreduce_f64 calls
+ * on one stream.  A reduction is one single-CTA kernel per rank (publish + epoch flag, wait for the peers' flags, sum in
+ * rank order: bit-identical on every rank); graph-capturable.  count <= slot_doubles.
+ */
+typedef struct te_peer te_peer;
+int te_peer_create(int32_t rank, int32_t world, int32_t slot_doubles, int32_t nslots, te_peer** out);
+int te_peer_export(te_peer* p, void* handle64);
+int te_peer_import(te_peer* p, const void* handles);
+int te_peer_allreduce_f64(te_peer* p, double* data, int32_t count, void* stream);
+int te_peer_destroy(te_peer* p);
+
 #ifdef __cplusplus
 }
 #endif

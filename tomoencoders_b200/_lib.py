@@ -208,6 +208,11 @@ _SIGNATURES = {
     "te_bp_box": (ctypes.c_int, [_P, _I32, _I32, _I32, _F, _I32, _I32, _I32, _I32, _I32, _I32, _P, _I32, _I32, _P]),
     "te_bp_patches": (ctypes.c_int, [_P, _I32, _I32, _I32, _F, _P, _I64, _I32, _P, _I32, _I32, _F, _F, _I32, _P]),
     "te_bp_points": (ctypes.c_int, [_P, _I32, _I32, _I32, _F, _P, _I32, _I32, _P, _I32, _P]),
+    "te_peer_create": (ctypes.c_int, [_I32, _I32, _I32, _I32, ctypes.POINTER(_P)]),
+    "te_peer_export": (ctypes.c_int, [_P, _P]),
+    "te_peer_import": (ctypes.c_int, [_P, _P]),
+    "te_peer_allreduce_f64": (ctypes.c_int, [_P, _P, _I32, _P]),
+    "te_peer_destroy": (ctypes.c_int, [_P]),
     "te_tr_adam": (ctypes.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I64, _F, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -373,7 +373,15 @@ class UnetTrainer:
                 raise ValueError(op)
         # ---------------- backward
         pending_pool = {}                     # id(skip activation) -> True once the decoder wrote its gradient
+        # the flat gradient buffer is in forward (Keras) order and the backward pass walks the layers in reverse, so the
+        # gradients are final from the tail of the buffer downwards: all-reduce them in buckets on a side stream while the
+        # remaining layers' backward kernels run (data-parallel steps only)
+        self._pend_hi = int(self.offsets[-1])
+        prev_w = None
         for lay in reversed(self.layers):
+            if prev_w is not None:
+                self._grad_ready(int(self.offsets[prev_w]))
+            prev_w = lay.get("w", prev_w)
             op = lay["op"]
             if op in ("head", "head_ae"):
                 continue
@@ -435,12 +443,41 @@ class UnetTrainer:
                 self._take(c, 2 * c, self._g(wi + 1), st)
             elif op == "reshape":
                 lay["src"].g.copy_(lay["a"].g.reshape(lay["src"].g.shape))
+        self._grad_ready(0, final=True)
         return self.loss
 
+    GRAD_BUCKET = 1 << 19                     # elements (2 MB of fp32): M_a01's 4.77 M gradients go out in ~5 buckets
+
+    def _grad_ready(self, lo, final=False):
+        """grad[lo:] is final.  Data-parallel steps: once a bucket's worth is pending (or at the end of the backward pass)
+        its all-reduce is issued on the communication stream behind an event, so it overlaps the backward kernels of the
+        layers still to come; _post_backward joins the stream.  OPT-IN (TOMOENC_GRAD_BUCKETS=1); the default is one flat
+        all-reduce at the end: validated at 2 ranks only (tests/test_multirank_gpu.py), and a run at 8 ranks with this AND the
+        peer-memory SyncBN reducer enabled hung -- two spin-waiting mechanisms on concurrent streams."""
+        if sharding.world(self.group)[1] == 1 or os.environ.get("TOMOENC_GRAD_BUCKETS", "0") != "1":
+            return
+        hi = self._pend_hi
+        if hi <= lo or not (final or hi - lo >= self.GRAD_BUCKET):
+            return
+        if getattr(self, "_comm", None) is None:
+            self._comm = torch.cuda.Stream()
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_event(ev)
+            torch.distributed.all_reduce(self.grad[lo:hi], op=torch.distributed.ReduceOp.SUM, group=self.group)
+        self._pend_hi = lo
+        self._bucketed = True
+
     def _post_backward(self):
-        """Gradient all-reduce over the ranks + BN moving statistics from the (global) batch statistics of the last
-        forward pass (graph-capturable: no host-side state)."""
-        sharding.allreduce_sum_(self.grad, self.group)
+        """Gradient all-reduce over the ranks (joined here when it went out in buckets during the backward pass) + BN
+        moving statistics from the (global) batch statistics of the last forward pass (graph-capturable: no host-side
+        state)."""
+        if getattr(self, "_bucketed", False):
+            torch.cuda.current_stream().wait_stream(self._comm)
+            self._bucketed = False
+        else:
+            sharding.allreduce_sum_(self.grad, self.group)
         # moving = moving * momentum + batch * (1 - momentum) for every BN layer at once: the batch statistics live in
         # a buffer laid out like theta (bn["mean"] / bn["var"] are views into it), mov_mask selects those entries
         self.theta.addcmul_(self.mov_mask, self.bstat - self.theta, value=1.0 - BN_MOMENTUM)

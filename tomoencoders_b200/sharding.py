@@ -111,9 +111,84 @@ def allreduce_minmax(lo, hi, device=None, group=None):
     return -float(t[0].item()), float(t[1].item())
 
 
+class PeerReducer:
+    """One-shot SUM all-reduce of small float64 CUDA vectors over NVLink peer memory (csrc/peer_comm.cu): every rank maps
+    every peer's slot buffer through CUDA IPC; a reduction is one single-CTA kernel per rank, no NCCL launch.  Used for the
+    SyncBN reductions of the training step (34 latency-bound all-reduces of <= 4 KB per step of M_a01).  All ranks must
+    make the same sequence of calls on their current stream."""
+    SLOT_DOUBLES = 2048
+    NSLOTS = 64
+
+    def __init__(self, group=None):
+        import ctypes
+        from . import _lib
+        self._L = _lib.lib()
+        rank, ws = world(group)
+        h = ctypes.c_void_p()
+        _lib.check(self._L.te_peer_create(rank, ws, self.SLOT_DOUBLES, self.NSLOTS, ctypes.byref(h)), "te_peer_create")
+        self._h = h
+        mine = (ctypes.c_ubyte * 64)()
+        _lib.check(self._L.te_peer_export(h, mine), "te_peer_export")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        t = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
+        outs = [torch.empty_like(t) for _ in range(ws)]
+        dist.all_gather(outs, t, group=group)
+        blob = bytes(torch.cat(outs).cpu().numpy().tobytes())
+        _lib.check(self._L.te_peer_import(h, blob), "te_peer_import")
+        dist.barrier(group=group)
+
+    def allreduce_(self, t):
+        from . import _device, _lib
+        _lib.check(self._L.te_peer_allreduce_f64(self._h, t.data_ptr(), t.numel(), _device.stream_ptr()), "te_peer_allreduce_f64")
+        return t
+
+    def __del__(self):
+        try:
+            self._L.te_peer_destroy(self._h)
+        except Exception:  # noqa: BLE001
+            pass
+
+
+_PEER = {}
+
+
+def peer_reducer(group=None):
+    """The process's PeerReducer for `group` (created on first use), or None when the peer path does not apply: a single
+    process, a backend other than NCCL (CPU / gloo rigs), several ranks sharing one GPU -- or when it was not asked for:
+    the path is OPT-IN (TOMOENC_PEER_ALLREDUCE=1).  It is validated at 2 ranks (tests/test_multirank_gpu.py: 200 reductions
+    against NCCL, CUDA-graph replay, a data-parallel fit step); a run at 8 ranks together with the bucketed gradient
+    all-reduce on a side stream hung, so NCCL stays the default for every reduction."""
+    import os
+    key = id(group)
+    if key in _PEER:
+        return _PEER[key]
+    red = None
+    ws = world(group)[1]
+    if (ws > 1 and os.environ.get("TOMOENC_PEER_ALLREDUCE", "0") == "1" and dist.get_backend(group) == "nccl"
+            and torch.cuda.is_available() and ws <= 16):
+        try:
+            red = PeerReducer(group)
+        except Exception as e:  # noqa: BLE001  (no IPC / no peer access: NCCL does the job)
+            import warnings
+            warnings.warn("peer-memory all-reduce unavailable (%s): using NCCL for the small reductions" % (e,))
+            red = None
+        # every rank must take the same path
+        ok = torch.tensor([1 if red is not None else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            red = None
+    _PEER[key] = red
+    return red
+
+
 def allreduce_sum_(t, group=None):
-    """In-place SUM all-reduce of a tensor (moments of LatentPCA); no-op for a single process."""
+    """In-place SUM all-reduce of a tensor (moments of LatentPCA, SyncBN sums, gradients); no-op for a single process.
+    Small contiguous float64 CUDA vectors go through the peer-memory reducer when it is available."""
     if world(group)[1] > 1:
+        if t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and 0 < t.numel() <= PeerReducer.SLOT_DOUBLES:
+            red = peer_reducer(group)
+            if red is not None:
+                return red.allreduce_(t)
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t
 
