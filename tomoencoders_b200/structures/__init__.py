@@ -1,4 +1,5 @@
 from .patches import Patches
 from .grid import Grid
+from .datafile import DataFile
 
-__all__ = ["Patches", "Grid"]
+__all__ = ["Patches", "Grid", "DataFile"]

@@ -36,8 +36,8 @@ class Grid(dict):
         if str(fpath).endswith(".npz"):
             np.savez(fpath, **data)
             return
-        import h5py
-        with h5py.File(fpath, "w") as hf:
+        from .hdf5_lite import h5_module           # h5py when installed, else the format subset in hdf5_lite.py
+        with h5_module().File(fpath, "w") as hf:
             for k, v in data.items():
                 hf.create_dataset(k, data=v)
 
@@ -58,8 +58,8 @@ class Grid(dict):
         if str(fpath).endswith(".npz"):
             hf = dict(np.load(fpath))
         else:
-            import h5py
-            with h5py.File(fpath, "r") as f:
+            from .hdf5_lite import h5_module
+            with h5_module().File(fpath, "r") as f:
                 hf = {k: np.asarray(f[k]) for k in f.keys()}
         self.vol_shape = tuple(int(v) for v in hf["vol_shape"])
         return np.asarray(hf["points"]).astype(np.uint32), int(hf["width"])

@@ -9,7 +9,8 @@ names and error behaviour.  Differences, all deliberate
 * the O(n) Python loops of the reference (grid construction, validity check, slices) are vectorised
   so that n = 10^6 patches is practical.
 * coordinates are validated in int64, so negative inputs raise instead of wrapping through uint32.
-* ``dump`` / ``initialize_by="file"`` use HDF5 when h5py is importable and ``.npz`` otherwise.
+* ``dump`` / ``initialize_by="file"`` write / read the reference's HDF5 schema through h5py when it is importable and
+  through ``structures/hdf5_lite.py`` (a dependency-free subset of the file format) otherwise; ``.npz`` paths also work.
 """
 import numpy as np
 from numpy.random import default_rng
@@ -76,7 +77,9 @@ class Patches(dict):
 
     # ------------------------------------------------------------------ disk
     def dump(self, fpath):
-        """patches.py:81-91; datasets vol_shape, points, widths, features, feature_names."""
+        """patches.py:81-91: HDF5 file with the datasets vol_shape, points, widths, features, feature_names (h5py when it is
+        installed, else the format subset in structures/hdf5_lite.py); a path ending in .npz writes a numpy archive of the
+        same arrays instead."""
         data = {"vol_shape": np.asarray(self.vol_shape), "points": self.points, "widths": self.widths}
         if self.features is not None:
             data["features"] = self.features
@@ -85,17 +88,18 @@ class Patches(dict):
         if str(fpath).endswith(".npz"):
             np.savez(fpath, **data)
             return
-        import h5py  # optional dependency, as in the reference
-        with h5py.File(fpath, "w") as hf:
+        from .hdf5_lite import h5_module
+        with h5_module().File(fpath, "w") as hf:
             for k, v in data.items():
                 hf.create_dataset(k, data=v)
 
     def _load_from_disk(self, fpath=None):
+        """patches.py:94-110 (initialize_by = "file")."""
         if str(fpath).endswith(".npz"):
             hf = dict(np.load(fpath))
         else:
-            import h5py
-            with h5py.File(fpath, "r") as f:
+            from .hdf5_lite import h5_module
+            with h5_module().File(fpath, "r") as f:
                 hf = {k: np.asarray(f[k]) for k in f.keys()}
         self.vol_shape = tuple(int(v) for v in hf["vol_shape"])
         self.points = np.asarray(hf["points"])
