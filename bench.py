@@ -700,6 +700,13 @@ def run_ours(args):
             "recon": recon,
             "cpu_baseline": cpu_baseline,
         }
+        if cfg3 is not None:
+            # "patches/s encoded" end to end = the configs[2] leg above: host volume + host coordinates in, host (n, 2) rows out
+            line["encode"]["e2e"] = {"value": cfg3["value"], "unit": cfg3["unit"], "ms_per_step": cfg3["ms_per_step"],
+                                     "h2d_bytes_per_step": cfg3["h2d_bytes_per_step_this_rank"],
+                                     "d2h_bytes_per_step": cfg3["d2h_bytes_per_step"],
+                                     "api": "Patches + SelfSupervisedCAE.embed_volume(host slab, ...) + LatentPCA.partial_fit / finalize / "
+                                            "transform_all_gather -> numpy rows (the `cfg3` leg: 1 M patches of one 2048^3 volume)"}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
