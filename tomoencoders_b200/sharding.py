@@ -120,22 +120,34 @@ class PeerReducer:
     NSLOTS = 64
 
     def __init__(self, group=None):
+        """Every rank runs the same collectives whatever happens locally (a rank that cannot allocate or map must not leave
+        the others waiting in a different collective): all-gather of (status, handle), then a MIN all-reduce of the import
+        status; raises RuntimeError on EVERY rank if any rank failed."""
         import ctypes
         from . import _lib
         self._L = _lib.lib()
+        self._h = None
         rank, ws = world(group)
-        h = ctypes.c_void_p()
-        _lib.check(self._L.te_peer_create(rank, ws, self.SLOT_DOUBLES, self.NSLOTS, ctypes.byref(h)), "te_peer_create")
-        self._h = h
-        mine = (ctypes.c_ubyte * 64)()
-        _lib.check(self._L.te_peer_export(h, mine), "te_peer_export")
         dev = torch.device("cuda", torch.cuda.current_device())
-        t = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
+        h = ctypes.c_void_p()
+        mine = (ctypes.c_ubyte * 64)()
+        ok = self._L.te_peer_create(rank, ws, self.SLOT_DOUBLES, self.NSLOTS, ctypes.byref(h)) == 0
+        ok = ok and self._L.te_peer_export(h, mine) == 0
+        t = torch.tensor([1 if ok else 0] + list(mine), dtype=torch.uint8, device=dev)
         outs = [torch.empty_like(t) for _ in range(ws)]
         dist.all_gather(outs, t, group=group)
-        blob = bytes(torch.cat(outs).cpu().numpy().tobytes())
-        _lib.check(self._L.te_peer_import(h, blob), "te_peer_import")
-        dist.barrier(group=group)
+        table = torch.stack(outs).cpu().numpy()
+        all_ok = bool(table[:, 0].all())
+        if all_ok:
+            all_ok = self._L.te_peer_import(h, table[:, 1:].tobytes()) == 0
+        flag = torch.tensor([1 if all_ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            if h.value:
+                self._L.te_peer_destroy(h)
+            raise RuntimeError("peer-memory buffers could not be created / mapped on every rank: %s"
+                               % self._L.te_last_error().decode(errors="replace"))
+        self._h = h
 
     def allreduce_(self, t):
         from . import _device, _lib
@@ -144,7 +156,8 @@ class PeerReducer:
 
     def __del__(self):
         try:
-            self._L.te_peer_destroy(self._h)
+            if self._h is not None:
+                self._L.te_peer_destroy(self._h)
         except Exception:  # noqa: BLE001
             pass
 
@@ -167,15 +180,10 @@ def peer_reducer(group=None):
     if (ws > 1 and os.environ.get("TOMOENC_PEER_ALLREDUCE", "0") == "1" and dist.get_backend(group) == "nccl"
             and torch.cuda.is_available() and ws <= 16):
         try:
-            red = PeerReducer(group)
-        except Exception as e:  # noqa: BLE001  (no IPC / no peer access: NCCL does the job)
+            red = PeerReducer(group)                # raises on every rank or on none: all ranks take the same path
+        except RuntimeError as e:                   # no IPC / no peer access: NCCL does the job
             import warnings
             warnings.warn("peer-memory all-reduce unavailable (%s): using NCCL for the small reductions" % (e,))
-            red = None
-        # every rank must take the same path
-        ok = torch.tensor([1 if red is not None else 0], dtype=torch.int32, device="cuda")
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-        if int(ok.item()) == 0:
             red = None
     _PEER[key] = red
     return red
