@@ -82,17 +82,21 @@ def conv3d_transpose(x, K, b, s):
     return out + b
 
 
-def _conv_block(x, take, cout, bn):
+def _conv_block(x, take, cout, bn, training=False):
     cin = x.shape[-1]
     y = conv3d_same(x, take((3, 3, 3, cin, cout)), take((cout,)))
     if bn:
-        y = batchnorm(y, take((cout,)), take((cout,)), take((cout,)), take((cout,)))
+        gamma, beta, mean, var = take((cout,)), take((cout,)), take((cout,)), take((cout,))
+        if training:        # Keras BatchNormalization(training=True): batch mean and BIASED batch variance over (N, D, H, W)
+            mean, var = y.mean(axis=(0, 1, 2, 3)), y.var(axis=(0, 1, 2, 3))
+        y = batchnorm(y, gamma, beta, mean, var)
     return lrelu(y)
 
 
 def unet_forward(x, weights, n_filters=(16, 32, 64), n_blocks=3, activation="lrelu", batch_norm=True, kern_size=3,
-                 kern_size_upconv=2, isconcat=None, pool_size=2, return_logits=False):
-    """build_Unet_3D (Unet3D.py:199-291).  x (N,D,H,W,1) -> (N,D,H,W,1) float64 probabilities or logits."""
+                 kern_size_upconv=2, isconcat=None, pool_size=2, return_logits=False, training=False):
+    """build_Unet_3D (Unet3D.py:199-291).  x (N,D,H,W,1) -> (N,D,H,W,1) float64 probabilities or logits.
+    training=True normalises every BatchNormalization layer with the statistics of the batch (model.fit)."""
     assert activation == "lrelu" and kern_size == 3 and kern_size_upconv == 2
     if isconcat is None:
         isconcat = [False] * n_blocks
@@ -102,26 +106,41 @@ def unet_forward(x, weights, n_filters=(16, 32, 64), n_blocks=3, activation="lre
     code = np.asarray(x, dtype=np.float64)
     skips = []
     for i in range(n_blocks):
-        code = _conv_block(code, take, n_filters[i], batch_norm)
-        code = _conv_block(code, take, 2 * n_filters[i], batch_norm)
+        code = _conv_block(code, take, n_filters[i], batch_norm, training)
+        code = _conv_block(code, take, 2 * n_filters[i], batch_norm, training)
         skips.append(code)
         if pool_size[i] > 1:
             code = maxpool(code, pool_size[i])
     nf = code.shape[-1]
-    code = _conv_block(code, take, nf, batch_norm)
-    dec = _conv_block(code, take, 2 * nf, batch_norm)
+    code = _conv_block(code, take, nf, batch_norm, training)
+    dec = _conv_block(code, take, 2 * nf, batch_norm, training)
     for i in range(n_blocks - 1, -1, -1):
         if pool_size[i] > 1:
             c = dec.shape[-1]
             dec = lrelu(conv3d_transpose(dec, take((2, 2, 2, c, c)), take((c,)), pool_size[i]))
             if isconcat[i]:
                 dec = np.concatenate([dec, skips[i]], axis=-1)          # up-sampled first, skip second (Unet3D.py:180)
-        dec = _conv_block(dec, take, 2 * n_filters[i], batch_norm)
-        dec = _conv_block(dec, take, 2 * n_filters[i], batch_norm)
+        dec = _conv_block(dec, take, 2 * n_filters[i], batch_norm, training)
+        dec = _conv_block(dec, take, 2 * n_filters[i], batch_norm, training)
     cin = dec.shape[-1]
     logits = np.einsum("nzyxi,io->nzyxo", dec, take((1, 1, 1, cin, 1))[0, 0, 0]) + take((1,))
     assert take.i == len(weights)
     return logits if return_logits else 1.0 / (1.0 + np.exp(-logits))
+
+
+def keras_bce(p, y):
+    """tf.keras.losses.BinaryCrossentropy on probabilities (surface_segmenter.py:322-323; Keras backend: clip to
+    [1e-7, 1 - 1e-7], log(p + 1e-7), mean over all voxels)."""
+    eps = 1e-7
+    pc = np.clip(p, eps, 1.0 - eps)
+    return float(-(y * np.log(pc + eps) + (1.0 - y) * np.log(1.0 - pc + eps)).mean())
+
+
+def unet_training_loss(x, y, weights, **model_params):
+    """Loss of one fit step of the segmenter (BatchNormalization in training mode + BCE), float64, no autograd: the
+    finite-difference reference for the gradient oracle (oracle/train_torch.py)."""
+    p = unet_forward(x, weights, training=True, **model_params)
+    return keras_bce(p, np.asarray(y, dtype=np.float64))
 
 
 def _dense(x, take, nout, bn):

@@ -64,3 +64,34 @@ def test_single_layer_known_answers():
     y4 = NP.conv3d_transpose(xt, Kt, np.array([0.5]), 4)
     assert y4.shape == (1, 8, 8, 8, 1) and y4[0, 6, 2, 6, 0] == 0.5 and y4[0, 4, 0, 4, 0] == 0.5
     assert y4[0, 5, 1, 5, 0] == 0.5 + 2.0 * 7
+
+
+def test_training_oracle_loss_and_gradients_against_torch_free_finite_differences():
+    """The gradient oracle of the training step (oracle/train_torch.py: torch autograd through BatchNormalization in
+    training mode + Keras BCE) against a torch-free pin: the numpy float64 loss of the same step equals its loss, and
+    central finite differences of that numpy loss along random directions of every trainable array equal the
+    autograd gradient's directional derivative."""
+    from oracle import train_torch as TT
+    P = dict(n_filters=[2, 3], n_blocks=2, activation="lrelu", batch_norm=True, isconcat=[True, True], pool_size=[2, 2])
+    spec = O.unet_spec(**P)
+    w = [np.asarray(a, dtype=np.float64) for a in OW.draw(spec, 5)]
+    rng = np.random.default_rng(1)
+    x = rng.uniform(0, 1, (3, 8, 8, 8, 1))
+    y = (rng.uniform(0, 1, (3, 8, 8, 8, 1)) < 0.4).astype(np.float64)
+    loss_t, grads, _ = TT.unet_loss_and_grads(x, y, w, **P)
+    loss_n = NP.unet_training_loss(x, y, w, **P)
+    assert abs(loss_n - loss_t) < 1e-12 * max(1.0, abs(loss_t))
+    checked = 0
+    for i, (kind, shape) in enumerate(spec):
+        if grads[i] is None:
+            continue                                            # moving statistics: not trainable, not used in training mode
+        d = rng.standard_normal(shape)
+        d /= np.linalg.norm(d)
+        h = 1e-5
+        wp, wm = list(w), list(w)
+        wp[i], wm[i] = w[i] + h * d, w[i] - h * d
+        fd = (NP.unet_training_loss(x, y, wp, **P) - NP.unet_training_loss(x, y, wm, **P)) / (2 * h)
+        an = float((grads[i] * d).sum())
+        assert abs(fd - an) < 1e-6 * max(1e-3, abs(an)) + 1e-9, (i, kind, fd, an)
+        checked += 1
+    assert checked >= 30
