@@ -320,3 +320,44 @@ def test_datafile_tiff_series(tmp_path, dt):
     assert auto.tiff_mode and auto.d_shape == vol.shape
     d2.create_new(overwrite=True)
     assert not os.path.exists(folder)
+
+
+def test_random_hyperslabs_match_numpy(tmp_path):
+    """Property check (seeded): reads and writes through arbitrary slices -- positive steps, negative bounds, integers,
+    partially out-of-range stops -- of contiguous and chunked datasets behave like the same operations on a numpy array."""
+    rng = np.random.default_rng(123)
+
+    def rand_key(shape):
+        key = []
+        for n in shape:
+            kind = rng.integers(0, 4)
+            if kind == 0:
+                key.append(slice(None))
+            elif kind == 1:
+                key.append(int(rng.integers(-n, n)))
+            else:
+                a, b = sorted(int(v) for v in rng.integers(-n - 2, n + 3, 2))
+                key.append(slice(a, b, int(rng.integers(1, 4)) if kind == 3 else None))
+        return tuple(key)
+
+    for trial in range(12):
+        rank = int(rng.integers(1, 4))
+        shape = tuple(int(v) for v in rng.integers(1, 14, rank))
+        chunks = None if trial % 2 == 0 else tuple(int(rng.integers(1, s + 1)) for s in shape)
+        ref = rng.integers(0, 1000, shape).astype(np.int32)
+        f = str(tmp_path / ("p%d.h5" % trial))
+        with H.File(f, "w") as hf:
+            hf.create_dataset("d", data=ref, chunks=chunks)
+        with H.File(f, "r+") as hf:
+            d = hf["d"]
+            for _ in range(25):
+                key = rand_key(shape)
+                got, want = d[key], ref[key]
+                assert np.shape(got) == np.shape(want), (shape, chunks, key)
+                np.testing.assert_array_equal(got, want)
+                if rng.integers(0, 3) == 0 and np.size(want):
+                    val = rng.integers(0, 1000, np.shape(want)).astype(np.int32)
+                    d[key] = val
+                    ref[key] = val
+        with H.File(f, "r") as hf:
+            np.testing.assert_array_equal(hf["d"][...], ref)
