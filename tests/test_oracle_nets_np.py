@@ -95,3 +95,22 @@ def test_training_oracle_loss_and_gradients_against_torch_free_finite_difference
         assert abs(fd - an) < 1e-6 * max(1e-3, abs(an)) + 1e-9, (i, kind, fd, an)
         checked += 1
     assert checked >= 30
+
+
+def test_toeplitz_formulation_of_the_first_layer_equals_the_direct_convolution():
+    """The index algebra of csrc/conv1_tz.cu (aligned 8-wide planes, two x phases, banded weight tiles) restated in numpy
+    equals Conv3D(f, 3, 'same') on one channel, exactly up to float64 rounding, for every width the kernel takes."""
+    from oracle import conv1_toeplitz_np as TZ
+    rng = np.random.default_rng(4)
+    for shape, co in (((2, 4, 5, 8), 16), ((1, 3, 4, 24), 16), ((1, 2, 3, 64), 5)):
+        x = rng.standard_normal(shape)
+        w = rng.standard_normal((3, 3, 3, 1, co))
+        b = rng.standard_normal(co)
+        want = NP.conv3d_same(x[..., None], w, b)
+        got = TZ.conv1_toeplitz(x, w, b)
+        assert np.abs(got - want).max() < 1e-12 * np.abs(want).max()
+    # the banded tiles hold each weight exactly XT times per (phase, tap) and nothing else
+    w = rng.standard_normal((3, 3, 3, 1, 16))
+    B = TZ.banded_weights(w)
+    assert B.shape == (2, 9, 16, 64) and np.count_nonzero(B) == 2 * 9 * 4 * 3 * 16
+    assert not B[0, :, :7].any() and not B[0, :, 13:].any() and not B[1, :, :3].any() and not B[1, :, 9:].any()
