@@ -79,3 +79,18 @@ def test_exact_pca_oracle_against_sklearn():
     ipca, zi = pca_np.incremental_pca_reference(h)
     s = np.linalg.svd(ipca.components_ @ comps.T, compute_uv=False)
     assert s.min() > 0.999
+
+
+def test_timer_cpu_mirrors_the_reference(capsys):
+    """misc/voxel_processing.py:53-70 of the reference: tic / toc(msg), units "ms" and "secs"."""
+    import time
+    from tomoencoders_b200.misc.voxel_processing import TimerCPU
+    t = TimerCPU("ms")
+    t.tic()
+    time.sleep(0.02)
+    ms = t.toc()
+    assert 15.0 < ms < 2000.0 and capsys.readouterr().out == ""
+    t = TimerCPU("secs")
+    t.tic()
+    s = t.toc("step")
+    assert 0.0 <= s < 1.0 and "TIME: step" in capsys.readouterr().out

@@ -18,6 +18,48 @@ from .. import _device, _lib
 _WHOLE_VOLUME_BYTES = 32 << 30      # host volumes up to this size are normalised in one upload
 
 
+class TimerGPU:
+    """voxel_processing.py:29-51: a CUDA-event pair on the current stream; toc() returns the elapsed time in `unit`
+    ("ms" or "secs") and prints it when a message is given."""
+
+    def __init__(self, unit):
+        self.unit = unit
+
+    def tic(self):
+        _device.require_cuda()
+        self.start = torch.cuda.Event(enable_timing=True)
+        self.end = torch.cuda.Event(enable_timing=True)
+        self.start.record()
+
+    def toc(self, msg="execution"):
+        self.end.record()
+        self.end.synchronize()
+        t_elapsed = self.start.elapsed_time(self.end)
+        if self.unit == "secs":
+            t_elapsed /= 1000.0
+        if msg != "execution":
+            print(f"\tTIME: {msg} {t_elapsed:.2f} {self.unit}")
+        return t_elapsed
+
+
+class TimerCPU:
+    """voxel_processing.py:53-70: wall-clock timer; unit "ms" or "secs"."""
+
+    def __init__(self, unit):
+        self.unit = unit
+
+    def tic(self):
+        self.start = time.time()
+
+    def toc(self, msg="execution"):
+        t_elapsed = time.time() - self.start
+        if self.unit == "ms":
+            t_elapsed *= 1000.0
+        if msg != "execution":
+            print(f"\tTIME: {msg} {t_elapsed:.2f} {self.unit}")
+        return t_elapsed
+
+
 def _msg_exec_time(func, t_exec):
     """voxel_processing.py:72-77."""
     print("TIME: %s: %.2f seconds" % (func if type(func) is str else func.__name__, t_exec))
