@@ -168,7 +168,7 @@ _PEER = {}
 def peer_reducer(group=None):
     """The process's PeerReducer for `group` (created on first use), or None when the peer path does not apply: a single
     process, a backend other than NCCL (CPU / gloo rigs), several ranks sharing one GPU -- or when it was not asked for:
-    the path is OPT-IN (TOMOENC_PEER_ALLREDUCE=1).  It is validated at 2 ranks (tests/test_multirank_gpu.py: 200 reductions
+    the path is OPT-IN (TOMOENC_PEER_ALLREDUCE=1).  It is validated at 2 ranks (tests/test_zz_late_additions_gpu.py: 200 reductions
     against NCCL, CUDA-graph replay, a data-parallel fit step); a run at 8 ranks together with the bucketed gradient
     all-reduce on a side stream hung, so NCCL stays the default for every reduction."""
     import os
