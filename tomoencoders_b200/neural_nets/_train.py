@@ -452,7 +452,7 @@ class UnetTrainer:
         """grad[lo:] is final.  Data-parallel steps: once a bucket's worth is pending (or at the end of the backward pass)
         its all-reduce is issued on the communication stream behind an event, so it overlaps the backward kernels of the
         layers still to come; _post_backward joins the stream.  OPT-IN (TOMOENC_GRAD_BUCKETS=1); the default is one flat
-        all-reduce at the end: validated at 2 ranks only (tests/test_multirank_gpu.py), and a run at 8 ranks with this AND the
+        all-reduce at the end: validated at 2 ranks only (tests/test_zz_late_additions_gpu.py), and a run at 8 ranks with this AND the
         peer-memory SyncBN reducer enabled hung -- two spin-waiting mechanisms on concurrent streams."""
         if sharding.world(self.group)[1] == 1 or os.environ.get("TOMOENC_GRAD_BUCKETS", "0") != "1":
             return
