@@ -48,6 +48,12 @@ def _worker(rank, world_size, port, h_all, out_dir):
         assert z_all.shape == (len(h_all), 2)
         t = sharding.max_over_ranks(10.0 + rank)
         assert t == 10.0 + world_size - 1
+        # the peer-memory reducer is opt-in AND needs NCCL + CUDA: on a gloo / CPU rig it never engages, whatever the switch
+        # says, and small float64 vectors (the SyncBN sums it would take) go through the backend's all-reduce
+        os.environ["TOMOENC_PEER_ALLREDUCE"] = "1"
+        assert sharding.peer_reducer() is None
+        small = sharding.allreduce_sum_(torch.full((8,), float(rank + 1), dtype=torch.float64))
+        assert torch.equal(small, torch.full((8,), 3.0, dtype=torch.float64))
         if rank == 0:
             np.save(os.path.join(out_dir, "z.npy"), z_all.numpy())
             np.save(os.path.join(out_dir, "comps.npy"), comps)
