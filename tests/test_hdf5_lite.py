@@ -361,3 +361,64 @@ def test_random_hyperslabs_match_numpy(tmp_path):
                     ref[key] = val
         with H.File(f, "r") as hf:
             np.testing.assert_array_equal(hf["d"][...], ref)
+
+
+def test_written_file_walks_like_the_specification_says(tmp_path):
+    """An independent structural walk of a written file (no code shared with the module's reader): every address the
+    superblock, the symbol-table entries, the B-tree and the heap hold must lead to the object the specification puts there."""
+    f = str(tmp_path / "s.h5")
+    a = np.arange(30, dtype=np.int16).reshape(5, 6)
+    with H.File(f, "w") as hf:
+        hf.create_dataset("zeta", data=a)
+        hf.create_dataset("alpha", data=np.float64(2.5))
+        hf.create_dataset("mid/inner", data=np.arange(3, dtype=np.uint8))
+    raw = open(f, "rb").read()
+    u16 = lambda o: struct.unpack_from("<H", raw, o)[0]        # noqa: E731
+    u64 = lambda o: struct.unpack_from("<Q", raw, o)[0]        # noqa: E731
+    assert raw[:8] == b"\x89HDF\r\n\x1a\n" and raw[8] == 0 and raw[13] == 8 and raw[14] == 8
+    assert u64(24) == 0 and u64(32) == 2 ** 64 - 1 and u64(40) == len(raw) and u64(48) == 2 ** 64 - 1
+    root_hdr, cache_type, bt, hp = u64(64), struct.unpack_from("<I", raw, 72)[0], u64(80), u64(88)
+    assert u64(56) == 0 and cache_type == 1 and root_hdr % 8 == 0
+
+    def group(hdr, bt_expected, hp_expected):
+        # object header: version 1, one message, the symbol-table message pointing at the same B-tree / heap as the entry
+        assert raw[hdr] == 1 and u16(hdr + 2) == 1 and struct.unpack_from("<I", raw, hdr + 8)[0] == 24
+        assert u16(hdr + 16) == 0x11 and u16(hdr + 18) == 16 and (u64(hdr + 24), u64(hdr + 32)) == (bt_expected, hp_expected)
+        assert raw[hp_expected:hp_expected + 4] == b"HEAP" and raw[hp_expected + 4] == 0
+        seg_size, free_head, seg = u64(hp_expected + 8), u64(hp_expected + 16), u64(hp_expected + 24)
+        assert free_head == 1 and seg_size % 8 == 0 and raw[seg:seg + 8] == b"\0" * 8
+        name = lambda off: raw[seg + off:raw.index(b"\0", seg + off)].decode()      # noqa: E731
+        assert raw[bt_expected:bt_expected + 4] == b"TREE" and raw[bt_expected + 4] == 0 and raw[bt_expected + 5] == 0
+        used = u16(bt_expected + 6)
+        assert u64(bt_expected + 8) == u64(bt_expected + 16) == 2 ** 64 - 1 and u64(bt_expected + 24) == 0
+        out = {}
+        for i in range(used):
+            snod = u64(bt_expected + 24 + 16 * i + 8)
+            assert raw[snod:snod + 4] == b"SNOD" and raw[snod + 4] == 1
+            n = u16(snod + 6)
+            names = []
+            for j in range(n):
+                e = snod + 8 + 40 * j
+                names.append(name(u64(e)))
+                out[names[-1]] = (u64(e + 8), struct.unpack_from("<I", raw, e + 16)[0], u64(e + 24), u64(e + 32))
+            assert names == sorted(names)
+            assert name(u64(bt_expected + 24 + 16 * (i + 1))) == names[-1]       # right key = largest name of the child
+        return out
+
+    root = group(root_hdr, bt, hp)
+    assert sorted(root) == ["alpha", "mid", "zeta"]
+    assert root["mid"][1] == 1 and sorted(group(root["mid"][0], root["mid"][2], root["mid"][3])) == ["inner"]
+    # the dataset "zeta": four messages; the contiguous layout's address holds the array bytes
+    hdr = root["zeta"][0]
+    assert raw[hdr] == 1 and u16(hdr + 2) == 4 and root["zeta"][1] == 0
+    o, kinds = hdr + 16, []
+    for _ in range(4):
+        mtype, size = u16(o), u16(o + 2)
+        assert size % 8 == 0
+        kinds.append(mtype)
+        if mtype == 8:
+            assert raw[o + 8] == 3 and raw[o + 9] == 1
+            addr, nbytes = u64(o + 10), u64(o + 18)
+            assert nbytes == a.nbytes and raw[addr:addr + nbytes] == a.tobytes()
+        o += 8 + size
+    assert kinds == [1, 3, 5, 8] and o - (hdr + 16) == struct.unpack_from("<I", raw, hdr + 8)[0]
